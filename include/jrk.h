@@ -1,0 +1,160 @@
+/* jrk.h -- C ABI of the B200-native Gram / fused K@W path for JaxRK.
+ *
+ * This is the drop-in boundary (DESIGN.md "Boundary").  The reference
+ * (zalandoresearch/JaxRK) has no native layer: the path is pure Python over jax.numpy.
+ * Every entry point below therefore cites the reference Python function it replaces;
+ * a maintainer binds these symbols with jax.ffi (XLA FFI handler shim in
+ * jaxrk_b200/csrc/xla_ffi_shim.cc) or ctypes (jaxrk_b200/_native.py).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / XLA types.
+ *   - All matrices are float32, row-major, with explicit leading dimensions (elements).
+ *   - Device entry points take DEVICE pointers, enqueue on `stream` (a cudaStream_t
+ *     passed as void*), never synchronise, retain nothing, never write their inputs.
+ *     Scratch memory, when needed, is taken from `workspace` if it is large enough
+ *     (query with the *_workspace_bytes function) and from the stream-ordered
+ *     allocator (cudaMallocAsync / cudaFreeAsync on `stream`) otherwise.
+ *   - *_host entry points take HOST pointers, run on CUDA device `device`, include
+ *     the host<->device copies, and return after the result is in host memory.
+ *   - Return value: 0 = ok; non-zero = JRK_ERR_*.  jrk_last_error() gives the text.
+ *     Nothing throws.  There is no CPU fallback: without a CUDA device every compute
+ *     entry point returns JRK_ERR_CUDA.
+ *
+ * Kernel family (GenGaussKernel, /root/reference/jaxrk/kern/rbf.py:27-105):
+ *     k(x, y) = nconst * exp( -( scale * || ds*x - ds*y ||_2 )^power ),  power in (0, 2]
+ *   scale     global 1/length_scale   (SimpleScaler.s, kern/util.py:34-50; gs in util.py:92-99)
+ *   dim_scale optional per-dimension ds (len d), applied to both inputs (util.py:92-99);
+ *             NULL = none.  When given, `scale` is normally 1.
+ *   nconst    power / (2 * scale_param * Gamma(1/power))   (kern/rbf.py:34), computed
+ *             by the caller exactly as the reference does.
+ */
+#ifndef JRK_H_
+#define JRK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JRK_ABI_VERSION 1
+
+/* error codes */
+#define JRK_OK 0
+#define JRK_ERR_INVALID_ARG 1   /* bad shape / pointer / parameter            */
+#define JRK_ERR_CUDA 2          /* CUDA runtime error (no device, launch, OOM) */
+#define JRK_ERR_UNSUPPORTED 3   /* valid request this build cannot serve       */
+
+/* distance path of jrk_gram_f32 */
+#define JRK_PATH_AUTO 0    /* direct for d < 64, 3xTF32 tcgen05 for d >= 64 */
+#define JRK_PATH_DIRECT 1  /* FP32 direct differencing (sum_k (x_k - y_k)^2)  */
+#define JRK_PATH_TF32X3 2  /* compensated 3xTF32 expansion on tcgen05/TMEM    */
+
+/* row reduction folded into jrk_kmatw_f32 (jaxrk/reduce/base.py) */
+#define JRK_REDUCE_NONE 0      /* out is N x m                                             */
+#define JRK_REDUCE_SUM 1       /* Sum  (reduce/base.py:132-140): out is 1 x m              */
+#define JRK_REDUCE_MEAN 2      /* Mean (reduce/base.py:142-150): out is 1 x m              */
+#define JRK_REDUCE_BALANCED 3  /* BalancedRed(group, average=False) (:152-181): (N/group) x m */
+#define JRK_REDUCE_BALANCED_MEAN 4 /* BalancedRed(group, average=True)                     */
+
+int jrk_abi_version(void);
+
+/* Copies the calling thread's last error message (NUL-terminated, truncated to n). */
+int jrk_last_error(char *buf, size_t n);
+
+/* Number of visible CUDA devices (0 when there is none / no driver). */
+int jrk_device_count(void);
+
+/* ------------------------------------------------------------------------------
+ * Gram matrix  K[i, j] = k(x_i, y_j),  N x M.
+ * Replaces GenGaussKernel.__call__(X, Y, diag=False)  (jaxrk/kern/rbf.py:104-105)
+ *   -> ScaledPairwiseDistance.__call__                (jaxrk/kern/util.py:107-116)
+ *   -> dist / eucldist / sqeucldist_simple            (jaxrk/utilities/distances.py:44-49,
+ *                                                      jaxrk/utilities/eucldist.py:10-18,37-48)
+ * Y == NULL or Y == X means the self-Gram (Kernel.__call__ with Y=None,
+ * jaxrk/kern/base.py:23-36); the result is then bitwise symmetric with an exact
+ * diagonal (jaxrk/utilities/gram.py:18 asserts G == G.T).
+ * ------------------------------------------------------------------------------ */
+int jrk_gram_f32(const float *X, const float *Y, float *K,
+                 int64_t N, int64_t M, int d,
+                 int64_t ldx, int64_t ldy, int64_t ldk,
+                 float scale, const float *dim_scale, float power, float nconst,
+                 int path, void *workspace, size_t workspace_bytes, void *stream);
+
+size_t jrk_gram_workspace_bytes(int64_t N, int64_t M, int d, int path);
+
+/* ------------------------------------------------------------------------------
+ * Scaled distance matrix  D[i, j] = (scale * ||ds*x_i - ds*y_j||_2)^power  (no exp).
+ * Replaces ScaledPairwiseDistance.__call__(X, Y, diag=False) (jaxrk/kern/util.py:107-116)
+ * and, with scale = 1, eucldist(a, b, power) (jaxrk/utilities/eucldist.py:37-48).
+ * Direct differencing only.
+ * ------------------------------------------------------------------------------ */
+int jrk_dist_f32(const float *X, const float *Y, float *D,
+                 int64_t N, int64_t M, int d,
+                 int64_t ldx, int64_t ldy, int64_t ldd,
+                 float scale, const float *dim_scale, float power, void *stream);
+
+/* ------------------------------------------------------------------------------
+ * Fused, never-materialised product with folded reduce maps:
+ *     T[i, c]  = row_pref[i] * sum_j k(x_i, y_j) * col_pref[j] * W[j, c]      (N x m)
+ *     out      = row_reduce(T)
+ * Replaces FiniteVec.inner(Y) (jaxrk/rkhs/vector.py:62-75) =
+ *     Reduce.apply(Reduce.apply(K, self.reduce, 0), Y.reduce, 1)  (jaxrk/reduce/base.py:39-47)
+ * for reduce chains that fold to: Y side  W = (LinearReduce / Sum / Mean / Prefactors
+ * chain)^T (jaxrk/reduce/lincomb.py:131-144, reduce/base.py:84-150), X side
+ * Prefactors then Sum / Mean / BalancedRed; and FiniteVec.__call__ (vector.py:203-204),
+ * FiniteOp.__matmul__'s inner() (jaxrk/rkhs/operator.py:46).
+ * W is M x m (ldw), out is rows x m (ldo) with rows = N, 1 or N/group.
+ * row_pref (len N) and col_pref (len M) are nullable.  `group` is used by the
+ * BALANCED modes only and must divide N.
+ * ------------------------------------------------------------------------------ */
+int jrk_kmatw_f32(const float *X, const float *Y, const float *W, float *out,
+                  int64_t N, int64_t M, int d, int m,
+                  int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo,
+                  float scale, const float *dim_scale, float power, float nconst,
+                  const float *row_pref, const float *col_pref,
+                  int row_reduce, int64_t group,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+size_t jrk_kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce, int64_t group);
+
+/* ------------------------------------------------------------------------------
+ * Group-reduced Gram:  out[a, b] = sum_{i in group a} sum_{j in group b}
+ *                                   row_pref[i] * k(x_i, y_j) * col_pref[j]
+ * (times 1/(gx*gy) when `average`), out is (N/gx) x (M/gy).
+ * Replaces FiniteVec.inner with BalancedRed on both vectors (jaxrk/reduce/base.py:152-181
+ * applied on axis 0 and 1 by jaxrk/rkhs/vector.py:73-74), never materialising K.
+ * ------------------------------------------------------------------------------ */
+int jrk_gram_groupsum_f32(const float *X, const float *Y, float *out,
+                          int64_t N, int64_t M, int d,
+                          int64_t ldx, int64_t ldy, int64_t ldo,
+                          float scale, const float *dim_scale, float power, float nconst,
+                          const float *row_pref, const float *col_pref,
+                          int64_t gx, int64_t gy, int average,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------
+ * Host-buffer (end-to-end) variants: same semantics, HOST pointers, copies included.
+ * The Gram variant streams row blocks (compute of block b+1 overlaps the device->host
+ * copy of block b).  `device` is the CUDA ordinal.
+ * ------------------------------------------------------------------------------ */
+int jrk_gram_f32_host(const float *X, const float *Y, float *K,
+                      int64_t N, int64_t M, int d,
+                      float scale, const float *dim_scale, float power, float nconst,
+                      int path, int device);
+
+int jrk_kmatw_f32_host(const float *X, const float *Y, const float *W, float *out,
+                       int64_t N, int64_t M, int d, int m,
+                       float scale, const float *dim_scale, float power, float nconst,
+                       const float *row_pref, const float *col_pref,
+                       int row_reduce, int64_t group, int device);
+
+/* Number of kernel launches issued by this library in the calling process (all
+ * threads), for bench.py's `gpu_launches` claim. */
+int64_t jrk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JRK_H_ */

@@ -1,0 +1,247 @@
+"""ctypes binding of include/jrk.h (the C-ABI drop-in boundary).
+
+This is binding "L1b" of SURVEY.md §8(b): device pointers come from torch CUDA tensors
+(`Tensor.data_ptr()`), the stream is torch's current CUDA stream.  torch is plumbing
+only (device memory + streams); every result is computed by libjaxrk_b200.so.
+
+There is NO fallback: if the shared library is missing, or there is no CUDA device, the
+calls raise.  Build the library with `python -m jaxrk_b200.build`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libjaxrk_b200.so")
+
+PATH_AUTO, PATH_DIRECT, PATH_TF32X3 = 0, 1, 2
+REDUCE_NONE, REDUCE_SUM, REDUCE_MEAN, REDUCE_BALANCED, REDUCE_BALANCED_MEAN = 0, 1, 2, 3, 4
+
+# every symbol include/jrk.h declares: name -> (restype, argtypes)
+_F = ctypes.POINTER(c_float)
+SIGNATURES = {
+    "jrk_abi_version": (c_int, []),
+    "jrk_last_error": (c_int, [ctypes.c_char_p, c_size_t]),
+    "jrk_device_count": (c_int, []),
+    "jrk_launch_count": (c_int64, []),
+    "jrk_gram_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "jrk_gram_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64,
+                             c_float, c_void_p, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "jrk_dist_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64,
+                             c_float, c_void_p, c_float, c_void_p]),
+    "jrk_kmatw_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int64]),
+    "jrk_kmatw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                              c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_float, c_float,
+                              c_void_p, c_void_p, c_int, c_int64, c_void_p, c_size_t, c_void_p]),
+    "jrk_gram_groupsum_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64,
+                                      c_int64, c_float, c_void_p, c_float, c_float, c_void_p, c_void_p,
+                                      c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "jrk_gram_f32_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p,
+                                  c_float, c_float, c_int, c_int]),
+    "jrk_kmatw_f32_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                                   c_float, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_int64, c_int]),
+}
+
+
+class JrkError(RuntimeError):
+    """Non-zero status from the C ABI (1 invalid arg, 2 CUDA, 3 unsupported)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libjaxrk_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libjaxrk_b200.so (once).  Raises -- never falls back -- when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m jaxrk_b200.build` "
+                "(jaxrk_b200 has no CPU or eager fallback).")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.jrk_abi_version() != 1:
+            raise ImportError("libjaxrk_b200.so ABI version mismatch; rebuild")
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    buf = ctypes.create_string_buffer(512)
+    lib().jrk_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise JrkError(rc, last_error())
+
+
+def launch_count() -> int:
+    return int(lib().jrk_launch_count())
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream(dev: torch.device):
+    return c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _dev2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 2):
+        raise TypeError(f"{name} must be a 2-D float32 CUDA tensor")
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return int(t.stride(0)) if t.shape[0] > 1 else int(t.shape[1])
+
+
+def _vec(t: Optional[torch.Tensor], n: int, name: str, dev) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    t = torch.as_tensor(t, dtype=torch.float32, device=dev).reshape(-1).contiguous()
+    if t.numel() != n:
+        raise ValueError(f"{name} must have {n} elements, got {t.numel()}")
+    return t
+
+
+def gram(X, Y, scale: float, power: float, nconst: float, dim_scale=None, path: int = PATH_AUTO,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """jrk_gram_f32: K[i, j] = nconst * exp(-(scale * ||ds*x_i - ds*y_j||)^power)."""
+    X = _dev2d(X, "X")
+    self_gram = Y is None
+    Yt = X if self_gram else _dev2d(Y, "Y")
+    N, d = X.shape
+    M = Yt.shape[0]
+    if Yt.shape[1] != d:
+        raise ValueError("X and Y must have the same number of columns")
+    ds = _vec(dim_scale, d, "dim_scale", X.device)
+    if out is None:
+        out = torch.empty((N, M), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        wsb = lib().jrk_gram_workspace_bytes(N, M, d, path)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=X.device) if wsb else None
+        _check(lib().jrk_gram_f32(_ptr(X), None if self_gram else _ptr(Yt), _ptr(out), N, M, d, _ld(X), _ld(Yt),
+                                  _ld(out) if N > 1 else M, scale, _ptr(ds), power, nconst, path, _ptr(ws), wsb,
+                                  _stream(X.device)))
+    return out
+
+
+def dist(X, Y, scale: float, power: float, dim_scale=None) -> torch.Tensor:
+    """jrk_dist_f32: D[i, j] = (scale * ||ds*x_i - ds*y_j||)^power."""
+    X = _dev2d(X, "X")
+    self_gram = Y is None
+    Yt = X if self_gram else _dev2d(Y, "Y")
+    N, d = X.shape
+    M = Yt.shape[0]
+    if Yt.shape[1] != d:
+        raise ValueError("X and Y must have the same number of columns")
+    ds = _vec(dim_scale, d, "dim_scale", X.device)
+    out = torch.empty((N, M), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        _check(lib().jrk_dist_f32(_ptr(X), None if self_gram else _ptr(Yt), _ptr(out), N, M, d, _ld(X), _ld(Yt), M,
+                                  scale, _ptr(ds), power, _stream(X.device)))
+    return out
+
+
+def kmatw(X, Y, W, scale: float, power: float, nconst: float, dim_scale=None, row_pref=None, col_pref=None,
+          row_reduce: int = REDUCE_NONE, group: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """jrk_kmatw_f32: row_reduce(diag(row_pref) K(X, Y) diag(col_pref) W), never materialising K."""
+    X = _dev2d(X, "X")
+    Y = _dev2d(Y, "Y")
+    W = _dev2d(W, "W")
+    N, d = X.shape
+    M, m = W.shape
+    if Y.shape != (M, d):
+        raise ValueError(f"Y must be {M} x {d}, got {tuple(Y.shape)}")
+    dev = X.device
+    ds = _vec(dim_scale, d, "dim_scale", dev)
+    rp = _vec(row_pref, N, "row_pref", dev)
+    cp = _vec(col_pref, M, "col_pref", dev)
+    if row_reduce in (REDUCE_SUM, REDUCE_MEAN):
+        rows = 1
+    elif row_reduce in (REDUCE_BALANCED, REDUCE_BALANCED_MEAN):
+        if group < 1 or N % group:
+            raise ValueError("group must divide N")
+        rows = N // group
+    else:
+        rows = N
+    if out is None:
+        out = torch.empty((rows, m), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        wsb = lib().jrk_kmatw_workspace_bytes(N, M, d, m, row_reduce, group)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
+        _check(lib().jrk_kmatw_f32(_ptr(X), _ptr(Y), _ptr(W), _ptr(out), N, M, d, m, _ld(X), _ld(Y), _ld(W), m,
+                                   scale, _ptr(ds), power, nconst, _ptr(rp), _ptr(cp), row_reduce, group,
+                                   _ptr(ws), wsb, _stream(dev)))
+    return out
+
+
+def gram_groupsum(X, Y, scale: float, power: float, nconst: float, gx: int, gy: int, average: bool,
+                  dim_scale=None, row_pref=None, col_pref=None) -> torch.Tensor:
+    """jrk_gram_groupsum_f32: BalancedRed on both axes of K(X, Y) without materialising it."""
+    X = _dev2d(X, "X")
+    self_gram = Y is None
+    Yt = X if self_gram else _dev2d(Y, "Y")
+    N, d = X.shape
+    M = Yt.shape[0]
+    dev = X.device
+    ds = _vec(dim_scale, d, "dim_scale", dev)
+    rp = _vec(row_pref, N, "row_pref", dev)
+    cp = _vec(col_pref, M, "col_pref", dev)
+    out = torch.empty((N // gx, M // gy), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().jrk_gram_groupsum_f32(_ptr(X), None if self_gram else _ptr(Yt), _ptr(out), N, M, d, _ld(X),
+                                           _ld(Yt), M // gy, scale, _ptr(ds), power, nconst, _ptr(rp), _ptr(cp),
+                                           gx, gy, int(bool(average)), None, 0, _stream(dev)))
+    return out
+
+
+# ---- host-buffer (end-to-end) entry points: numpy / pinned torch CPU tensors in and out ----
+def _host_ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        assert a.device.type == "cpu" and a.dtype == torch.float32 and a.is_contiguous()
+        return c_void_p(a.data_ptr())
+    import numpy as np
+    assert isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return c_void_p(a.ctypes.data)
+
+
+def gram_host(X, Y, out, scale: float, power: float, nconst: float, dim_scale=None, path: int = PATH_AUTO,
+              device: int = 0):
+    """jrk_gram_f32_host: host arrays in, host Gram out (copies inside the call)."""
+    N, d = X.shape
+    M = N if Y is None else Y.shape[0]
+    assert tuple(out.shape) == (N, M)
+    _check(lib().jrk_gram_f32_host(_host_ptr(X), _host_ptr(Y), _host_ptr(out), N, M, d, scale,
+                                   _host_ptr(dim_scale), power, nconst, path, device))
+    return out
+
+
+def kmatw_host(X, Y, W, out, scale: float, power: float, nconst: float, dim_scale=None, row_pref=None,
+               col_pref=None, row_reduce: int = REDUCE_NONE, group: int = 0, device: int = 0):
+    """jrk_kmatw_f32_host: host arrays in, host result out (copies inside the call)."""
+    N, d = X.shape
+    M, m = W.shape
+    _check(lib().jrk_kmatw_f32_host(_host_ptr(X), _host_ptr(Y), _host_ptr(W), _host_ptr(out), N, M, d, m, scale,
+                                    _host_ptr(dim_scale), power, nconst, _host_ptr(row_pref), _host_ptr(col_pref),
+                                    row_reduce, group, device))
+    return out

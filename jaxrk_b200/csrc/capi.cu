@@ -1,0 +1,284 @@
+// extern "C" entry points declared in include/jrk.h: argument validation, path
+// selection, host-buffer (end-to-end) variants.  No torch / XLA types here.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace jrk {
+
+thread_local char g_last_error[512] = {0};
+std::atomic<int64_t> g_launches{0};
+
+// kernels (one translation unit each)
+int gram_direct(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
+                int64_t ldk, float scale, const float* dim_scale, float power, float nconst, int out_kind,
+                cudaStream_t st);
+int gram_tf32x3(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
+                int64_t ldk, float scale, const float* dim_scale, float power, float nconst, void* workspace,
+                size_t workspace_bytes, cudaStream_t st);
+size_t gram_tf32x3_workspace_bytes(int64_t N, int64_t M, int d);
+int kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,
+          int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale, const float* dim_scale, float power,
+          float nconst, const float* row_pref, const float* col_pref, int row_reduce, int64_t group,
+          void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce, int64_t group);
+int gram_groupsum(const float* X, const float* Y, float* out, int64_t N, int64_t M, int d, int64_t ldx,
+                  int64_t ldy, int64_t ldo, float scale, const float* dim_scale, float power, float nconst,
+                  const float* row_pref, const float* col_pref, int64_t gx, int64_t gy, int average,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+static int check_kernel_params(const char* fn, int d, float scale, float power, float nconst) {
+    if (d < 1) return fail(JRK_ERR_INVALID_ARG, "%s: d must be >= 1 (got %d)", fn, d);
+    if (!(scale > 0.f) || !std::isfinite(scale))
+        return fail(JRK_ERR_INVALID_ARG, "%s: scale must be positive and finite (got %g)", fn, (double)scale);
+    // GenGaussKernel.make asserts 0 < shape <= 2 (jaxrk/kern/rbf.py:71)
+    if (!(power > 0.f) || power > 2.f)
+        return fail(JRK_ERR_INVALID_ARG, "%s: power must be in (0, 2] (got %g)", fn, (double)power);
+    if (!std::isfinite(nconst)) return fail(JRK_ERR_INVALID_ARG, "%s: nconst must be finite", fn);
+    return JRK_OK;
+}
+
+static int have_device(const char* fn) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(JRK_ERR_CUDA, "%s: no CUDA device available (%s); this library has no CPU fallback", fn,
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return JRK_OK;
+}
+
+static int resolve_gram_path(int path, int d) {
+    if (path == JRK_PATH_AUTO) return d >= 64 ? JRK_PATH_TF32X3 : JRK_PATH_DIRECT;
+    return path;
+}
+
+}  // namespace jrk
+
+using namespace jrk;
+
+extern "C" {
+
+int jrk_abi_version(void) { return JRK_ABI_VERSION; }
+
+int jrk_last_error(char* buf, size_t n) {
+    if (!buf || n == 0) return JRK_ERR_INVALID_ARG;
+    std::strncpy(buf, g_last_error, n - 1);
+    buf[n - 1] = 0;
+    return JRK_OK;
+}
+
+int jrk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int64_t jrk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t jrk_gram_workspace_bytes(int64_t N, int64_t M, int d, int path) {
+    if (resolve_gram_path(path, d) == JRK_PATH_TF32X3) return gram_tf32x3_workspace_bytes(N, M, d);
+    return 0;
+}
+
+int jrk_gram_f32(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
+                 int64_t ldk, float scale, const float* dim_scale, float power, float nconst, int path,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+    if (!X || !K) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: X and K must not be NULL");
+    if (!Y) { Y = X; M = N; ldy = ldx; }
+    if (N < 0 || M < 0) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: negative size");
+    if (int rc = check_kernel_params("jrk_gram_f32", d, scale, power, nconst)) return rc;
+    if (ldx < d || ldy < d || ldk < M) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: leading dimension too small");
+    if (path < JRK_PATH_AUTO || path > JRK_PATH_TF32X3) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: bad path %d", path);
+    if (N == 0 || M == 0) return JRK_OK;
+    if (int rc = have_device("jrk_gram_f32")) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (resolve_gram_path(path, d) == JRK_PATH_TF32X3)
+        return gram_tf32x3(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, workspace,
+                           workspace_bytes, st);
+    return gram_direct(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, 0, st);
+}
+
+int jrk_dist_f32(const float* X, const float* Y, float* D, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
+                 int64_t ldd, float scale, const float* dim_scale, float power, void* stream) {
+    if (!X || !D) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_f32: X and D must not be NULL");
+    if (!Y) { Y = X; M = N; ldy = ldx; }
+    if (N < 0 || M < 0 || d < 1) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_f32: bad size");
+    if (!(scale > 0.f) || !(power > 0.f)) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_f32: scale and power must be positive");
+    if (ldx < d || ldy < d || ldd < M) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_f32: leading dimension too small");
+    if (N == 0 || M == 0) return JRK_OK;
+    if (int rc = have_device("jrk_dist_f32")) return rc;
+    return gram_direct(X, Y, D, N, M, d, ldx, ldy, ldd, scale, dim_scale, power, 1.f, 1, (cudaStream_t)stream);
+}
+
+size_t jrk_kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce, int64_t group) {
+    return kmatw_workspace_bytes(N, M, d, m, row_reduce, group);
+}
+
+static int check_kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d,
+                       int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale, float power,
+                       float nconst, int row_reduce, int64_t group) {
+    if (!X || !Y || !W || !out) return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_f32: NULL pointer");
+    if (N < 1 || M < 1 || m < 1) return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_f32: N, M, m must be >= 1");
+    if (int rc = check_kernel_params("jrk_kmatw_f32", d, scale, power, nconst)) return rc;
+    if (ldx < d || ldy < d || ldw < m || ldo < m) return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_f32: leading dimension too small");
+    if (row_reduce < JRK_REDUCE_NONE || row_reduce > JRK_REDUCE_BALANCED_MEAN)
+        return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_f32: bad row_reduce %d", row_reduce);
+    if (row_reduce == JRK_REDUCE_BALANCED || row_reduce == JRK_REDUCE_BALANCED_MEAN) {
+        // BalancedRed.new_len asserts original_len % points_per_split == 0 (jaxrk/reduce/base.py:179-181)
+        if (group < 1 || N % group != 0)
+            return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_f32: group (%lld) must divide N (%lld)", (long long)group, (long long)N);
+    }
+    return JRK_OK;
+}
+
+int jrk_kmatw_f32(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,
+                  int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale, const float* dim_scale,
+                  float power, float nconst, const float* row_pref, const float* col_pref, int row_reduce,
+                  int64_t group, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_kmatw(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, power, nconst, row_reduce, group)) return rc;
+    if (int rc = have_device("jrk_kmatw_f32")) return rc;
+    return kmatw(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, dim_scale, power, nconst, row_pref, col_pref,
+                 row_reduce, group, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int jrk_gram_groupsum_f32(const float* X, const float* Y, float* out, int64_t N, int64_t M, int d, int64_t ldx,
+                          int64_t ldy, int64_t ldo, float scale, const float* dim_scale, float power, float nconst,
+                          const float* row_pref, const float* col_pref, int64_t gx, int64_t gy, int average,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    if (!X || !out) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_groupsum_f32: NULL pointer");
+    if (!Y) { Y = X; M = N; ldy = ldx; }
+    if (N < 1 || M < 1) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_groupsum_f32: N, M must be >= 1");
+    if (int rc = check_kernel_params("jrk_gram_groupsum_f32", d, scale, power, nconst)) return rc;
+    if (gx < 1 || gy < 1 || N % gx || M % gy)
+        return fail(JRK_ERR_INVALID_ARG, "jrk_gram_groupsum_f32: group sizes must divide N and M");
+    if (ldx < d || ldy < d || ldo < M / gy) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_groupsum_f32: leading dimension too small");
+    if (int rc = have_device("jrk_gram_groupsum_f32")) return rc;
+    return gram_groupsum(X, Y, out, N, M, d, ldx, ldy, ldo, scale, dim_scale, power, nconst, row_pref, col_pref, gx,
+                         gy, average, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------
+// host-buffer variants (end to end: H2D, compute, D2H inside the call)
+// ---------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T* as() { return (T*)p; }
+};
+struct StreamGuard {
+    cudaStream_t s = nullptr;
+    ~StreamGuard() { if (s) cudaStreamDestroy(s); }
+};
+struct EventGuard {
+    cudaEvent_t e = nullptr;
+    ~EventGuard() { if (e) cudaEventDestroy(e); }
+};
+}  // namespace
+
+extern "C" {
+
+int jrk_gram_f32_host(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, float scale,
+                      const float* dim_scale, float power, float nconst, int path, int device) {
+    if (!X || !K) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32_host: X and K must not be NULL");
+    const bool self = (!Y || Y == X);
+    if (self) { Y = X; M = N; }
+    if (N < 0 || M < 0) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32_host: negative size");
+    if (int rc = check_kernel_params("jrk_gram_f32_host", d, scale, power, nconst)) return rc;
+    if (N == 0 || M == 0) return JRK_OK;
+    if (int rc = have_device("jrk_gram_f32_host")) return rc;
+    JRK_CUDA_OK(cudaSetDevice(device));
+
+    StreamGuard sc, sd;  // compute / download
+    JRK_CUDA_OK(cudaStreamCreateWithFlags(&sc.s, cudaStreamNonBlocking));
+    JRK_CUDA_OK(cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking));
+    DevBuf dX, dY, dS, dK[2], dW;
+    JRK_CUDA_OK(dX.alloc((size_t)N * d * 4));
+    JRK_CUDA_OK(cudaMemcpyAsync(dX.p, X, (size_t)N * d * 4, cudaMemcpyHostToDevice, sc.s));
+    const float* dYp = dX.as<float>();
+    if (!self) {
+        JRK_CUDA_OK(dY.alloc((size_t)M * d * 4));
+        JRK_CUDA_OK(cudaMemcpyAsync(dY.p, Y, (size_t)M * d * 4, cudaMemcpyHostToDevice, sc.s));
+        dYp = dY.as<float>();
+    }
+    const float* dSp = nullptr;
+    if (dim_scale) {
+        JRK_CUDA_OK(dS.alloc((size_t)d * 4));
+        JRK_CUDA_OK(cudaMemcpyAsync(dS.p, dim_scale, (size_t)d * 4, cudaMemcpyHostToDevice, sc.s));
+        dSp = dS.as<float>();
+    }
+    // row blocks of ~256 MiB: block b+1 is computed while block b is copied out
+    int64_t B = std::max<int64_t>(128, ((int64_t)256 << 20) / (M * 4) / 128 * 128);
+    B = std::min(B, (N + 127) / 128 * 128);
+    JRK_CUDA_OK(dK[0].alloc((size_t)B * M * 4));
+    JRK_CUDA_OK(dK[1].alloc((size_t)B * M * 4));
+    const size_t wsb = jrk_gram_workspace_bytes(B, M, d, path);
+    if (wsb) JRK_CUDA_OK(dW.alloc(wsb));
+    EventGuard done[2], freed[2];
+    for (int i = 0; i < 2; ++i) {
+        JRK_CUDA_OK(cudaEventCreateWithFlags(&done[i].e, cudaEventDisableTiming));
+        JRK_CUDA_OK(cudaEventCreateWithFlags(&freed[i].e, cudaEventDisableTiming));
+    }
+    int b = 0;
+    for (int64_t r = 0; r < N; r += B, ++b) {
+        const int64_t n = std::min(B, N - r);
+        const int s = b & 1;
+        if (b >= 2) JRK_CUDA_OK(cudaStreamWaitEvent(sc.s, freed[s].e, 0));
+        int rc = jrk_gram_f32(dX.as<float>() + r * d, dYp, dK[s].as<float>(), n, M, d, d, d, M, scale, dSp, power,
+                              nconst, path, dW.p, wsb, sc.s);
+        if (rc) return rc;
+        JRK_CUDA_OK(cudaEventRecord(done[s].e, sc.s));
+        JRK_CUDA_OK(cudaStreamWaitEvent(sd.s, done[s].e, 0));
+        JRK_CUDA_OK(cudaMemcpyAsync(K + r * M, dK[s].p, (size_t)n * M * 4, cudaMemcpyDeviceToHost, sd.s));
+        JRK_CUDA_OK(cudaEventRecord(freed[s].e, sd.s));
+    }
+    JRK_CUDA_OK(cudaStreamSynchronize(sc.s));
+    JRK_CUDA_OK(cudaStreamSynchronize(sd.s));
+    return JRK_OK;
+}
+
+int jrk_kmatw_f32_host(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d,
+                       int m, float scale, const float* dim_scale, float power, float nconst, const float* row_pref,
+                       const float* col_pref, int row_reduce, int64_t group, int device) {
+    if (int rc = check_kmatw(X, Y, W, out, N, M, d, m, d, d, m, m, scale, power, nconst, row_reduce, group)) return rc;
+    if (int rc = have_device("jrk_kmatw_f32_host")) return rc;
+    JRK_CUDA_OK(cudaSetDevice(device));
+    StreamGuard sc;
+    JRK_CUDA_OK(cudaStreamCreateWithFlags(&sc.s, cudaStreamNonBlocking));
+    int64_t out_rows = N;
+    if (row_reduce == JRK_REDUCE_SUM || row_reduce == JRK_REDUCE_MEAN) out_rows = 1;
+    else if (row_reduce != JRK_REDUCE_NONE) out_rows = N / group;
+    DevBuf dX, dY, dWt, dO, dS, dRP, dCP;
+    auto up = [&](DevBuf& b, const float* h, size_t count) -> cudaError_t {
+        cudaError_t e = b.alloc(count * 4);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(b.p, h, count * 4, cudaMemcpyHostToDevice, sc.s);
+    };
+    JRK_CUDA_OK(up(dX, X, (size_t)N * d));
+    JRK_CUDA_OK(up(dY, Y, (size_t)M * d));
+    JRK_CUDA_OK(up(dWt, W, (size_t)M * m));
+    if (dim_scale) JRK_CUDA_OK(up(dS, dim_scale, (size_t)d));
+    if (row_pref) JRK_CUDA_OK(up(dRP, row_pref, (size_t)N));
+    if (col_pref) JRK_CUDA_OK(up(dCP, col_pref, (size_t)M));
+    JRK_CUDA_OK(dO.alloc((size_t)out_rows * m * 4));
+    int rc = jrk_kmatw_f32(dX.as<float>(), dY.as<float>(), dWt.as<float>(), dO.as<float>(), N, M, d, m, d, d, m, m,
+                           scale, dim_scale ? dS.as<float>() : nullptr, power, nconst,
+                           row_pref ? dRP.as<float>() : nullptr, col_pref ? dCP.as<float>() : nullptr, row_reduce,
+                           group, nullptr, 0, sc.s);
+    if (rc) return rc;
+    JRK_CUDA_OK(cudaMemcpyAsync(out, dO.p, (size_t)out_rows * m * 4, cudaMemcpyDeviceToHost, sc.s));
+    JRK_CUDA_OK(cudaStreamSynchronize(sc.s));
+    return JRK_OK;
+}
+
+}  // extern "C"
