@@ -1,0 +1,64 @@
+"""LinearReduce / SparseReduce -- drop-in for jaxrk/reduce/lincomb.py.
+
+`LinearReduce(A)` is `A @ gram` (lincomb.py:131-144): on the Y side of an inner product
+it is the W = A^T of the fused, never-materialised K(X, Y) @ W kernel.
+"""
+from typing import List
+
+import numpy as np
+import torch
+
+from .._array import asarray
+from .base import Reduce
+
+
+class LinearReduce(Reduce):
+    def __init__(self, linear_map):
+        self.linear_map = asarray(linear_map)
+
+    def reduce_first_ax(self, inp):
+        assert len(inp.shape) == 2
+        assert self.linear_map.shape[1] == inp.shape[0]
+        return self.linear_map.to(inp.device) @ inp
+
+    def new_len(self, original_len: int):
+        assert self.linear_map.shape[1] == original_len, \
+            self.__class__.__name__ + " expects a gram with %d columns" % self.linear_map.shape[1]
+        return self.linear_map.shape[0]
+
+    @classmethod
+    def sum_from_unique(cls, input, mean: bool = True):
+        """lincomb.py:146-154: one output row per unique value of `input`."""
+        inp = np.asarray(input.detach().cpu().numpy() if isinstance(input, torch.Tensor) else input)
+        un, inverse, cts = np.unique(inp, return_inverse=True, return_counts=True)
+        m = np.zeros((un.size, inp.shape[0]), np.float32)
+        m[inverse.reshape(-1), np.arange(inp.shape[0])] = 1.
+        if mean:
+            m /= cts[:, None]
+        return un, cts, LinearReduce(m)
+
+
+class SparseReduce(Reduce):
+    """Sum / average rows of the input selected by index arrays (lincomb.py:27-87).  Index
+    structured, so it is applied to a materialised Gram (not folded into the fused kernels)."""
+
+    def __init__(self, idcs: List, average: bool = True, max_idx=None):
+        self.idcs = [torch.as_tensor(np.asarray(i), dtype=torch.long) for i in idcs]
+        self.average = average
+        self.max_idx = max_idx if max_idx is not None else max(int(i.max()) for i in self.idcs if i.numel())
+
+    def reduce_first_ax(self, inp):
+        assert self.max_idx + 1 <= len(inp)
+        assert len(inp.shape) == 2
+        rval = []
+        for idx in self.idcs:
+            if idx.shape[1] == 0:
+                rval.append(torch.zeros((idx.shape[0], inp.shape[1]), dtype=inp.dtype, device=inp.device))
+            else:
+                g = inp[idx.reshape(-1).to(inp.device), :].reshape(-1, idx.shape[1], inp.shape[1])
+                rval.append(g.mean(1) if self.average else g.sum(1))
+        return torch.cat(rval, 0)
+
+    def new_len(self, original_len: int):
+        assert self.max_idx + 1 <= original_len
+        return len(self.idcs)  # as the reference (lincomb.py:62-64)

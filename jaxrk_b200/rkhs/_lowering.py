@@ -1,0 +1,157 @@
+"""Lowering of  R_X . K(X, Y) . R_Y^T  onto the fused sm_100a kernels.
+
+The reference's FiniteVec.inner (jaxrk/rkhs/vector.py:62-75) materialises the N x M Gram
+and then applies both reduce chains with Reduce.apply (jaxrk/reduce/base.py:39-47).
+Every chain element is a linear map on one axis, so a chain factors as
+R = R_post . R_fold, where R_fold is something the kernels apply in registers:
+
+    fold  := Prefactors*  then one of  { nothing, Sum, Mean, BalancedRed, LinearReduce(+ more) }
+
+and R_post (whatever follows) acts on the already reduced -- small -- result with the
+ordinary array-level Reduce.apply.  Once a LinearReduce(A) has been reached, every later
+element is folded into A itself (it is applied to A's rows).
+
+Kernel choice, with (rx, ry) the folded row / column maps:
+    ry = LINEAR | SUM | MEAN          -> jrk_kmatw_f32(X, Y, W = R_y^T, row_reduce = rx)
+    rx = LINEAR | SUM | MEAN, ry else -> the same on the transposed problem (k is symmetric:
+                                          K(X, Y)^T = K(Y, X)), result transposed back
+    rx = ry = BALANCED                -> jrk_gram_groupsum_f32
+    rx = ry = NONE                    -> jrk_gram_f32 (materialised), prefactors scaled in place
+    anything else                     -> Gram by jrk_gram_f32, then Reduce.apply (generic)
+Nothing here computes a kernel value on the host or in torch: all k(x, y) evaluations are
+done by libjaxrk_b200.so.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from .. import _native as nat
+from ..reduce.base import BalancedRed, Mean, Prefactors, Reduce, Sum
+from ..reduce.lincomb import LinearReduce
+
+NONE, SUM, MEAN, BALANCED, LINEAR = "none", "sum", "mean", "balanced", "linear"
+
+
+@dataclass
+class Folded:
+    n: int                                  # input length of the chain
+    pref: Optional[torch.Tensor] = None     # product of the leading Prefactors (len n)
+    kind: str = NONE
+    group: int = 0                          # BALANCED: points per split
+    average: bool = False                   # BALANCED: mean instead of sum
+    A: Optional[torch.Tensor] = None        # LINEAR: (m x n) map, later elements already applied
+    post: List[Reduce] = field(default_factory=list)
+
+    @property
+    def out_len(self) -> int:
+        if self.kind in (SUM, MEAN):
+            return 1
+        if self.kind == BALANCED:
+            return self.n // self.group
+        if self.kind == LINEAR:
+            return int(self.A.shape[0])
+        return self.n
+
+
+def fold_chain(chain: Optional[List[Reduce]], n: int, dev) -> Folded:
+    f = Folded(n=n)
+    chain = list(chain or [])
+    for idx, r in enumerate(chain):
+        if f.kind == LINEAR:
+            # every Reduce is linear on the first axis: apply it to A's rows (m x n -> m' x n)
+            f.A = r.reduce_first_ax(f.A)
+            continue
+        if f.kind != NONE:
+            f.post = chain[idx:]
+            break
+        if type(r) is Prefactors:
+            assert r.prefactors.shape[0] == n
+            p = r.prefactors.to(dev)
+            f.pref = p if f.pref is None else f.pref * p
+        elif type(r) is Sum:
+            f.kind = SUM
+        elif type(r) is Mean:
+            f.kind = MEAN
+        elif type(r) is BalancedRed:
+            assert n % r.points_per_split == 0
+            f.kind, f.group, f.average = BALANCED, r.points_per_split, r.average
+        elif type(r) is LinearReduce:
+            assert r.linear_map.shape[1] == n
+            f.kind, f.A = LINEAR, r.linear_map.to(dev)
+        else:  # Center, TileView, SparseReduce, user types: not folded
+            f.post = chain[idx:]
+            break
+    return f
+
+
+def _w_of(f: Folded, dev) -> torch.Tensor:
+    """The (n x m) matrix W = R^T of a LINEAR / SUM / MEAN fold (prefactors stay separate)."""
+    if f.kind == LINEAR:
+        return f.A.t().contiguous()
+    w = torch.ones((f.n, 1), dtype=torch.float32, device=dev)
+    return w / f.n if f.kind == MEAN else w
+
+
+def _row_reduce_of(f: Folded):
+    if f.kind == SUM:
+        return nat.REDUCE_SUM, 0
+    if f.kind == MEAN:
+        return nat.REDUCE_MEAN, 0
+    if f.kind == BALANCED:
+        return (nat.REDUCE_BALANCED_MEAN if f.average else nat.REDUCE_BALANCED), f.group
+    return nat.REDUCE_NONE, 0
+
+
+def _kmatw_side(X, Y, fx: Folded, fy: Folded, kargs) -> torch.Tensor:
+    """fold_x(K(X, Y)) applied with W = fold_y^T; fy is LINEAR / SUM / MEAN."""
+    scale, dim_scale, power, nconst = kargs
+    W = _w_of(fy, X.device)
+    if fx.kind == LINEAR:
+        T = nat.kmatw(X, Y, W, scale, power, nconst, dim_scale=dim_scale, row_pref=fx.pref, col_pref=fy.pref)
+        return fx.A @ T  # (mx x N) @ (N x my): small dense GEMM, stays in the library path
+    rr, group = _row_reduce_of(fx)
+    return nat.kmatw(X, Y, W, scale, power, nconst, dim_scale=dim_scale, row_pref=fx.pref, col_pref=fy.pref,
+                     row_reduce=rr, group=group)
+
+
+def reduced_gram(k, X, chain_x, Y, chain_y, self_gram: bool = False) -> torch.Tensor:
+    """R_X K(X, Y) R_Y^T.  `self_gram` says Y is X (enables the symmetric self-Gram kernel)."""
+    dev = X.device
+    kargs = k.kernel_args() if hasattr(k, "kernel_args") else None
+    if kargs is None:  # not a kernel the C ABI knows: the reference's own sequence
+        return Reduce.apply(Reduce.apply(k(X, Y), chain_x, 0), chain_y, 1)
+    scale, dim_scale, power, nconst = kargs
+    fx = fold_chain(chain_x, X.shape[0], dev)
+    fy = fold_chain(chain_y, Y.shape[0], dev)
+    skinny = (LINEAR, SUM, MEAN)
+
+    if fy.kind in skinny and (fx.kind not in skinny or fy.out_len <= fx.out_len):
+        out = _kmatw_side(X, Y, fx, fy, kargs)
+    elif fx.kind in skinny:
+        out = _kmatw_side(Y, X, fy, fx, kargs).t()
+    elif fx.kind == BALANCED and fy.kind == BALANCED and fx.group % 128 == 0:
+        out = nat.gram_groupsum(X, None if self_gram else Y, scale, power, nconst, fx.group, fy.group,
+                                False, dim_scale=dim_scale, row_pref=fx.pref, col_pref=fy.pref)
+        if fx.average or fy.average:
+            out = out * (1.0 / ((fx.group if fx.average else 1) * (fy.group if fy.average else 1)))
+    elif fx.kind == BALANCED and fy.kind == BALANCED and fy.group % 128 == 0:
+        out = nat.gram_groupsum(Y, None if self_gram else X, scale, power, nconst, fy.group, fx.group,
+                                False, dim_scale=dim_scale, row_pref=fy.pref, col_pref=fx.pref).t()
+        if fx.average or fy.average:
+            out = out * (1.0 / ((fx.group if fx.average else 1) * (fy.group if fy.average else 1)))
+    else:
+        G = nat.gram(X, None if self_gram else Y, scale, power, nconst, dim_scale=dim_scale)
+        if fx.pref is not None:
+            G.mul_(fx.pref[:, None])
+        if fy.pref is not None:
+            G.mul_(fy.pref[None, :])
+        if fx.kind == BALANCED:
+            G = BalancedRed(fx.group, fx.average)(G, 0)
+        if fy.kind == BALANCED:
+            G = BalancedRed(fy.group, fy.average)(G, 1)
+        out = G
+    out = Reduce.apply(out, fx.post, 0)
+    return Reduce.apply(out, fy.post, 1)

@@ -1,0 +1,133 @@
+"""FiniteVec and inner -- drop-in for jaxrk/rkhs/vector.py (the consumer / fusion point
+of the hot path).
+
+A FiniteVec is (kernel, input-space points, reduce chain).  `inner` is
+R_X . K(X, Y) . R_Y^T (vector.py:62-75); the reference materialises K and applies the
+chains, here `_lowering.reduced_gram` maps the triple onto the fused K@W / group-sum /
+Gram kernels of libjaxrk_b200.so.
+"""
+from copy import copy
+from typing import List, Union
+
+import torch
+
+from .._array import as2d, asarray
+from ..kern.base import Kernel
+from ..reduce.base import Center, Mean, Prefactors, Reduce, Sum
+from ..reduce.lincomb import LinearReduce
+from . import _lowering
+from .base import Vec
+
+
+class FiniteVec(Vec):
+    """RKHS feature vector(s) built from input space points."""
+
+    def __init__(self, k: Kernel, insp_pts, reduce: List[Reduce] = []):
+        if not isinstance(insp_pts, Vec):
+            insp_pts = as2d(insp_pts)
+        self.reduce = [] if reduce is None else reduce
+        self.k = k
+        self.insp_pts = insp_pts
+        self.__len = Reduce.final_len(len(self.insp_pts), self.reduce)
+        self._raw_gram_cache = None
+        self._inner_cache = None
+
+    def __len__(self):
+        return self.__len
+
+    def inner(self, Y=None, full=True):
+        if not full and Y is not None:
+            raise ValueError("Ambiguous inputs: `full` and `y` are not compatible.")
+        if not full:  # diagonal of the self inner product (the reference's branch is dead: vector.py:66-67)
+            return torch.diagonal(self.inner())
+        if Y is not None:
+            assert self.k == Y.k  # object identity, as in the reference (quirk Q5)
+        else:
+            Y = self
+        self_gram = Y is self or Y.insp_pts is self.insp_pts
+        if Y is self:  # Cov_solve asks for inner(inp_feat) twice (operator.py:138 and :46): keep it
+            key = tuple(id(r) for r in self.reduce)
+            if self._inner_cache is None or self._inner_cache[0] != key:
+                self._inner_cache = (key, _lowering.reduced_gram(self.k, self.insp_pts, self.reduce,
+                                                                 self.insp_pts, self.reduce, True))
+            return self._inner_cache[1]
+        return _lowering.reduced_gram(self.k, self.insp_pts, self.reduce, Y.insp_pts, Y.reduce, self_gram)
+
+    def normalized(self) -> "FiniteVec":
+        r = self.reduce
+        if isinstance(r[-1], Prefactors):
+            return self.updated(r[-1].prefactors / torch.sum(r[-1].prefactors))
+        elif isinstance(r[-1], LinearReduce):
+            return self.updated(r[-1].linear_map / torch.sum(r[-1].linear_map, 1, keepdim=True))
+        assert False
+
+    def updated(self, prefactors) -> "FiniteVec":
+        prefactors = asarray(prefactors)
+        _r = copy(self.reduce)
+        previous_reduction = None
+        if len(_r) > 0 and isinstance(_r[-1], (Prefactors, LinearReduce)):
+            final_len = Reduce.final_len(len(self.insp_pts), _r)
+            assert (final_len == prefactors.shape[0]) or (final_len == 1 and prefactors.dim() == 1)
+            previous_reduction = _r[-1]
+            _r = _r[:-1]
+        if prefactors.dim() == 1:
+            assert previous_reduction is None or isinstance(previous_reduction, Prefactors)
+            _r.append(Prefactors(prefactors))
+        elif prefactors.dim() == 2:
+            assert previous_reduction is None or isinstance(previous_reduction, LinearReduce)
+            assert len(self) == prefactors.shape[0]
+            _r.append(LinearReduce(prefactors))
+        return FiniteVec(self.k, self.insp_pts, _r)
+
+    def centered(self) -> "FiniteVec":
+        return self.extend_reduce([Center()])
+
+    def extend_reduce(self, r: List[Reduce]) -> "FiniteVec":
+        if r is None or len(r) == 0:
+            return self
+        _r = copy(self.reduce)
+        _r.extend(r)
+        return FiniteVec(self.k, self.insp_pts, _r)
+
+    def reduce_gram(self, gram, axis=0):
+        return Reduce.apply(gram, self.reduce, axis)
+
+    def nsamps(self, mean=False):
+        n = len(self.insp_pts)
+        rval = Reduce.apply(torch.ones((n, 1), dtype=torch.float32, device=self.insp_pts.device) * n, self.reduce, 0)
+        return rval.mean() if mean else rval
+
+    def get_mean_var(self, keepdims=False):
+        mean = self.reduce_gram(self.insp_pts, 0)
+        variance_of_expectations = self.reduce_gram(self.insp_pts ** 2, 0) - mean ** 2
+        var = torch.as_tensor(self.k.var(), device=mean.device) + variance_of_expectations
+        if keepdims:
+            return (mean, var)
+        return (torch.squeeze(mean), torch.squeeze(var))
+
+    def sum(self, use_linear_reduce=False) -> "FiniteVec":
+        if use_linear_reduce:
+            return self.extend_reduce([LinearReduce(torch.ones((1, len(self)), dtype=torch.float32))])
+        return self.extend_reduce([Sum()])
+
+    def mean(self) -> "FiniteVec":
+        return self.extend_reduce([Mean()])
+
+    @classmethod
+    def construct_RKHS_Elem(cls, kern, inspace_points, prefactors=None) -> "FiniteVec":
+        p = asarray(prefactors).squeeze()
+        assert p.dim() == 1
+        return FiniteVec(kern, inspace_points, [LinearReduce(p[None, :])])
+
+    @property
+    def _raw_gram(self):
+        if self._raw_gram_cache is None:
+            self._raw_gram_cache = self.k(self.insp_pts)
+        return self._raw_gram_cache
+
+    def __call__(self, argument):
+        return inner(self, FiniteVec(self.k, argument, []))
+
+
+def inner(X, Y=None, full=True):
+    return X.inner(Y, full)

@@ -194,7 +194,8 @@ def gengauss_gram_truth64(X, Y, s, power: float, nconst=None) -> np.ndarray:
         r = np.sqrt(sqeucldist_truth64(Xs, Ys))
     nc = np.asarray(nconst, dtype=np.float64)
     nc = float(nc.reshape(-1)[0]) if nc.size == 1 else nc
-    return nc * np.exp(-np.power(r, float(power)))
+    # the power reaches the device (and the reference's float32 `**`) rounded to float32
+    return nc * np.exp(-np.power(r, float(f32(power))))
 
 
 # ---------------------------------------------------------------------------------

@@ -1,0 +1,243 @@
+"""Host logic of the reference-shaped API (kern / reduce / rkhs) on CPU.
+
+The product path has no CPU fallback, so here the four native calls are replaced by
+oracle-backed stand-ins (tests may use oracle/; the product never does).  What is under
+test is everything ABOVE the C ABI: parameter conventions of GenGaussKernel, the Reduce
+family's array semantics, and the lowering of (chain_x, chain_y) onto Gram / K@W /
+group-sum descriptors -- checked against the outputs of the reference's own Python code
+(tests/golden/reference_numpy_shim.npz).  tests/test_gpu_api.py repeats the battery with
+the real kernels.
+"""
+import numpy as np
+import pytest
+import torch
+
+import jaxrk_b200._array as arr
+from jaxrk_b200 import _native as nat
+from jaxrk_b200.kern import GenGaussKernel
+from jaxrk_b200.reduce import BalancedRed, Center, LinearReduce, Mean, Prefactors, Reduce, Sum, TileView
+from jaxrk_b200.rkhs import Cdo, Cmo, Cov_inv, CovOp, FiniteOp, FiniteVec, inner
+from jaxrk_b200.rkhs import _lowering as low
+from oracle import jaxrk_oracle as orc
+
+f32 = np.float32
+CALLS = []
+
+
+def _np(t):
+    return None if t is None else np.asarray(t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else t, dtype=np.float64)
+
+
+def _truth_gram(X, Y, scale, power, nconst, dim_scale):
+    X = _np(X).astype(f32)
+    Y = X if Y is None else _np(Y).astype(f32)
+    if dim_scale is not None:
+        ds = np.asarray(dim_scale, f32)[None, :]
+        X, Y = (X * ds).astype(f32), (Y * ds).astype(f32)
+    return orc.gengauss_gram_truth64(X, Y, np.array([[scale]], f32), power, nconst=f32(nconst))
+
+
+def fake_gram(X, Y, scale, power, nconst, dim_scale=None, path=0, out=None):
+    CALLS.append("gram")
+    return torch.from_numpy(_truth_gram(X, Y, scale, power, nconst, dim_scale).astype(f32))
+
+
+def fake_dist(X, Y, scale, power, dim_scale=None):
+    CALLS.append("dist")
+    g = _truth_gram(X, Y, scale, power, 1.0, dim_scale)
+    return torch.from_numpy((-np.log(g)).astype(f32))
+
+
+def fake_kmatw(X, Y, W, scale, power, nconst, dim_scale=None, row_pref=None, col_pref=None, row_reduce=0, group=0, out=None):
+    CALLS.append("kmatw")
+    G = _truth_gram(X, Y, scale, power, nconst, dim_scale)
+    if row_pref is not None:
+        G = G * _np(row_pref)[:, None]
+    if col_pref is not None:
+        G = G * _np(col_pref)[None, :]
+    T = G @ _np(W)
+    if row_reduce == nat.REDUCE_SUM:
+        T = T.sum(0, keepdims=True)
+    elif row_reduce == nat.REDUCE_MEAN:
+        T = T.mean(0, keepdims=True)
+    elif row_reduce in (nat.REDUCE_BALANCED, nat.REDUCE_BALANCED_MEAN):
+        T = T.reshape(-1, group, T.shape[1])
+        T = T.sum(1) if row_reduce == nat.REDUCE_BALANCED else T.mean(1)
+    return torch.from_numpy(T.astype(f32))
+
+
+def fake_groupsum(X, Y, scale, power, nconst, gx, gy, average, dim_scale=None, row_pref=None, col_pref=None):
+    CALLS.append("groupsum")
+    G = _truth_gram(X, Y, scale, power, nconst, dim_scale)
+    if row_pref is not None:
+        G = G * _np(row_pref)[:, None]
+    if col_pref is not None:
+        G = G * _np(col_pref)[None, :]
+    G = G.reshape(G.shape[0] // gx, gx, G.shape[1] // gy, gy).sum((1, 3))
+    return torch.from_numpy((G / (gx * gy) if average else G).astype(f32))
+
+
+@pytest.fixture(autouse=True)
+def cpu_standins(monkeypatch):
+    monkeypatch.setattr(arr, "_device", torch.device("cpu"))
+    monkeypatch.setattr(nat, "gram", fake_gram)
+    monkeypatch.setattr(nat, "dist", fake_dist)
+    monkeypatch.setattr(nat, "kmatw", fake_kmatw)
+    monkeypatch.setattr(nat, "gram_groupsum", fake_groupsum)
+    CALLS.clear()
+    yield
+
+
+def chains_x(g):
+    pp, Ap = g["ch_pp"], g["ch_Ap"]
+    return {"none": [], "pref": [Prefactors(pp)], "sum": [Sum()], "mean": [Mean()], "pref_sum": [Prefactors(pp), Sum()],
+            "bal4": [BalancedRed(4)], "bal4avg": [BalancedRed(4, True)], "pref_bal3": [Prefactors(pp), BalancedRed(3)],
+            "lin": [LinearReduce(Ap)], "pref_lin": [Prefactors(pp), LinearReduce(Ap)], "center": [Center()],
+            "bal2_center": [BalancedRed(2), Center()]}
+
+
+def chains_y(g):
+    pq, Aq, Aq12 = g["ch_pq"], g["ch_Aq"], g["ch_Aq12"]
+    return {"none": [], "pref": [Prefactors(pq)], "sum": [Sum()], "mean": [Mean()], "lin": [LinearReduce(Aq)],
+            "pref_lin": [Prefactors(pq), LinearReduce(Aq)], "bal3_lin": [BalancedRed(3), LinearReduce(Aq12)],
+            "bal6avg": [BalancedRed(6, True)], "tile": [Mean(), TileView(4)]}
+
+
+def test_kernel_parameters_match_reference(golden):
+    for row, nconst, var, (kind, ls, sh) in zip(golden["rbf_row0"], golden["rbf_nconst"], golden["rbf_var"],
+                                                golden["rbf_params"]):
+        ls = f32(ls)
+        k = (GenGaussKernel.make_gauss(ls) if kind == 0 else GenGaussKernel.make_laplace(ls) if kind == 1
+             else GenGaussKernel.make(ls, float(sh)))
+        assert k.nconst.shape == (1, 1) and k.nconst.dtype == f32
+        np.testing.assert_allclose(k.nconst.reshape(-1)[0], nconst, rtol=3e-7)
+        np.testing.assert_allclose(np.asarray(k.var()).reshape(-1)[0], var, rtol=1e-6)
+        assert k.dist.power == sh
+        got = k(np.arange(8)[:, None])  # int input, as tests/test_kern.py:17
+        np.testing.assert_allclose(got[0].numpy(), row, rtol=2e-5, atol=1e-7)
+    with pytest.raises(AssertionError):
+        GenGaussKernel.make(1.0, 2.5)
+    with pytest.raises(AssertionError):
+        GenGaussKernel.make(1.0, 0.0)
+    with pytest.raises(AssertionError):
+        GenGaussKernel.make(-1.0, 1.0)
+
+
+def test_perdim_scale_and_diag(golden):
+    kd = GenGaussKernel.make(golden["perdim_ls"], 1.5)
+    np.testing.assert_allclose(kd.nconst, golden["perdim_nconst"], rtol=3e-7)
+    assert kd.kernel_args() is None and not kd.dist.is_global
+    np.testing.assert_allclose(kd.dist(golden["gram_X"], golden["gram_Y"]).numpy(), golden["perdim_dist_XY"], rtol=2e-5, atol=1e-6)
+    X = golden["gram_X"]
+    for name, k in (("gauss", GenGaussKernel.make_gauss(1.3)), ("laplace", GenGaussKernel.make_laplace(0.7)),
+                    ("gg15", GenGaussKernel.make(2.0, 1.5)), ("gg05", GenGaussKernel.make(0.9, 0.5))):
+        np.testing.assert_allclose(k(X, X[::-1].copy(), diag=True).numpy().reshape(-1), golden[f"gram_{name}_diag"].reshape(-1),
+                                   rtol=2e-5, atol=1e-9)
+        assert torch.all(k.dist(X, diag=True) == 0)
+
+
+def test_inner_chain_battery_against_reference_outputs(golden):
+    kg = GenGaussKernel.make(1.7, 1.5)
+    P, Q = golden["ch_P"], golden["ch_Q"]
+    cx, cy = chains_x(golden), chains_y(golden)
+    for nx in cx:
+        for ny in cy:
+            got = inner(FiniteVec(kg, P, cx[nx]), FiniteVec(kg, Q, cy[ny])).numpy()
+            want = golden[f"ch_inner__{nx}__{ny}"]
+            assert got.shape == want.shape, (nx, ny, got.shape, want.shape)
+            np.testing.assert_allclose(got, want, rtol=3e-5, atol=3e-6, err_msg=f"{nx}/{ny}")
+    for nx in cx:
+        got = FiniteVec(kg, P, cx[nx]).inner().numpy()
+        want = golden[f"ch_self__{nx}"]
+        assert got.shape == want.shape
+        # the reference misses truth on self-Gram diagonals for p < 2: 1e-4 there
+        np.testing.assert_allclose(got, want, rtol=3e-5, atol=2e-4 if nx in ("none", "pref", "center", "bal2_center") else 2e-5,
+                                   err_msg=nx)
+    el = FiniteVec.construct_RKHS_Elem(kg, P, golden["ch_pp"])
+    np.testing.assert_allclose(el(Q).numpy(), golden["ch_eval_elem_at_Q"], rtol=3e-5, atol=3e-6)
+    np.testing.assert_allclose(FiniteVec(kg, P, [LinearReduce(golden["ch_Ap"])])(Q).numpy(), golden["ch_eval_lin_at_Q"],
+                               rtol=3e-5, atol=3e-6)
+
+
+def test_lowering_picks_the_fused_kernels(golden):
+    kg = GenGaussKernel.make(1.7, 1.5)
+    P, Q = golden["ch_P"], golden["ch_Q"]
+    cx, cy = chains_x(golden), chains_y(golden)
+
+    def calls(a, b):
+        CALLS.clear()
+        inner(FiniteVec(kg, P, a), FiniteVec(kg, Q, b))
+        return list(CALLS)
+
+    assert calls(cx["none"], cy["none"]) == ["gram"]
+    assert calls(cx["pref"], cy["lin"]) == ["kmatw"]
+    assert calls(cx["mean"], cy["pref_lin"]) == ["kmatw"]
+    assert calls(cx["lin"], cy["none"]) == ["kmatw"]        # transposed problem
+    assert calls(cx["pref_bal3"], cy["sum"]) == ["kmatw"]   # BalancedRed folded as row reduce
+    assert calls(cx["sum"], cy["bal6avg"]) == ["kmatw"]     # transposed, balanced on the other side
+    assert calls(cx["bal2_center"], cy["mean"]) == ["kmatw"]  # Center acts on the reduced result
+    assert calls(cx["center"], cy["none"]) == ["gram"]      # not foldable: materialise + Reduce.apply
+    X = np.random.RandomState(0).randn(256, 3).astype(f32)
+    CALLS.clear()
+    v = FiniteVec(kg, X, [BalancedRed(128, True)])
+    got = v.inner()
+    assert CALLS == ["groupsum"] and tuple(got.shape) == (2, 2)
+    G = orc.gengauss_gram_truth64(X, None, orc.simple_scaler_s(1.7), 1.5)
+    np.testing.assert_allclose(got.numpy(), G.reshape(2, 128, 2, 128).mean((1, 3)), rtol=1e-5)
+    v.inner()
+    assert CALLS == ["groupsum"], "the self inner product is cached (Cov_solve asks for it twice)"
+
+
+def test_fold_chain_rules(golden):
+    dev = torch.device("cpu")
+    pp = torch.from_numpy(golden["ch_pp"])
+    f = low.fold_chain([Prefactors(pp), Prefactors(pp), BalancedRed(3, True), Center(), Sum()], 24, dev)
+    assert f.kind == low.BALANCED and f.group == 3 and f.average and len(f.post) == 2 and f.out_len == 8
+    np.testing.assert_allclose(f.pref.numpy(), (pp * pp).numpy())
+    A = torch.from_numpy(golden["ch_Ap"])
+    f = low.fold_chain([LinearReduce(A), Prefactors(torch.tensor([1., 2., 3.])), Sum()], 24, dev)
+    assert f.kind == low.LINEAR and tuple(f.A.shape) == (1, 24) and f.post == []
+    np.testing.assert_allclose(f.A.numpy(), (A * torch.tensor([[1.], [2.], [3.]])).sum(0, keepdim=True).numpy(), rtol=1e-6)
+    f = low.fold_chain([TileView(48)], 24, dev)
+    assert f.kind == low.NONE and len(f.post) == 1
+    assert Reduce.final_len(24, [BalancedRed(4), LinearReduce(torch.ones(2, 6))]) == 2
+    with pytest.raises(AssertionError):
+        Reduce.final_len(25, [BalancedRed(4)])
+    with pytest.raises(AssertionError):
+        LinearReduce(torch.ones(2, 5)).new_len(6)
+
+
+def test_operators_against_reference_outputs(golden):
+    g = golden
+    kx, ky = GenGaussKernel.make_gauss(0.9), GenGaussKernel.make_laplace(1.1)
+    inp, outp, ref = FiniteVec(kx, g["op_X"]), FiniteVec(ky, g["op_Y"]), FiniteVec(ky, g["op_R"])
+    op = FiniteOp(inp, outp, g["op_M"])
+    res = op @ FiniteVec(kx, g["op_Xt"])
+    np.testing.assert_allclose(res.reduce[-1].linear_map.numpy(), g["op_matmul_vec_lin"], rtol=3e-5, atol=3e-6)
+    np.testing.assert_allclose(res(g["op_Yt"]).numpy(), g["op_matmul_vec_eval"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose((op @ FiniteVec(kx, g["op_Xt"][:1]))(g["op_Yt"]).numpy(), g["op_matmul_vec1_eval"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose((op @ g["op_Xt"])(g["op_Yt"]).numpy(), g["op_matmul_arr_eval"], rtol=1e-4, atol=1e-5)
+    op2 = FiniteOp(outp, inp, g["op_M"].T.copy())
+    np.testing.assert_allclose((op @ op2).matr.numpy(), g["op_matmul_op_matr"], rtol=1e-4, atol=1e-4)
+    # the regularised inverse amplifies the (correct) ~1e-4 diagonal difference to the reference
+    np.testing.assert_allclose(Cov_inv(CovOp(inp), regul=0.1).matr.numpy(), g["cov_inv_matr"], rtol=1e-3, atol=5e-2)
+    cmo = Cmo(inp, outp, regul=0.1)
+    assert tuple(cmo.matr.shape) == g["cmo_matr"].shape
+    np.testing.assert_allclose((cmo @ FiniteVec(kx, g["op_Xt"]))(g["op_Yt"]).numpy(), g["cmo_apply_eval"], rtol=1e-3, atol=1e-3)
+    cdo = Cdo(inp, outp, ref, regul=0.1)
+    assert tuple(cdo.matr.shape) == g["cdo_matr"].shape
+    np.testing.assert_allclose((cdo @ FiniteVec(kx, g["op_Xt"]))(g["op_Yt"]).numpy(), g["cdo_apply_eval"], rtol=2e-3, atol=2e-3)
+
+
+def test_errors_match_reference_conventions(golden):
+    kg = GenGaussKernel.make(1.7, 1.5)
+    v = FiniteVec(kg, golden["ch_P"])
+    with pytest.raises(ValueError):
+        v.inner(v, full=False)
+    with pytest.raises(AssertionError):
+        v.inner(FiniteVec(GenGaussKernel.make(1.7, 1.5), golden["ch_Q"]))  # kernels compare by identity (quirk Q5)
+    with pytest.raises(AssertionError):
+        FiniteVec(kg, np.zeros(5, f32))
+    with pytest.raises(AssertionError):
+        FiniteOp(v, v, np.zeros((3, 3), f32))
+    assert len(v.sum()) == 1 and len(v.mean()) == 1 and len(v.extend_reduce([BalancedRed(4)])) == 6

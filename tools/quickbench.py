@@ -1,0 +1,90 @@
+"""Kernel-only timings of the C-ABI entry points (CUDA events, resident inputs).
+Usage: python tools/quickbench.py [gram|kmatw|groupsum|all]   -> JSON lines on stdout."""
+import json
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+from jaxrk_b200 import _native as nat  # noqa: E402
+
+dev = torch.device("cuda:0")
+HBM = 6542.1e9
+FMA = 3.69e13  # measured FFMA2 lanes/s (profiles/microbench)
+
+
+def randn(seed, *shape):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    return torch.randn(*shape, generator=g, device=dev, dtype=torch.float32)
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return min(ts), float(np.median(ts))
+
+
+def kp(power, d):
+    s = 1.0 / np.sqrt(d)
+    return float(s), float(power), 0.25
+
+
+def bench_gram():
+    for (N, M, d, path) in [(1024, 1024, 8, 1), (32768, 32768, 8, 1), (32768, 32768, 16, 1), (32768, 32768, 32, 1),
+                            (32768, 32768, 64, 1), (32768, 32768, 64, 2), (65536, 65536, 64, 2), (65536, 65536, 128, 2)]:
+        X, Y = randn(0, N, d), randn(1, M, d)
+        K = torch.empty((N, M), device=dev, dtype=torch.float32)
+        for power in (2.0, 1.0, 1.5):
+            s, p, nc = kp(power, d)
+            best, med = timeit(lambda: nat.gram(X, Y, s, p, nc, path=path, out=K))
+            ev = N * M / best
+            print(json.dumps({"op": "gram", "N": N, "M": M, "d": d, "path": path, "power": power, "ms": best * 1e3,
+                              "ms_med": med * 1e3, "evals_per_s": ev, "hbm_frac": 4 * ev / HBM,
+                              "fma_frac_direct": ev * (2 * d + 2) / FMA}), flush=True)
+        del K
+
+
+def bench_kmatw():
+    for (N, M, d, m) in [(131072, 1 << 20, 16, 16), (131072, 1 << 20, 16, 1), (131072, 1 << 20, 8, 16),
+                         (131072, 1 << 20, 32, 16), (65536, 1 << 20, 64, 16), (131072, 1 << 20, 16, 32)]:
+        X, Y, W = randn(0, N, d), randn(1, M, d), randn(2, M, m)
+        for power in (2.0, 1.0, 1.5):
+            s, p, nc = kp(power, d)
+            for rr in (0, 2):
+                if rr and (power != 2.0):
+                    continue
+                best, med = timeit(lambda: nat.kmatw(X, Y, W, s, p, nc, row_reduce=rr), reps=3, warm=1)
+                ev = N * M / best
+                print(json.dumps({"op": "kmatw", "N": N, "M": M, "d": d, "m": m, "power": power, "row_reduce": rr,
+                                  "ms": best * 1e3, "ms_med": med * 1e3, "evals_per_s": ev,
+                                  "fma_frac": ev * (2 * d + m + 2) / FMA}), flush=True)
+
+
+def bench_groupsum():
+    g, groups, d = 4096, 32, 32
+    X = randn(0, g * groups, d)
+    s, p, nc = kp(2.0, d)
+    best, med = timeit(lambda: nat.gram_groupsum(X, None, s, p, nc, g, g, True), reps=3, warm=1)
+    ev = (g * groups) ** 2 / best
+    print(json.dumps({"op": "groupsum", "N": g * groups, "d": d, "ms": best * 1e3, "evals_per_s": ev,
+                      "fma_frac": ev * (2 * d + 2) / FMA}), flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("gram", "all"):
+        bench_gram()
+    if what in ("kmatw", "all"):
+        bench_kmatw()
+    if what in ("groupsum", "all"):
+        bench_groupsum()
