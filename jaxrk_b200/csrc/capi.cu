@@ -90,9 +90,9 @@ size_t jrk_gram_workspace_bytes(int64_t N, int64_t M, int d, int path) {
 int jrk_gram_f32(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
                  int64_t ldk, float scale, const float* dim_scale, float power, float nconst, int path,
                  void* workspace, size_t workspace_bytes, void* stream) {
-    if (!X || !K) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: X and K must not be NULL");
-    if (!Y) { Y = X; M = N; ldy = ldx; }
     if (N < 0 || M < 0) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: negative size");
+    if (!Y) { Y = X; M = N; ldy = ldx; }
+    if (N > 0 && M > 0 && (!X || !K)) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: X and K must not be NULL");
     if (int rc = check_kernel_params("jrk_gram_f32", d, scale, power, nconst)) return rc;
     if (ldx < d || ldy < d || ldk < M) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: leading dimension too small");
     if (path < JRK_PATH_AUTO || path > JRK_PATH_TF32X3) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: bad path %d", path);
@@ -107,9 +107,9 @@ int jrk_gram_f32(const float* X, const float* Y, float* K, int64_t N, int64_t M,
 
 int jrk_dist_f32(const float* X, const float* Y, float* D, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
                  int64_t ldd, float scale, const float* dim_scale, float power, void* stream) {
-    if (!X || !D) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_f32: X and D must not be NULL");
-    if (!Y) { Y = X; M = N; ldy = ldx; }
     if (N < 0 || M < 0 || d < 1) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_f32: bad size");
+    if (!Y) { Y = X; M = N; ldy = ldx; }
+    if (N > 0 && M > 0 && (!X || !D)) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_f32: X and D must not be NULL");
     if (!(scale > 0.f) || !(power > 0.f)) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_f32: scale and power must be positive");
     if (ldx < d || ldy < d || ldd < M) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_f32: leading dimension too small");
     if (N == 0 || M == 0) return JRK_OK;
