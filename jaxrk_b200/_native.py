@@ -134,6 +134,8 @@ def gram(X, Y, scale: float, power: float, nconst: float, dim_scale=None, path: 
     ds = _vec(dim_scale, d, "dim_scale", X.device)
     if out is None:
         out = torch.empty((N, M), dtype=torch.float32, device=X.device)
+    if N == 0 or M == 0:  # empty tensors have NULL data pointers; nothing to compute
+        return out
     with torch.cuda.device(X.device):
         wsb = lib().jrk_gram_workspace_bytes(N, M, d, path)
         ws = torch.empty(wsb, dtype=torch.uint8, device=X.device) if wsb else None
@@ -154,6 +156,8 @@ def dist(X, Y, scale: float, power: float, dim_scale=None) -> torch.Tensor:
         raise ValueError("X and Y must have the same number of columns")
     ds = _vec(dim_scale, d, "dim_scale", X.device)
     out = torch.empty((N, M), dtype=torch.float32, device=X.device)
+    if N == 0 or M == 0:
+        return out
     with torch.cuda.device(X.device):
         _check(lib().jrk_dist_f32(_ptr(X), None if self_gram else _ptr(Yt), _ptr(out), N, M, d, _ld(X), _ld(Yt), M,
                                   scale, _ptr(ds), power, _stream(X.device)))

@@ -39,8 +39,8 @@ def kp(power, d):
     return float(s), float(power), 0.25
 
 
-def bench_gram():
-    for (N, M, d, path) in [(1024, 1024, 8, 1), (32768, 32768, 8, 1), (32768, 32768, 16, 1), (32768, 32768, 32, 1),
+def bench_gram(only_tf32=False):
+    for (N, M, d, path) in [(32768, 32768, 64, 2), (65536, 65536, 64, 2), (65536, 65536, 96, 2), (65536, 65536, 128, 2)] if only_tf32 else [(1024, 1024, 8, 1), (32768, 32768, 8, 1), (32768, 32768, 16, 1), (32768, 32768, 32, 1),
                             (32768, 32768, 64, 1), (32768, 32768, 64, 2), (65536, 65536, 64, 2), (65536, 65536, 128, 2)]:
         X, Y = randn(0, N, d), randn(1, M, d)
         K = torch.empty((N, M), device=dev, dtype=torch.float32)
@@ -84,6 +84,8 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gram", "all"):
         bench_gram()
+    if what == "tf32":
+        bench_gram(True)
     if what in ("kmatw", "all"):
         bench_kmatw()
     if what in ("groupsum", "all"):
