@@ -20,9 +20,10 @@
 //   warp 0      TMA producer: cp.async.bulk of raw FP32 X tiles (NT x DP) into a 3-stage ring
 //   warp 1      MMA issuer (one thread) + TMEM allocation (all 512 columns)
 //   warps 2-5   converter: split the raw tile into tf32 hi / lo images in the K-major
-//               128B-swizzled layout the UMMA descriptor expects, and compute |x_i|^2
-//   warps 6-13  epilogue: tcgen05.ld the three accumulators, sq = |x|^2+|y|^2-2acc, the
-//               exp2 epilogue, coalesced streaming stores.  At the start of every work unit
+//               128B-swizzled layout the UMMA descriptor expects
+//   warps 6-13  epilogue: tcgen05.ld the three accumulators, sq = |x|^2+|y|^2-2acc (packed
+//               FADD2 / FFMA2), the exp2 epilogue, coalesced streaming stores; the row norms
+//               come from a small pre-pass kernel.  At the start of every work unit
 //               the same warps load their Y rows, split them and park hi / lo in TMEM
 //               (tcgen05.st): the A operand is read from TMEM (no shared-memory traffic for A,
 //               which would otherwise exceed the 128 B/clk shared-memory port).
@@ -46,7 +47,7 @@ namespace {
 constexpr int TF_BM = 128;        // rows of Y per work unit = TMEM lanes = output columns
 constexpr int TF_THREADS = 448;   // 14 warps
 constexpr int TF_CONV_WARP0 = 2, TF_EPI_WARP0 = 6, TF_EPI_THREADS = 256, TF_CONV_THREADS = 128;
-constexpr int S_RAW = 3, S_OP = 2, X2_SLOTS = 8;
+constexpr int S_RAW = 3, S_OP = 2;
 constexpr float TF_TAU = 1.0f / 64.0f;
 
 template <int DP, int NT>
@@ -56,9 +57,7 @@ struct TfCfg {
     static constexpr int HALF_BYTES = NT * DP * 4;        // one swizzled image (hi or lo)
     static constexpr int OFF_RAW = 0;
     static constexpr int OFF_OP = S_RAW * RAW_BYTES;      // multiple of 1024 for all supported (DP, NT)
-    static constexpr int OFF_X2 = OFF_OP + S_OP * 2 * HALF_BYTES;
-    static constexpr int OFF_YSUM = OFF_X2 + X2_SLOTS * NT * 4;
-    static constexpr int OFF_BAR = OFF_YSUM + 4 * TF_BM * 4;
+    static constexpr int OFF_BAR = OFF_OP + S_OP * 2 * HALF_BYTES;
     static constexpr int NUM_BARS = 2 * S_RAW + 2 * S_OP + 4 + 1;
     static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
     static constexpr int BYTES = OFF_TMEM_SLOT + 16;
@@ -121,19 +120,25 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// tf32 split: hi = rna(x), lo = rna(x - hi); both are valid tf32 bit patterns (low 13 bits zero)
+// tf32 split: hi = x rounded to tf32 (nearest, ties away: add half an ulp to the bit pattern, mask),
+// lo = x - hi (exact in FP32; the tensor core reads its leading 11 significant bits).  3 ALU ops.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
-// canonical partial of a row norm over one 16-byte chunk (4 elements, in k order)
-__device__ __forceinline__ float chunk_norm(const float4& v) {
-    float q = v.x * v.x;
-    q = fmaf(v.y, v.y, q);
-    q = fmaf(v.z, v.z, q);
-    q = fmaf(v.w, v.w, q);
-    return q;
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
+    // try_wait with a suspend-time hint: the warp sleeps in hardware instead of spinning on issue slots
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(20000u)
+        : "memory");
 }
 
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart (sm_100 format)
@@ -147,11 +152,36 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
     return d;
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 __device__ __forceinline__ void st_global_cs(float* p, float v) {
     asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// Epilogue constants (see the epilogue): u = a * dot + (xs_i + ys_j), with xs = mult |x|^2 + add/2 from
+// tf_norm_kernel (the additive constant is split evenly so that xs_i + ys_j stays commutative -> symmetric K)
+struct TfEpi {
+    float a;       // PM_SQEXP: -2c (c = -s^2 log2 e);  otherwise -2
+    float add_y;   // PM_SQEXP: log2(nconst), folded into the exponent through xs / ys;  otherwise 0
+    float w0;      // refinement threshold for w = u - tau (xs + ys): PM_SQEXP add_y (1 - tau), else 0
+};
+
+// out[r] = mult * |row r|^2 + add -- ONE function for X and Y, so the norms are role independent (bitwise
+// symmetric self-Gram).  One warp per row: 16-byte chunks, xor-shuffle tree.
+__global__ void tf_norm_kernel(const float* __restrict__ A, int64_t rows, int64_t rows_padded, int DP, float mult,
+                               float add, float* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows_padded) return;
+    const int lane = threadIdx.x & 31;
+    float q = 0.f;
+    if (r < rows && lane * 4 < DP) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(A + r * DP) + lane);
+        q = v.x * v.x;
+        q = fmaf(v.y, v.y, q);
+        q = fmaf(v.z, v.z, q);
+        q = fmaf(v.w, v.w, q);
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) out[r] = (r < rows) ? fmaf(mult, q, add) : 0.f;
 }
 
 // ---------------------------------------------------------------------------------
@@ -159,8 +189,9 @@ __device__ __forceinline__ void st_global_cs(float* p, float v) {
 // ---------------------------------------------------------------------------------
 template <int DP, int NT, int PM>
 __global__ void __launch_bounds__(TF_THREADS, 1)
-gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, float* __restrict__ K, int64_t N,
-                 int64_t M, int64_t ldk, EpiParams ep, int n_it, int tpu, int n_jb, int n_units) {
+gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ xn,
+                 const float* __restrict__ yn, float* __restrict__ K, int64_t N, int64_t M, int64_t ldk,
+                 EpiParams ep, TfEpi te, int n_it, int tpu, int n_jb, int n_units) {
     using C = TfCfg<DP, NT>;
     extern __shared__ unsigned char tf_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tf_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -173,8 +204,6 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, flo
     uint64_t* acc_empty = acc_full + 2;        // [2]
     uint64_t* a_ready = acc_empty + 2;         // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM_SLOT);
-    float* x2s = reinterpret_cast<float*>(smem + C::OFF_X2);      // [X2_SLOTS][NT]
-    float* ysum = reinterpret_cast<float*>(smem + C::OFF_YSUM);   // [4][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -199,7 +228,7 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, flo
                 const int it0 = (u / n_jb) * tpu, it1 = min(it0 + tpu, n_it);
                 for (int it = it0; it < it1; ++it, ++tc) {
                     const int s = tc % S_RAW;
-                    mbar_wait(&raw_empty[s], ((tc / S_RAW) & 1) ^ 1);
+                    mbar_wait_hint(&raw_empty[s], ((tc / S_RAW) & 1) ^ 1);
                     const int64_t i0 = (int64_t)it * NT;
                     const uint32_t rows = (uint32_t)min((int64_t)NT, N - i0);
                     const uint32_t bytes = rows * DP * 4;
@@ -216,11 +245,11 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, flo
             uint32_t tc = 0, uc = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
                 const int it0 = (u / n_jb) * tpu, it1 = min(it0 + tpu, n_it);
-                mbar_wait(a_ready, uc & 1);
+                mbar_wait_hint(a_ready, uc & 1);
                 for (int it = it0; it < it1; ++it, ++tc) {
                     const int q = tc % S_OP, a = tc & 1;
-                    mbar_wait(&acc_empty[a], ((tc >> 1) & 1) ^ 1);
-                    mbar_wait(&op_full[q], (tc / S_OP) & 1);
+                    mbar_wait_hint(&acc_empty[a], ((tc >> 1) & 1) ^ 1);
+                    mbar_wait_hint(&op_full[q], (tc / S_OP) & 1);
                     tc_fence_after();
                     const uint32_t b_hi = smem_u32(smem + C::OFF_OP + q * 2 * C::HALF_BYTES);
                     const uint32_t b_lo = b_hi + C::HALF_BYTES;
@@ -251,16 +280,14 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, flo
             const int it0 = (u / n_jb) * tpu, it1 = min(it0 + tpu, n_it);
             for (int it = it0; it < it1; ++it, ++tc) {
                 const int s = tc % S_RAW, q = tc % S_OP;
-                mbar_wait(&raw_full[s], (tc / S_RAW) & 1);
-                mbar_wait(&op_empty[q], ((tc / S_OP) & 1) ^ 1);
+                mbar_wait_hint(&raw_full[s], (tc / S_RAW) & 1);
+                mbar_wait_hint(&op_empty[q], ((tc / S_OP) & 1) ^ 1);
                 const unsigned char* raw = smem + C::OFF_RAW + s * C::RAW_BYTES;
                 unsigned char* img_hi = smem + C::OFF_OP + q * 2 * C::HALF_BYTES;
                 unsigned char* img_lo = img_hi + C::HALF_BYTES;
-                float* x2 = x2s + (tc % X2_SLOTS) * NT;
 #pragma unroll
                 for (int pass = 0; pass < NT / 16; ++pass) {
                     const int r = pass * 16 + cw * 4 + rsub;
-                    float nrm = 0.f;
 #pragma unroll
                     for (int kc = 0; kc < C::KC; ++kc) {
                         const float4 v = *reinterpret_cast<const float4*>(raw + r * DP * 4 + kc * 128 + c * 16);
@@ -272,13 +299,7 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, flo
                         const int off = kc * NT * 128 + r * 128 + ((c ^ (r & 7)) << 4);
                         *reinterpret_cast<uint4*>(img_hi + off) = h;
                         *reinterpret_cast<uint4*>(img_lo + off) = l;
-                        float t = chunk_norm(v);
-                        t += __shfl_xor_sync(0xffffffffu, t, 1);
-                        t += __shfl_xor_sync(0xffffffffu, t, 2);
-                        t += __shfl_xor_sync(0xffffffffu, t, 4);
-                        nrm = (kc == 0) ? t : nrm + t;
                     }
-                    if (c == 0) x2[r] = nrm;
                 }
                 fence_proxy_async();           // generic-proxy writes -> visible to the tensor core (async proxy)
                 mbar_arrive(&op_full[q]);
@@ -299,16 +320,14 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, flo
             const int it0 = (u / n_jb) * tpu, it1 = min(it0 + tpu, n_it);
             const int64_t j = (int64_t)jb * TF_BM + jl;
             const bool jok = j < M;
-            // ---- park this unit's Y block in TMEM as tf32 hi / lo; |y_j|^2 by the canonical order ----
+            // ---- park this unit's Y block in TMEM as tf32 hi / lo (this warp: k-chunks kc = ch mod 2) ----
             const float* yrow = Yp + (jok ? j : 0) * DP;
 #pragma unroll
             for (int kc = 0; kc < C::KC; ++kc) {
                 if ((kc & 1) != ch) continue;
-                float tsum = 0.f;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t hi[16], lo[16];
-                    float q4[4];
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -317,31 +336,32 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, flo
                         split_tf32(v.y, hi[cc * 4 + 1], lo[cc * 4 + 1]);
                         split_tf32(v.z, hi[cc * 4 + 2], lo[cc * 4 + 2]);
                         split_tf32(v.w, hi[cc * 4 + 3], lo[cc * 4 + 3]);
-                        q4[cc] = chunk_norm(v);
                     }
-                    const float hsum = (q4[0] + q4[1]) + (q4[2] + q4[3]);   // same tree as the converter's shuffles
-                    tsum = (half == 0) ? hsum : tsum + hsum;
                     tmem_st16(tmem_base + lane_addr + kc * 32 + half * 16, hi);
                     tmem_st16(tmem_base + lane_addr + DP + kc * 32 + half * 16, lo);
                 }
-                ysum[kc * TF_BM + jl] = tsum;
             }
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(a_ready);
-            named_bar_sync(1, TF_EPI_THREADS);
-            float y2 = ysum[jl];
-#pragma unroll
-            for (int kc = 1; kc < C::KC; ++kc) y2 += ysum[kc * TF_BM + jl];
-            named_bar_sync(1, TF_EPI_THREADS);
+            // (scaled) |y_j|^2 plus the folded constant, both lanes of a packed pair
+            const float ys = jok ? __ldg(yn + j) : 0.f;
+            const f32x2 ys2 = pack2(ys, ys);
+            const f32x2 a2 = pack2(te.a, te.a), ntau2 = pack2(-TF_TAU, -TF_TAU);
 
             // ---- tiles of this unit ----
             for (int it = it0; it < it1; ++it, ++tc) {
                 const int a = tc & 1;
-                mbar_wait(&acc_full[a], (tc >> 1) & 1);
+                const int64_t i0 = (int64_t)it * NT + ch * NTH;
+                const int nvalid = (int)min((int64_t)NTH, N - i0);   // warp-uniform; <= 0 for rows past N
+                // (scaled) |x_i|^2 of this warp's rows: uniform 16-byte loads, issued before the wait
+                float4 xv[NTH / 4];   // xn is zero-padded to a multiple of NT rows
+#pragma unroll
+                for (int g = 0; g < NTH / 4; ++g) xv[g] = __ldg(reinterpret_cast<const float4*>(xn + i0) + g);
+                mbar_wait_hint(&acc_full[a], (tc >> 1) & 1);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + lane_addr + C::ACC_COL0 + a * 3 * NT + ch * NTH;
-                float dot[NTH];
+                f32x2 dot2[NTH / 2];
 #pragma unroll
                 for (int g = 0; g < NTH / 16; ++g) {
                     float c1[16], c2[16], c3[16];
@@ -350,35 +370,42 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, flo
                     tmem_ld16(acc + 2 * NT + g * 16, c3);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) dot[g * 16 + i] = c1[i] + (c2[i] + c3[i]);
+                    for (int i = 0; i < 8; ++i)   // c1 + (c2 + c3): symmetric in the two cross terms
+                        dot2[g * 8 + i] = add2(pack2(c1[2 * i], c1[2 * i + 1]),
+                                               add2(pack2(c2[2 * i], c2[2 * i + 1]), pack2(c3[2 * i], c3[2 * i + 1])));
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[a]);    // TMEM stage free: the next tile's MMAs overlap the math below
 
-                // sq = |x_i|^2 + |y_j|^2 - 2 x_i.y_j for the NTH rows of this warp (branch-free fast path)
-                const float4* x2v = reinterpret_cast<const float4*>(x2s + (tc % X2_SLOTS) * NT + ch * NTH);
-                const int64_t i0 = (int64_t)it * NT + ch * NTH;
-                bool refine = false;
+                // u = a * dot + (xs_i + ys_j)  and the near-zero test  w = u - tau * (xs_i + ys_j):
+                //   PM_SQEXP : a = -2c, xs/ys = c|.|^2 (c < 0), ys carries log2(nconst): u = log2 K; refine if w > w0
+                //   otherwise: a = -2,  xs/ys = |.|^2: u = sq;                                   refine if w < 0
+                float u[NTH];
+                float wext = te.w0;
 #pragma unroll
                 for (int g = 0; g < NTH / 4; ++g) {
-                    const float4 xn = x2v[g];
-                    const float xs[4] = {xn.x, xn.y, xn.z, xn.w};
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const float t = xs[b] + y2;
-                        const float sq = fmaf(-2.f, dot[g * 4 + b], t);
-                        refine |= (sq < TF_TAU * t);
-                        dot[g * 4 + b] = sq;
-                    }
+                    const f32x2 t01 = add2(pack2(xv[g].x, xv[g].y), ys2), t23 = add2(pack2(xv[g].z, xv[g].w), ys2);
+                    const f32x2 u01 = fma2(dot2[g * 2], a2, t01), u23 = fma2(dot2[g * 2 + 1], a2, t23);
+                    const f32x2 w01 = fma2(t01, ntau2, u01), w23 = fma2(t23, ntau2, u23);
+                    float w0, w1, w2, w3;
+                    unpack2(u01, u[g * 4], u[g * 4 + 1]);
+                    unpack2(u23, u[g * 4 + 2], u[g * 4 + 3]);
+                    unpack2(w01, w0, w1);
+                    unpack2(w23, w2, w3);
+                    if (PM == PM_SQEXP) wext = fmaxf(fmaxf(wext, w0), fmaxf(fmaxf(w1, w2), w3));
+                    else wext = fminf(fminf(wext, w0), fminf(fminf(w1, w2), w3));
                 }
-                const int nvalid = (int)min((int64_t)NTH, N - i0);   // warp-uniform; <= 0 for rows past N
+                const bool refine = (PM == PM_SQEXP) ? (wext > te.w0) : (wext < te.w0);
                 if (__any_sync(0xffffffffu, refine && jok)) {
                     // near-coincident pairs (the self-Gram diagonal, duplicates): the expansion has no relative
                     // accuracy left there; recompute those entries by FP32 direct differencing (rare path)
 #pragma unroll
-                    for (int i = 0; i < NTH; ++i) {   // unrolled: dot[] must stay in registers
-                        const float t = x2s[(tc % X2_SLOTS) * NT + ch * NTH + i] + y2;
-                        if (i < nvalid && jok && dot[i] < TF_TAU * t) {
+                    for (int i = 0; i < NTH; ++i) {   // unrolled: u[] must stay in registers
+                        const float xs = __ldg(xn + i0 + i);
+                        const float t = xs + ys;
+                        const float w = fmaf(t, -TF_TAU, u[i]);
+                        const bool bad = (PM == PM_SQEXP) ? (w > te.w0) : (w < te.w0);
+                        if (i < nvalid && jok && bad) {
                             const float* xr = Xp + (i0 + i) * DP;
                             float acc2 = 0.f;
 #pragma unroll 1
@@ -386,7 +413,7 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, flo
                                 const float df = __ldg(xr + k) - __ldg(yrow + k);
                                 acc2 = fmaf(df, df, acc2);
                             }
-                            dot[i] = acc2;
+                            u[i] = (PM == PM_SQEXP) ? fmaf(acc2, ep.c, te.add_y) : acc2;
                         }
                     }
                 }
@@ -394,12 +421,14 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, flo
                 if (nvalid == NTH) {
                     if (jok) {
 #pragma unroll
-                        for (int i = 0; i < NTH; ++i) st_global_cs(kp + (int64_t)i * ldk, ep.nconst * kexp_unnorm<PM>(dot[i], ep));
+                        for (int i = 0; i < NTH; ++i, kp += ldk)
+                            st_global_cs(kp, (PM == PM_SQEXP) ? ex2_approx(u[i]) : ep.nconst * kexp_unnorm<PM>(u[i], ep));
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < NTH; ++i)
-                        if (i < nvalid && jok) st_global_cs(kp + (int64_t)i * ldk, ep.nconst * kexp_unnorm<PM>(dot[i], ep));
+                    for (int i = 0; i < NTH; ++i, kp += ldk)
+                        if (i < nvalid && jok)
+                            st_global_cs(kp, (PM == PM_SQEXP) ? ex2_approx(u[i]) : ep.nconst * kexp_unnorm<PM>(u[i], ep));
                 }
             }
         }
@@ -439,8 +468,8 @@ int sm_count() {
 }
 
 template <int DP, int NT, int PM>
-int tf_launch(const float* Xp, const float* Yp, float* K, int64_t N, int64_t M, int64_t ldk, const EpiParams& ep,
-              cudaStream_t st) {
+int tf_launch(const float* Xp, const float* Yp, const float* xn, const float* yn, float* K, int64_t N, int64_t M,
+              int64_t ldk, const EpiParams& ep, const TfEpi& te, cudaStream_t st) {
     using C = TfCfg<DP, NT>;
     auto kern = gram_tf32_kernel<DP, NT, PM>;
     JRK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::DYN_BYTES));
@@ -460,17 +489,18 @@ int tf_launch(const float* Xp, const float* Yp, float* K, int64_t N, int64_t M, 
     if (n_units > 2147483647LL || n_it > 2147483647LL)
         return fail(JRK_ERR_UNSUPPORTED, "gram_tf32x3: problem too large (%lld units)", (long long)n_units);
     const int grid = (int)std::min<int64_t>(grid_max, n_units);
-    kern<<<grid, TF_THREADS, C::DYN_BYTES, st>>>(Xp, Yp, K, N, M, ldk, ep, (int)n_it, (int)tpu, (int)n_jb, (int)n_units);
+    kern<<<grid, TF_THREADS, C::DYN_BYTES, st>>>(Xp, Yp, xn, yn, K, N, M, ldk, ep, te, (int)n_it, (int)tpu, (int)n_jb,
+                                                 (int)n_units);
     JRK_LAUNCHED();
     return JRK_OK;
 }
 
 template <int DP, int NT>
-int tf_dispatch_pm(int pm, const float* Xp, const float* Yp, float* K, int64_t N, int64_t M, int64_t ldk,
-                   const EpiParams& ep, cudaStream_t st) {
-    if (pm == PM_SQEXP) return tf_launch<DP, NT, PM_SQEXP>(Xp, Yp, K, N, M, ldk, ep, st);
-    if (pm == PM_LAPLACE) return tf_launch<DP, NT, PM_LAPLACE>(Xp, Yp, K, N, M, ldk, ep, st);
-    return tf_launch<DP, NT, PM_GENERAL>(Xp, Yp, K, N, M, ldk, ep, st);
+int tf_dispatch_pm(int pm, const float* Xp, const float* Yp, const float* xn, const float* yn, float* K, int64_t N,
+                   int64_t M, int64_t ldk, const EpiParams& ep, const TfEpi& te, cudaStream_t st) {
+    if (pm == PM_SQEXP) return tf_launch<DP, NT, PM_SQEXP>(Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
+    if (pm == PM_LAPLACE) return tf_launch<DP, NT, PM_LAPLACE>(Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
+    return tf_launch<DP, NT, PM_GENERAL>(Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
 }
 
 inline int tf_dp(int d) { return d <= 64 ? 64 : d <= 96 ? 96 : 128; }
@@ -480,10 +510,13 @@ inline bool tf_usable_in_place(const float* A, int64_t lda, int d, int DP, const
 
 }  // namespace
 
+inline int64_t tf_pad64(int64_t n) { return (n + 63) / 64 * 64; }
+
 size_t gram_tf32x3_workspace_bytes(int64_t N, int64_t M, int d) {
     if (d > 128) return 0;
     const int DP = tf_dp(d);
-    return align256((size_t)N * DP * 4) + align256((size_t)M * DP * 4) + 512;
+    return align256((size_t)N * DP * 4) + align256((size_t)M * DP * 4) + align256((size_t)tf_pad64(N) * 4) +
+           align256((size_t)tf_pad64(M) * 4) + 1024;
 }
 
 int gram_tf32x3(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
@@ -496,36 +529,61 @@ int gram_tf32x3(const float* X, const float* Y, float* K, int64_t N, int64_t M, 
     const bool y_ok = tf_usable_in_place(Y, ldy, d, DP, dim_scale);
     const bool same = (X == Y && ldx == ldy && N == M);
     Scratch scr(workspace, workspace_bytes, st);
+    JRK_CUDA_OK(scr.reserve(gram_tf32x3_workspace_bytes(N, M, d)));
     const float *Xp = X, *Yp = Y;
-    if (!x_ok || !y_ok) {
-        size_t need = 512;
-        if (!x_ok) need += align256((size_t)N * DP * 4);
-        if (!y_ok && !same) need += align256((size_t)M * DP * 4);
-        JRK_CUDA_OK(scr.reserve(need));
-        if (!x_ok) {
-            float* buf = scr.take<float>((size_t)N * DP);
-            const int64_t tot = N * DP;
-            tf_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, N, d, ldx, dim_scale, buf, DP);
-            JRK_LAUNCHED();
-            Xp = buf;
-        }
-        if (!y_ok) {
-            if (same) {
-                Yp = Xp;
-            } else {
-                float* buf = scr.take<float>((size_t)M * DP);
-                const int64_t tot = M * DP;
-                tf_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, dim_scale, buf, DP);
-                JRK_LAUNCHED();
-                Yp = buf;
-            }
-        }
+    if (!x_ok) {
+        float* buf = scr.take<float>((size_t)N * DP);
+        const int64_t tot = N * DP;
+        tf_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, N, d, ldx, dim_scale, buf, DP);
+        JRK_LAUNCHED();
+        Xp = buf;
     }
-    const EpiParams ep = make_epi(scale, power, nconst);
-    const int pm = pick_pmode(power);
-    if (DP == 64) return tf_dispatch_pm<64, 64>(pm, Xp, Yp, K, N, M, ldk, ep, st);
-    if (DP == 96) return tf_dispatch_pm<96, 32>(pm, Xp, Yp, K, N, M, ldk, ep, st);
-    return tf_dispatch_pm<128, 32>(pm, Xp, Yp, K, N, M, ldk, ep, st);
+    if (same) {
+        Yp = Xp;
+    } else if (!y_ok) {
+        float* buf = scr.take<float>((size_t)M * DP);
+        const int64_t tot = M * DP;
+        tf_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, dim_scale, buf, DP);
+        JRK_LAUNCHED();
+        Yp = buf;
+    }
+
+    // epilogue constants.  p == 2 with nconst > 0: everything folds into one exp2 argument.
+    EpiParams ep = make_epi(scale, power, nconst);
+    int pm = pick_pmode(power);
+    if (pm == PM_SQEXP && !(nconst > 0.f)) {   // cannot fold log2(nconst): use the general epilogue with p = 2
+        pm = PM_GENERAL;
+        ep.c = scale * scale;
+        ep.hp = 1.f;
+    }
+    TfEpi te;
+    float mult;
+    if (pm == PM_SQEXP) {
+        mult = ep.c;
+        te.a = -2.f * ep.c;
+        te.add_y = log2f(nconst);
+        te.w0 = te.add_y * (1.f - TF_TAU);
+    } else {
+        mult = 1.f;
+        te.a = -2.f;
+        te.add_y = 0.f;
+        te.w0 = 0.f;
+    }
+
+    // row norms (one function for both operands)
+    const int64_t Np = tf_pad64(N), Mp = tf_pad64(M);
+    float* xn = scr.take<float>((size_t)Np);
+    tf_norm_kernel<<<(unsigned)((Np + 7) / 8), 256, 0, st>>>(Xp, N, Np, DP, mult, 0.5f * te.add_y, xn);
+    JRK_LAUNCHED();
+    float* yn = xn;
+    if (!same) {
+        yn = scr.take<float>((size_t)Mp);
+        tf_norm_kernel<<<(unsigned)((Mp + 7) / 8), 256, 0, st>>>(Yp, M, Mp, DP, mult, 0.5f * te.add_y, yn);
+        JRK_LAUNCHED();
+    }
+    if (DP == 64) return tf_dispatch_pm<64, 64>(pm, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
+    if (DP == 96) return tf_dispatch_pm<96, 32>(pm, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
+    return tf_dispatch_pm<128, 32>(pm, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
 }
 
 }  // namespace jrk
