@@ -126,6 +126,19 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
+// one lane of a converged warp (ptxas recognises the elect.sync predicate and issues tcgen05 instructions
+// under it without a per-thread waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
     // try_wait with a suspend-time hint: the warp sleeps in hardware instead of spinning on issue slots
     asm volatile(
@@ -219,6 +232,7 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tmem_base != 0) __trap();   // all 512 columns are ours, so the allocation starts at lane 0 / column 0
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -239,36 +253,40 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TF_BM >> 4) << 24);
-            const uint32_t a_hi = tmem_base, a_lo = tmem_base + DP;
-            uint32_t tc = 0, uc = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
-                const int it0 = (u / n_jb) * tpu, it1 = min(it0 + tpu, n_it);
-                mbar_wait_hint(a_ready, uc & 1);
-                for (int it = it0; it < it1; ++it, ++tc) {
-                    const int q = tc % S_OP, a = tc & 1;
-                    mbar_wait_hint(&acc_empty[a], ((tc >> 1) & 1) ^ 1);
-                    mbar_wait_hint(&op_full[q], (tc / S_OP) & 1);
-                    tc_fence_after();
-                    const uint32_t b_hi = smem_u32(smem + C::OFF_OP + q * 2 * C::HALF_BYTES);
-                    const uint32_t b_lo = b_hi + C::HALF_BYTES;
-                    const uint32_t acc = tmem_base + C::ACC_COL0 + a * 3 * NT;
+        // The whole warp runs the (warp-uniform) control flow so that descriptors and TMEM addresses live in
+        // uniform registers; only the tcgen05 instructions themselves are predicated to one lane.  (Issuing
+        // from inside an `if (lane == 0)` region makes the compiler wrap every MMA in an ELECT / R2UR
+        // waterfall loop -- ~13 instructions per MMA on the critical path.)
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TF_BM >> 4) << 24);
+        const uint32_t op_base = smem_u32(smem + C::OFF_OP);
+        uint32_t tc = 0, uc = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+            const int it0 = (u / n_jb) * tpu, it1 = min(it0 + tpu, n_it);
+            mbar_wait_hint(a_ready, uc & 1);
+            for (int it = it0; it < it1; ++it, ++tc) {
+                const uint32_t q = tc % S_OP, a = tc & 1;
+                mbar_wait_hint(&acc_empty[a], ((tc >> 1) & 1) ^ 1);
+                mbar_wait_hint(&op_full[q], (tc / S_OP) & 1);
+                tc_fence_after();
+                const uint64_t dh0 = make_b_desc(op_base + q * 2 * C::HALF_BYTES);
+                const uint64_t dl0 = make_b_desc(op_base + q * 2 * C::HALF_BYTES + C::HALF_BYTES);
+                const uint32_t acc = C::ACC_COL0 + a * 3 * NT;      // TMEM base is 0 (checked at start-up)
+                if (elect_one()) {
 #pragma unroll
                     for (int kc = 0; kc < C::KC; ++kc) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint32_t k = kc * 4 + ks;
-                            const uint32_t off = kc * NT * 128 + ks * 32;
-                            const uint64_t dh = make_b_desc(b_hi + off), dl = make_b_desc(b_lo + off);
-                            mma_tf32_ts(acc, a_hi + k * 8, dh, idesc, k);             // hi_y . hi_x
-                            mma_tf32_ts(acc + NT, a_hi + k * 8, dl, idesc, k);        // hi_y . lo_x
-                            mma_tf32_ts(acc + 2 * NT, a_lo + k * 8, dh, idesc, k);    // lo_y . hi_x
+                            const uint64_t off = (uint64_t)((kc * NT * 128 + ks * 32) >> 4);   // start-address field
+                            mma_tf32_ts(acc, k * 8, dh0 + off, idesc, k);               // hi_y . hi_x
+                            mma_tf32_ts(acc + NT, k * 8, dl0 + off, idesc, k);          // hi_y . lo_x
+                            mma_tf32_ts(acc + 2 * NT, DP + k * 8, dh0 + off, idesc, k); // lo_y . hi_x
                         }
                     }
                     tc_commit(&op_empty[q]);   // operand stage may be refilled
                     tc_commit(&acc_full[a]);   // accumulators complete
                 }
+                __syncwarp();
             }
         }
     } else if (warp < TF_EPI_WARP0) {
