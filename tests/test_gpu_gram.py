@@ -75,11 +75,19 @@ def test_self_gram_is_bitwise_symmetric_with_exact_diagonal(d, path, kname):
     nconst on the diagonal where the reference's expansion form is off by up to 1e-4."""
     X = gauss(3, 777, d)
     s, scale, p, nconst = kparams(kname, np.sqrt(d))
-    for Y in (None, cu(X)):  # Y=None and Y aliasing-equal X
-        K = nat.gram(cu(X), Y, scale, p, nconst, path=path).cpu().numpy()
+    Xd = cu(X)
+    truth = orc.gengauss_gram_truth64(X, None, s, p)
+    for Y in (None, Xd):  # Y = None and Y aliasing X: the C ABI's definition of a self-Gram
+        K = nat.gram(Xd, Y, scale, p, nconst, path=path).cpu().numpy()
         assert (K == K.T).all()
         np.testing.assert_allclose(np.diag(K), nconst, rtol=1e-6 if path == nat.PATH_DIRECT else 1e-5)
-        assert_close_truth(K, orc.gengauss_gram_truth64(X, None, s, p), kname)
+        assert_close_truth(K, truth, kname)
+    # an equal COPY of X is not a self-Gram for the library: same tolerance, symmetry only to rounding
+    K = nat.gram(Xd, cu(X), scale, p, nconst, path=path).cpu().numpy()
+    assert_close_truth(K, truth, kname)
+    np.testing.assert_allclose(K, K.T, rtol=2e-6, atol=1e-9)
+    if path == nat.PATH_DIRECT:
+        assert (K == K.T).all()
 
 
 def test_near_duplicate_points_tight_at_zero_distance():
