@@ -38,6 +38,33 @@ __global__ void tf_pack_kernel(const float* __restrict__ A, int64_t rows, int co
     out[idx] = v;
 }
 
+// Tile images of X for the tensor core: for tile t (rows [t NT, (t+1) NT), zero padded) the block
+//   img + t * 2 * NT * DP  holds the tf32 "hi" image followed by the "lo" image, each in the K-major
+// 128B-swizzled shared-memory layout of the UMMA descriptor: 128-byte k-chunk kc of row r at byte
+//   kc * NT * 128 + r * 128, its 16-byte piece c at position (c ^ (r & 7)).  One thread per 16-byte piece.
+// hi = x rounded to tf32, lo = x - hi (split_tf32, the function the A-operand loader uses as well).
+__global__ void tf_split_kernel(const float* __restrict__ Xp, int64_t rows, int64_t rows_padded, int DP, int NT,
+                                float* __restrict__ img) {
+    const int cpr = DP / 4;                                  // 16-byte pieces per row
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows_padded * cpr) return;
+    const int64_t row = idx / cpr;
+    const int piece = (int)(idx % cpr), kc = piece >> 3, c = piece & 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows) v = __ldg(reinterpret_cast<const float4*>(Xp + row * DP) + piece);
+    uint4 h, l;
+    split_tf32(v.x, h.x, l.x);
+    split_tf32(v.y, h.y, l.y);
+    split_tf32(v.z, h.z, l.z);
+    split_tf32(v.w, h.w, l.w);
+    const int64_t t = row / NT;
+    const int r = (int)(row % NT);
+    unsigned char* base = reinterpret_cast<unsigned char*>(img + t * 2 * NT * DP);
+    const int off = kc * NT * 128 + r * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(base + off) = h;
+    *reinterpret_cast<uint4*>(base + (size_t)NT * DP * 4 + off) = l;
+}
+
 // out[r] = mult * |row r|^2 + add (0 for padded rows) -- ONE function for X and Y, so the norms are role
 // independent (bitwise symmetric self-Gram).  One warp per row: 16-byte chunks, xor-shuffle tree.  The block's
 // largest |mult| |row|^2 goes to *gmax by atomicMax on the (non-negative) float's bit pattern.
@@ -84,7 +111,7 @@ size_t gram_tf32x3_workspace_bytes(int64_t N, int64_t M, int d) {
     if (d > 128) return 0;
     const int DP = tf_dp(d);
     return align256((size_t)N * DP * 4) + align256((size_t)M * DP * 4) + align256((size_t)tf_pad64(N) * 4) +
-           align256((size_t)tf_pad64(M) * 4) + 1024;
+           align256((size_t)tf_pad64(M) * 4) + align256((size_t)tf_pad64(N) * DP * 8) + 1024;
 }
 
 int gram_tf32x3(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
@@ -157,9 +184,18 @@ int gram_tf32x3(const float* X, const float* Y, float* K, int64_t N, int64_t M, 
     te.norm_max = nmax;
 
     const int nacc = same ? 3 : 2;
-    if (pm == PM_SQEXP) return tf_run_pm<PM_SQEXP>(DP, nacc, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
-    if (pm == PM_LAPLACE) return tf_run_pm<PM_LAPLACE>(DP, nacc, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
-    return tf_run_pm<PM_GENERAL>(DP, nacc, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
+
+    // tf32 hi / lo tile images of X (pre-swizzled; one bulk copy per tile in the main kernel)
+    const int NT = tf_nt(DP, nacc);
+    float* ximg = scr.take<float>((size_t)Np * DP * 2);
+    {
+        const int64_t tot = Np * (DP / 4);
+        tf_split_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Xp, N, Np, DP, NT, ximg);
+        JRK_LAUNCHED();
+    }
+    if (pm == PM_SQEXP) return tf_run_pm<PM_SQEXP>(DP, nacc, ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
+    if (pm == PM_LAPLACE) return tf_run_pm<PM_LAPLACE>(DP, nacc, ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
+    return tf_run_pm<PM_GENERAL>(DP, nacc, ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
 }
 
 }  // namespace jrk

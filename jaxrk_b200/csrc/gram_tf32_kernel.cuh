@@ -15,20 +15,25 @@
 // X (output rows i).  An accumulator lane therefore runs along the contiguous output
 // dimension: a warp's 32 lanes hold 32 consecutive floats of one output row.
 //
-// One persistent CTA per SM, 22 warps:
-//   warp 0      TMA producer: cp.async.bulk of raw FP32 X tiles (NT x DP) into a ring
+// A pre-pass kernel (gram_tf32.cu: tf_split_kernel) splits X once into tf32 hi / lo tile images that are
+// already in the K-major 128B-swizzled layout the UMMA shared-memory descriptor expects, one contiguous
+// 2 x NT x DP x 4 byte block per tile, so the main kernel needs no in-SM conversion pass: a tile arrives
+// with ONE cp.async.bulk and is consumed by the tensor core directly.  (A first version converted raw FP32
+// tiles inside the SM with four extra warps; knock-out timing showed the stages contending for the
+// 128 B/clk shared-memory / L1 data pipe -- TMA fill 16 KB + converter 48 KB + MMA operand reads 48 KB +
+// global stores 32 KB per 32 KB of output.  Pre-split images trade that for L2 reads, which have headroom.)
+//
+// One persistent CTA per SM, 18 warps:
+//   warp 0      TMA producer: one cp.async.bulk per tile (hi + lo images) into a 3-stage ring
 //   warp 1      MMA issuer (one elected lane) + TMEM allocation (all 512 columns)
-//   warps 2-5   converter: split the raw tile into tf32 hi / lo images in the K-major
-//               128B-swizzled layout the UMMA descriptor expects
-//   warps 6-21  epilogue: tcgen05.ld the accumulators, u = a.dot + (xs_i + ys_j) with packed
+//   warps 2-17  epilogue: tcgen05.ld the accumulators, u = a.dot + (xs_i + ys_j) with packed
 //               FADD2 / FFMA2 (the row norms xs / ys come from a pre-pass kernel with the scale
 //               and log2(nconst) folded in), exp2, and one coalesced 128-byte st.global per warp and
 //               output row straight from registers.  (Staging the tile in shared memory for TMA
-//               stores -- per-row bulk copies or one 2-D tensor store per tile -- was measured slower:
-//               the kernel is limited by the shared-memory / L1 data pipe, which staging loads further.)
+//               stores -- per-row bulk copies or one 2-D tensor store per tile -- was measured slower.)
 //               At the start of every work unit the same warps load their Y rows, split them
 //               and park hi / lo in TMEM (tcgen05.st): the A operand is read from TMEM, which
-//               keeps it off the 128 B/clk shared-memory port.
+//               keeps it off the shared-memory port.
 // TMEM (512 columns): [0, DP) A hi | [DP, 2DP) A lo | 2 stages x NACC accumulators x NT columns.
 //   NACC = 3 (self-Gram): hi.hi, hi.lo and lo.hi go to separate accumulators and are combined as
 //            c1 + (c2 + c3); with the split and the norms being role-independent functions,
@@ -46,29 +51,27 @@ namespace jrk {
 namespace tf32 {
 
 constexpr int TF_BM = 128;        // rows of Y per work unit = TMEM lanes = output columns
-constexpr int TF_CONV_WARP0 = 2, TF_EPI_WARP0 = 6, TF_CONV_THREADS = 128;
+constexpr int TF_EPI_WARP0 = 2;
 constexpr int EW = 16;            // epilogue warps
 constexpr int TF_THREADS = (TF_EPI_WARP0 + EW) * 32;
-constexpr int S_OP = 2;
+constexpr int S_OP = 3;           // operand stages (hi + lo images of one X tile each)
 constexpr float TF_TAU = 1.0f / 64.0f;
 constexpr float TF_SKIP_BOUND = 4.0f;   // |c| (max|x|^2 + max|y|^2) below which the p = 2 near-zero test is skipped
 
 template <int DP, int NT, int NACC>
 struct TfCfg {
     static constexpr int KC = DP / 32;                    // 128-byte k-chunks per row
-    static constexpr int RAW_BYTES = NT * DP * 4;         // one raw X tile
     static constexpr int HALF_BYTES = NT * DP * 4;        // one swizzled image (hi or lo)
-    static constexpr int S_RAW = (RAW_BYTES > 16384) ? 2 : 3;
-    static constexpr int OFF_RAW = 0;
-    static constexpr int OFF_OP = S_RAW * RAW_BYTES;
-    static constexpr int OFF_BAR = OFF_OP + S_OP * 2 * HALF_BYTES;
-    static constexpr int NUM_BARS = 2 * S_RAW + 2 * S_OP + 4 + 1;
+    static constexpr int STAGE_BYTES = 2 * HALF_BYTES;    // what one cp.async.bulk brings
+    static constexpr int OFF_OP = 0;
+    static constexpr int OFF_BAR = OFF_OP + S_OP * STAGE_BYTES;
+    static constexpr int NUM_BARS = 2 * S_OP + 4 + 1;
     static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
     static constexpr int BYTES = OFF_TMEM_SLOT + 16;
     static constexpr int DYN_BYTES = BYTES + 1024;        // slack to align the base to 1024 B
     static constexpr int ACC_COL0 = 2 * DP;               // first accumulator column
     static_assert(DP % 32 == 0 && DP <= 128 && NT % 16 == 0, "unsupported tile");
-    static_assert(OFF_OP % 1024 == 0 && HALF_BYTES % 1024 == 0, "swizzled images must be 1024 B aligned");
+    static_assert(HALF_BYTES % 1024 == 0, "swizzled images must be 1024 B aligned");
     static_assert(2 * DP + 2 * NACC * NT <= 512, "TMEM budget");
     static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -200,17 +203,15 @@ __device__ __forceinline__ void st_global_cs(float* p, float v) {
 // ---------------------------------------------------------------------------------
 template <int DP, int NT, int PM, int NACC>
 __global__ void __launch_bounds__(TF_THREADS, 1)
-gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, const float* __restrict__ xn,
+gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, const float* __restrict__ Yp,
+                 const float* __restrict__ xn,
                  const float* __restrict__ yn, float* __restrict__ K, int64_t N, int64_t M, int64_t ldk,
                  EpiParams ep, TfEpi te, int n_it, int tpu, int n_jb, int n_units) {
     using C = TfCfg<DP, NT, NACC>;
-    constexpr int S_RAW = C::S_RAW;
     extern __shared__ unsigned char tf_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tf_smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-    uint64_t* raw_full = bars;                 // [S_RAW]
-    uint64_t* raw_empty = raw_full + S_RAW;    // [S_RAW]
-    uint64_t* op_full = raw_empty + S_RAW;     // [S_OP]
+    uint64_t* op_full = bars;                  // [S_OP]
     uint64_t* op_empty = op_full + S_OP;       // [S_OP]
     uint64_t* acc_full = op_empty + S_OP;      // [2]
     uint64_t* acc_empty = acc_full + 2;        // [2]
@@ -220,10 +221,8 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        // consumers arrive once per WARP (after __syncwarp): 512 per-thread arrivals on one mbarrier per tile
-        // serialise on the shared-memory atomic unit and cost more than the tile's HBM time
-        for (int s = 0; s < S_RAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], TF_CONV_THREADS / 32); }
-        for (int s = 0; s < S_OP; ++s) { mbar_init(&op_full[s], TF_CONV_THREADS / 32); mbar_init(&op_empty[s], 1); }
+        // consumers arrive once per WARP (after __syncwarp), not once per thread
+        for (int s = 0; s < S_OP; ++s) { mbar_init(&op_full[s], 1); mbar_init(&op_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EW); }
         mbar_init(a_ready, EW);
         fence_mbar_init();
@@ -241,14 +240,12 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, con
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int it0 = (u / n_jb) * tpu, it1 = min(it0 + tpu, n_it);
             for (int it = it0; it < it1; ++it, ++tc) {
-                const int s = tc % S_RAW;
-                mbar_wait_hint(&raw_empty[s], ((tc / S_RAW) & 1) ^ 1);
-                const int64_t i0 = (int64_t)it * NT;
-                const uint32_t rows = (uint32_t)min((int64_t)NT, N - i0);
-                const uint32_t bytes = rows * DP * 4;
+                const int s = tc % S_OP;
+                mbar_wait_hint(&op_empty[s], ((tc / S_OP) & 1) ^ 1);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&raw_full[s], bytes);
-                    bulk_g2s(smem + C::OFF_RAW + s * C::RAW_BYTES, Xp + i0 * DP, bytes, &raw_full[s]);
+                    mbar_arrive_expect_tx(&op_full[s], C::STAGE_BYTES);
+                    bulk_g2s(smem + C::OFF_OP + s * C::STAGE_BYTES, Ximg + (int64_t)it * (C::STAGE_BYTES / 4), C::STAGE_BYTES,
+                             &op_full[s]);
                 }
                 __syncwarp();
             }
@@ -270,8 +267,8 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, con
                 mbar_wait_hint(&acc_empty[a], ((tc >> 1) & 1) ^ 1);
                 mbar_wait_hint(&op_full[q], (tc / S_OP) & 1);
                 tc_fence_after();
-                const uint64_t dh0 = make_b_desc(op_base + q * 2 * C::HALF_BYTES);
-                const uint64_t dl0 = make_b_desc(op_base + q * 2 * C::HALF_BYTES + C::HALF_BYTES);
+                const uint64_t dh0 = make_b_desc(op_base + q * C::STAGE_BYTES);
+                const uint64_t dl0 = make_b_desc(op_base + q * C::STAGE_BYTES + C::HALF_BYTES);
                 const uint32_t acc = C::ACC_COL0 + a * NACC * NT;      // TMEM base is 0 (checked at start-up)
                 if (elect_one()) {
 #pragma unroll
@@ -290,44 +287,6 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, con
                     tc_commit(&acc_full[a]);   // accumulators complete
                 }
                 __syncwarp();
-            }
-        }
-    } else if (warp < TF_EPI_WARP0) {
-        // ===================== converter: raw FP32 tile -> swizzled tf32 hi / lo images =====================
-        const int cw = warp - TF_CONV_WARP0;           // 0..3
-        const int c = lane & 7, rsub = lane >> 3;      // 16-byte chunk within the 128-byte k-chunk, row within the pass
-        uint32_t tc = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const int it0 = (u / n_jb) * tpu, it1 = min(it0 + tpu, n_it);
-            for (int it = it0; it < it1; ++it, ++tc) {
-                const int s = tc % S_RAW, q = tc % S_OP;
-                mbar_wait_hint(&raw_full[s], (tc / S_RAW) & 1);
-                mbar_wait_hint(&op_empty[q], ((tc / S_OP) & 1) ^ 1);
-                const unsigned char* raw = smem + C::OFF_RAW + s * C::RAW_BYTES;
-                unsigned char* img_hi = smem + C::OFF_OP + q * 2 * C::HALF_BYTES;
-                unsigned char* img_lo = img_hi + C::HALF_BYTES;
-#pragma unroll
-                for (int pass = 0; pass < NT / 16; ++pass) {
-                    const int r = pass * 16 + cw * 4 + rsub;
-#pragma unroll
-                    for (int kc = 0; kc < C::KC; ++kc) {
-                        const float4 v = *reinterpret_cast<const float4*>(raw + r * DP * 4 + kc * 128 + c * 16);
-                        uint4 h, l;
-                        split_tf32(v.x, h.x, l.x);
-                        split_tf32(v.y, h.y, l.y);
-                        split_tf32(v.z, h.z, l.z);
-                        split_tf32(v.w, h.w, l.w);
-                        const int off = kc * NT * 128 + r * 128 + ((c ^ (r & 7)) << 4);
-                        *reinterpret_cast<uint4*>(img_hi + off) = h;
-                        *reinterpret_cast<uint4*>(img_lo + off) = l;
-                    }
-                }
-                fence_proxy_async();           // generic-proxy writes -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&op_full[q]);
-                    mbar_arrive(&raw_empty[s]);
-                }
             }
         }
     } else {
@@ -488,8 +447,8 @@ gram_tf32_kernel(const float* __restrict__ Xp, const float* __restrict__ Yp, con
 int tf_sm_count();
 
 template <int DP, int NT, int PM, int NACC>
-int tf_launch(const float* Xp, const float* Yp, const float* xn, const float* yn, float* K, int64_t N, int64_t M,
-              int64_t ldk, const EpiParams& ep, const TfEpi& te, cudaStream_t st) {
+int tf_launch(const float* Ximg, const float* Xp, const float* Yp, const float* xn, const float* yn, float* K, int64_t N,
+              int64_t M, int64_t ldk, const EpiParams& ep, const TfEpi& te, cudaStream_t st) {
     using C = TfCfg<DP, NT, NACC>;
     auto kern = gram_tf32_kernel<DP, NT, PM, NACC>;
     JRK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::DYN_BYTES));
@@ -508,31 +467,34 @@ int tf_launch(const float* Xp, const float* Yp, const float* xn, const float* yn
     if (n_units > 2147483647LL || n_it > 2147483647LL)
         return fail(JRK_ERR_UNSUPPORTED, "gram_tf32x3: problem too large (%lld units)", (long long)n_units);
     const int grid = (int)(grid_max < n_units ? grid_max : n_units);
-    kern<<<grid, TF_THREADS, C::DYN_BYTES, st>>>(Xp, Yp, xn, yn, K, N, M, ldk, ep, te, (int)n_it, (int)tpu, (int)n_jb,
+    kern<<<grid, TF_THREADS, C::DYN_BYTES, st>>>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, (int)n_it, (int)tpu, (int)n_jb,
                                                  (int)n_units);
     JRK_LAUNCHED();
     return JRK_OK;
 }
 
+// Row-tile height of the X tile images for (DP, nacc): must match the dispatch table below.
+inline int tf_nt(int DP, int nacc) { return (DP == 64 || (DP == 96 && nacc == 2)) ? 64 : 32; }
+
 // One translation unit per epilogue mode (gram_tf32_pm{0,1,2}.cu) instantiates this.
 //   nacc 3 = symmetric accumulation (self-Gram), 2 = X != Y (frees TMEM: NT = 64 also for DP = 96)
 template <int PM>
-int tf_run_pm(int DP, int nacc, const float* Xp, const float* Yp, const float* xn, const float* yn, float* K, int64_t N,
-              int64_t M, int64_t ldk, const EpiParams& ep, const TfEpi& te, cudaStream_t st);
+int tf_run_pm(int DP, int nacc, const float* Ximg, const float* Xp, const float* Yp, const float* xn, const float* yn,
+              float* K, int64_t N, int64_t M, int64_t ldk, const EpiParams& ep, const TfEpi& te, cudaStream_t st);
 
-#define JRK_TF32_DEFINE_RUN_PM(PM_)                                                                              \
-    template <>                                                                                                 \
-    int tf_run_pm<PM_>(int DP, int nacc, const float* Xp, const float* Yp, const float* xn, const float* yn,    \
-                       float* K, int64_t N, int64_t M, int64_t ldk, const EpiParams& ep, const TfEpi& te,       \
-                       cudaStream_t st) {                                                                       \
-        if (nacc == 3) {                                                                                        \
-            if (DP == 64) return tf_launch<64, 64, PM_, 3>(Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);           \
-            if (DP == 96) return tf_launch<96, 32, PM_, 3>(Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);           \
-            return tf_launch<128, 32, PM_, 3>(Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);                        \
-        }                                                                                                       \
-        if (DP == 64) return tf_launch<64, 64, PM_, 2>(Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);               \
-        if (DP == 96) return tf_launch<96, 64, PM_, 2>(Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);               \
-        return tf_launch<128, 32, PM_, 2>(Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);                            \
+#define JRK_TF32_DEFINE_RUN_PM(PM_)                                                                                  \
+    template <>                                                                                                     \
+    int tf_run_pm<PM_>(int DP, int nacc, const float* Ximg, const float* Xp, const float* Yp, const float* xn,      \
+                       const float* yn, float* K, int64_t N, int64_t M, int64_t ldk, const EpiParams& ep,           \
+                       const TfEpi& te, cudaStream_t st) {                                                          \
+        if (nacc == 3) {                                                                                            \
+            if (DP == 64) return tf_launch<64, 64, PM_, 3>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);         \
+            if (DP == 96) return tf_launch<96, 32, PM_, 3>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);         \
+            return tf_launch<128, 32, PM_, 3>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);                      \
+        }                                                                                                           \
+        if (DP == 64) return tf_launch<64, 64, PM_, 2>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);             \
+        if (DP == 96) return tf_launch<96, 64, PM_, 2>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);             \
+        return tf_launch<128, 32, PM_, 2>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);                          \
     }
 
 }  // namespace tf32
