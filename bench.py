@@ -104,7 +104,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def start(self):
         if self.nv:

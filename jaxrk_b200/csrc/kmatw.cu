@@ -19,7 +19,11 @@
 //     shuffles and a per-CTA shared-memory pass; one partial per CTA, summed in a fixed
 //     order by a finalize kernel (deterministic; no float atomics);
 //   * few rows (N small): the j range is split over blockIdx.y and the partials are
-//     summed by the same finalize kernel.
+//     summed by the same finalize kernel;
+//   * long j ranges: a float32 running sum of 2^20 positive terms is off by ~2e-5 relative
+//     (measured), outside the 1e-5 tolerance, so every 32 tiles (4096 j) the register
+//     accumulators are folded into a per-thread second-level accumulator kept in shared
+//     memory (conflict-free 16-byte slots) and restarted from zero.
 // Roofline: FP32 issue (2d + m + ~3 lane-ops per pair), see DESIGN.md.
 #include "common.cuh"
 
@@ -27,11 +31,15 @@ namespace jrk {
 
 constexpr int KW_THREADS = 128;
 constexpr int KW_TJ = 128;  // rows of Y / W per stage
+constexpr int KW_FLUSH_TILES = 32;  // fold the register accumulators into the second level every 32 tiles
 
-template <int D, int MT>
+template <int D, int MT, int RI = 0>
 struct KwSmem {
     static constexpr int kStageFloats = KW_TJ * (D + MT);
-    static constexpr size_t kBytes = 2 * kStageFloats * sizeof(float) + 2 * sizeof(uint64_t);
+    static constexpr size_t kRingBytes = 2 * kStageFloats * sizeof(float);
+    static constexpr size_t kBarOff = kRingBytes;
+    static constexpr size_t kAccOff = kRingBytes + 16;                       // second-level accumulators
+    static constexpr size_t kBytes = kAccOff + (size_t)RI * MT * KW_THREADS * sizeof(float);
 };
 
 // epi_mode: 0 = write rows (out ld = ldo, rows N), 1 = write one partial per CTA
@@ -44,7 +52,9 @@ kmatw_kernel(const float* __restrict__ X, int64_t ldx, int d, const float* __res
              const float* __restrict__ row_pref, EpiParams ep, int epi_mode, int x_vec) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_base = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * KwSmem<D, MT>::kStageFloats * sizeof(float));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + KwSmem<D, MT, RI>::kBarOff);
+    // second-level accumulators: slot s of thread t at float4 index s * KW_THREADS + t (conflict-free)
+    float4* acc2 = reinterpret_cast<float4*>(smem_raw + KwSmem<D, MT, RI>::kAccOff) + threadIdx.x;
 
     constexpr int R = KW_THREADS * RI;
     const int64_t i0 = (int64_t)blockIdx.x * R;
@@ -111,6 +121,24 @@ kmatw_kernel(const float* __restrict__ X, int64_t ldx, int d, const float* __res
     for (int r = 0; r < RI; ++r)
 #pragma unroll
         for (int c = 0; c < MT / 2; ++c) acc[r][c] = 0ull;
+#pragma unroll
+    for (int sl = 0; sl < RI * MT / 4; ++sl) acc2[sl * KW_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // acc2 += acc; acc = 0   (slot r * MT/4 + q holds columns 4q..4q+3 of row r)
+    auto fold = [&]() {
+#pragma unroll
+        for (int r = 0; r < RI; ++r)
+#pragma unroll
+            for (int q = 0; q < MT / 4; ++q) {
+                float4 v = acc2[(r * (MT / 4) + q) * KW_THREADS];
+                float a0, a1, a2, a3;
+                unpack2(acc[r][2 * q], a0, a1);
+                unpack2(acc[r][2 * q + 1], a2, a3);
+                v.x += a0; v.y += a1; v.z += a2; v.w += a3;
+                acc2[(r * (MT / 4) + q) * KW_THREADS] = v;
+                acc[r][2 * q] = 0ull;
+                acc[r][2 * q + 1] = 0ull;
+            }
+    };
 
     // ---- stream Y / W tiles ------------------------------------------------------------
     for (int t = t0, it = 0; t < t1; ++t, ++it) {
@@ -156,8 +184,18 @@ kmatw_kernel(const float* __restrict__ X, int64_t ldx, int d, const float* __res
                 }
             }
         }
+        if ((it + 1) % KW_FLUSH_TILES == 0) fold();
         __syncthreads();  // stage fully consumed before it is refilled
     }
+    fold();   // totals now live in the second-level accumulators
+#pragma unroll
+    for (int r = 0; r < RI; ++r)
+#pragma unroll
+        for (int q = 0; q < MT / 4; ++q) {
+            const float4 v = acc2[(r * (MT / 4) + q) * KW_THREADS];
+            acc[r][2 * q] = pack2(v.x, v.y);
+            acc[r][2 * q + 1] = pack2(v.z, v.w);
+        }
 
     // ---- epilogue -------------------------------------------------------------------------
     float* outp = out + (int64_t)blockIdx.y * out_split_stride;
@@ -254,7 +292,7 @@ static int kw_launch(dim3 grid, cudaStream_t st, const float* X, int64_t ldx, in
                      int64_t M, int m, int tiles_per_split, const float* row_pref, const EpiParams& ep,
                      int epi_mode, int x_vec) {
     auto kern = kmatw_kernel<D, MT, RI, PM>;
-    const size_t smem = KwSmem<D, MT>::kBytes;
+    const size_t smem = KwSmem<D, MT, RI>::kBytes;
     if (smem > 48 * 1024) JRK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, KW_THREADS, smem, st>>>(X, ldx, d, dim_scale, Yp, Wp, out, ldo, split_stride, N, M, m,
                                         tiles_per_split, row_pref, ep, epi_mode, x_vec);

@@ -180,3 +180,24 @@ def test_kmatw_invalid_arguments():
         nat.kmatw(X, Y, W, 1.0, 3.0, 1.0)
     with pytest.raises(nat.JrkError):
         nat.gram_groupsum(X, Y, 1.0, 2.0, 1.0, 4, 2, False)
+
+
+def test_kmatw_long_accumulation_all_positive_weights():
+    """cfg3-sized j range (M = 2^20) with W = 1 (kernel mean embedding: every term positive, the worst case for a
+    float32 running sum), N large enough that no j-split is used.  Sampled rows against float64."""
+    N, M, d = 1 << 19, 1 << 20, 16
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    X = torch.randn(N, d, generator=g, device="cuda:0")
+    Y = torch.randn(M, d, generator=g, device="cuda:0")
+    W = torch.ones(M, 1, device="cuda:0")
+    s, scale, p, nconst = kparams("sqexp", 4.0)
+    T = nat.kmatw(X, Y, W, scale, p, nconst)
+    rows = torch.tensor([0, 1, 777, N // 2, N - 1], device="cuda:0")
+    d2 = torch.cdist(X[rows].double(), Y.double()) ** 2
+    truth = (nconst * torch.exp(-(scale * scale) * d2)).sum(1, keepdim=True)
+    err = ((T[rows].double() - truth).abs() / truth).max().item()
+    assert err < 1e-5, f"relative error {err:.2e} of a 2^20-term positive sum"
+    mean = nat.kmatw(X[:4096], Y, W, scale, p, nconst, row_reduce=nat.REDUCE_MEAN)
+    d2 = torch.cdist(X[:4096].double(), Y.double()) ** 2
+    tm = (nconst * torch.exp(-(scale * scale) * d2)).sum(1).mean()
+    assert abs(mean.item() - tm.item()) / tm.item() < 1e-5
