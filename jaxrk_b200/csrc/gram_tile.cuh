@@ -17,7 +17,12 @@ __device__ __forceinline__ void gd_fill(float (*s)[GD_LD], const float* __restri
     constexpr int QPR = KC / 4;              // float4 per row
     constexpr int TOTAL = GD_BM * QPR;       // float4 in the tile
     for (int idx = threadIdx.x; idx < TOTAL; idx += GD_THREADS) {
-        int row = idx / QPR, kq = idx % QPR;
+        // narrow tiles (d <= 8): consecutive threads take consecutive ROWS of one 4-wide k group, so the
+        // transposed shared-memory stores below are conflict-free (measured +6 % at d = 8); wider tiles keep
+        // the row-major assignment, whose global loads are coalesced (measured better for d >= 16)
+        int row, kq;
+        if (KC <= 8) { row = idx % GD_BM; kq = idx / GD_BM; }
+        else { row = idx / QPR; kq = idx % QPR; }
         int64_t gr = r0 + row;
         int k = k0 + kq * 4;
         float v[4] = {0.f, 0.f, 0.f, 0.f};

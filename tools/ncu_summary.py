@@ -30,7 +30,11 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "dram__bytes_read.su
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio"]
+seen_raw = set()
 for r in rows[2:]:
+    if r[idx["Kernel Name"]] in seen_raw:
+        continue
+    seen_raw.add(r[idx["Kernel Name"]])
     print("==", r[idx["Kernel Name"]][:110])
     for w in want:
         if w in idx:
@@ -48,7 +52,11 @@ for r in srows:
         cur["hdr"] = r
     elif cur is not None and r:
         cur["rows"].append(r)
-for b in blocks[:2]:
+seen = set()
+for b in blocks:
+    if b["name"] in seen:
+        continue
+    seen.add(b["name"])
     h = {k: i for i, k in enumerate(b["hdr"])}
     data = b["rows"]
     tot = sum(int(r[h["Instructions Executed"]] or 0) for r in data)
