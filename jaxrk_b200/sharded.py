@@ -83,6 +83,7 @@ def gather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
     rank, world = _world(group)
     if world == 1:
         return local
+    local = local.contiguous()
     h = torch.tensor([local.shape[0]], device=local.device, dtype=torch.int64)
     hs = [torch.zeros_like(h) for _ in range(world)]
     dist.all_gather(hs, h, group=group)
@@ -117,7 +118,7 @@ def sharded_inner_local(k, X_local, chain_x: Optional[List[Reduce]], n_global: i
     """As `sharded_inner`, given only this rank's row block X_local = X[start : start + len(X_local)]."""
     stop = start + X_local.shape[0]
     lchain, kind, post, divisor = local_chain(chain_x, n_global, start, stop)
-    part = low.reduced_gram(k, X_local, lchain, y.insp_pts, y.reduce)
+    part = low.reduced_gram(k, X_local, lchain, y.insp_pts, y.reduce).contiguous()   # NCCL needs dense buffers
     _, world = _world(group)
     if kind == "sum":
         if world > 1:
