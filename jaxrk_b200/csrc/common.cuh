@@ -110,9 +110,11 @@ struct EpiParams {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
-template <int PM>
+// NONNEG: the caller guarantees sq >= 0 (a sum of squares from direct differencing), so the clip of
+// eucldist.py:48 is a no-op and is skipped.
+template <int PM, bool NONNEG = false>
 __device__ __forceinline__ float kexp_unnorm(float sq, const EpiParams& e) {
-    sq = fmaxf(sq, 0.f);
+    if (!NONNEG) sq = fmaxf(sq, 0.f);
     if (PM == PM_SQEXP) {
         return ex2_approx(sq * e.c);
     } else if (PM == PM_LAPLACE) {

@@ -62,9 +62,8 @@ gram_direct_kernel(const float* __restrict__ X, const float* __restrict__ Y, flo
                 unpack2(acc[p][c], lo, hi);
                 float sq = h ? hi : lo;
                 if (OUT == 0) {
-                    v[c] = ep.nconst * kexp_unnorm<PM>(sq, ep);
+                    v[c] = ep.nconst * kexp_unnorm<PM, true>(sq, ep);
                 } else {
-                    sq = fmaxf(sq, 0.f);
                     if (PM == PM_SQEXP) v[c] = (ep.s * ep.s) * sq;
                     else if (PM == PM_LAPLACE) v[c] = ep.s * sqrtf(sq);
                     else v[c] = powf(ep.s * sqrtf(sq), ep.p);

@@ -11,7 +11,9 @@
 // tiles with the direct-differencing tile core (gram_tile.cuh), keeps the weighted sums
 // of its 8 x 8 micro-tile in registers, and reduces once at the end (shuffles + shared
 // memory) to one partial per CTA.  A finalize kernel adds the gx/128 row-tile partials
-// of each cell in a fixed order (deterministic).
+// of each cell in a fixed order (deterministic).  For a self inner product (X == Y, same groups and prefactors)
+// only the cells on and above the diagonal are computed and the finalize kernel mirrors them: half the work, and
+// the result is exactly symmetric.
 #include "gram_tile.cuh"
 
 namespace jrk {
@@ -21,11 +23,13 @@ __global__ void __launch_bounds__(GD_THREADS, 2)
 gram_groupsum_kernel(const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ part,
                      int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
                      const float* __restrict__ dim_scale, const float* __restrict__ row_pref,
-                     const float* __restrict__ col_pref, int64_t gy, EpiParams ep, int vec_in) {
+                     const float* __restrict__ col_pref, int64_t gy, EpiParams ep, int vec_in, int sym_tiles_per_group) {
     __shared__ __align__(16) float sX[KC][GD_LD];
     __shared__ __align__(16) float sY[KC][GD_LD];
     __shared__ float red[GD_THREADS / 32];
 
+    // symmetric problem: cells below the diagonal are mirrored by the finalize kernel
+    if (sym_tiles_per_group && (int)blockIdx.x < (int)blockIdx.y / sym_tiles_per_group) return;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int64_t i0 = (int64_t)blockIdx.y * GD_BM;          // row tile
     const int64_t jbeg = (int64_t)blockIdx.x * gy, jend = jbeg + gy;  // column group
@@ -67,8 +71,8 @@ gram_groupsum_kernel(const float* __restrict__ X, const float* __restrict__ Y, f
             for (int c = 0; c < 8; ++c) {
                 float lo, hi;
                 unpack2(acc[p][c], lo, hi);
-                r0 = fmaf(kexp_unnorm<PM>(lo, ep), cp[c], r0);
-                r1 = fmaf(kexp_unnorm<PM>(hi, ep), cp[c], r1);
+                r0 = fmaf(kexp_unnorm<PM, true>(lo, ep), cp[c], r0);
+                r1 = fmaf(kexp_unnorm<PM, true>(hi, ep), cp[c], r1);
             }
             tile = fmaf(rp[p * 2], r0, tile);
             tile = fmaf(rp[p * 2 + 1], r1, tile);
@@ -90,12 +94,13 @@ gram_groupsum_kernel(const float* __restrict__ X, const float* __restrict__ Y, f
 // out[a, b] = scale * sum_{t < tiles_per_group} part[(a * tiles_per_group + t) * ncolg + b]
 __global__ void groupsum_finalize_kernel(const float* __restrict__ part, int64_t nrowg, int64_t ncolg,
                                          int64_t tiles_per_group, float scale, float* __restrict__ out,
-                                         int64_t ldo) {
+                                         int64_t ldo, int sym) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nrowg * ncolg) return;
     const int64_t a = idx / ncolg, b = idx % ncolg;
+    const int64_t pa = (sym && b < a) ? b : a, pb = (sym && b < a) ? a : b;   // mirrored cell
     float s = 0.f;
-    for (int64_t t = 0; t < tiles_per_group; ++t) s += part[(a * tiles_per_group + t) * ncolg + b];
+    for (int64_t t = 0; t < tiles_per_group; ++t) s += part[(pa * tiles_per_group + t) * ncolg + pb];
     out[a * ldo + b] = scale * s;
 }
 
@@ -117,11 +122,14 @@ int gram_groupsum(const float* X, const float* Y, float* out, int64_t N, int64_t
     int vec_in = 0;
     if (((uintptr_t)X % 16 == 0) && (ldx % 4 == 0)) vec_in |= 1;
     if (((uintptr_t)Y % 16 == 0) && (ldy % 4 == 0)) vec_in |= 2;
+    // self inner product with identical groups / prefactors on both sides: compute the upper triangle only
+    const bool sym = (X == Y && ldx == ldy && N == M && gx == gy && row_pref == col_pref);
+    const int sym_tpg = sym ? (int)(gx / GD_BM) : 0;
     dim3 grid((unsigned)ncolg, (unsigned)nrow_tiles);
     const int kc = gd_pick_kc(d);
 #define GS_GO(PM_, KC_)                                                                                      \
     gram_groupsum_kernel<PM_, KC_><<<grid, GD_THREADS, 0, st>>>(X, Y, part, N, M, d, ldx, ldy, dim_scale,    \
-                                                                row_pref, col_pref, gy, ep, vec_in)
+                                                                row_pref, col_pref, gy, ep, vec_in, sym_tpg)
 #define GS_KC(PM_)                          \
     do {                                    \
         if (kc == 4) GS_GO(PM_, 4);         \
@@ -138,7 +146,7 @@ int gram_groupsum(const float* X, const float* Y, float* out, int64_t N, int64_t
     if (average) fscale = (float)((double)nconst / ((double)gx * (double)gy));
     const int64_t tot = nrowg * ncolg;
     groupsum_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(part, nrowg, ncolg, gx / GD_BM, fscale,
-                                                                            out, ldo);
+                                                                            out, ldo, sym ? 1 : 0);
     JRK_LAUNCHED();
     return JRK_OK;
 }

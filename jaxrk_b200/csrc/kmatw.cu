@@ -170,7 +170,7 @@ kmatw_kernel(const float* __restrict__ X, int64_t ldx, int d, const float* __res
             for (int r = 0; r < RI; ++r) {
                 float lo, hi;
                 unpack2(sq2[r], lo, hi);
-                const float e = kexp_unnorm<PM>(lo + hi, ep);
+                const float e = kexp_unnorm<PM, true>(lo + hi, ep);
                 e2[r] = pack2(e, e);
             }
 #pragma unroll
