@@ -148,7 +148,7 @@ kmatw_kernel(const float* __restrict__ X, int64_t ldx, int d, const float* __res
         const float* sy = stage_base + stage * KwSmem<D, MT>::kStageFloats;
         const float* sw = sy + KW_TJ * D;
         const int rows = (int)min((int64_t)KW_TJ, M - (int64_t)t * KW_TJ);
-#pragma unroll 2
+#pragma unroll 8
         for (int j = 0; j < rows; ++j) {
             f32x2 sq2[RI];
 #pragma unroll
