@@ -82,3 +82,24 @@ def test_workspace_queries_are_pure():
     assert L.jrk_gram_workspace_bytes(1024, 1024, 8, nat.PATH_DIRECT) == 0
     assert L.jrk_kmatw_workspace_bytes(1 << 20, 1 << 20, 16, 16, 0, 0) > 0
     assert L.jrk_launch_count() >= 0
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under jaxrk_b200/ may import, load or execute it."""
+    pkg = os.path.join(ROOT, "jaxrk_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"\boracle\b", src):
+                    offenders.append(os.path.join(dirpath, f))
+    assert offenders == [], offenders
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setattr(nat, "LIB_PATH", str(tmp_path / "libjaxrk_b200.so"))
+    with pytest.raises(ImportError) as e:
+        nat.lib()
+    assert "no CPU or eager fallback" in str(e.value)
