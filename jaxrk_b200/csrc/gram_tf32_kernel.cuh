@@ -45,8 +45,6 @@
 // relative accuracy.  For p = 2 the test is skipped when the pre-pass finds
 // s^2 log2(e) (max|x|^2 + max|y|^2) <= 4, where the expansion error is < 1.4e-6 relative.
 #pragma once
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace jrk {
@@ -66,9 +64,7 @@ struct TfCfg {
     static constexpr int HALF_BYTES = NT * DP * 4;        // one swizzled image (hi or lo)
     static constexpr int STAGE_BYTES = 2 * HALF_BYTES;    // what one cp.async.bulk brings
     static constexpr int OFF_OP = 0;
-    static constexpr int XPOSE_BYTES = (NT / (EW / 4)) * 32 * 4;   // per-warp transpose scratch: NTH rows x 32 floats
-    static constexpr int OFF_XPOSE = OFF_OP + S_OP * STAGE_BYTES;
-    static constexpr int OFF_BAR = OFF_XPOSE + EW * XPOSE_BYTES;
+    static constexpr int OFF_BAR = OFF_OP + S_OP * STAGE_BYTES;
     static constexpr int NUM_BARS = 2 * S_OP + 4 + 1;
     static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
     static constexpr int BYTES = OFF_TMEM_SLOT + 16;
@@ -210,7 +206,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1)
 gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, const float* __restrict__ Yp,
                  const float* __restrict__ xn,
                  const float* __restrict__ yn, float* __restrict__ K, int64_t N, int64_t M, int64_t ldk,
-                 EpiParams ep, TfEpi te, int n_it, int tpu, int n_jb, int n_units, int vec_out) {
+                 EpiParams ep, TfEpi te, int n_it, int tpu, int n_jb, int n_units) {
     using C = TfCfg<DP, NT, NACC>;
     extern __shared__ unsigned char tf_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tf_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -419,43 +415,24 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
                         }
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < NTH; ++i)
-                    uu[i] = (PM == PM_SQEXP) ? ex2_approx(uu[i]) : ep.nconst * kexp_unnorm<PM>(uu[i], ep);
-                const uint32_t pitch = (uint32_t)ldk * 4u;   // host guarantees ldk * 4 * NT < 2^32
-                if (vec_out) {
-                    // A lane owns one output COLUMN, so storing from registers is 4 bytes per lane.  Transposing the
-                    // warp's NTH x 32 block through a private shared-memory scratch (conflict-free both ways) gives
-                    // every lane 4 consecutive columns of one row: 16-byte stores, 4 x fewer store instructions.
-                    float* xp = reinterpret_cast<float*>(smem + C::OFF_XPOSE) + e * (NTH * 32);
-#pragma unroll
-                    for (int i = 0; i < NTH; ++i) xp[i * 32 + lane] = uu[i];
-                    __syncwarp();
-                    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-                    const int64_t jv = (int64_t)jb * TF_BM + quad * 32 + c4;     // first of this lane's 4 columns
-                    const char* kb = reinterpret_cast<const char*>(K + i0 * ldk + jv);
-#pragma unroll
-                    for (int b = 0; b < NTH / 4; ++b) {
-                        const int r = b * 4 + rsub;
-                        const float4 v = *reinterpret_cast<const float4*>(xp + r * 32 + c4);
-                        float* dst = (float*)(kb + (uint64_t)((uint32_t)r * pitch));
-                        if (r < nvalid) {
-                            if (jv + 3 < M) {
-                                st_global_cs_v4(dst, v);
-                            } else {
-                                if (jv < M) st_global_cs(dst, v.x);
-                                if (jv + 1 < M) st_global_cs(dst + 1, v.y);
-                                if (jv + 2 < M) st_global_cs(dst + 2, v.z);
-                            }
-                        }
-                    }
-                    __syncwarp();   // scratch is reused by the next tile
-                } else {
-                    // unaligned output: one 4-byte store per lane and row
+                {
+                    // row i of this warp's block: base + i * pitch, one 32 x 32 -> 64-bit multiply-add per store
                     const char* kb = reinterpret_cast<const char*>(K + i0 * ldk + j);
+                    const uint32_t pitch = (uint32_t)ldk * 4u;   // host guarantees ldk * 4 * NT < 2^32
+                    if (nvalid == NTH) {
+                        if (jok) {
 #pragma unroll
-                    for (int i = 0; i < NTH; ++i)
-                        if (i < nvalid && jok) st_global_cs((float*)(kb + (uint64_t)((uint32_t)i * pitch)), uu[i]);
+                            for (int i = 0; i < NTH; ++i)
+                                st_global_cs((float*)(kb + (uint64_t)((uint32_t)i * pitch)),
+                                             (PM == PM_SQEXP) ? ex2_approx(uu[i]) : ep.nconst * kexp_unnorm<PM>(uu[i], ep));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NTH; ++i)
+                            if (i < nvalid && jok)
+                                st_global_cs((float*)(kb + (uint64_t)((uint32_t)i * pitch)),
+                                             (PM == PM_SQEXP) ? ex2_approx(uu[i]) : ep.nconst * kexp_unnorm<PM>(uu[i], ep));
+                    }
                 }
             }
         }
@@ -491,7 +468,7 @@ int tf_launch(const float* Ximg, const float* Xp, const float* Yp, const float* 
         return fail(JRK_ERR_UNSUPPORTED, "gram_tf32x3: problem too large (%lld units)", (long long)n_units);
     const int grid = (int)(grid_max < n_units ? grid_max : n_units);
     kern<<<grid, TF_THREADS, C::DYN_BYTES, st>>>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, (int)n_it, (int)tpu, (int)n_jb,
-                                                 (int)n_units, ((((uintptr_t)K % 16 == 0) && (ldk % 4 == 0)) && !getenv("JRK_TF32_NOVEC")) ? 1 : 0);
+                                                 (int)n_units);
     JRK_LAUNCHED();
     return JRK_OK;
 }
