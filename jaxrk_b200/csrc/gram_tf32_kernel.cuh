@@ -337,14 +337,23 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
             const f32x2 a2 = pack2(te.a, te.a), ntau2 = pack2(-TF_TAU, -TF_TAU);
 
             // ---- tiles of this unit ----
+            // (scaled) |x_i|^2 of this warp's rows: uniform 16-byte loads, software-pipelined one tile ahead -- loaded
+            // at the top of the tile they were the kernel's top stall (24 % of the epilogue's samples: an L2 round trip
+            // exposed once per tile).  xn is zero-padded to a multiple of 64 rows, so the look-ahead never faults.
+            float4 xnext[NTH / 4];
+#pragma unroll
+            for (int g = 0; g < NTH / 4; ++g) xnext[g] = __ldg(reinterpret_cast<const float4*>(xn + (int64_t)it0 * NT + ch * NTH) + g);
             for (int it = it0; it < it1; ++it, ++tc) {
                 const int a = tc & 1;
                 const int64_t i0 = (int64_t)it * NT + ch * NTH;
                 const int nvalid = (int)min((int64_t)NTH, N - i0);   // warp-uniform; <= 0 for rows past N
-                // (scaled) |x_i|^2 of this warp's rows: uniform 16-byte loads, issued before the wait
-                float4 xv[NTH / 4];   // xn is zero-padded to a multiple of 64 rows
+                float4 xv[NTH / 4];
 #pragma unroll
-                for (int g = 0; g < NTH / 4; ++g) xv[g] = __ldg(reinterpret_cast<const float4*>(xn + i0) + g);
+                for (int g = 0; g < NTH / 4; ++g) xv[g] = xnext[g];
+                if (it + 1 < it1) {
+#pragma unroll
+                    for (int g = 0; g < NTH / 4; ++g) xnext[g] = __ldg(reinterpret_cast<const float4*>(xn + i0 + NT) + g);
+                }
                 mbar_wait_hint(&acc_full[a], (tc >> 1) & 1);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + lane_addr + C::ACC_COL0 + a * NACC * NT + ch * NTH;
