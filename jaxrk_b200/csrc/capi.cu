@@ -51,9 +51,15 @@ static int have_device(const char* fn) {
     return JRK_OK;
 }
 
-static int resolve_gram_path(int path, int d) {
-    if (path == JRK_PATH_AUTO) return d >= 64 ? JRK_PATH_TF32X3 : JRK_PATH_DIRECT;
-    return path;
+// AUTO: the tcgen05 3xTF32 path for d >= 64 (where the distance is a dense contraction), and -- measured on B200,
+// tools/small_d_paths.py -- also for 16 <= d < 64 once the Gram is large (>= 2^24 entries): padded to 64 columns it
+// stays HBM-write-bound (3.7 ms at 65536^2) while direct differencing is FP32-bound (6.1 / 10.3 / 14.3 ms at
+// d = 16 / 32 / 48).  Small problems and d < 16 use direct differencing (one launch, exact diagonal).
+static int resolve_gram_path(int path, int d, int64_t N, int64_t M) {
+    if (path != JRK_PATH_AUTO) return path;
+    if (d >= 64) return JRK_PATH_TF32X3;
+    if (d >= 16 && N * M >= ((int64_t)1 << 24)) return JRK_PATH_TF32X3;
+    return JRK_PATH_DIRECT;
 }
 
 }  // namespace jrk
@@ -83,7 +89,7 @@ int jrk_device_count(void) {
 int64_t jrk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t jrk_gram_workspace_bytes(int64_t N, int64_t M, int d, int path) {
-    if (resolve_gram_path(path, d) == JRK_PATH_TF32X3) return gram_tf32x3_workspace_bytes(N, M, d);
+    if (resolve_gram_path(path, d, N, M) == JRK_PATH_TF32X3) return gram_tf32x3_workspace_bytes(N, M, d);
     return 0;
 }
 
@@ -99,7 +105,7 @@ int jrk_gram_f32(const float* X, const float* Y, float* K, int64_t N, int64_t M,
     if (N == 0 || M == 0) return JRK_OK;
     if (int rc = have_device("jrk_gram_f32")) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (resolve_gram_path(path, d) == JRK_PATH_TF32X3)
+    if (resolve_gram_path(path, d, N, M) == JRK_PATH_TF32X3)
         return gram_tf32x3(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, workspace,
                            workspace_bytes, st);
     return gram_direct(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, 0, st);

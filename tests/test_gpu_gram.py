@@ -143,7 +143,24 @@ def test_golden_grams_from_the_reference_code(golden, name, mk, p):
     np.testing.assert_allclose(Ks[off], golden[f"gram_{name}_XX"][off], rtol=2e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("d,path", [(16, nat.PATH_DIRECT), (64, nat.PATH_TF32X3)])
+@pytest.mark.parametrize("d", [16, 24, 32, 48, 63])
+def test_tensor_path_for_small_d(d):
+    """PATH_TF32X3 pads d < 64 to 64 columns; AUTO picks it for 16 <= d < 64 once N*M >= 2^24."""
+    N, M = 4200, 4100   # N*M >= 2^24: AUTO takes the tensor path
+    X, Y = gauss(d, N, d), gauss(100 + d, M, d)
+    for kname in ("sqexp", "laplace", "gg15"):
+        s, scale, p, nconst = kparams(kname, np.sqrt(d))
+        Ka = nat.gram(cu(X), cu(Y), scale, p, nconst, path=nat.PATH_AUTO)
+        Kt = nat.gram(cu(X), cu(Y), scale, p, nconst, path=nat.PATH_TF32X3)
+        assert torch.equal(Ka, Kt)
+        rows = np.arange(0, N, 41)
+        truth = orc.gengauss_gram_truth64(X[rows], Y, s, p)
+        assert_close_truth(Kt.cpu().numpy()[rows], truth, f"{kname} d={d}")
+        Kd = nat.gram(cu(X), cu(Y), scale, p, nconst, path=nat.PATH_DIRECT)
+        assert torch.allclose(Kd, Kt, rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("d,path", [(16, nat.PATH_DIRECT), (16, nat.PATH_AUTO), (64, nat.PATH_TF32X3)])
 def test_full_size_properties(d, path):
     """At sizes the oracle cannot hold: row-block independence, symmetry, sampled entries."""
     N = 16384
@@ -153,7 +170,9 @@ def test_full_size_properties(d, path):
     K = nat.gram(Xd, None, scale, p, nconst, path=path)
     assert torch.equal(K, K.T)
     blk = nat.gram(Xd[4096:4096 + 512], Xd, scale, p, nconst, path=path)
-    assert torch.allclose(K[4096:4096 + 512], blk, rtol=1e-6, atol=1e-9)
+    # (under AUTO the 512-row block is small enough for the direct path while the full Gram takes the tensor path)
+    tight = path != nat.PATH_AUTO
+    assert torch.allclose(K[4096:4096 + 512], blk, rtol=1e-6 if tight else 2e-5, atol=1e-9 if tight else 2e-6)
     rows = np.random.RandomState(1).choice(N, 64, replace=False)
     truth = orc.gengauss_gram_truth64(X[rows], X, s, p)
     assert_close_truth(K[torch.from_numpy(rows).to(K.device)].cpu().numpy(), truth)

@@ -1,0 +1,25 @@
+"""Smallest launches that touch every kernel and every ragged edge, for `compute-sanitizer --tool memcheck`."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jaxrk_b200 import _native as nat
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(0)
+r = lambda *s: torch.randn(*s, generator=g, device=dev)
+for p in (2.0, 1.0, 1.5):
+    for (N, M, d) in ((130, 67, 5), (257, 131, 16), (129, 200, 33)):
+        nat.gram(r(N, d), r(M, d), 0.3, p, 0.2, path=nat.PATH_DIRECT)
+    for (N, M, d) in ((130, 67, 64), (65, 129, 70), (200, 130, 128)):
+        X = r(N, d)
+        nat.gram(X, r(M, d), 0.1, p, 0.2, path=nat.PATH_TF32X3)
+        nat.gram(X, None, 0.1, p, 0.2, path=nat.PATH_TF32X3)
+    for (N, M, d, m) in ((130, 300, 16, 16), (700, 129, 3, 5), (64, 1000, 17, 33)):
+        X, Y, W = r(N, d), r(M, d), r(M, m)
+        nat.kmatw(X, Y, W, 0.3, p, 0.2)
+        nat.kmatw(X, Y, W, 0.3, p, 0.2, row_reduce=nat.REDUCE_MEAN)
+    X = r(512, 8)
+    nat.gram_groupsum(X, None, 0.3, p, 0.2, 128, 128, True)
+    nat.gram_groupsum(X, r(300, 8), 0.3, p, 0.2, 256, 100, False)
+nat.dist(r(100, 7), r(50, 7), 1.0, 1.0)
+torch.cuda.synchronize()
+print("done", nat.launch_count())
