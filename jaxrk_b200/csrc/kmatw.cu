@@ -25,9 +25,18 @@
 //     accumulators are folded into a per-thread second-level accumulator kept in shared
 //     memory (conflict-free 16-byte slots) and restarted from zero.
 // Roofline: FP32 issue (2d + m + ~3 lane-ops per pair), see DESIGN.md.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace jrk {
+
+// tensor-core variant (kmatw_tc.cu)
+bool kmatw_tc_eligible(int64_t N, int64_t M, int d, int m, const float* dim_scale, int row_reduce, float nconst);
+size_t kmatw_tc_workspace_bytes(int64_t N, int64_t M);
+int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
+             int64_t ldy, int64_t ldw, int64_t ldo, float scale, float power, float nconst, const float* row_pref,
+             const float* col_pref, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 constexpr int KW_THREADS = 128;
 constexpr int KW_TJ = 128;  // rows of Y / W per stage
@@ -345,7 +354,11 @@ size_t kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce,
         b += align256((size_t)p.nsplit * (size_t)((N > p.nblk) ? N : p.nblk) * p.MT * 4);
         if (b > total) total = b;
     }
-    (void)row_reduce; (void)group;
+    (void)group;
+    if (kmatw_tc_eligible(N, M, d, m, nullptr, row_reduce, 1.f)) {
+        const size_t t = kmatw_tc_workspace_bytes(N, M);
+        if (t > total) total = t;
+    }
     return total + 1024;
 }
 
@@ -450,6 +463,14 @@ int kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N,
           float nconst, const float* row_pref, const float* col_pref, int row_reduce, int64_t group,
           void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (d > 128) return fail(JRK_ERR_UNSUPPORTED, "kmatw: d = %d > 128 not supported by the fused kernel", d);
+    // both contractions on the tensor cores when the problem is large, narrow and plain (kmatw_tc.cu);
+    // JRK_KMATW_TC=0 forces the FP32-pipe kernel below
+    {
+        const char* e = getenv("JRK_KMATW_TC");
+        if (!(e && e[0] == '0') && kmatw_tc_eligible(N, M, d, m, dim_scale, row_reduce, nconst))
+            return kmatw_tc(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, power, nconst, row_pref, col_pref,
+                            workspace, workspace_bytes, st);
+    }
     Scratch scr(workspace, workspace_bytes, st);
     JRK_CUDA_OK(scr.reserve(kmatw_workspace_bytes(N, M, d, m, row_reduce, group)));
     for (int c0 = 0; c0 < m; c0 += 32) {  // wide W: column blocks of 32 (K is recomputed per block)

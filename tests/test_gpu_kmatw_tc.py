@@ -1,0 +1,96 @@
+"""Tensor-core K@W path (kmatw_tc.cu: both contractions on tcgen05) against the oracle and against the FP32-pipe
+kernel.  The path is taken automatically for d <= 32, m <= 16, N >= 8192, M >= 4096 with no row reduce."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from jaxrk_b200 import _native as nat
+from oracle import jaxrk_oracle as orc
+from gpu_util import assert_kmatw_close, cu, f32, gauss, kparams
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def force(monkeypatch):
+    def _set(on):
+        monkeypatch.setenv("JRK_KMATW_TC", "1" if on else "0")
+    return _set
+
+
+def _sample_truth(X, Y, W, s, p, rows, rp=None, cp=None):
+    G = orc.gengauss_gram_truth64(X[rows], Y, s, p)
+    if cp is not None:
+        G = G * cp.astype(np.float64)[None, :]
+    if rp is not None:
+        G = G * rp[rows].astype(np.float64)[:, None]
+    W64 = W.astype(np.float64)
+    return G @ W64, np.abs(G) @ np.abs(W64)
+
+
+@pytest.mark.parametrize("kname", ["sqexp", "laplace", "gg15", "gg05"])
+@pytest.mark.parametrize("d,m", [(16, 16), (7, 5), (32, 1), (1, 3), (20, 16)])
+def test_tc_path_matches_oracle_and_fp32_kernel(kname, d, m, force):
+    N, M = 8192 + 77, 4096 + 33        # ragged in both directions
+    X, Y, W = gauss(0, N, d), gauss(1, M, d), gauss(2, M, m)
+    s, scale, p, nconst = kparams(kname, np.sqrt(d) * 1.2)
+    force(True)
+    n0 = nat.launch_count()
+    T = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst)
+    assert nat.launch_count() - n0 == 4, "pack + 2 norms + tensor-core kernel"
+    force(False)
+    F = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst)
+    rows = np.r_[0:64, N - 64:N]
+    truth, bound = _sample_truth(X, Y, W, s, p, rows)
+    assert_kmatw_close(T.cpu().numpy()[rows], truth, bound, f"tc {kname} d={d} m={m}")
+    assert_kmatw_close(F.cpu().numpy()[rows], truth, bound, f"fp32 {kname} d={d} m={m}")
+    b = torch.from_numpy(bound.max(0)).to(T.device).float()
+    assert ((T - F).abs() <= 2e-6 + 2e-5 * b).all()
+
+
+def test_tc_path_prefactors_strides_and_positive_weights(force):
+    N, M, d, m = 16384, 16384, 16, 8
+    Xb, Yb, Wb = cu(gauss(3, N, 24)), cu(gauss(4, M, 20)), cu(np.abs(gauss(5, M, 12)))
+    X, Y, W = Xb[:, 3:3 + d], Yb[:, 1:1 + d], Wb[:, 2:2 + m]          # strided, unaligned views
+    rp = np.random.RandomState(6).rand(N).astype(f32)
+    cp = np.random.RandomState(7).rand(M).astype(f32)
+    s, scale, p, nconst = kparams("sqexp", 4.0)
+    force(True)
+    T = nat.kmatw(X, Y, W, scale, p, nconst, row_pref=rp, col_pref=cp)
+    rows = np.arange(0, N, 257)
+    truth, bound = _sample_truth(X.cpu().numpy(), Y.cpu().numpy(), W.cpu().numpy(), s, p, rows, rp, cp)
+    assert_kmatw_close(T.cpu().numpy()[rows], truth, bound, "all-positive sum through the tensor core")
+
+
+def test_tc_path_near_duplicates_are_refined(force):
+    rng = np.random.RandomState(9)
+    N, M, d, m = 8192, 8192, 16, 4
+    X = (rng.randn(N, d) * 3).astype(f32)
+    Y = (X[rng.permutation(N)][:M] + rng.randn(M, d).astype(f32) * 1e-4).astype(f32)   # every y_j sits next to some x_i
+    W = gauss(2, M, m)
+    for kname in ("laplace", "gg05", "sqexp"):
+        s, scale, p, nconst = kparams(kname, 0.5)    # short length scale: the near pairs dominate the sums
+        force(True)
+        T = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst)
+        rows = np.arange(0, N, 131)
+        truth, bound = _sample_truth(X, Y, W, s, p, rows)
+        assert_kmatw_close(T.cpu().numpy()[rows], truth, bound, kname)
+
+
+def test_tc_path_through_the_api_cfg5_apply_shape(force):
+    """operator apply: K(X_test, X) @ W -- the inner() with a LinearReduce on the Y side picks the tensor-core path."""
+    from jaxrk_b200.kern import GenGaussKernel
+    from jaxrk_b200.reduce import LinearReduce
+    from jaxrk_b200.rkhs import FiniteVec, inner
+    rng = np.random.RandomState(0)
+    T_, N, d, m = 16384, 8192, 16, 16
+    Xt, X, A = rng.randn(T_, d).astype(f32), rng.randn(N, d).astype(f32), rng.randn(m, N).astype(f32)
+    k = GenGaussKernel.make_gauss(4.0)
+    force(True)
+    out = inner(FiniteVec(k, Xt), FiniteVec(k, X, [LinearReduce(A)]))
+    force(False)
+    ref = inner(FiniteVec(k, Xt), FiniteVec(k, X, [LinearReduce(A)]))
+    assert tuple(out.shape) == (T_, m)
+    assert torch.allclose(out, ref, rtol=1e-4, atol=2e-5)

@@ -1,0 +1,44 @@
+"""Numerical check + timing of the tensor-core K@W path against the FP32-pipe kernel and float64."""
+import os, sys, subprocess
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jaxrk_b200 import _native as nat
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(0)
+def t(fn, reps=3):
+    fn(); torch.cuda.synchronize(); best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
+    return best
+def run(N, M, d, m, p, positive=False, timing=False):
+    X = torch.randn(N, d, generator=g, device=dev); Y = torch.randn(M, d, generator=g, device=dev)
+    W = torch.rand(M, m, generator=g, device=dev) if positive else torch.randn(M, m, generator=g, device=dev)
+    s, nc = float(0.70710695 / np.sqrt(d)) if p == 2.0 else float(1 / np.sqrt(d)), 0.25
+    os.environ["JRK_KMATW_TC"] = "1"; A = nat.kmatw(X, Y, W, s, p, nc); torch.cuda.synchronize()
+    os.environ["JRK_KMATW_TC"] = "0"; B = nat.kmatw(X, Y, W, s, p, nc); torch.cuda.synchronize()
+    rows = torch.arange(0, N, max(1, N // 64), device=dev)[:64]
+    Kt = nc * torch.exp(-(s * torch.cdist(X[rows].double(), Y.double())) ** p)
+    T = Kt @ W.double(); bound = Kt @ W.double().abs()
+    ea = ((A[rows].double() - T).abs() / (1e-6 + 1e-5 * bound)).max().item()
+    eb = ((B[rows].double() - T).abs() / (1e-6 + 1e-5 * bound)).max().item()
+    msg = f"N={N} M={M} d={d} m={m} p={p} pos={positive}: tc err/lim {ea:.3f}  fp32 err/lim {eb:.3f}"
+    if timing:
+        os.environ["JRK_KMATW_TC"] = "1"; ta = t(lambda: nat.kmatw(X, Y, W, s, p, nc))
+        os.environ["JRK_KMATW_TC"] = "0"; tb = t(lambda: nat.kmatw(X, Y, W, s, p, nc))
+        msg += f" | tc {ta:.2f} ms ({N*M/ta/1e6:.0f} Gpairs/s)  fp32 {tb:.2f} ms ({N*M/tb/1e6:.0f} Gpairs/s)"
+    print(msg, flush=True)
+import sys as _s
+if len(_s.argv) > 1 and _s.argv[1] == "win":
+    for w in ("1", "2", "4", "16", "64"):
+        os.environ["JRK_TC_WIN"] = w; print("WIN", w, end=": "); run(65536, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
+    _s.exit(0)
+run(8192, 4096, 16, 16, 2.0)
+run(8192 + 77, 4096 + 33, 16, 16, 2.0)
+run(8192, 8192, 7, 5, 1.0)
+run(8192, 8192, 32, 1, 1.5)
+run(16384, 65536, 16, 16, 2.0, positive=True)
+run(131072, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
+run(131072, 1 << 20, 16, 16, 1.0, timing=True)
+run(131072, 1 << 20, 32, 16, 2.0, timing=True)
+print("ok")
