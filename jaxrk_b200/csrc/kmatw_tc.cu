@@ -8,14 +8,21 @@
 //   GEMM1   S = x.y   by 3xTF32 (hi.hi + hi.lo + lo.hi), X block resident in TMEM (A), Y tiles in shared memory (B)
 //   epilogue           e = exp2(a S + xs_i + ys_j), split into tf32 hi / lo, written back over S in TMEM
 //   GEMM2   O += e.W   by 3xTF32, A = e from TMEM, B = W^T tiles in shared memory, O accumulates in TMEM
-// so a pair costs ~7 issued instructions and one MUFU instead of ~33 instructions: the kernel is bound by the
+// so a pair costs ~10 issued instructions and one MUFU instead of ~33 instructions: the kernel is bound by the
 // MUFU / issue rate, not by FP32 FMAs (DESIGN.md "Rooflines").
 //
-// A pre-pass writes, per 64-row tile of Y, one contiguous 24 KB image [Y hi | Y lo | W^T hi | W^T lo] in the K-major
-// 128B-swizzled layout of the UMMA descriptor, so a tile arrives with one cp.async.bulk.  Persistent CTAs, one per
-// SM, each owning 128-row blocks of X; 18 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation),
-// warps 2-17 epilogue (TMEM lane = row i; 16 columns j per warp and tile).
-// TMEM columns: X hi [0,32) | X lo [32,64) | 2 stages x {c1 [64), c2 [64)} -> overwritten by {e hi, e lo} | 2 x {O main [16), O cross [16)}.
+// A pre-pass writes, per 64-row tile of Y, one contiguous image [Y hi, Y lo | W^T hi | W^T lo | 64 scaled |y|^2] in the
+// K-major 128B-swizzled layout of the UMMA descriptor, so a tile arrives with one cp.async.bulk.  For d <= 16 the
+// hi and lo halves of a Y row share one 128-byte swizzle row (16.25 KB per tile), else they are separate (24.25 KB).
+// The first version of this kernel gave each CTA one 128-row block of X and was bound by the L2 -> SM operand
+// stream (24 KB per 8192 pairs = 7.2 TB/s chip-wide; measured 58 ms of 89 with the MMAs and the epilogue switched
+// off).  So a CTA now owns TWO 128-row blocks that share every tile image (half the L2 bytes per pair): the
+// S / e stage of block r is TMEM stage r, epilogue group r (8 warps) owns block r, and the two groups alternate
+// naturally -- while group 0 converts tile t of block 0, the tensor core runs GEMM1 of block 1 / GEMM2 of block 0.
+// Persistent CTAs, one per SM; 18 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-17
+// epilogue (TMEM lane = row i; 32 columns j per warp and tile, in two 16-column chunks).
+// TMEM columns: X of block r [r*64, +64) = hi [32) lo [32) | S / e of block r [128 + r*128, +128) = {c1, c2} -> {e hi, e lo}
+//               | O of block r, buffer b [384 + r*64 + b*32, +32) = {main [16), cross [16)}.
 // The tensor core's accumulation is not round-to-nearest: for all-positive sums the error grows with the number of
 // MMAs that add into one accumulator (measured: 4.8x the tolerance with 64-tile windows, 0.5x with 1-4 tiles).
 // So (i) O accumulates in TMEM across a window of TC_WIN tiles only; the epilogue then folds the window into FP32
@@ -23,6 +30,8 @@
 // hi_e.hi_w and the two small cross terms go to separate accumulators (8 instead of 24 MMAs per tile on the one
 // that matters).
 // Near-coincident pairs (sq < (|x|^2+|y|^2)/64) are recomputed by FP32 direct differencing, as in the Gram kernel.
+#include <type_traits>
+
 #include "gram_tf32_kernel.cuh"
 
 namespace jrk {
@@ -32,30 +41,83 @@ using namespace tf32;
 namespace {
 
 constexpr int TC_BM = 128, TC_NT = 64, TC_DP = 32, TC_MT = 16;
-constexpr int TC_YH = TC_NT * 128;                       // bytes of one Y image (hi or lo)
+constexpr int TC_SS = 3;                                 // S / e stages in TMEM
 constexpr int TC_WH = 2 * TC_MT * 128;                   // bytes of one W^T image: 2 k-chunks x 16 rows x 128 B
-constexpr int TC_STAGE = 2 * TC_YH + 2 * TC_WH;          // 24576
+constexpr int TC_STAGE = 25600;                          // stage stride (1024-byte aligned, fits the wide image)
 constexpr int TC_SOP = 6;
 constexpr int TC_EW = 16;
-constexpr int TC_THREADS = (2 + TC_EW) * 32;
-constexpr int TC_WIN = 2;                                // tiles per O window (128 j)
-constexpr int TC_COL_X = 0, TC_COL_S = 64, TC_COL_O = 64 + 2 * 128;   // TMEM columns
+constexpr int TC_THREADS = (3 + TC_EW) * 32;
+constexpr int TC_WIN = 2;                                // tiles per O window (128 j); a power of two
+constexpr int TC_COL_X = 0, TC_COL_S = 64, TC_COL_O = 64 + TC_SS * 128;   // TMEM columns
 constexpr int TC_OFF_BAR = TC_SOP * TC_STAGE;
-constexpr int TC_NBAR = 2 * TC_SOP + 6 + 4 + 1;          // op full/empty, s_full/e_ready/s_empty x2, o_full/o_empty x2, x_ready
+constexpr int TC_NBAR = 2 * TC_SOP + 3 * TC_SS + 4 + 1;  // op full/empty, s_full/e_ready/s_empty, o_full/o_empty x2, x_ready
 constexpr int TC_SMEM = TC_OFF_BAR + TC_NBAR * 8 + 16 + 1024;
+static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
+
+// Byte layout of one tile image.  packed (d <= 16): a Y row is [16 hi | 16 lo] floats in one 128-byte swizzle row.
+struct TcImage {
+    int y_lo;      // offset of the lo half relative to the hi half (what the GEMM1 descriptors differ by)
+    int w;         // offset of W^T hi; W^T lo follows at + TC_WH
+    int yn;        // offset of the 64 scaled squared norms
+    int bytes;     // image size (multiple of 16)
+    int ypieces;   // 16-byte pieces of Y per row handled by the pack kernel (4 or 8)
+};
+inline TcImage tc_image(int d) {
+    TcImage L;
+    const bool packed = d <= 16;
+    const int ybytes = packed ? TC_NT * 128 : 2 * TC_NT * 128;
+    L.y_lo = packed ? 64 : TC_NT * 128;
+    L.w = ybytes;
+    L.yn = ybytes + 2 * TC_WH;
+    L.bytes = L.yn + TC_NT * 4;
+    L.ypieces = packed ? 4 : 8;
+    return L;
+}
+
+// mbarrier wait / arrive on a precomputed 32-bit shared address (the generic -> shared conversion costs an S2R)
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity), "r"(20000u)
+        : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void tc_commit_addr(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// tf32 split of a positive kernel value for GEMM2: hi by truncation (one LOP), lo = e - hi >= 0 exact
+__device__ __forceinline__ void split_trunc(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
 
 struct TcParams {
     const float* X; int64_t ldx; int d;
     const float* Y; int64_t ldy;
-    const float* xn; const float* yn;      // scaled row norms (yn zero padded to a multiple of 64)
-    const float* img;                      // tile images
+    const float* xn;                       // scaled row norms of X
+    const unsigned char* img;              // tile images
+    TcImage L;
     const float* row_pref;
     float* out; int64_t ldo; int m;
     int64_t N, M;
     int n_tiles, n_units, ksteps;
     float a;                               // PM_SQEXP: -2c; else -2
-    int check;                             // near-zero refinement enabled
-    int win;                               // tiles per O window
+    int check;                             // 1: near-zero refinement always; 0: only if the norm maxima demand it
+    const unsigned* nmax;                  // [2] bit patterns of max |mult| |x|^2, max |mult| |y|^2
 };
 
 template <int PM>
@@ -65,10 +127,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
     uint64_t* op_full = bars;                    // [TC_SOP]
     uint64_t* op_empty = op_full + TC_SOP;       // [TC_SOP]
-    uint64_t* s_full = op_empty + TC_SOP;        // [2]  GEMM1 of the stage complete
-    uint64_t* e_ready = s_full + 2;              // [2]  epilogue wrote e hi / lo
-    uint64_t* s_empty = e_ready + 2;             // [2]  GEMM2 of the stage complete
-    uint64_t* o_full = s_empty + 2;              // [2]  window complete in O buffer
+    uint64_t* s_full = op_empty + TC_SOP;        // [TC_SS]  GEMM1 of the stage complete
+    uint64_t* e_ready = s_full + TC_SS;          // [TC_SS]  epilogue wrote e hi / lo
+    uint64_t* s_empty = e_ready + TC_SS;         // [TC_SS]  GEMM2 of the stage complete
+    uint64_t* o_full = s_empty + TC_SS;          // [2]  window complete in O buffer
     uint64_t* o_empty = o_full + 2;              // [2]  epilogue folded the O buffer
     uint64_t* x_ready = o_empty + 2;             // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + TC_NBAR * 8);
@@ -76,10 +138,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_SOP; ++s) { mbar_init(&op_full[s], 1); mbar_init(&op_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&s_full[s], 1); mbar_init(&e_ready[s], TC_EW); mbar_init(&s_empty[s], 1);
-            mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4);
-        }
+        for (int s = 0; s < TC_SS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&e_ready[s], TC_EW); mbar_init(&s_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4); }
         mbar_init(x_ready, TC_EW);
         fence_mbar_init();
     }
@@ -92,58 +152,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
 
     const int T = P.n_tiles;
     if (warp == 0) {
-        // ===================== TMA producer: one 24 KB image per tile =====================
+        // ===================== TMA producer: one image per tile =====================
         uint32_t tc = 0;
+        const uint32_t bytes = (uint32_t)P.L.bytes;
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
             for (int t = 0; t < T; ++t, ++tc) {
                 const int s = tc % TC_SOP;
                 mbar_wait_hint(&op_empty[s], ((tc / TC_SOP) & 1) ^ 1);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&op_full[s], TC_STAGE);
-                    bulk_g2s(smem + s * TC_STAGE, P.img + (int64_t)t * (TC_STAGE / 4), TC_STAGE, &op_full[s]);
+                    mbar_arrive_expect_tx(&op_full[s], bytes);
+                    bulk_g2s(smem + s * TC_STAGE, P.img + (int64_t)t * bytes, bytes, &op_full[s]);
                 }
                 __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== GEMM1 issuer:  S[stage] = x . y  (3xTF32) =====================
+        // A single warp issuing both GEMMs was the bottleneck of the first versions (it was ~90 % busy executing its
+        // own ~250 instructions per tile while everything else waited), so each GEMM has its own issuing warp and
+        // all stage / phase bookkeeping is incremental.  This warp runs up to TC_SS tiles ahead of the epilogue.
         constexpr uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_NT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_MT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        const uint32_t smem_base = smem_u32(smem);
+        const uint64_t dbase = make_b_desc(smem_u32(smem));
+        const uint32_t b_opfull = smem_u32(op_full), b_sempty = smem_u32(s_empty), b_sfull = smem_u32(s_full), b_xready = smem_u32(x_ready);
         const int ksteps = P.ksteps;
-        uint32_t tc = 0, uc = 0, wc = 0;   // tiles, units, windows issued so far
-        auto gemm1 = [&](uint32_t tcx) {
-            const uint32_t s = tcx % TC_SOP, a = tcx & 1;
-            mbar_wait_hint(&op_full[s], (tcx / TC_SOP) & 1);
-            mbar_wait_hint(&s_empty[a], ((tcx >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint64_t dyh = make_b_desc(smem_base + s * TC_STAGE), dyl = make_b_desc(smem_base + s * TC_STAGE + TC_YH);
-            const uint32_t c1 = TC_COL_S + a * 128, c2 = c1 + 64;
-            if (elect_one()) {
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint64_t off = (uint64_t)((ks * 32) >> 4);
-                    mma_tf32_ts(c1, TC_COL_X + ks * 8, dyh + off, idesc1, ks);            // hi_x . hi_y
-                    mma_tf32_ts(c2, TC_COL_X + ks * 8, dyl + off, idesc1, ks);            // hi_x . lo_y
-                    mma_tf32_ts(c2, TC_COL_X + TC_DP + ks * 8, dyh + off, idesc1, 1u);    // lo_x . hi_y
-                }
-                tc_commit(&s_full[a]);
-            }
-            __syncwarp();
-        };
+        const uint64_t y_lo = (uint64_t)(P.L.y_lo >> 4);
+        uint32_t s = 0, s_ph = 0, a = 0, a_ph = 0, uc = 0;
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, ++uc) {
-            mbar_wait_hint(x_ready, uc & 1);
-            gemm1(tc);
-            for (int t = 0; t < T; ++t, ++tc) {
-                if (t + 1 < T) gemm1(tc + 1);
-                // ---- GEMM2 of tile t: O[window] += e . W ----
-                const uint32_t s = tc % TC_SOP, a = tc & 1;
-                const bool win_first = (t % P.win) == 0, win_last = ((t % P.win) == P.win - 1) || (t == T - 1);
-                const uint32_t ob = wc & 1;
-                if (win_first) mbar_wait_hint(&o_empty[ob], ((wc >> 1) & 1) ^ 1);
-                mbar_wait_hint(&e_ready[a], (tc >> 1) & 1);
+            bar_wait(b_xready, uc & 1);
+            for (int t = 0; t < T; ++t) {
+                bar_wait(b_opfull + s * 8, s_ph);
+                bar_wait(b_sempty + a * 8, a_ph ^ 1);
                 tc_fence_after();
-                const uint64_t dwh = make_b_desc(smem_base + s * TC_STAGE + 2 * TC_YH);
-                const uint64_t dwl = make_b_desc(smem_base + s * TC_STAGE + 2 * TC_YH + TC_WH);
+                const uint64_t dyh = dbase + (uint64_t)((s * TC_STAGE) >> 4), dyl = dyh + y_lo;
+                const uint32_t c1 = TC_COL_S + a * 128, c2 = c1 + 64;
+                if (elect_one()) {
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t off = (uint64_t)(ks * 2);
+                        mma_tf32_ts(c1, TC_COL_X + ks * 8, dyh + off, idesc1, ks);            // hi_x . hi_y
+                        mma_tf32_ts(c2, TC_COL_X + ks * 8, dyl + off, idesc1, ks);            // hi_x . lo_y
+                        mma_tf32_ts(c2, TC_COL_X + TC_DP + ks * 8, dyh + off, idesc1, 1u);    // lo_x . hi_y
+                    }
+                    tc_commit_addr(b_sfull + a * 8);
+                }
+                __syncwarp();
+                if (++s == TC_SOP) { s = 0; s_ph ^= 1; }
+                if (++a == TC_SS) { a = 0; a_ph ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== GEMM2 issuer:  O[window] += e . W  (3xTF32) =====================
+        constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_MT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        const uint64_t dbase = make_b_desc(smem_u32(smem));
+        const uint32_t b_opfull = smem_u32(op_full), b_opempty = smem_u32(op_empty), b_sempty = smem_u32(s_empty),
+                       b_eready = smem_u32(e_ready), b_ofull = smem_u32(o_full), b_oempty = smem_u32(o_empty);
+        const uint64_t w_off = (uint64_t)(P.L.w >> 4);
+        uint32_t s = 0, s_ph = 0, a = 0, a_ph = 0, ob = 0, ob_ph = 0;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+            for (int t = 0; t < T; ++t) {
+                const bool win_first = (t & (TC_WIN - 1)) == 0, win_last = ((t & (TC_WIN - 1)) == TC_WIN - 1) || (t == T - 1);
+                if (win_first) bar_wait(b_oempty + ob * 8, ob_ph ^ 1);
+                bar_wait(b_opfull + s * 8, s_ph);
+                bar_wait(b_eready + a * 8, a_ph);
+                tc_fence_after();
+                const uint64_t dwh = dbase + (uint64_t)((s * TC_STAGE) >> 4) + w_off, dwl = dwh + (uint64_t)(TC_WH >> 4);
                 const uint32_t eh = TC_COL_S + a * 128, el = eh + 64, oc = TC_COL_O + ob * 2 * TC_MT, ox = oc + TC_MT;
                 if (elect_one()) {
 #pragma unroll
@@ -154,28 +225,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                         mma_tf32_ts(ox, eh + k * 8, dwl + off, idesc2, acc0);   // hi_e . lo_w   (cross accumulator)
                         mma_tf32_ts(ox, el + k * 8, dwh + off, idesc2, 1u);     // lo_e . hi_w
                     }
-                    tc_commit(&s_empty[a]);      // S / e stage reusable
-                    tc_commit(&op_empty[s]);     // operand stage reusable
-                    if (win_last) tc_commit(&o_full[ob]);
+                    tc_commit_addr(b_sempty + a * 8);      // S / e stage reusable
+                    tc_commit_addr(b_opempty + s * 8);     // operand stage reusable
+                    if (win_last) tc_commit_addr(b_ofull + ob * 8);
                 }
                 __syncwarp();
-                if (win_last) ++wc;
+                if (win_last) { ob ^= 1; if (ob == 0) ob_ph ^= 1; }
+                if (++s == TC_SOP) { s = 0; s_ph ^= 1; }
+                if (++a == TC_SS) { a = 0; a_ph ^= 1; }
             }
         }
     } else {
         // ===================== epilogue (and X loader) =====================
-        const int e = warp - 2;
-        const int quad = warp & 3;
+        const int e = warp - 3;
+        const int quad = warp & 3;                          // TMEM lane quarter this warp may touch
         const int cg = e >> 2;                              // 16-column group of the tile
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const f32x2 a2 = pack2(P.a, P.a), ntau2 = pack2(-TF_TAU, -TF_TAU);
-        uint32_t tc = 0, wc = 0;
+        // shared addresses of the barriers this role touches, computed once
+        const uint32_t b_sfull = smem_u32(s_full), b_eready = smem_u32(e_ready), b_ofull = smem_u32(o_full),
+                       b_oempty = smem_u32(o_empty), b_opfull = smem_u32(op_full);
+        const uint32_t yn_base = smem_u32(smem) + P.L.yn + cg * 64;
+        // near-zero test needed?  (p = 2: only when the norms are large against the length scale)
+        bool check = true;
+        if (PM == PM_SQEXP && !P.check)
+            check = (__uint_as_float(__ldg(P.nmax)) + __uint_as_float(__ldg(P.nmax + 1))) > TF_SKIP_BOUND;
+        uint32_t wc = 0;
+        uint32_t st = 0, st_ph = 0;      // operand stage of the current tile and its phase
+        uint32_t sa = 0, sa_ph = 0;      // S / e stage of the current tile and its phase
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
             const int64_t i = (int64_t)u * TC_BM + quad * 32 + lane;
             const bool iok = i < P.N;
             const float* xrow = P.X + (iok ? i : 0) * P.ldx;
             // ---- park the X block in TMEM as tf32 hi / lo: column groups 0 and 1 take 16 columns each ----
-            if (cg < 2) {
+            // (every GEMM1 that read the previous block has completed: this warp waited for the last s_full)
+            if (cg * 16 < P.d) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
@@ -196,9 +280,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
 #pragma unroll
             for (int c = 0; c < TC_MT; ++c) oacc[c] = 0.f;
 
-            auto fold_window = [&]() {   // column group 0 only: O buffer of window wc -> registers
+            auto fold_window = [&]() {   // column group 0 only: O buffers of window wc -> registers
                 const uint32_t ob = wc & 1;
-                mbar_wait_hint(&o_full[ob], (wc >> 1) & 1);
+                bar_wait(b_ofull + ob * 8, (wc >> 1) & 1);
                 tc_fence_after();
                 float o[16], ox[16];
                 tmem_ld16(tmem_base + lane_addr + TC_COL_O + ob * 2 * TC_MT, o);
@@ -206,27 +290,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&o_empty[ob]);
+                if (lane == 0) bar_arrive(b_oempty + ob * 8);
 #pragma unroll
                 for (int c = 0; c < TC_MT; ++c) oacc[c] += o[c] + ox[c];
                 ++wc;
             };
 
-            float4 ynext[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) ynext[g] = __ldg(reinterpret_cast<const float4*>(P.yn + cg * 16) + g);
-            for (int t = 0; t < T; ++t, ++tc) {
-                const int a = tc & 1;
+            // one tile: S -> e for this warp's 32 rows x 16 columns
+            auto tile = [&](int t, auto chk) {
+                constexpr bool CHECK = decltype(chk)::value;
+                // the tile's (scaled) |y_j|^2 arrived with the operand image: observe the TMA completion, then
+                // broadcast 16-byte reads from shared memory (the stage is released only after GEMM2 of this tile)
+                bar_wait(b_opfull + st * 8, st_ph);
                 float4 yv[4];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) yv[g] = ynext[g];
-                if (t + 1 < T) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) ynext[g] = __ldg(reinterpret_cast<const float4*>(P.yn + (int64_t)(t + 1) * TC_NT + cg * 16) + g);
-                }
-                mbar_wait_hint(&s_full[a], (tc >> 1) & 1);
+                for (int g = 0; g < 4; ++g) yv[g] = lds_v4(yn_base + st * TC_STAGE + g * 16);
+                bar_wait(b_sfull + sa * 8, sa_ph);
                 tc_fence_after();
-                const uint32_t sc = tmem_base + lane_addr + TC_COL_S + a * 128 + cg * 16;
+                const uint32_t sc = tmem_base + lane_addr + TC_COL_S + sa * 128 + cg * 16;
                 float c1[16], c2[16];
                 tmem_ld16(sc, c1);
                 tmem_ld16(sc + 64, c2);
@@ -241,7 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                     const f32x2 u01 = fma2(d01, a2, t01), u23 = fma2(d23, a2, t23);
                     unpack2(u01, uu[4 * g], uu[4 * g + 1]);
                     unpack2(u23, uu[4 * g + 2], uu[4 * g + 3]);
-                    if (P.check) {
+                    if (CHECK) {
                         float w0, w1, w2, w3;
                         unpack2(fma2(t01, ntau2, u01), w0, w1);
                         unpack2(fma2(t23, ntau2, u23), w2, w3);
@@ -249,44 +330,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                         else wext = fminf(fminf(wext, w0), fminf(fminf(w1, w2), w3));
                     }
                 }
-                const bool refine = P.check && ((PM == PM_SQEXP) ? (wext > 0.f) : (wext < 0.f));
-                if (__any_sync(0xffffffffu, refine && iok)) {
-                    // near-coincident pairs: recompute by FP32 direct differencing (rare path)
-                    const float ys_arr[16] = {yv[0].x, yv[0].y, yv[0].z, yv[0].w, yv[1].x, yv[1].y, yv[1].z, yv[1].w,
-                                              yv[2].x, yv[2].y, yv[2].z, yv[2].w, yv[3].x, yv[3].y, yv[3].z, yv[3].w};
+                if (CHECK) {
+                    const bool refine = (PM == PM_SQEXP) ? (wext > 0.f) : (wext < 0.f);
+                    if (__any_sync(0xffffffffu, refine && iok)) {
+                        // near-coincident pairs: recompute by FP32 direct differencing (rare path)
+                        const float ys_arr[16] = {yv[0].x, yv[0].y, yv[0].z, yv[0].w, yv[1].x, yv[1].y, yv[1].z, yv[1].w,
+                                                  yv[2].x, yv[2].y, yv[2].z, yv[2].w, yv[3].x, yv[3].y, yv[3].z, yv[3].w};
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const float tt = xs + ys_arr[c];
-                        const float w = fmaf(tt, -TF_TAU, uu[c]);
-                        const bool bad = (PM == PM_SQEXP) ? (w > 0.f) : (w < 0.f);
-                        const int64_t j = (int64_t)t * TC_NT + cg * 16 + c;
-                        if (iok && bad && j < P.M) {
-                            const float* yr = P.Y + j * P.ldy;
-                            float acc2 = 0.f;
+                        for (int c = 0; c < 16; ++c) {
+                            const float tt = xs + ys_arr[c];
+                            const float w = fmaf(tt, -TF_TAU, uu[c]);
+                            const bool bad = (PM == PM_SQEXP) ? (w > 0.f) : (w < 0.f);
+                            const int64_t j = (int64_t)t * TC_NT + cg * 16 + c;
+                            if (iok && bad && j < P.M) {
+                                const float* yr = P.Y + j * P.ldy;
+                                float acc2 = 0.f;
 #pragma unroll 1
-                            for (int k = 0; k < P.d; ++k) {
-                                const float df = __ldg(xrow + k) - __ldg(yr + k);
-                                acc2 = fmaf(df, df, acc2);
+                                for (int k = 0; k < P.d; ++k) {
+                                    const float df = __ldg(xrow + k) - __ldg(yr + k);
+                                    acc2 = fmaf(df, df, acc2);
+                                }
+                                uu[c] = (PM == PM_SQEXP) ? acc2 * ep.c : acc2;
                             }
-                            uu[c] = (PM == PM_SQEXP) ? acc2 * ep.c : acc2;
                         }
                     }
                 }
-                // e = unnormalised kernel value; split into tf32 hi / lo and write back over S
+                // e = unnormalised kernel value (> 0); split into tf32 hi / lo and write back over S
                 uint32_t ehi[16], elo[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const float ev = (PM == PM_SQEXP) ? ex2_approx(uu[c]) : kexp_unnorm<PM>(uu[c], ep);
-                    split_tf32(ev, ehi[c], elo[c]);
+                    split_trunc(ev, ehi[c], elo[c]);
                 }
                 tmem_st16(sc, ehi);
                 tmem_st16(sc + 64, elo);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&e_ready[a]);
+                if (lane == 0) bar_arrive(b_eready + sa * 8);
+                if (++st == TC_SOP) { st = 0; st_ph ^= 1; }
+                if (++sa == TC_SS) { sa = 0; sa_ph ^= 1; }
+            };
+
+            for (int t = 0; t < T; ++t) {
+                if (check) tile(t, std::true_type{});
+                else tile(t, std::false_type{});
                 // fold the previous window once its last GEMM2 has been issued (one tile later)
-                if (cg == 0 && t > 0 && (t % P.win) == 0) fold_window();
+                if (cg == 0 && t > 0 && (t & (TC_WIN - 1)) == 0) fold_window();
             }
             if (cg == 0) {
                 fold_window();   // the unit's last (possibly partial) window
@@ -297,9 +387,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                     for (int c = 0; c < TC_MT; ++c)
                         if (c < P.m) dst[c] = f * oacc[c];
                 }
-            } else {
-                // keep the window counter in step with column group 0
-                wc += (uint32_t)((T + P.win - 1) / P.win);
             }
         }
     }
@@ -310,20 +397,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
     if (warp == 1) tmem_dealloc_512(tmem_base);
 }
 
-// ---- pre-pass: per-tile images [Y hi | Y lo | W^T hi | W^T lo], one thread per 16-byte piece ----
+// ---- pre-pass: per-tile images [Y hi, Y lo | W^T hi | W^T lo | yn], one thread per 16-byte piece ----
 __global__ void tc_pack_kernel(const float* __restrict__ Y, int64_t M, int d, int64_t ldy, const float* __restrict__ W,
-                               int m, int64_t ldw, const float* __restrict__ col_pref, int n_tiles,
-                               float* __restrict__ img) {
+                               int m, int64_t ldw, const float* __restrict__ col_pref, int n_tiles, float mult,
+                               TcImage L, unsigned char* __restrict__ img) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    constexpr int PER_TILE = 512 + 256;
-    if (idx >= (int64_t)n_tiles * PER_TILE) return;
-    const int64_t t = idx / PER_TILE;
-    const int p = (int)(idx % PER_TILE);
-    unsigned char* base = reinterpret_cast<unsigned char*>(img) + t * TC_STAGE;
+    const int ypt = TC_NT * L.ypieces;            // Y pieces per tile (256 or 512: whole warps)
+    const int per_tile = ypt + 256;
+    if (idx >= (int64_t)n_tiles * per_tile) return;
+    const int64_t t = idx / per_tile;
+    const int p = (int)(idx % per_tile);
+    unsigned char* base = img + t * L.bytes;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     int off_hi, off_lo;
-    if (p < 512) {   // Y: row r of the tile, 16-byte piece c (columns 4c .. 4c+3)
-        const int r = p >> 3, c = p & 7;
+    if (p < ypt) {   // Y: row r of the tile, 16-byte piece c (columns 4c .. 4c+3)
+        const int r = p / L.ypieces, c = p % L.ypieces;
         const int64_t j = t * TC_NT + r;
         if (j < M) {
 #pragma unroll
@@ -331,16 +419,26 @@ __global__ void tc_pack_kernel(const float* __restrict__ Y, int64_t M, int d, in
                 if (4 * c + q < d) v[q] = __ldg(Y + j * ldy + 4 * c + q);
         }
         off_hi = r * 128 + ((c ^ (r & 7)) << 4);
-        off_lo = TC_YH + off_hi;
+        // lo half: a separate 8 KB image, or pieces 4..7 of the same swizzle row (offset 64 B before swizzling)
+        off_lo = (L.ypieces == 8) ? L.y_lo + off_hi : r * 128 + (((c + 4) ^ (r & 7)) << 4);
+        // the row's scaled squared norm rides along with the tile: xor-shuffle over the row's 4 or 8 lanes
+        float q = v[0] * v[0];
+        q = fmaf(v[1], v[1], q);
+        q = fmaf(v[2], v[2], q);
+        q = fmaf(v[3], v[3], q);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        if (L.ypieces == 8) q += __shfl_xor_sync(0xffffffffu, q, 4);
+        if (c == 0) reinterpret_cast<float*>(base + L.yn)[r] = mult * q;
     } else {         // W^T: row = output column cc, K = j; piece holds 4 consecutive j
-        const int pw = p - 512;
+        const int pw = p - ypt;
         const int kc = pw >> 7, cc = (pw >> 3) & 15, c = pw & 7;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int64_t j = t * TC_NT + kc * 32 + 4 * c + q;
             if (j < M && cc < m) v[q] = __ldg(W + j * ldw + cc) * (col_pref ? __ldg(col_pref + j) : 1.f);
         }
-        off_hi = 2 * TC_YH + kc * (TC_MT * 128) + cc * 128 + ((c ^ (cc & 7)) << 4);
+        off_hi = L.w + kc * (TC_MT * 128) + cc * 128 + ((c ^ (cc & 7)) << 4);
         off_lo = off_hi + TC_WH;
     }
     uint4 h, l;
@@ -392,7 +490,7 @@ bool kmatw_tc_eligible(int64_t N, int64_t M, int d, int m, const float* dim_scal
 
 size_t kmatw_tc_workspace_bytes(int64_t N, int64_t M) {
     const int64_t n_tiles = (M + TC_NT - 1) / TC_NT;
-    return align256((size_t)n_tiles * TC_STAGE) + align256((size_t)N * 4) + align256((size_t)n_tiles * TC_NT * 4) + 1024;
+    return align256((size_t)n_tiles * tc_image(TC_DP).bytes) + align256((size_t)N * 4) + 1024;
 }
 
 int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
@@ -401,9 +499,9 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     Scratch scr(workspace, workspace_bytes, st);
     JRK_CUDA_OK(scr.reserve(kmatw_tc_workspace_bytes(N, M)));
     const int64_t n_tiles = (M + TC_NT - 1) / TC_NT;
-    float* img = scr.take<float>((size_t)n_tiles * (TC_STAGE / 4));
+    const TcImage L = tc_image(d);
+    unsigned char* img = scr.take<unsigned char>((size_t)n_tiles * L.bytes);
     float* xn = scr.take<float>((size_t)N);
-    float* yn = scr.take<float>((size_t)n_tiles * TC_NT);
     unsigned* nmax = scr.take<unsigned>(2);
 
     EpiParams ep = make_epi(scale, power, nconst);
@@ -411,26 +509,26 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     const float mult = (pm == PM_SQEXP) ? ep.c : 1.f;
     JRK_CUDA_OK(cudaMemsetAsync(nmax, 0, 2 * sizeof(unsigned), st));
     {
-        const int64_t tot = n_tiles * (512 + 256);
-        tc_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, col_pref, (int)n_tiles, img);
+        const int64_t tot = n_tiles * (TC_NT * L.ypieces + 256);
+        tc_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, col_pref, (int)n_tiles, mult, L, img);
         JRK_LAUNCHED();
         tc_rownorm_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(X, N, N, d, ldx, mult, xn, nmax);
         JRK_LAUNCHED();
-        const int64_t Mp = n_tiles * TC_NT;
-        tc_rownorm_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, st>>>(Y, M, Mp, d, ldy, mult, yn, nmax + 1);
+        // maximum of the Y norms for the skip decision (the norms themselves ride in the images)
+        tc_rownorm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(Y, M, 0, d, ldy, mult, nullptr, nmax + 1);
         JRK_LAUNCHED();
     }
     TcParams P;
-    P.X = X; P.ldx = ldx; P.d = d; P.Y = Y; P.ldy = ldy; P.xn = xn; P.yn = yn; P.img = img; P.row_pref = row_pref;
+    P.X = X; P.ldx = ldx; P.d = d; P.Y = Y; P.ldy = ldy; P.xn = xn; P.img = img; P.L = L; P.row_pref = row_pref;
     P.out = out; P.ldo = ldo; P.m = m; P.N = N; P.M = M;
     P.n_tiles = (int)n_tiles;
     P.n_units = (int)((N + TC_BM - 1) / TC_BM);
     P.ksteps = (d + 7) / 8;
     P.a = (pm == PM_SQEXP) ? -2.f * ep.c : -2.f;
-    // p = 2: the near-zero test only matters when the norms are large against the length scale; deciding that needs
-    // the device-side maxima, so it stays enabled here unless the host can rule it out cheaply (it cannot): keep it on
-    P.check = 1;
-    P.win = TC_WIN;
+    // p = 2: the near-zero test only matters when the norms are large against the length scale; the kernel decides
+    // from the device-side maxima of the pre-pass (no host synchronisation)
+    P.check = 0;
+    P.nmax = nmax;
     if (pm == PM_SQEXP) return tc_launch<PM_SQEXP>(P, ep, st);
     if (pm == PM_LAPLACE) return tc_launch<PM_LAPLACE>(P, ep, st);
     return tc_launch<PM_GENERAL>(P, ep, st);

@@ -1,5 +1,5 @@
 """Small fixed launches of the hot kernels for `ncu --set full` captures (one launch each, after one warm-up).
-Usage: python tools/profile_target.py [gram64|gram16|gram8|kmatw|all]"""
+Usage: python tools/profile_target.py [gram64|gram16|gram8|kmatw|kmatw_tc|all]"""
 import os
 import sys
 
@@ -34,6 +34,14 @@ def kmatw():
     torch.cuda.synchronize()
 
 
+def kmatw_tc():
+    N, M, d, m = 148 * 256, 131072, 16, 16
+    X, Y, W = randn(0, N, d), randn(1, M, d), randn(2, M, m)
+    for _ in range(2):
+        nat.kmatw(X, Y, W, 0.1767767, 2.0, 0.25)
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gram64", "all"):
@@ -44,4 +52,6 @@ if __name__ == "__main__":
         gram(8)
     if what in ("kmatw", "all"):
         kmatw()
+    if what == "kmatw_tc":
+        kmatw_tc()
     print("done", nat.launch_count())
