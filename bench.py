@@ -64,6 +64,14 @@ def fp32_pipe_peak():
     return 148 * 128 * 1.965e9, "nominal 148 SM x 128 lanes x 1.965 GHz"
 
 
+def mufu_peak():
+    """MUFU ex2 results/s: measured on B200 (profiles/microbench/pipes.cu); the tensor-core K@W path issues one per pair."""
+    p = os.path.join(ROOT, "profiles", "microbench", "pipes_b200.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["mufu_ex2_per_s"]), "measured (profiles/microbench/pipes_b200.json)"
+    return 148 * 16 * 1.965e9, "nominal 148 SM x 16 MUFU lanes x 1.965 GHz"
+
+
 def traffic_for(name):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
@@ -249,12 +257,23 @@ def run_workload(name, args, torch, nat, dist_ctx, with_cpu):
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                 "traffic": traffic_for(name), "peak_source": hbm_src, "kernel_ms": t_local / steps * 1e3,
                 "algorithmic_bytes_per_launch": alg_bytes}
+    elif nat.lib().jrk_kmatw_uses_tensor_cores(n_local, M, d, m, 0, 0):
+        # both contractions on tcgen05 (kmatw_tc.cu): what remains per pair is one MUFU ex2 and ~9 issue slots, so
+        # the bound is the MUFU pipe; the FP32-pipe kernel's figure of merit is kept alongside for comparison
+        pk, src = mufu_peak()
+        achieved = float(n_local) * M / (t_local / steps)
+        fpk, _ = fp32_pipe_peak()
+        roof = {"bound": "mufu", "achieved": achieved / 1e12, "peak": pk / 1e12, "unit": "T ex2/s",
+                "frac": achieved / pk, "traffic": traffic_for("kmatw_tc"), "peak_source": src,
+                "kernel_ms": t_local / steps * 1e3, "mufu_per_eval": 1, "path": "tcgen05 3xTF32 (kmatw_tc.cu)",
+                "fp32_pipe_equiv_frac": alg_ops / (t_local / steps) / fpk,
+                "tflops_equiv": float(n_local) * M * (3 * d + 2 * m + 4) / (t_local / steps) / 1e12}
     else:
         pk, src = fp32_pipe_peak()
         achieved = alg_ops / (t_local / steps)
         roof = {"bound": "fp32_pipe", "achieved": achieved / 1e12, "peak": pk / 1e12, "unit": "T lane-op/s",
                 "frac": achieved / pk, "traffic": traffic_for(name), "peak_source": src,
-                "kernel_ms": t_local / steps * 1e3, "lane_ops_per_eval": 2 * d + m + 2,
+                "kernel_ms": t_local / steps * 1e3, "lane_ops_per_eval": 2 * d + m + 2, "path": "FP32 pipe (kmatw.cu)",
                 "mufu_per_eval": 1, "tflops_equiv": float(n_local) * M * (3 * d + 2 * m + 4) / (t_local / steps) / 1e12}
 
     # ---- end to end through the host-buffer C-ABI entry point ---------------------------------

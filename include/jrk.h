@@ -119,6 +119,11 @@ int jrk_kmatw_f32(const float *X, const float *Y, const float *W, float *out,
 
 size_t jrk_kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce, int64_t group);
 
+/* 1 when jrk_kmatw_f32 would run both contractions of this problem on the tensor cores (kmatw_tc.cu: d <= 32,
+ * m <= 16, no per-dimension scale, row_reduce NONE, large N and M, JRK_KMATW_TC != "0"), else 0 (FP32-pipe kernel).
+ * Introspection only (bench.py picks the roofline by it); results agree within the documented tolerance. */
+int jrk_kmatw_uses_tensor_cores(int64_t N, int64_t M, int d, int m, int has_dim_scale, int row_reduce);
+
 /* ------------------------------------------------------------------------------
  * Group-reduced Gram:  out[a, b] = sum_{i in group a} sum_{j in group b}
  *                                   row_pref[i] * k(x_i, y_j) * col_pref[j]

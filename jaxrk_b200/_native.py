@@ -35,6 +35,7 @@ SIGNATURES = {
     "jrk_dist_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64,
                              c_float, c_void_p, c_float, c_void_p]),
     "jrk_kmatw_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int64]),
+    "jrk_kmatw_uses_tensor_cores": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "jrk_kmatw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                               c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_float, c_float,
                               c_void_p, c_void_p, c_int, c_int64, c_void_p, c_size_t, c_void_p]),

@@ -24,6 +24,7 @@ int kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N,
           float nconst, const float* row_pref, const float* col_pref, int row_reduce, int64_t group,
           void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce, int64_t group);
+bool kmatw_uses_tc(int64_t N, int64_t M, int d, int m, bool has_dim_scale, int row_reduce);
 int gram_groupsum(const float* X, const float* Y, float* out, int64_t N, int64_t M, int d, int64_t ldx,
                   int64_t ldy, int64_t ldo, float scale, const float* dim_scale, float power, float nconst,
                   const float* row_pref, const float* col_pref, int64_t gx, int64_t gy, int average,
@@ -125,6 +126,10 @@ int jrk_dist_f32(const float* X, const float* Y, float* D, int64_t N, int64_t M,
 
 size_t jrk_kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce, int64_t group) {
     return kmatw_workspace_bytes(N, M, d, m, row_reduce, group);
+}
+
+int jrk_kmatw_uses_tensor_cores(int64_t N, int64_t M, int d, int m, int has_dim_scale, int row_reduce) {
+    return kmatw_uses_tc(N, M, d, m, has_dim_scale != 0, row_reduce) ? 1 : 0;
 }
 
 static int check_kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d,

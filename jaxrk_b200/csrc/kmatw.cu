@@ -458,19 +458,23 @@ static int kmatw_block(const float* X, const float* Y, const float* W, float* ou
     return JRK_OK;
 }
 
+// The dispatch rule, in one place (also behind jrk_kmatw_uses_tensor_cores): JRK_KMATW_TC=0 forces the FP32-pipe kernel.
+bool kmatw_uses_tc(int64_t N, int64_t M, int d, int m, bool has_dim_scale, int row_reduce) {
+    const char* e = getenv("JRK_KMATW_TC");
+    if (e && e[0] == '0') return false;
+    static const float dummy = 1.f;
+    return kmatw_tc_eligible(N, M, d, m, has_dim_scale ? &dummy : nullptr, row_reduce, 1.f);
+}
+
 int kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,
           int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale, const float* dim_scale, float power,
           float nconst, const float* row_pref, const float* col_pref, int row_reduce, int64_t group,
           void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (d > 128) return fail(JRK_ERR_UNSUPPORTED, "kmatw: d = %d > 128 not supported by the fused kernel", d);
-    // both contractions on the tensor cores when the problem is large, narrow and plain (kmatw_tc.cu);
-    // JRK_KMATW_TC=0 forces the FP32-pipe kernel below
-    {
-        const char* e = getenv("JRK_KMATW_TC");
-        if (!(e && e[0] == '0') && kmatw_tc_eligible(N, M, d, m, dim_scale, row_reduce, nconst))
-            return kmatw_tc(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, power, nconst, row_pref, col_pref,
-                            workspace, workspace_bytes, st);
-    }
+    // both contractions on the tensor cores when the problem is large, narrow and plain (kmatw_tc.cu)
+    if (kmatw_uses_tc(N, M, d, m, dim_scale != nullptr, row_reduce))
+        return kmatw_tc(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, power, nconst, row_pref, col_pref,
+                        workspace, workspace_bytes, st);
     Scratch scr(workspace, workspace_bytes, st);
     JRK_CUDA_OK(scr.reserve(kmatw_workspace_bytes(N, M, d, m, row_reduce, group)));
     for (int c0 = 0; c0 < m; c0 += 32) {  // wide W: column blocks of 32 (K is recomputed per block)

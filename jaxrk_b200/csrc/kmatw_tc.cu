@@ -242,10 +242,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
         const int cg = e >> 2;                              // 16-column group of the tile
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const f32x2 a2 = pack2(P.a, P.a), ntau2 = pack2(-TF_TAU, -TF_TAU);
-        // shared addresses of the barriers this role touches, computed once
-        const uint32_t b_sfull = smem_u32(s_full), b_eready = smem_u32(e_ready), b_ofull = smem_u32(o_full),
-                       b_oempty = smem_u32(o_empty), b_opfull = smem_u32(op_full);
-        const uint32_t yn_base = smem_u32(smem) + P.L.yn + cg * 64;
+        // shared-window base in an opaque register (otherwise the address conversion is rematerialised per tile)
+        uint32_t sbase;
+        asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));
+        const uint32_t b_opfull = sbase + TC_OFF_BAR, b_sfull = b_opfull + 2 * TC_SOP * 8, b_eready = b_sfull + TC_SS * 8,
+                       b_ofull = b_eready + 2 * TC_SS * 8, b_oempty = b_ofull + 16;
+        const uint32_t yn_base = sbase + P.L.yn + cg * 64;
         // near-zero test needed?  (p = 2: only when the norms are large against the length scale)
         bool check = true;
         if (PM == PM_SQEXP && !P.check)
@@ -358,9 +360,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 // e = unnormalised kernel value (> 0); split into tf32 hi / lo and write back over S
                 uint32_t ehi[16], elo[16];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float ev = (PM == PM_SQEXP) ? ex2_approx(uu[c]) : kexp_unnorm<PM>(uu[c], ep);
-                    split_trunc(ev, ehi[c], elo[c]);
+                for (int c = 0; c < 16; c += 2) {
+                    const float e0 = (PM == PM_SQEXP) ? ex2_approx(uu[c]) : kexp_unnorm<PM>(uu[c], ep);
+                    const float e1 = (PM == PM_SQEXP) ? ex2_approx(uu[c + 1]) : kexp_unnorm<PM>(uu[c + 1], ep);
+                    ehi[c] = __float_as_uint(e0) & 0xFFFFE000u;          // hi by truncation, lo = e - hi >= 0 exact
+                    ehi[c + 1] = __float_as_uint(e1) & 0xFFFFE000u;
+                    float l0, l1;
+                    unpack2(sub2(pack2(e0, e1), pack2(__uint_as_float(ehi[c]), __uint_as_float(ehi[c + 1]))), l0, l1);
+                    elo[c] = __float_as_uint(l0);
+                    elo[c + 1] = __float_as_uint(l1);
                 }
                 tmem_st16(sc, ehi);
                 tmem_st16(sc + 64, elo);
