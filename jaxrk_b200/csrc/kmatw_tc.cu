@@ -30,6 +30,7 @@
 // hi_e.hi_w and the two small cross terms go to separate accumulators (8 instead of 24 MMAs per tile on the one
 // that matters).
 // Near-coincident pairs (sq < (|x|^2+|y|^2)/64) are recomputed by FP32 direct differencing, as in the Gram kernel.
+#include <cstdlib>
 #include <type_traits>
 
 #include "gram_tf32_kernel.cuh"
@@ -48,6 +49,12 @@ constexpr int TC_SOP = 6;
 constexpr int TC_EW = 16;
 constexpr int TC_THREADS = (3 + TC_EW) * 32;
 constexpr int TC_WIN = 2;                                // tiles per O window (128 j); a power of two
+// p = 2 "factored" fast path: taken when |c| (max|x|^2 + max|y|^2) <= TC_FAST_BOUND (decided on the device from
+// the pre-pass maxima).  There K_ij = 2^(c|x_i|^2) . 2^(-2c x_i.y_j) . 2^(c|y_j|^2) with every factor inside
+// [2^-8, 2^8]: the column factor is folded into W and the scale -2c into Y by the pack pre-pass, the row factor is
+// applied once per output row, and the epilogue is reduced to  e = ex2(S)  (no norms, no near-zero test, one
+// accumulator).  Worst-case relative error of a term: ~4e-7 * bound (3xTF32 + truncating accumulation), < 1e-5.
+constexpr float TC_FAST_BOUND = 8.0f;
 constexpr int TC_COL_X = 0, TC_COL_S = 64, TC_COL_O = 64 + TC_SS * 128;   // TMEM columns
 constexpr int TC_OFF_BAR = TC_SOP * TC_STAGE;
 constexpr int TC_NBAR = 2 * TC_SOP + 3 * TC_SS + 4 + 1;  // op full/empty, s_full/e_ready/s_empty, o_full/o_empty x2, x_ready
@@ -118,7 +125,21 @@ struct TcParams {
     float a;                               // PM_SQEXP: -2c; else -2
     int check;                             // 1: near-zero refinement always; 0: only if the norm maxima demand it
     const unsigned* nmax;                  // [2] bit patterns of max |mult| |x|^2, max |mult| |y|^2
+    int allow_fast;                        // 0 disables the factored p = 2 path (JRK_TC_FAST=0, tests)
 };
+
+__device__ __forceinline__ bool tc_fast_regime(const unsigned* nmax) {
+    return (__uint_as_float(__ldg(nmax)) + __uint_as_float(__ldg(nmax + 1))) <= TC_FAST_BOUND;
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 
 template <int PM>
 __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, EpiParams ep) {
@@ -136,10 +157,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + TC_NBAR * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // factored p = 2 path?  (warp-uniform, the same decision in every CTA and in the pack pre-pass)
+    const bool fast = (PM == PM_SQEXP) && P.allow_fast && tc_fast_regime(P.nmax);
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_SOP; ++s) { mbar_init(&op_full[s], 1); mbar_init(&op_empty[s], 1); }
         for (int s = 0; s < TC_SS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&e_ready[s], TC_EW); mbar_init(&s_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4); }
+        // the O windows are folded by the 4 warps of column group 0 (generic path) or by all 16 warps (fast path)
+        for (int s = 0; s < 2; ++s) { mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], fast ? TC_EW : 4); }
         mbar_init(x_ready, TC_EW);
         fence_mbar_init();
     }
@@ -186,11 +210,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 const uint64_t dyh = dbase + (uint64_t)((s * TC_STAGE) >> 4), dyl = dyh + y_lo;
                 const uint32_t c1 = TC_COL_S + a * 128, c2 = c1 + 64;
                 if (elect_one()) {
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint64_t off = (uint64_t)(ks * 2);
-                        mma_tf32_ts(c1, TC_COL_X + ks * 8, dyh + off, idesc1, ks);            // hi_x . hi_y
-                        mma_tf32_ts(c2, TC_COL_X + ks * 8, dyl + off, idesc1, ks);            // hi_x . lo_y
-                        mma_tf32_ts(c2, TC_COL_X + TC_DP + ks * 8, dyh + off, idesc1, 1u);    // lo_x . hi_y
+                    if (fast) {
+                        // one accumulator: the small cross terms first, the hi.hi terms last (the accumulator
+                        // truncates, so only the last `ksteps` additions carry a rounding error that matters)
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t off = (uint64_t)(ks * 2);
+                            mma_tf32_ts(c1, TC_COL_X + ks * 8, dyl + off, idesc1, ks);            // hi_x . lo_y
+                            mma_tf32_ts(c1, TC_COL_X + TC_DP + ks * 8, dyh + off, idesc1, 1u);    // lo_x . hi_y
+                        }
+                        for (int ks = 0; ks < ksteps; ++ks)
+                            mma_tf32_ts(c1, TC_COL_X + ks * 8, dyh + (uint64_t)(ks * 2), idesc1, 1u);   // hi_x . hi_y
+                    } else {
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t off = (uint64_t)(ks * 2);
+                            mma_tf32_ts(c1, TC_COL_X + ks * 8, dyh + off, idesc1, ks);            // hi_x . hi_y
+                            mma_tf32_ts(c2, TC_COL_X + ks * 8, dyl + off, idesc1, ks);            // hi_x . lo_y
+                            mma_tf32_ts(c2, TC_COL_X + TC_DP + ks * 8, dyh + off, idesc1, 1u);    // lo_x . hi_y
+                        }
                     }
                     tc_commit_addr(b_sfull + a * 8);
                 }
@@ -233,6 +269,96 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 if (win_last) { ob ^= 1; if (ob == 0) ob_ph ^= 1; }
                 if (++s == TC_SOP) { s = 0; s_ph ^= 1; }
                 if (++a == TC_SS) { a = 0; a_ph ^= 1; }
+            }
+        }
+    } else if (fast) {
+        // ===================== epilogue of the factored p = 2 path (and X loader) =====================
+        // S already holds -2c x_i.y_j (the scale rides in the Y image), so a tile is: LDTM, 16 MUFU.EX2, tf32
+        // split, 2 STTM.  Every warp folds its own 4 + 4 columns of the O window (balanced), and the row factor
+        // nconst . pref_i . 2^(c|x_i|^2) is applied once per output row.
+        const int e = warp - 3;
+        const int quad = warp & 3;
+        const int cg = e >> 2;
+        uint32_t lane_base;      // TMEM address of this warp's lane quarter, in an opaque register
+        asm volatile("mov.u32 %0, %1;" : "=r"(lane_base) : "r"(tmem_base + ((uint32_t)(quad * 32) << 16)));
+        uint32_t sbase;
+        asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));
+        const uint32_t b_sfull0 = sbase + TC_OFF_BAR + 2 * TC_SOP * 8, b_ofull = b_sfull0 + 3 * TC_SS * 8, b_oempty = b_ofull + 16;
+        const uint32_t s_col0 = lane_base + TC_COL_S + cg * 16, o_col0 = lane_base + TC_COL_O + cg * 4;
+        uint32_t wc = 0;
+        uint32_t sa = 0, sa_ph = 0;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+            const int64_t i = (int64_t)u * TC_BM + quad * 32 + lane;
+            const bool iok = i < P.N;
+            const float* xrow = P.X + (iok ? i : 0) * P.ldx;
+            if (cg * 16 < P.d) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int kk = cg * 16 + k;
+                    const float v = (iok && kk < P.d) ? __ldg(xrow + kk) : 0.f;
+                    split_tf32(v, hi[k], lo[k]);
+                }
+                tmem_st16(lane_base + TC_COL_X + cg * 16, hi);
+                tmem_st16(lane_base + TC_COL_X + TC_DP + cg * 16, lo);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(x_ready);
+            float oacc[4] = {0.f, 0.f, 0.f, 0.f};
+
+            auto fold_window = [&]() {   // O buffers of window wc, this warp's 4 columns -> registers
+                const uint32_t ob = wc & 1;
+                bar_wait(b_ofull + ob * 8, (wc >> 1) & 1);
+                tc_fence_after();
+                float o[4], ox[4];
+                tmem_ld4(o_col0 + ob * 2 * TC_MT, o);
+                tmem_ld4(o_col0 + ob * 2 * TC_MT + TC_MT, ox);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive(b_oempty + ob * 8);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) oacc[c] += o[c] + ox[c];
+                ++wc;
+            };
+
+            for (int t = 0; t < T; ++t) {
+                bar_wait(b_sfull0 + sa * 8, sa_ph);
+                tc_fence_after();
+                const uint32_t sc = s_col0 + sa * 128;
+                float sv[16];
+                tmem_ld16(sc, sv);
+                tmem_ld_wait();
+                uint32_t ehi[16], elo[16];
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    const float e0 = ex2_approx(sv[c]), e1 = ex2_approx(sv[c + 1]);
+                    ehi[c] = __float_as_uint(e0) & 0xFFFFE000u;          // hi by truncation, lo = e - hi >= 0 exact
+                    ehi[c + 1] = __float_as_uint(e1) & 0xFFFFE000u;
+                    float l0, l1;
+                    unpack2(sub2(pack2(e0, e1), pack2(__uint_as_float(ehi[c]), __uint_as_float(ehi[c + 1]))), l0, l1);
+                    elo[c] = __float_as_uint(l0);
+                    elo[c + 1] = __float_as_uint(l1);
+                }
+                tmem_st16(sc, ehi);
+                tmem_st16(sc + 64, elo);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive(b_sfull0 + TC_SS * 8 + sa * 8);      // e_ready[sa]
+                if (++sa == TC_SS) { sa = 0; sa_ph ^= 1; }
+                // fold the previous window once its last GEMM2 has been issued (one tile later)
+                if (t > 0 && (t & (TC_WIN - 1)) == 0) fold_window();
+            }
+            fold_window();   // the unit's last (possibly partial) window
+            if (iok) {
+                const float f = ep.nconst * ex2_approx(__ldg(P.xn + i)) * (P.row_pref ? __ldg(P.row_pref + i) : 1.f);
+                float* dst = P.out + i * P.ldo + cg * 4;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (cg * 4 + c < P.m) dst[c] = f * oacc[c];
             }
         }
     } else {
@@ -406,9 +532,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
 }
 
 // ---- pre-pass: per-tile images [Y hi, Y lo | W^T hi | W^T lo | yn], one thread per 16-byte piece ----
+// Factored p = 2 path (fast_ok and the norm maxima inside TC_FAST_BOUND): Y is stored as a.y (a = -2c) and W_j as
+// W_j . 2^(c|y_j|^2) (yn_all: the scaled norms from tc_rownorm_kernel), see TC_FAST_BOUND.
 __global__ void tc_pack_kernel(const float* __restrict__ Y, int64_t M, int d, int64_t ldy, const float* __restrict__ W,
                                int m, int64_t ldw, const float* __restrict__ col_pref, int n_tiles, float mult,
-                               TcImage L, unsigned char* __restrict__ img) {
+                               TcImage L, unsigned char* __restrict__ img, int fast_ok, float a,
+                               const float* __restrict__ yn_all, const unsigned* __restrict__ nmax) {
+    const bool fast = fast_ok && tc_fast_regime(nmax);
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int ypt = TC_NT * L.ypieces;            // Y pieces per tile (256 or 512: whole warps)
     const int per_tile = ypt + 256;
@@ -438,13 +568,20 @@ __global__ void tc_pack_kernel(const float* __restrict__ Y, int64_t M, int d, in
         q += __shfl_xor_sync(0xffffffffu, q, 2);
         if (L.ypieces == 8) q += __shfl_xor_sync(0xffffffffu, q, 4);
         if (c == 0) reinterpret_cast<float*>(base + L.yn)[r] = mult * q;
+        if (fast) {
+#pragma unroll
+            for (int q2 = 0; q2 < 4; ++q2) v[q2] *= a;
+        }
     } else {         // W^T: row = output column cc, K = j; piece holds 4 consecutive j
         const int pw = p - ypt;
         const int kc = pw >> 7, cc = (pw >> 3) & 15, c = pw & 7;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int64_t j = t * TC_NT + kc * 32 + 4 * c + q;
-            if (j < M && cc < m) v[q] = __ldg(W + j * ldw + cc) * (col_pref ? __ldg(col_pref + j) : 1.f);
+            if (j < M && cc < m) {
+                v[q] = __ldg(W + j * ldw + cc) * (col_pref ? __ldg(col_pref + j) : 1.f);
+                if (fast) v[q] *= ex2_approx(__ldg(yn_all + j));
+            }
         }
         off_hi = L.w + kc * (TC_MT * 128) + cc * 128 + ((c ^ (cc & 7)) << 4);
         off_lo = off_hi + TC_WH;
@@ -498,7 +635,7 @@ bool kmatw_tc_eligible(int64_t N, int64_t M, int d, int m, const float* dim_scal
 
 size_t kmatw_tc_workspace_bytes(int64_t N, int64_t M) {
     const int64_t n_tiles = (M + TC_NT - 1) / TC_NT;
-    return align256((size_t)n_tiles * tc_image(TC_DP).bytes) + align256((size_t)N * 4) + 1024;
+    return align256((size_t)n_tiles * tc_image(TC_DP).bytes) + align256((size_t)N * 4) + align256((size_t)M * 4) + 1024;
 }
 
 int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
@@ -510,20 +647,26 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     const TcImage L = tc_image(d);
     unsigned char* img = scr.take<unsigned char>((size_t)n_tiles * L.bytes);
     float* xn = scr.take<float>((size_t)N);
+    float* yn_all = scr.take<float>((size_t)M);
     unsigned* nmax = scr.take<unsigned>(2);
 
     EpiParams ep = make_epi(scale, power, nconst);
     const int pm = pick_pmode(power);
     const float mult = (pm == PM_SQEXP) ? ep.c : 1.f;
     JRK_CUDA_OK(cudaMemsetAsync(nmax, 0, 2 * sizeof(unsigned), st));
+    const float a_scale = (pm == PM_SQEXP) ? -2.f * ep.c : -2.f;
+    const char* fast_env = getenv("JRK_TC_FAST");
+    const int allow_fast = (pm == PM_SQEXP) && !(fast_env && fast_env[0] == '0');
     {
-        const int64_t tot = n_tiles * (TC_NT * L.ypieces + 256);
-        tc_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, col_pref, (int)n_tiles, mult, L, img);
-        JRK_LAUNCHED();
+        // scaled row norms and their maxima first: the pack kernel and the main kernel both decide from the maxima
+        // (on the device, no host synchronisation) whether the factored p = 2 path applies
         tc_rownorm_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(X, N, N, d, ldx, mult, xn, nmax);
         JRK_LAUNCHED();
-        // maximum of the Y norms for the skip decision (the norms themselves ride in the images)
-        tc_rownorm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(Y, M, 0, d, ldy, mult, nullptr, nmax + 1);
+        tc_rownorm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(Y, M, M, d, ldy, mult, yn_all, nmax + 1);
+        JRK_LAUNCHED();
+        const int64_t tot = n_tiles * (TC_NT * L.ypieces + 256);
+        tc_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, col_pref, (int)n_tiles, mult, L, img,
+                                                                      allow_fast, a_scale, yn_all, nmax);
         JRK_LAUNCHED();
     }
     TcParams P;
@@ -532,7 +675,8 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     P.n_tiles = (int)n_tiles;
     P.n_units = (int)((N + TC_BM - 1) / TC_BM);
     P.ksteps = (d + 7) / 8;
-    P.a = (pm == PM_SQEXP) ? -2.f * ep.c : -2.f;
+    P.a = a_scale;
+    P.allow_fast = allow_fast;
     // p = 2: the near-zero test only matters when the norms are large against the length scale; the kernel decides
     // from the device-side maxima of the pre-pass (no host synchronisation)
     P.check = 0;

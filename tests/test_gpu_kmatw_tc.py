@@ -94,3 +94,30 @@ def test_tc_path_through_the_api_cfg5_apply_shape(force):
     ref = inner(FiniteVec(k, Xt), FiniteVec(k, X, [LinearReduce(A)]))
     assert tuple(out.shape) == (T_, m)
     assert torch.allclose(out, ref, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("ls_factor,expect", [(1.0, "fast"), (0.75, "fast-edge"), (0.4, "generic")])
+def test_tc_factored_sqexp_path_regimes(ls_factor, expect, force, monkeypatch):
+    """p = 2: below |c| (max|x|^2 + max|y|^2) = 8 the kernel factors K_ij = 2^(c|x|^2) 2^(-2c x.y) 2^(c|y|^2)
+    (kmatw_tc.cu: TC_FAST_BOUND); above it the generic epilogue runs.  Both must agree with the oracle and with the
+    generic epilogue forced by JRK_TC_FAST=0."""
+    N, M, d, m = 8192 + 5, 8192 + 64 + 3, 16, 16
+    X, Y, W = gauss(0, N, d), gauss(1, M, d), np.abs(gauss(2, M, m))      # all-positive sums: the hard case
+    s, scale, p, nconst = kparams("sqexp", np.sqrt(d) * ls_factor)
+    c = float(scale) ** 2 * 1.4426950408889634
+    bound_val = c * ((X.astype(np.float64) ** 2).sum(1).max() + (Y.astype(np.float64) ** 2).sum(1).max())
+    if expect == "generic":
+        assert bound_val > 8.0
+    else:
+        assert bound_val <= 8.0 and (expect == "fast" or bound_val > 5.0)
+    force(True)
+    T = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst)
+    monkeypatch.setenv("JRK_TC_FAST", "0")
+    G = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst)
+    monkeypatch.delenv("JRK_TC_FAST")
+    rows = np.r_[0:96, N - 96:N]
+    truth, bound = _sample_truth(X, Y, W, s, p, rows)
+    assert_kmatw_close(T.cpu().numpy()[rows], truth, bound, f"tc sqexp {expect}")
+    assert_kmatw_close(G.cpu().numpy()[rows], truth, bound, f"tc sqexp {expect}, generic epilogue")
+    b = torch.from_numpy(bound.max(0)).to(T.device).float()
+    assert ((T - G).abs() <= 2e-6 + 2e-5 * b).all()

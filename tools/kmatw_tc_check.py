@@ -33,6 +33,14 @@ if len(_s.argv) > 1 and _s.argv[1] == "dbg":
     for w in ("0", "4", "8", "1", "2", "3", "11", "27", "31"):
         os.environ["JRK_TC_DBG"] = w; print("DBG", w, end=": "); run(131072, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
     _s.exit(0)
+if len(_s.argv) > 1 and _s.argv[1] == "fast":
+    for f in ("1", "0"):
+        os.environ["JRK_TC_FAST"] = f; print("JRK_TC_FAST", f)
+        run(16384, 65536, 16, 16, 2.0, positive=True)
+        run(131072, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
+        run(131072, 1 << 20, 8, 16, 2.0, timing=True)
+        run(131072, 1 << 20, 32, 16, 2.0, timing=True)
+    _s.exit(0)
 run(8192, 4096, 16, 16, 2.0)
 run(8192 + 77, 4096 + 33, 16, 16, 2.0)
 run(8192, 8192, 7, 5, 1.0)
