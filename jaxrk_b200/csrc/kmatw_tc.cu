@@ -64,7 +64,7 @@ static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
 // Byte layout of one tile image.  packed (d <= 16): a Y row is [16 hi | 16 lo] floats in one 128-byte swizzle row.
 struct TcImage {
     int y_lo;      // offset of the lo half relative to the hi half (what the GEMM1 descriptors differ by)
-    int w;         // offset of W^T hi; W^T lo follows at + TC_WH
+    int w;         // offset of the W^T image: per 32-column k-chunk 16 rows hi then 16 rows lo (2 x TC_WH bytes in all)
     int yn;        // offset of the 64 scaled squared norms
     int bytes;     // image size (multiple of 16)
     int ypieces;   // 16-byte pieces of Y per row handled by the pack kernel (4 or 8)
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
     } else if (warp == 2) {
         // ===================== GEMM2 issuer:  O[window] += e . W  (3xTF32) =====================
         constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_MT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        constexpr uint32_t idesc2w = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * TC_MT) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
         const uint64_t dbase = make_b_desc(smem_u32(smem));
         const uint32_t b_opfull = smem_u32(op_full), b_opempty = smem_u32(op_empty), b_sempty = smem_u32(s_empty),
                        b_eready = smem_u32(e_ready), b_ofull = smem_u32(o_full), b_oempty = smem_u32(o_empty);
@@ -250,16 +251,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 bar_wait(b_opfull + s * 8, s_ph);
                 bar_wait(b_eready + a * 8, a_ph);
                 tc_fence_after();
-                const uint64_t dwh = dbase + (uint64_t)((s * TC_STAGE) >> 4) + w_off, dwl = dwh + (uint64_t)(TC_WH >> 4);
+                const uint64_t dwh = dbase + (uint64_t)((s * TC_STAGE) >> 4) + w_off;
                 const uint32_t eh = TC_COL_S + a * 128, el = eh + 64, oc = TC_COL_O + ob * 2 * TC_MT, ox = oc + TC_MT;
                 if (elect_one()) {
+                    // an MMA of N <= 32 costs ~20 clk whatever N is (profiles/microbench/mma_rate.cu), so hi_e meets
+                    // [W^T hi ; W^T lo] in ONE MMA of N = 32 whose 32 result columns are {main | cross}
 #pragma unroll
                     for (int k = 0; k < TC_NT / 8; ++k) {
-                        const uint64_t off = (uint64_t)(((k >> 2) * TC_MT * 128 + (k & 3) * 32) >> 4);
+                        const uint64_t off = (uint64_t)(((k >> 2) * 2 * TC_MT * 128 + (k & 3) * 32) >> 4);
                         const uint32_t acc0 = (win_first && k == 0) ? 0u : 1u;
-                        mma_tf32_ts(oc, eh + k * 8, dwh + off, idesc2, acc0);   // hi_e . hi_w   (main accumulator)
-                        mma_tf32_ts(ox, eh + k * 8, dwl + off, idesc2, acc0);   // hi_e . lo_w   (cross accumulator)
-                        mma_tf32_ts(ox, el + k * 8, dwh + off, idesc2, 1u);     // lo_e . hi_w
+                        mma_tf32_ts(oc, eh + k * 8, dwh + off, idesc2w, acc0);  // hi_e . [hi_w | lo_w] -> {main, cross}
+                        mma_tf32_ts(ox, el + k * 8, dwh + off, idesc2, 1u);     // lo_e . hi_w          -> cross
                     }
                     tc_commit_addr(b_sempty + a * 8);      // S / e stage reusable
                     tc_commit_addr(b_opempty + s * 8);     // operand stage reusable
@@ -583,8 +585,9 @@ __global__ void tc_pack_kernel(const float* __restrict__ Y, int64_t M, int d, in
                 if (fast) v[q] *= ex2_approx(__ldg(yn_all + j));
             }
         }
-        off_hi = L.w + kc * (TC_MT * 128) + cc * 128 + ((c ^ (cc & 7)) << 4);
-        off_lo = off_hi + TC_WH;
+        // per k-chunk: 16 rows of W^T hi, then 16 rows of W^T lo (together the N = 32 operand of GEMM2)
+        off_hi = L.w + kc * (2 * TC_MT * 128) + cc * 128 + ((c ^ (cc & 7)) << 4);
+        off_lo = off_hi + TC_MT * 128;
     }
     uint4 h, l;
     split_tf32(v[0], h.x, l.x);

@@ -33,6 +33,9 @@ if len(_s.argv) > 1 and _s.argv[1] == "dbg":
     for w in ("0", "4", "8", "1", "2", "3", "11", "27", "31"):
         os.environ["JRK_TC_DBG"] = w; print("DBG", w, end=": "); run(131072, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
     _s.exit(0)
+if len(_s.argv) > 1 and _s.argv[1] == "fast1":
+    run(131072, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
+    _s.exit(0)
 if len(_s.argv) > 1 and _s.argv[1] == "fast":
     for f in ("1", "0"):
         os.environ["JRK_TC_FAST"] = f; print("JRK_TC_FAST", f)
