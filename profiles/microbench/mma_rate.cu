@@ -96,5 +96,14 @@ int main() {
                 printf("{\"bench\": \"mma_tf32\", \"a_from\": \"%s\", \"M\": 128, \"N\": %d, \"K\": 8, \"accumulators\": %d, \"clk_per_mma\": %.2f, \"tflops_chip\": %.1f}\n",
                        mode == 0 ? "tmem" : "smem", N, ndst, avg / iters, 2.0 * 128 * N * 8 * iters / avg * 1.965e9 * sms / 1e12);
             }
+    // latency of issue -> commit -> mbarrier observed by the issuing warp, for a few MMAs (N = 64, A from TMEM)
+    for (int it : {1, 2, 4, 8}) {
+        for (int rep = 0; rep < 2; ++rep) { k_mma<0><<<sms, 128, smem>>>(clk, 64, it, 1); CK(cudaDeviceSynchronize()); }
+        long long h[256];
+        CK(cudaMemcpy(h, clk, sms * 8, cudaMemcpyDeviceToHost));
+        double avg = 0;
+        for (int i = 0; i < sms; ++i) avg += (double)h[i];
+        printf("{\"bench\": \"mma_commit_latency\", \"N\": 64, \"mmas\": %d, \"clk_issue_to_barrier\": %.0f}\n", it, avg / sms);
+    }
     return 0;
 }
