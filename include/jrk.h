@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define JRK_ABI_VERSION 1
+#define JRK_ABI_VERSION 2
 
 /* error codes */
 #define JRK_OK 0
@@ -57,6 +57,17 @@ extern "C" {
 #define JRK_REDUCE_MEAN 2      /* Mean (reduce/base.py:142-150): out is 1 x m              */
 #define JRK_REDUCE_BALANCED 3  /* BalancedRed(group, average=False) (:152-181): (N/group) x m */
 #define JRK_REDUCE_BALANCED_MEAN 4 /* BalancedRed(group, average=True)                     */
+
+/* kernel families of the *_kind_f32 entry points: all share the ScaledPairwiseDistance front-end
+ * (jaxrk/kern/util.py:71-116) and differ in the epilogue.  `kparams` is a HOST array:
+ *   JRK_KIND_GENGAUSS     {scale, power, nconst}                        GenGaussKernel    jaxrk/kern/rbf.py:104-105
+ *   JRK_KIND_PERIODIC     {1/period, length_scale}                      PeriodicKernel    jaxrk/kern/rbf.py:109-154
+ *                         k = exp(-2 (sin(pi ||x-y|| / period) / length_scale)^2)
+ *   JRK_KIND_THRESHSPIKE  {scale, power, spike, non_spike, threshold}   ThreshSpikeKernel jaxrk/kern/rbf.py:156-206
+ *                         k = (scale ||x-y||)^power <= threshold ? spike : non_spike   (power > 0) */
+#define JRK_KIND_GENGAUSS 0
+#define JRK_KIND_PERIODIC 1
+#define JRK_KIND_THRESHSPIKE 2
 
 int jrk_abi_version(void);
 
@@ -118,6 +129,35 @@ int jrk_kmatw_f32(const float *X, const float *Y, const float *W, float *out,
                   void *workspace, size_t workspace_bytes, void *stream);
 
 size_t jrk_kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce, int64_t group);
+
+/* ------------------------------------------------------------------------------
+ * The same two operations for any kernel family of the ScaledPairwiseDistance front-end (JRK_KIND_*).
+ * JRK_KIND_GENGAUSS forwards to jrk_gram_f32 / jrk_kmatw_f32 (all paths); the sibling kernels
+ * (PeriodicKernel / ThreshSpikeKernel, jaxrk/kern/rbf.py:107-206) run on the direct-differencing Gram kernel
+ * and the FP32-pipe K@W kernel with their own epilogue.  The self-Gram (Y == NULL or Y == X) is bitwise
+ * symmetric with an exact diagonal (distance 0: Periodic 1, ThreshSpike `spike`).
+ * ------------------------------------------------------------------------------ */
+int jrk_gram_kind_f32(const float *X, const float *Y, float *K,
+                      int64_t N, int64_t M, int d,
+                      int64_t ldx, int64_t ldy, int64_t ldk,
+                      int kind, const float *kparams, int n_kparams, const float *dim_scale,
+                      int path, void *workspace, size_t workspace_bytes, void *stream);
+
+int jrk_kmatw_kind_f32(const float *X, const float *Y, const float *W, float *out,
+                       int64_t N, int64_t M, int d, int m,
+                       int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo,
+                       int kind, const float *kparams, int n_kparams, const float *dim_scale,
+                       const float *row_pref, const float *col_pref,
+                       int row_reduce, int64_t group,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------
+ * Row-wise ("diag = True") scaled distance, out[i] = scale * sum_k |ds_k x_ik - ds_k y_ik|^power  (len N).
+ * Replaces the diag branch of ScaledPairwiseDistance.__call__ (jaxrk/kern/util.py:108-113) -- NB a different
+ * formula from the full matrix (l_p^p of the scaled difference, global scale applied linearly).
+ * ------------------------------------------------------------------------------ */
+int jrk_dist_diag_f32(const float *X, const float *Y, float *out, int64_t N, int d,
+                      int64_t ldx, int64_t ldy, float scale, const float *dim_scale, float power, void *stream);
 
 /* 1 when jrk_kmatw_f32 would run both contractions of this problem on the tensor cores (kmatw_tc.cu: d <= 32,
  * m <= 16, no per-dimension scale, row_reduce NONE, large N and M, JRK_KMATW_TC != "0"), else 0 (FP32-pipe kernel).

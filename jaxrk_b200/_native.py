@@ -20,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libjaxrk_b200.so")
 
 PATH_AUTO, PATH_DIRECT, PATH_TF32X3 = 0, 1, 2
+KIND_GENGAUSS, KIND_PERIODIC, KIND_THRESHSPIKE = 0, 1, 2
 REDUCE_NONE, REDUCE_SUM, REDUCE_MEAN, REDUCE_BALANCED, REDUCE_BALANCED_MEAN = 0, 1, 2, 3, 4
 
 # every symbol include/jrk.h declares: name -> (restype, argtypes)
@@ -34,6 +35,13 @@ SIGNATURES = {
                              c_float, c_void_p, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "jrk_dist_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64,
                              c_float, c_void_p, c_float, c_void_p]),
+    "jrk_dist_diag_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_float, c_void_p,
+                                  c_float, c_void_p]),
+    "jrk_gram_kind_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64,
+                                  c_int, _F, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "jrk_kmatw_kind_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                                   c_int64, c_int64, c_int64, c_int64, c_int, _F, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_int, c_int64, c_void_p, c_size_t, c_void_p]),
     "jrk_kmatw_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int64]),
     "jrk_kmatw_uses_tensor_cores": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "jrk_kmatw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
@@ -72,7 +80,7 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.jrk_abi_version() != 1:
+        if L.jrk_abi_version() != 2:
             raise ImportError("libjaxrk_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -215,6 +223,96 @@ def gram_groupsum(X, Y, scale: float, power: float, nconst: float, gx: int, gy: 
         _check(lib().jrk_gram_groupsum_f32(_ptr(X), None if self_gram else _ptr(Yt), _ptr(out), N, M, d, _ld(X),
                                            _ld(Yt), M // gy, scale, _ptr(ds), power, nconst, _ptr(rp), _ptr(cp),
                                            gx, gy, int(bool(average)), None, 0, _stream(dev)))
+    return out
+
+
+def dist_diag(X, Y, scale: float, power: float, dim_scale=None) -> torch.Tensor:
+    """jrk_dist_diag_f32: out[i] = scale * sum_k |ds_k x_ik - ds_k y_ik|^power (the diag=True formula)."""
+    X = _dev2d(X, "X")
+    Y = _dev2d(Y, "Y")
+    if X.shape != Y.shape:
+        raise ValueError("X and Y must have the same shape")
+    N, d = X.shape
+    ds = _vec(dim_scale, d, "dim_scale", X.device)
+    out = torch.empty((N,), dtype=torch.float32, device=X.device)
+    if N == 0:
+        return out
+    with torch.cuda.device(X.device):
+        _check(lib().jrk_dist_diag_f32(_ptr(X), _ptr(Y), _ptr(out), N, d, _ld(X), _ld(Y), scale, _ptr(ds), power,
+                                       _stream(X.device)))
+    return out
+
+
+class KernelSpec:
+    """(kind, kparams, dim_scale) of include/jrk.h's *_kind_f32 entry points."""
+    __slots__ = ("kind", "kparams", "dim_scale")
+
+    def __init__(self, kind: int, kparams, dim_scale=None):
+        self.kind, self.kparams, self.dim_scale = int(kind), [float(v) for v in kparams], dim_scale
+
+    def _c(self):
+        return (c_float * len(self.kparams))(*self.kparams), len(self.kparams)
+
+
+def gram_spec(X, Y, spec: KernelSpec, path: int = PATH_AUTO, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """jrk_gram_kind_f32 (GENGAUSS forwards to jrk_gram_f32 with all its paths)."""
+    if spec.kind == KIND_GENGAUSS:
+        scale, power, nconst = spec.kparams
+        return gram(X, Y, scale, power, nconst, dim_scale=spec.dim_scale, path=path, out=out)
+    X = _dev2d(X, "X")
+    self_gram = Y is None
+    Yt = X if self_gram else _dev2d(Y, "Y")
+    N, d = X.shape
+    M = Yt.shape[0]
+    if Yt.shape[1] != d:
+        raise ValueError("X and Y must have the same number of columns")
+    ds = _vec(spec.dim_scale, d, "dim_scale", X.device)
+    if out is None:
+        out = torch.empty((N, M), dtype=torch.float32, device=X.device)
+    if N == 0 or M == 0:
+        return out
+    kp, nkp = spec._c()
+    with torch.cuda.device(X.device):
+        _check(lib().jrk_gram_kind_f32(_ptr(X), None if self_gram else _ptr(Yt), _ptr(out), N, M, d, _ld(X), _ld(Yt),
+                                       _ld(out) if N > 1 else M, spec.kind, kp, nkp, _ptr(ds), PATH_AUTO, None, 0,
+                                       _stream(X.device)))
+    return out
+
+
+def kmatw_spec(X, Y, W, spec: KernelSpec, row_pref=None, col_pref=None, row_reduce: int = REDUCE_NONE,
+               group: int = 0) -> torch.Tensor:
+    """jrk_kmatw_kind_f32."""
+    if spec.kind == KIND_GENGAUSS:
+        scale, power, nconst = spec.kparams
+        return kmatw(X, Y, W, scale, power, nconst, dim_scale=spec.dim_scale, row_pref=row_pref, col_pref=col_pref,
+                     row_reduce=row_reduce, group=group)
+    X = _dev2d(X, "X")
+    Y = _dev2d(Y, "Y")
+    W = _dev2d(W, "W")
+    N, d = X.shape
+    M, m = W.shape
+    if Y.shape != (M, d):
+        raise ValueError(f"Y must be {M} x {d}, got {tuple(Y.shape)}")
+    dev = X.device
+    ds = _vec(spec.dim_scale, d, "dim_scale", dev)
+    rp = _vec(row_pref, N, "row_pref", dev)
+    cp = _vec(col_pref, M, "col_pref", dev)
+    if row_reduce in (REDUCE_SUM, REDUCE_MEAN):
+        rows = 1
+    elif row_reduce in (REDUCE_BALANCED, REDUCE_BALANCED_MEAN):
+        if group < 1 or N % group:
+            raise ValueError("group must divide N")
+        rows = N // group
+    else:
+        rows = N
+    out = torch.empty((rows, m), dtype=torch.float32, device=dev)
+    kp, nkp = spec._c()
+    with torch.cuda.device(dev):
+        wsb = lib().jrk_kmatw_workspace_bytes(N, M, d, m, row_reduce, group)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
+        _check(lib().jrk_kmatw_kind_f32(_ptr(X), _ptr(Y), _ptr(W), _ptr(out), N, M, d, m, _ld(X), _ld(Y), _ld(W), m,
+                                        spec.kind, kp, nkp, _ptr(ds), _ptr(rp), _ptr(cp), row_reduce, group,
+                                        _ptr(ws), wsb, _stream(dev)))
     return out
 
 

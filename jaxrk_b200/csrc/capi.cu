@@ -9,6 +9,9 @@
 namespace jrk {
 
 thread_local char g_last_error[512] = {0};
+thread_local ExtraKind g_extra_kind;
+int dist_diag(const float* X, const float* Y, float* out, int64_t N, int d, int64_t ldx, int64_t ldy, float scale,
+              const float* dim_scale, float power, cudaStream_t st);
 std::atomic<int64_t> g_launches{0};
 
 // kernels (one translation unit each)
@@ -34,8 +37,8 @@ static int check_kernel_params(const char* fn, int d, float scale, float power, 
     if (d < 1) return fail(JRK_ERR_INVALID_ARG, "%s: d must be >= 1 (got %d)", fn, d);
     if (!(scale > 0.f) || !std::isfinite(scale))
         return fail(JRK_ERR_INVALID_ARG, "%s: scale must be positive and finite (got %g)", fn, (double)scale);
-    // GenGaussKernel.make asserts 0 < shape <= 2 (jaxrk/kern/rbf.py:71)
-    if (!(power > 0.f) || power > 2.f)
+    // GenGaussKernel.make asserts 0 < shape <= 2 (jaxrk/kern/rbf.py:71); ThreshSpikeKernel takes any positive shape
+    if (!(power > 0.f) || (power > 2.f && g_extra_kind.kind == 0))
         return fail(JRK_ERR_INVALID_ARG, "%s: power must be in (0, 2] (got %g)", fn, (double)power);
     if (!std::isfinite(nconst)) return fail(JRK_ERR_INVALID_ARG, "%s: nconst must be finite", fn);
     return JRK_OK;
@@ -122,6 +125,71 @@ int jrk_dist_f32(const float* X, const float* Y, float* D, int64_t N, int64_t M,
     if (N == 0 || M == 0) return JRK_OK;
     if (int rc = have_device("jrk_dist_f32")) return rc;
     return gram_direct(X, Y, D, N, M, d, ldx, ldy, ldd, scale, dim_scale, power, 1.f, 1, (cudaStream_t)stream);
+}
+
+int jrk_dist_diag_f32(const float* X, const float* Y, float* out, int64_t N, int d, int64_t ldx, int64_t ldy,
+                      float scale, const float* dim_scale, float power, void* stream) {
+    if (N < 0 || d < 1) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_diag_f32: bad size");
+    if (N > 0 && (!X || !Y || !out)) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_diag_f32: NULL pointer");
+    if (!(scale > 0.f) || !(power > 0.f)) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_diag_f32: scale and power must be positive");
+    if (ldx < d || ldy < d) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_diag_f32: leading dimension too small");
+    if (N == 0) return JRK_OK;
+    if (int rc = have_device("jrk_dist_diag_f32")) return rc;
+    return dist_diag(X, Y, out, N, d, ldx, ldy, scale, dim_scale, power, (cudaStream_t)stream);
+}
+
+// kparams -> (scale, power, nconst) of the shared launchers + the sibling-kernel selector
+static int parse_kind(const char* fn, int kind, const float* kp, int n, float& scale, float& power, float& nconst,
+                      ExtraKind& ex) {
+    if (!kp) return fail(JRK_ERR_INVALID_ARG, "%s: kparams is NULL", fn);
+    ex = ExtraKind();
+    if (kind == JRK_KIND_GENGAUSS) {
+        if (n < 3) return fail(JRK_ERR_INVALID_ARG, "%s: GENGAUSS needs {scale, power, nconst}", fn);
+        scale = kp[0]; power = kp[1]; nconst = kp[2];
+    } else if (kind == JRK_KIND_PERIODIC) {
+        if (n < 2) return fail(JRK_ERR_INVALID_ARG, "%s: PERIODIC needs {1/period, length_scale}", fn);
+        if (!(kp[0] > 0.f) || !(kp[1] > 0.f))   // PeriodicKernel.__init__ asserts both positive (jaxrk/kern/rbf.py:118)
+            return fail(JRK_ERR_INVALID_ARG, "%s: period and length_scale must be positive", fn);
+        scale = kp[0]; power = 1.f; nconst = 1.f;
+        ex.kind = kind; ex.a0 = 1.f / kp[1];
+    } else if (kind == JRK_KIND_THRESHSPIKE) {
+        if (n < 5) return fail(JRK_ERR_INVALID_ARG, "%s: THRESHSPIKE needs {scale, power, spike, non_spike, threshold}", fn);
+        // ThreshSpikeKernel.__init__ (jaxrk/kern/rbf.py:166-168)
+        if (!(kp[2] > 0.f) || !(std::fabs(kp[3]) < kp[2]) || !(kp[4] >= 0.f))
+            return fail(JRK_ERR_INVALID_ARG, "%s: need spike > 0, |non_spike| < spike, threshold >= 0", fn);
+        scale = kp[0]; power = kp[1]; nconst = 1.f;
+        ex.kind = kind; ex.a0 = kp[4]; ex.a1 = kp[2]; ex.a2 = kp[3];
+    } else {
+        return fail(JRK_ERR_INVALID_ARG, "%s: unknown kernel kind %d", fn, kind);
+    }
+    return JRK_OK;
+}
+
+int jrk_gram_kind_f32(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
+                      int64_t ldk, int kind, const float* kparams, int n_kparams, const float* dim_scale, int path,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    float scale, power, nconst;
+    ExtraKind ex;
+    if (int rc = parse_kind("jrk_gram_kind_f32", kind, kparams, n_kparams, scale, power, nconst, ex)) return rc;
+    if (ex.kind == 0)
+        return jrk_gram_f32(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, path, workspace,
+                            workspace_bytes, stream);
+    if (path == JRK_PATH_TF32X3) return fail(JRK_ERR_UNSUPPORTED, "jrk_gram_kind_f32: sibling kernels use the direct path");
+    ExtraKindScope scope(ex.kind, ex.a0, ex.a1, ex.a2);
+    return jrk_gram_f32(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, JRK_PATH_DIRECT, workspace,
+                        workspace_bytes, stream);
+}
+
+int jrk_kmatw_kind_f32(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,
+                       int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, int kind, const float* kparams,
+                       int n_kparams, const float* dim_scale, const float* row_pref, const float* col_pref,
+                       int row_reduce, int64_t group, void* workspace, size_t workspace_bytes, void* stream) {
+    float scale, power, nconst;
+    ExtraKind ex;
+    if (int rc = parse_kind("jrk_kmatw_kind_f32", kind, kparams, n_kparams, scale, power, nconst, ex)) return rc;
+    ExtraKindScope scope(ex.kind, ex.a0, ex.a1, ex.a2);
+    return jrk_kmatw_f32(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, dim_scale, power, nconst, row_pref,
+                         col_pref, row_reduce, group, workspace, workspace_bytes, stream);
 }
 
 size_t jrk_kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce, int64_t group) {

@@ -97,7 +97,10 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 // `nconst` is NOT applied here when the caller folds it elsewhere (K@W applies it once
 // per output element).
 // ---------------------------------------------------------------------------------
-enum { PM_SQEXP = 0, PM_LAPLACE = 1, PM_GENERAL = 2 };
+//   PM_EXTRA          : sibling kernels on the same distance front-end (jrk_*_kind_f32), sub-kind in EpiParams:
+//       JRK_KIND_PERIODIC    k = exp(-2 (sin(pi s r) / ls)^2)            PeriodicKernel,    jaxrk/kern/rbf.py:152-154
+//       JRK_KIND_THRESHSPIKE k = (s r)^p <= threshold ? spike : non_spike ThreshSpikeKernel, jaxrk/kern/rbf.py:203-206
+enum { PM_SQEXP = 0, PM_LAPLACE = 1, PM_GENERAL = 2, PM_EXTRA = 3 };
 
 struct EpiParams {
     float c;       // PM_SQEXP: c2;  PM_LAPLACE: c1;  PM_GENERAL: s^2
@@ -106,6 +109,23 @@ struct EpiParams {
     // distance-only output (jrk_dist_f32): d = (s * sqrt(sq))^p
     float s;
     float p;
+    // PM_EXTRA
+    int kind;      // JRK_KIND_*
+    float a0;      // PERIODIC: 1 / length_scale;  THRESHSPIKE: threshold
+    float a1;      // THRESHSPIKE: spike
+    float a2;      // THRESHSPIKE: non_spike
+};
+
+// The sibling-kernel entry points (capi.cu) reuse the GenGauss launchers: they set this thread-local selector
+// (RAII: ExtraKindScope) around the call, make_epi / pick_pmode pick it up, and the tensor-core paths refuse it.
+struct ExtraKind {
+    int kind = 0;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+};
+extern thread_local ExtraKind g_extra_kind;
+struct ExtraKindScope {
+    ExtraKindScope(int kind, float a0, float a1, float a2) { g_extra_kind.kind = kind; g_extra_kind.a0 = a0; g_extra_kind.a1 = a1; g_extra_kind.a2 = a2; }
+    ~ExtraKindScope() { g_extra_kind = ExtraKind(); }
 };
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -119,13 +139,31 @@ __device__ __forceinline__ float kexp_unnorm(float sq, const EpiParams& e) {
         return ex2_approx(sq * e.c);
     } else if (PM == PM_LAPLACE) {
         return ex2_approx(sqrt_approx(sq) * e.c);
-    } else {
+    } else if (PM == PM_GENERAL) {
         float u = ex2_approx(e.hp * lg2_approx(sq * e.c));
         return ex2_approx(u * -kLog2e);
+    } else {
+        if (e.kind == JRK_KIND_PERIODIC) {
+            // distance in periods; sin(pi t) has period 2 in t, so reduce t to [-1, 1] exactly before the MUFU sine
+            // (sin.approx is only accurate on a few periods around 0)
+            const float t = e.s * sqrtf(sq);
+            const float r = fmaf(-2.f, rintf(0.5f * t), t);
+            float sn;
+            asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(r * 3.14159265358979323846f));
+            const float q = sn * e.a0;
+            return ex2_approx(q * q * (-2.f * kLog2e));
+        }
+        // ThreshSpike: the same distance expression as jrk_dist_f32, so that K == where(D <= threshold, ...)
+        float dist;
+        if (e.p == 2.f) dist = (e.s * e.s) * sq;
+        else if (e.p == 1.f) dist = e.s * sqrtf(sq);
+        else dist = powf(e.s * sqrtf(sq), e.p);
+        return dist <= e.a0 ? e.a1 : e.a2;
     }
 }
 
 inline int pick_pmode(float power) {
+    if (g_extra_kind.kind != 0) return PM_EXTRA;
     if (power == 2.0f) return PM_SQEXP;
     if (power == 1.0f) return PM_LAPLACE;
     return PM_GENERAL;
@@ -135,6 +173,7 @@ inline EpiParams make_epi(float scale, float power, float nconst) {
     EpiParams e;
     double s = (double)scale;
     int pm = pick_pmode(power);
+    if (pm == PM_EXTRA) pm = (power == 2.0f) ? PM_SQEXP : (power == 1.0f) ? PM_LAPLACE : PM_GENERAL;   // e.c unused
     if (pm == PM_SQEXP) e.c = (float)(-s * s * 1.4426950408889634);
     else if (pm == PM_LAPLACE) e.c = (float)(-s * 1.4426950408889634);
     else e.c = (float)(s * s);
@@ -142,6 +181,10 @@ inline EpiParams make_epi(float scale, float power, float nconst) {
     e.nconst = nconst;
     e.s = scale;
     e.p = power;
+    e.kind = g_extra_kind.kind;
+    e.a0 = g_extra_kind.a0;
+    e.a1 = g_extra_kind.a1;
+    e.a2 = g_extra_kind.a2;
     return e;
 }
 

@@ -66,7 +66,7 @@ gram_direct_kernel(const float* __restrict__ X, const float* __restrict__ Y, flo
                 } else {
                     if (PM == PM_SQEXP) v[c] = (ep.s * ep.s) * sq;
                     else if (PM == PM_LAPLACE) v[c] = ep.s * sqrtf(sq);
-                    else v[c] = powf(ep.s * sqrtf(sq), ep.p);
+                    else if (PM == PM_GENERAL) v[c] = powf(ep.s * sqrtf(sq), ep.p);
                 }
             }
 #pragma unroll
@@ -106,6 +106,28 @@ static int launch_gd(const float* X, const float* Y, float* K, int64_t N, int64_
     return JRK_OK;
 }
 
+// diag = True branch of ScaledPairwiseDistance.__call__ (jaxrk/kern/util.py:112-113): one thread per row
+__global__ void dist_diag_kernel(const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ out,
+                                 int64_t N, int d, int64_t ldx, int64_t ldy, float scale,
+                                 const float* __restrict__ dim_scale, float power) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float acc = 0.f;
+    for (int k = 0; k < d; ++k) {
+        const float ds = dim_scale ? __ldg(dim_scale + k) : 1.f;
+        const float df = fabsf(ds * __ldg(X + i * ldx + k) - ds * __ldg(Y + i * ldy + k));
+        acc += (power == 2.f) ? df * df : (power == 1.f) ? df : powf(df, power);
+    }
+    out[i] = scale * acc;
+}
+
+int dist_diag(const float* X, const float* Y, float* out, int64_t N, int d, int64_t ldx, int64_t ldy, float scale,
+              const float* dim_scale, float power, cudaStream_t st) {
+    dist_diag_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(X, Y, out, N, d, ldx, ldy, scale, dim_scale, power);
+    JRK_LAUNCHED();
+    return JRK_OK;
+}
+
 // Host launcher.  out_kind: 0 kernel values, 1 scaled distances.  Rows are processed in
 // slabs so that gridDim.y stays within limits for N up to 2^31.
 int gram_direct(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
@@ -124,7 +146,8 @@ int gram_direct(const float* X, const float* Y, float* K, int64_t N, int64_t M, 
                        : launch_gd<PM_, 1>(Xs, Y, Ks, n, M, d, ldx, ldy, ldk, dim_scale, ep, st)
         if (pm == PM_SQEXP) GD_CASE(PM_SQEXP);
         else if (pm == PM_LAPLACE) GD_CASE(PM_LAPLACE);
-        else GD_CASE(PM_GENERAL);
+        else if (pm == PM_GENERAL) GD_CASE(PM_GENERAL);
+        else rc = launch_gd<PM_EXTRA, 0>(Xs, Y, Ks, n, M, d, ldx, ldy, ldk, dim_scale, ep, st);   // kernel values only
 #undef GD_CASE
         if (rc) return rc;
     }

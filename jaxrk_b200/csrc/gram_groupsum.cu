@@ -119,6 +119,7 @@ int gram_groupsum(const float* X, const float* Y, float* out, int64_t N, int64_t
 
     const EpiParams ep = make_epi(scale, power, nconst);
     const int pm = pick_pmode(power);
+    if (pm == PM_EXTRA) return fail(JRK_ERR_UNSUPPORTED, "gram_groupsum: sibling kernels are not supported");
     int vec_in = 0;
     if (((uintptr_t)X % 16 == 0) && (ldx % 4 == 0)) vec_in |= 1;
     if (((uintptr_t)Y % 16 == 0) && (ldy % 4 == 0)) vec_in |= 2;

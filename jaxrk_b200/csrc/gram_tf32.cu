@@ -148,6 +148,7 @@ int gram_tf32x3(const float* X, const float* Y, float* K, int64_t N, int64_t M, 
     // epilogue constants.  p == 2 with nconst > 0: everything folds into one exp2 argument.
     EpiParams ep = make_epi(scale, power, nconst);
     int pm = pick_pmode(power);
+    if (pm == PM_EXTRA) return fail(JRK_ERR_UNSUPPORTED, "gram_tf32x3: sibling kernels use the direct path");
     if (pm == PM_SQEXP && !(nconst > 0.f)) {   // cannot fold log2(nconst): use the general epilogue with p = 2
         pm = PM_GENERAL;
         ep.c = scale * scale;

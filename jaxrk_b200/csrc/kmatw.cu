@@ -431,7 +431,8 @@ static int kmatw_block(const float* X, const float* Y, const float* W, float* ou
     int rc = JRK_OK;
     if (pm == PM_SQEXP) KW_D(PM_SQEXP);
     else if (pm == PM_LAPLACE) KW_D(PM_LAPLACE);
-    else KW_D(PM_GENERAL);
+    else if (pm == PM_GENERAL) KW_D(PM_GENERAL);
+    else KW_D(PM_EXTRA);
 #undef KW_D
 #undef KW_MT
 #undef KW_GO
@@ -462,6 +463,7 @@ static int kmatw_block(const float* X, const float* Y, const float* W, float* ou
 bool kmatw_uses_tc(int64_t N, int64_t M, int d, int m, bool has_dim_scale, int row_reduce) {
     const char* e = getenv("JRK_KMATW_TC");
     if (e && e[0] == '0') return false;
+    if (g_extra_kind.kind != 0) return false;   // sibling kernels: FP32-pipe kernel only
     static const float dummy = 1.f;
     return kmatw_tc_eligible(N, M, d, m, has_dim_scale ? &dummy : nullptr, row_reduce, 1.f);
 }

@@ -655,6 +655,7 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
 
     EpiParams ep = make_epi(scale, power, nconst);
     const int pm = pick_pmode(power);
+    if (pm == PM_EXTRA) return fail(JRK_ERR_UNSUPPORTED, "kmatw_tc: sibling kernels use the FP32-pipe kernel");
     const float mult = (pm == PM_SQEXP) ? ep.c : 1.f;
     JRK_CUDA_OK(cudaMemsetAsync(nmax, 0, 2 * sizeof(unsigned), st));
     const float a_scale = (pm == PM_SQEXP) ? -2.f * ep.c : -2.f;

@@ -12,7 +12,7 @@ import torch
 
 from .. import _native as nat
 from .._array import as2d
-from .base import DensityKernel
+from .base import DensityKernel, Kernel
 from .util import ScaledPairwiseDistance, SimpleScaler
 
 f32 = np.float32
@@ -81,3 +81,52 @@ class GenGaussKernel(DensityKernel):
             return nc * torch.exp(-self.dist(X, Y, diag))  # rbf.py:104-105 literally (O(N d) / quirk Q2)
         scale, dim_scale, power, nconst = args
         return nat.gram(X, Y, scale, power, nconst, dim_scale=dim_scale)
+
+
+class PeriodicKernel(Kernel):
+    """exp(-2 (sin(pi ||x - y|| / period) / length_scale)^2) -- drop-in for jaxrk/kern/rbf.py:107-154.  The Gram comes
+    from the direct-differencing kernel with the periodic epilogue (jrk_gram_kind_f32, JRK_KIND_PERIODIC); inner
+    products with reduce chains go through jrk_kmatw_kind_f32."""
+
+    def __init__(self, period, length_scale: float):
+        period, length_scale = float(period), float(length_scale)
+        assert period > 0 and length_scale > 0
+        self.dist = ScaledPairwiseDistance(scaler=SimpleScaler(1. / period), power=1.)
+        self.ls = length_scale
+
+    def kernel_spec(self):
+        scale, dim_scale = self.dist.kernel_args()
+        return nat.KernelSpec(nat.KIND_PERIODIC, (scale, self.ls), dim_scale)
+
+    def __call__(self, X, Y=None, diag=False):
+        X = as2d(X)
+        Y = None if Y is None else as2d(Y, X.device)
+        if diag:  # O(N d): rbf.py:152-154 literally over the diag distance formula
+            d = self.dist(X, Y, True)
+            return torch.exp(-2. * (torch.sin(math.pi * d) / self.ls) ** 2.)
+        return nat.gram_spec(X, Y, self.kernel_spec())
+
+
+class ThreshSpikeKernel(Kernel):
+    """`spike` where the scaled distance is <= threshold, else `non_spike` -- drop-in for jaxrk/kern/rbf.py:156-206
+    (jrk_gram_kind_f32, JRK_KIND_THRESHSPIKE: the comparison runs on the same distance expression as jrk_dist_f32)."""
+
+    def __init__(self, dist: ScaledPairwiseDistance, spike: float, non_spike: float, threshold: float):
+        spike, non_spike, threshold = float(spike), float(non_spike), float(threshold)
+        assert spike > 0
+        assert abs(non_spike) < spike
+        assert threshold >= 0
+        self.dist = dist
+        self.spike, self.non_spike, self.threshold = spike, non_spike, threshold
+
+    def kernel_spec(self):
+        scale, dim_scale = self.dist.kernel_args()
+        return nat.KernelSpec(nat.KIND_THRESHSPIKE, (scale, float(self.dist.power), self.spike, self.non_spike,
+                                                     self.threshold), dim_scale)
+
+    def __call__(self, X, Y=None, diag=False):
+        X = as2d(X)
+        assert X.dim() == 2
+        assert not diag
+        Y = None if Y is None else as2d(Y, X.device)
+        return nat.gram_spec(X, Y, self.kernel_spec())

@@ -103,6 +103,7 @@ class ScaledPairwiseDistance:
             if Y is None:
                 return torch.zeros(X.shape[0], dtype=torch.float32, device=X.device)
             assert X.shape == Y.shape
-            return self.gs(torch.sum(torch.abs(self.ds(X) - self.ds(Y)) ** self.power, 1))
+            scale, dim_scale = self.kernel_args()
+            return nat.dist_diag(X, Y, scale, float(self.power), dim_scale=dim_scale)
         scale, dim_scale = self.kernel_args()
         return nat.dist(X, Y, scale, float(self.power), dim_scale=dim_scale)

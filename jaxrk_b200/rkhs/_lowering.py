@@ -18,6 +18,8 @@ Kernel choice, with (rx, ry) the folded row / column maps:
     rx = ry = BALANCED                -> jrk_gram_groupsum_f32
     rx = ry = NONE                    -> jrk_gram_f32 (materialised), prefactors scaled in place
     anything else                     -> Gram by jrk_gram_f32, then Reduce.apply (generic)
+The sibling kernels of the same distance front-end (PeriodicKernel, ThreshSpikeKernel) take the same routes
+through jrk_kmatw_kind_f32 / jrk_gram_kind_f32 (no group-sum kernel: Gram, then the array-level BalancedRed).
 Nothing here computes a kernel value on the host or in torch: all k(x, y) evaluations are
 done by libjaxrk_b200.so.
 """
@@ -105,45 +107,58 @@ def _row_reduce_of(f: Folded):
     return nat.REDUCE_NONE, 0
 
 
-def _kmatw_side(X, Y, fx: Folded, fy: Folded, kargs) -> torch.Tensor:
+def _kmatw_side(X, Y, fx: Folded, fy: Folded, spec) -> torch.Tensor:
     """fold_x(K(X, Y)) applied with W = fold_y^T; fy is LINEAR / SUM / MEAN."""
-    scale, dim_scale, power, nconst = kargs
     W = _w_of(fy, X.device)
     if fx.kind == LINEAR:
-        T = nat.kmatw(X, Y, W, scale, power, nconst, dim_scale=dim_scale, row_pref=fx.pref, col_pref=fy.pref)
+        T = nat.kmatw_spec(X, Y, W, spec, row_pref=fx.pref, col_pref=fy.pref)
         return fx.A @ T  # (mx x N) @ (N x my): small dense GEMM, stays in the library path
     rr, group = _row_reduce_of(fx)
-    return nat.kmatw(X, Y, W, scale, power, nconst, dim_scale=dim_scale, row_pref=fx.pref, col_pref=fy.pref,
-                     row_reduce=rr, group=group)
+    return nat.kmatw_spec(X, Y, W, spec, row_pref=fx.pref, col_pref=fy.pref, row_reduce=rr, group=group)
+
+
+def kernel_spec_of(k):
+    """KernelSpec of a kernel object: `kernel_spec()` (sibling kernels) or GenGauss `kernel_args()`; None when the
+    C ABI cannot represent it."""
+    if hasattr(k, "kernel_spec"):
+        return k.kernel_spec()
+    kargs = k.kernel_args() if hasattr(k, "kernel_args") else None
+    if kargs is None:
+        return None
+    scale, dim_scale, power, nconst = kargs
+    return nat.KernelSpec(nat.KIND_GENGAUSS, (scale, power, nconst), dim_scale)
 
 
 def reduced_gram(k, X, chain_x, Y, chain_y, self_gram: bool = False) -> torch.Tensor:
     """R_X K(X, Y) R_Y^T.  `self_gram` says Y is X (enables the symmetric self-Gram kernel)."""
     dev = X.device
-    kargs = k.kernel_args() if hasattr(k, "kernel_args") else None
-    if kargs is None:  # not a kernel the C ABI knows: the reference's own sequence
+    spec = kernel_spec_of(k)
+    if spec is None:  # not a kernel the C ABI knows: the reference's own sequence
         return Reduce.apply(Reduce.apply(k(X, Y), chain_x, 0), chain_y, 1)
-    scale, dim_scale, power, nconst = kargs
+    gg = spec.kind == nat.KIND_GENGAUSS
+    if gg:
+        scale, power, nconst = spec.kparams
+        dim_scale = spec.dim_scale
     fx = fold_chain(chain_x, X.shape[0], dev)
     fy = fold_chain(chain_y, Y.shape[0], dev)
     skinny = (LINEAR, SUM, MEAN)
 
     if fy.kind in skinny and (fx.kind not in skinny or fy.out_len <= fx.out_len):
-        out = _kmatw_side(X, Y, fx, fy, kargs)
+        out = _kmatw_side(X, Y, fx, fy, spec)
     elif fx.kind in skinny:
-        out = _kmatw_side(Y, X, fy, fx, kargs).t()
-    elif fx.kind == BALANCED and fy.kind == BALANCED and fx.group % 128 == 0:
+        out = _kmatw_side(Y, X, fy, fx, spec).t()
+    elif gg and fx.kind == BALANCED and fy.kind == BALANCED and fx.group % 128 == 0:
         out = nat.gram_groupsum(X, None if self_gram else Y, scale, power, nconst, fx.group, fy.group,
                                 False, dim_scale=dim_scale, row_pref=fx.pref, col_pref=fy.pref)
         if fx.average or fy.average:
             out = out * (1.0 / ((fx.group if fx.average else 1) * (fy.group if fy.average else 1)))
-    elif fx.kind == BALANCED and fy.kind == BALANCED and fy.group % 128 == 0:
+    elif gg and fx.kind == BALANCED and fy.kind == BALANCED and fy.group % 128 == 0:
         out = nat.gram_groupsum(Y, None if self_gram else X, scale, power, nconst, fy.group, fx.group,
                                 False, dim_scale=dim_scale, row_pref=fy.pref, col_pref=fx.pref).t()
         if fx.average or fy.average:
             out = out * (1.0 / ((fx.group if fx.average else 1) * (fy.group if fy.average else 1)))
     else:
-        G = nat.gram(X, None if self_gram else Y, scale, power, nconst, dim_scale=dim_scale)
+        G = nat.gram_spec(X, None if self_gram else Y, spec)
         if fx.pref is not None:
             G.mul_(fx.pref[:, None])
         if fy.pref is not None:

@@ -179,6 +179,69 @@ def gengauss_gram_ref32(X, Y, s: np.ndarray, power: float, diag: bool = False) -
     return (nconst * np.exp(-d, dtype=f32)).astype(f32)
 
 
+def scaled_dist_truth64(X, Y, s, power: float) -> np.ndarray:
+    """float64 (s |x - y|)^p by direct differencing on the float32 inputs / parameters (global or per-dim s)."""
+    s = np.asarray(s, dtype=f32)
+    if s.size == 1:
+        r = float(s.reshape(())) * np.sqrt(sqeucldist_truth64(X, Y))
+    else:
+        Xs = (s * _as2d_f32(X)).astype(f32)
+        Ys = None if Y is None else (s * _as2d_f32(Y)).astype(f32)
+        r = np.sqrt(sqeucldist_truth64(Xs, Ys))
+    return np.power(r, float(f32(power)))
+
+
+def scaled_dist_diag_truth64(X, Y, s, power: float) -> np.ndarray:
+    """float64 restatement of the diag branch (kern/util.py:112-113): gs * sum_k |ds x - ds y|^p."""
+    s = np.asarray(s, dtype=f32)
+    X, Y = _as2d_f32(X), _as2d_f32(Y)
+    if s.size == 1:
+        return float(s.reshape(())) * np.sum(np.abs(X.astype(np.float64) - Y.astype(np.float64)) ** float(f32(power)), 1)
+    df = (s * X).astype(f32).astype(np.float64) - (s * Y).astype(f32).astype(np.float64)
+    return np.sum(np.abs(df) ** float(f32(power)), 1)
+
+
+def periodic_gram_ref32(X, Y, period: float, length_scale: float, diag: bool = False) -> np.ndarray:
+    """PeriodicKernel.__call__ (kern/rbf.py:152-154) over ScaledPairwiseDistance(SimpleScaler(1/period), power=1)
+    (rbf.py:120): d = dist(X, Y, diag); exp(-2 * (sin(pi * d) / ls) ** 2), float32 op by op."""
+    s = simple_scaler_s(period)
+    d = scaled_dist_ref32(X, Y, s, 1.0, diag)
+    sn = np.sin((f32(np.pi) * d).astype(f32), dtype=f32)
+    return np.exp(f32(-2.) * (sn / f32(length_scale)) ** f32(2.), dtype=f32).astype(f32)
+
+
+def periodic_gram_truth64(X, Y, period: float, length_scale: float) -> np.ndarray:
+    """float64 truth; the scale and the length scale are the float32 values the device kernel receives."""
+    s = simple_scaler_s(period)
+    d = scaled_dist_truth64(X, Y, s, 1.0)
+    return np.exp(-2. * (np.sin(np.pi * d) * float(f32(1.) / f32(length_scale))) ** 2)
+
+
+def periodic_gram_cond64(X, Y, period: float, length_scale: float) -> np.ndarray:
+    """|dK / dd| * d: how far one relative float32 rounding of the distance (unavoidable: d is a float32 quantity in
+    the reference and on the device) moves the kernel value.  Parity tolerance for PeriodicKernel is
+    atol + rtol |K| + 4 eps32 cond  (sin(pi d) is ill-conditioned at many periods' distance)."""
+    s = simple_scaler_s(period)
+    d = scaled_dist_truth64(X, Y, s, 1.0)
+    K = periodic_gram_truth64(X, Y, period, length_scale)
+    il2 = float(f32(1.) / f32(length_scale)) ** 2
+    return np.abs(K * 4. * np.sin(np.pi * d) * np.cos(np.pi * d) * np.pi * il2) * d
+
+
+def threshspike_gram_ref32(X, Y, s, power: float, spike: float, non_spike: float, threshold: float) -> np.ndarray:
+    """ThreshSpikeKernel.__call__ (kern/rbf.py:203-206): where(dist(X, Y) <= threshold, spike, non_spike)."""
+    d = scaled_dist_ref32(X, Y, s, power, False)
+    return np.where(d <= f32(threshold), f32(spike), f32(non_spike)).astype(f32)
+
+
+def threshspike_gram_truth64(X, Y, s, power: float, spike: float, non_spike: float, threshold: float):
+    """(values, margin): float64 restatement and |dist - threshold| -- entries whose margin is below the float32
+    resolution of the distance are undecidable and excluded from parity."""
+    d = scaled_dist_truth64(X, Y, s, power)
+    thr = float(f32(threshold))
+    return np.where(d <= thr, float(f32(spike)), float(f32(non_spike))), np.abs(d - thr)
+
+
 def gengauss_gram_truth64(X, Y, s, power: float, nconst=None) -> np.ndarray:
     """float64 truth for a GLOBAL scale: nconst * exp(-(s*|x-y|)^p) with direct
     differencing; s, nconst are the float32 values the device kernel receives."""

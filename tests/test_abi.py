@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(raw, n), f"{n} declared in include/jrk.h but not exported"
         assert n in nat.SIGNATURES, f"{n} has no ctypes signature in jaxrk_b200/_native.py"
     assert sorted(nat.SIGNATURES) == names
-    assert nat.lib().jrk_abi_version() == 1
+    assert nat.lib().jrk_abi_version() == 2
 
 
 def test_sm100a_code_is_embedded():
@@ -62,6 +62,16 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert rc == 1 and "divide" in nat.last_error()
     rc = L.jrk_gram_groupsum_f32(p, None, p, 6, 6, 2, 2, 2, 2, 1.0, None, 1.0, 1.0, None, None, 4, 3, 0, None, 0, None)
     assert rc == 1
+    # sibling kernels (jrk_*_kind_f32): parameter checks of PeriodicKernel / ThreshSpikeKernel.__init__
+    kp = (ctypes.c_float * 5)(1.0, 1.0, 1.0, 2.0, 0.5)          # |non_spike| >= spike
+    rc = L.jrk_gram_kind_f32(p, None, p, 4, 4, 2, 2, 2, 4, nat.KIND_THRESHSPIKE, kp, 5, None, 0, None, 0, None)
+    assert rc == 1 and "non_spike" in nat.last_error()
+    rc = L.jrk_gram_kind_f32(p, None, p, 4, 4, 2, 2, 2, 4, nat.KIND_PERIODIC, kp, 1, None, 0, None, 0, None)
+    assert rc == 1 and "PERIODIC needs" in nat.last_error()
+    rc = L.jrk_kmatw_kind_f32(p, p, p, p, 4, 4, 2, 1, 2, 2, 1, 1, 9, kp, 5, None, None, None, 0, 0, None, 0, None)
+    assert rc == 1 and "unknown kernel kind" in nat.last_error()
+    rc = L.jrk_dist_diag_f32(p, p, p, 4, 2, 1, 2, 1.0, None, 1.0, None)
+    assert rc == 1 and "leading" in nat.last_error()
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

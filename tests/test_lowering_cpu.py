@@ -77,6 +77,12 @@ def fake_groupsum(X, Y, scale, power, nconst, gx, gy, average, dim_scale=None, r
     return torch.from_numpy((G / (gx * gy) if average else G).astype(f32))
 
 
+def fake_dist_diag(X, Y, scale, power, dim_scale=None):
+    CALLS.append("dist_diag")
+    s = np.array([[scale]], f32) if dim_scale is None else np.asarray(dim_scale, f32)[None, :]
+    return torch.from_numpy(orc.scaled_dist_diag_truth64(_np(X).astype(f32), _np(Y).astype(f32), s, power).astype(f32))
+
+
 @pytest.fixture(autouse=True)
 def cpu_standins(monkeypatch):
     monkeypatch.setattr(arr, "_device", torch.device("cpu"))
@@ -84,6 +90,7 @@ def cpu_standins(monkeypatch):
     monkeypatch.setattr(nat, "dist", fake_dist)
     monkeypatch.setattr(nat, "kmatw", fake_kmatw)
     monkeypatch.setattr(nat, "gram_groupsum", fake_groupsum)
+    monkeypatch.setattr(nat, "dist_diag", fake_dist_diag)
     CALLS.clear()
     yield
 
