@@ -180,6 +180,34 @@ int jrk_gram_groupsum_f32(const float *X, const float *Y, float *out,
                           void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------
+ * Vector-Jacobian products of the two operations above with respect to the points and the global scale
+ * (what jax.grad derives from the reference's materialised chain; README.md:3, examples/Using_FLAX_Optax.ipynb,
+ * jaxrk/rkhs/vector.py:206-222), fused and never materialising K:
+ *   jrk_kmatw_grad_f32:  out = K(X, Y) W,  G = dL/dout (N x m):
+ *       gX[i, :]   = sum_j (G[i, :] . W[j, :]) dK_ij/dx_i                       (N x d)
+ *       gs_rows[i] = sum_j (G[i, :] . W[j, :]) dK_ij/dscale  at fixed nconst    (len N, nullable; dL/dscale = its sum)
+ *   jrk_gram_grad_f32:   K = K(X, Y),  Gbar = dL/dK (N x M): the same with G[i,:].W[j,:] replaced by Gbar[i, j].
+ * dL/dY is the same call with the roles exchanged -- (Y, X, G, W) resp. (Y, X, Gbar^T) -- and dL/dW = K(Y, X) G is
+ * jrk_kmatw_f32.  GenGauss family only, global scale only (dim_scale unsupported), d <= 64, m <= 32.
+ * Pairs at distance zero contribute nothing (p <= 1: the derivative does not exist there, jax.grad gives NaN).
+ * ------------------------------------------------------------------------------ */
+int jrk_kmatw_grad_f32(const float *X, const float *Y, const float *W, const float *G,
+                       float *gX, float *gs_rows,
+                       int64_t N, int64_t M, int d, int m,
+                       int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx,
+                       float scale, float power, float nconst,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+int jrk_gram_grad_f32(const float *X, const float *Y, const float *Gbar,
+                      float *gX, float *gs_rows,
+                      int64_t N, int64_t M, int d,
+                      int64_t ldx, int64_t ldy, int64_t ldgb, int64_t ldgx,
+                      float scale, float power, float nconst,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+size_t jrk_grad_workspace_bytes(int64_t N, int64_t M, int d);
+
+/* ------------------------------------------------------------------------------
  * Host-buffer (end-to-end) variants: same semantics, HOST pointers, copies included.
  * The Gram variant streams row blocks (compute of block b+1 overlaps the device->host
  * copy of block b).  `device` is the CUDA ordinal.

@@ -42,6 +42,13 @@ SIGNATURES = {
     "jrk_kmatw_kind_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                    c_int64, c_int64, c_int64, c_int64, c_int, _F, c_int, c_void_p,
                                    c_void_p, c_void_p, c_int, c_int64, c_void_p, c_size_t, c_void_p]),
+    "jrk_grad_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "jrk_kmatw_grad_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                   c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_float, c_float,
+                                   c_void_p, c_size_t, c_void_p]),
+    "jrk_gram_grad_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                  c_int64, c_int64, c_int64, c_int64, c_float, c_float, c_float,
+                                  c_void_p, c_size_t, c_void_p]),
     "jrk_kmatw_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int64]),
     "jrk_kmatw_uses_tensor_cores": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "jrk_kmatw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
@@ -241,6 +248,42 @@ def dist_diag(X, Y, scale: float, power: float, dim_scale=None) -> torch.Tensor:
         _check(lib().jrk_dist_diag_f32(_ptr(X), _ptr(Y), _ptr(out), N, d, _ld(X), _ld(Y), scale, _ptr(ds), power,
                                        _stream(X.device)))
     return out
+
+
+def kmatw_grad(X, Y, W, G, scale: float, power: float, nconst: float, want_scale: bool = True):
+    """jrk_kmatw_grad_f32: (gX, gs_rows) for out = K(X, Y) W with cotangent G (N x m); m <= 32, d <= 64."""
+    X, Y, W, G = _dev2d(X, "X"), _dev2d(Y, "Y"), _dev2d(W, "W"), _dev2d(G, "G")
+    N, d = X.shape
+    M, m = W.shape
+    if Y.shape != (M, d) or G.shape != (N, m):
+        raise ValueError("shape mismatch")
+    dev = X.device
+    gX = torch.empty((N, d), dtype=torch.float32, device=dev)
+    gs = torch.empty((N,), dtype=torch.float32, device=dev) if want_scale else None
+    with torch.cuda.device(dev):
+        wsb = lib().jrk_grad_workspace_bytes(N, M, d)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        _check(lib().jrk_kmatw_grad_f32(_ptr(X), _ptr(Y), _ptr(W), _ptr(G), _ptr(gX), _ptr(gs), N, M, d, m, _ld(X), _ld(Y),
+                                        _ld(W), _ld(G), d, scale, power, nconst, _ptr(ws), wsb, _stream(dev)))
+    return gX, gs
+
+
+def gram_grad(X, Y, Gbar, scale: float, power: float, nconst: float, want_scale: bool = True):
+    """jrk_gram_grad_f32: (gX, gs_rows) for K = K(X, Y) with cotangent Gbar (N x M); d <= 64."""
+    X, Y, Gbar = _dev2d(X, "X"), _dev2d(Y, "Y"), _dev2d(Gbar, "Gbar")
+    N, d = X.shape
+    M = Y.shape[0]
+    if Y.shape[1] != d or Gbar.shape != (N, M):
+        raise ValueError("shape mismatch")
+    dev = X.device
+    gX = torch.empty((N, d), dtype=torch.float32, device=dev)
+    gs = torch.empty((N,), dtype=torch.float32, device=dev) if want_scale else None
+    with torch.cuda.device(dev):
+        wsb = lib().jrk_grad_workspace_bytes(N, M, d)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        _check(lib().jrk_gram_grad_f32(_ptr(X), _ptr(Y), _ptr(Gbar), _ptr(gX), _ptr(gs), N, M, d, _ld(X), _ld(Y),
+                                       _ld(Gbar), d, scale, power, nconst, _ptr(ws), wsb, _stream(dev)))
+    return gX, gs
 
 
 class KernelSpec:

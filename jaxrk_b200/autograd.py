@@ -1,0 +1,118 @@
+"""Differentiable Gram / fused K@W: torch.autograd over the fused backward kernels (csrc/kgrad.cu).
+
+JaxRK is written to be differentiated with jax.grad (README.md:3; examples/Using_FLAX_Optax.ipynb cells 6-10 fit kernel
+parameters and prefactors by gradient descent; jaxrk/rkhs/vector.py:206-222 and jaxrk/utilities/gram.py:62-65 run
+L-BFGS over jax.grad).  With torch tensors as the array type of this package, the same role is played by
+torch.autograd: `gengauss_gram` and `gengauss_kmatw` are the differentiable forms of GenGaussKernel.__call__
+(jaxrk/kern/rbf.py:104-105) and of FiniteVec.inner's K @ W contraction (jaxrk/rkhs/vector.py:62-75), with gradients
+with respect to the points X, Y, the weights W and the global scale (1 / length_scale) computed by ONE fused pass
+each (jrk_kmatw_grad_f32 / jrk_gram_grad_f32) that never materialises K or dK.
+
+Not differentiated: the shape parameter `power` (a Python float here), per-dimension scales.
+"""
+import math
+
+import torch
+
+from . import _native as nat
+
+__all__ = ["gengauss_gram", "gengauss_kmatw", "gengauss_nconst"]
+
+
+def gengauss_nconst(scale, power: float):
+    """nconst = power / (2 * (1 / scale) * Gamma(1 / power))  (jaxrk/kern/rbf.py:34), differentiable in `scale`."""
+    return scale * (power / (2.0 * math.exp(math.lgamma(1.0 / power))))
+
+
+def _scale_tensor(scale, dev):
+    if isinstance(scale, torch.Tensor):
+        return scale.to(device=dev, dtype=torch.float32)
+    return torch.tensor(float(scale), dtype=torch.float32, device=dev)
+
+
+class _UnnormGram(torch.autograd.Function):
+    """E[i, j] = exp(-(s ||x_i - y_j||)^p)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, scale_t, power, self_gram):
+        s = float(scale_t)
+        E = nat.gram(X, None if self_gram else Y, s, power, 1.0)
+        ctx.save_for_backward(X, Y, scale_t)
+        ctx.power = power
+        return E
+
+    @staticmethod
+    def backward(ctx, Gbar):
+        X, Y, scale_t = ctx.saved_tensors
+        s, p = float(scale_t), ctx.power
+        need_x, need_y, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        Gbar = Gbar.contiguous().float()
+        gX = gY = gs = None
+        if need_x or need_s:
+            gX, gs_rows = nat.gram_grad(X, Y, Gbar, s, p, 1.0, want_scale=need_s)
+            if need_s:
+                gs = gs_rows.sum().reshape(scale_t.shape)
+            if not need_x:
+                gX = None
+        if need_y:
+            gY, _ = nat.gram_grad(Y, X, Gbar.t().contiguous(), s, p, 1.0, want_scale=False)
+        return gX, gY, gs, None, None
+
+
+class _UnnormKmatw(torch.autograd.Function):
+    """T[i, c] = sum_j exp(-(s ||x_i - y_j||)^p) W[j, c], never materialised (forward or backward)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, W, scale_t, power):
+        s = float(scale_t)
+        T = nat.kmatw(X, Y, W, s, power, 1.0)
+        ctx.save_for_backward(X, Y, W, scale_t)
+        ctx.power = power
+        return T
+
+    @staticmethod
+    def backward(ctx, G):
+        X, Y, W, scale_t = ctx.saved_tensors
+        s, p = float(scale_t), ctx.power
+        need_x, need_y, need_w, need_s = ctx.needs_input_grad[:4]
+        G = G.contiguous().float()
+        m = W.shape[1]
+        gX = gY = gW = gs = None
+        for c0 in range(0, m, 32):       # the fused backward kernel takes m <= 32; the gradient adds up over column blocks
+            Wb, Gb = W[:, c0:c0 + 32], G[:, c0:c0 + 32]
+            if need_x or need_s:
+                gx_b, gs_rows = nat.kmatw_grad(X, Y, Wb, Gb, s, p, 1.0, want_scale=need_s)
+                if need_x:
+                    gX = gx_b if gX is None else gX + gx_b
+                if need_s:
+                    gs_b = gs_rows.sum()
+                    gs = gs_b if gs is None else gs + gs_b
+            if need_y:
+                gy_b, _ = nat.kmatw_grad(Y, X, Gb, Wb, s, p, 1.0, want_scale=False)
+                gY = gy_b if gY is None else gY + gy_b
+        if need_w:
+            gW = nat.kmatw(Y, X, G, s, p, 1.0)        # K(Y, X) @ G = K^T G
+        if gs is not None:
+            gs = gs.reshape(scale_t.shape)
+        return gX, gY, gW, gs, None
+
+
+def gengauss_gram(X, Y, scale, power: float, nconst=None):
+    """K = nconst * exp(-(scale ||x - y||)^power) with gradients to X, Y and `scale` (a float or a 0-dim tensor).
+    Y=None is the self-Gram (symmetric kernel, gradient through both arguments).  nconst=None derives it from
+    `scale` as the reference does (rbf.py:34), differentiably."""
+    dev = X.device
+    scale_t = _scale_tensor(scale, dev)
+    self_gram = Y is None
+    E = _UnnormGram.apply(X, X if self_gram else Y, scale_t, float(power), self_gram)
+    nc = gengauss_nconst(scale_t, float(power)) if nconst is None else nconst
+    return nc * E
+
+
+def gengauss_kmatw(X, Y, W, scale, power: float, nconst=None):
+    """K(X, Y) @ W, never materialised, with gradients to X, Y, W and `scale`."""
+    dev = X.device
+    scale_t = _scale_tensor(scale, dev)
+    T = _UnnormKmatw.apply(X, Y, W, scale_t, float(power))
+    nc = gengauss_nconst(scale_t, float(power)) if nconst is None else nconst
+    return nc * T

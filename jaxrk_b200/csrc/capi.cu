@@ -10,6 +10,10 @@ namespace jrk {
 
 thread_local char g_last_error[512] = {0};
 thread_local ExtraKind g_extra_kind;
+int kgrad(int mode, const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, int64_t N,
+          int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float scale,
+          float power, float nconst, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t kgrad_workspace_bytes(int64_t N, int64_t M, int d);
 int dist_diag(const float* X, const float* Y, float* out, int64_t N, int d, int64_t ldx, int64_t ldy, float scale,
               const float* dim_scale, float power, cudaStream_t st);
 std::atomic<int64_t> g_launches{0};
@@ -190,6 +194,35 @@ int jrk_kmatw_kind_f32(const float* X, const float* Y, const float* W, float* ou
     ExtraKindScope scope(ex.kind, ex.a0, ex.a1, ex.a2);
     return jrk_kmatw_f32(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, dim_scale, power, nconst, row_pref,
                          col_pref, row_reduce, group, workspace, workspace_bytes, stream);
+}
+
+size_t jrk_grad_workspace_bytes(int64_t N, int64_t M, int d) { return kgrad_workspace_bytes(N, M, d); }
+
+int jrk_kmatw_grad_f32(const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows,
+                       int64_t N, int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg,
+                       int64_t ldgx, float scale, float power, float nconst, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+    if (!X || !Y || !W || !G || !gX) return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_grad_f32: NULL pointer");
+    if (N < 1 || M < 1 || m < 1) return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_grad_f32: N, M, m must be >= 1");
+    if (int rc = check_kernel_params("jrk_kmatw_grad_f32", d, scale, power, nconst)) return rc;
+    if (ldx < d || ldy < d || ldw < m || ldg < m || ldgx < d)
+        return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_grad_f32: leading dimension too small");
+    if (int rc = have_device("jrk_kmatw_grad_f32")) return rc;
+    return kgrad(0, X, Y, W, G, gX, gs_rows, N, M, d, m, ldx, ldy, ldw, ldg, ldgx, scale, power, nconst, workspace,
+                 workspace_bytes, (cudaStream_t)stream);
+}
+
+int jrk_gram_grad_f32(const float* X, const float* Y, const float* Gbar, float* gX, float* gs_rows, int64_t N, int64_t M,
+                      int d, int64_t ldx, int64_t ldy, int64_t ldgb, int64_t ldgx, float scale, float power, float nconst,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    if (!X || !Y || !Gbar || !gX) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_grad_f32: NULL pointer");
+    if (N < 1 || M < 1) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_grad_f32: N, M must be >= 1");
+    if (int rc = check_kernel_params("jrk_gram_grad_f32", d, scale, power, nconst)) return rc;
+    if (ldx < d || ldy < d || ldgb < M || ldgx < d)
+        return fail(JRK_ERR_INVALID_ARG, "jrk_gram_grad_f32: leading dimension too small");
+    if (int rc = have_device("jrk_gram_grad_f32")) return rc;
+    return kgrad(1, X, Y, nullptr, Gbar, gX, gs_rows, N, M, d, 0, ldx, ldy, 0, ldgb, ldgx, scale, power, nconst,
+                 workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t jrk_kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce, int64_t group) {

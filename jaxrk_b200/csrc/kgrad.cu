@@ -1,0 +1,233 @@
+// Kernel (g): fused backward of the Gram / K@W path with respect to the points and the scale.
+//
+// JaxRK exists to be differentiated (README.md:3 "... differentiable ...", examples/Using_FLAX_Optax.ipynb cells
+// 6-10, the scipy/L-BFGS helpers jaxrk/rkhs/vector.py:206-222 and jaxrk/utilities/gram.py:62-65): jax.grad of a loss
+// through GenGaussKernel.__call__ (jaxrk/kern/rbf.py:104-105) and FiniteVec.inner (jaxrk/rkhs/vector.py:62-75) is what
+// XLA derives from the materialised N x M chain.  Here the vector-Jacobian product is ONE fused pass that never
+// materialises K (nor dK):
+//     forward      out[i, c] = sum_j K_ij W[j, c]                   (jrk_kmatw_f32),   K_ij = nconst exp(-(s r_ij)^p)
+//     cotangent    a_ij = sum_c G[i, c] W[j, c]        MODE 0  (K@W: G = dL/dout, N x m)
+//                  a_ij = Gbar[i, j]                   MODE 1  (Gram: Gbar = dL/dK, N x M, read once: HBM-bound)
+//     dL/dx_i      = sum_j a_ij dK_ij/dx_i = fac * sum_j t_ij (y_j - x_i)
+//     dL/ds        = -(fac / s) * sum_ij t_ij r_ij^2
+//   with  dK/dx_i = -K p s^p r^(p-2) (x_i - y_j)  and  t_ij = a_ij * (K_ij / nconst) * {1 | 1/r | u/r^2},
+//   fac = nconst * {2 s^2 | s | p} for p = 2 | p = 1 | general p (u = (s r)^p).  Pairs at distance zero contribute
+//   nothing (for p <= 1 the derivative does not exist there and the reference's jax.grad returns NaN; 0 is the
+//   subgradient that keeps the self-Gram usable).
+// dL/dy_j is the same kernel with the roles of (X, G) and (Y, W) exchanged; dL/dW = K^T G is the forward kernel.
+//
+// Layout: one thread per row i (x_i, S1 = sum t y, S0 = sum t, S2 = sum t r^2 in registers), 128 rows per CTA, tiles
+// of 32 columns j staged in shared memory (Y tile, W tile or the 128 x 32 block of Gbar) and read as broadcasts;
+// the j range is split over blockIdx.y when there are few rows, partial sums are combined in a fixed order by
+// kgrad_finalize_kernel (deterministic, no float atomics).  FP32-pipe bound: 3d + m + ~8 lane-ops per pair (MODE 0).
+#include "common.cuh"
+
+namespace jrk {
+
+namespace {
+
+constexpr int KG_ROWS = 128, KG_TJ = 32;
+
+template <int D, int MT, int MODE, int PM>
+__global__ void __launch_bounds__(KG_ROWS, 2)
+kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ Y, int64_t ldy, int d,
+             const float* __restrict__ W, int64_t ldw, const float* __restrict__ G, int64_t ldg, int m,
+             int64_t N, int64_t M, int64_t cols_per_split, EpiParams ep, float* __restrict__ part, int stride) {
+    // part layout: [split][row][stride], stride = d + 2: {dL/dx contribution (d), S0 (unused by finalize), S2}
+    __shared__ __align__(16) float sY[KG_TJ][D];
+    __shared__ __align__(16) float sA[(MODE == 0) ? KG_TJ * MT : KG_ROWS * (KG_TJ + 1)];
+
+    const int tid = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * KG_ROWS + tid;
+    const bool iok = i < N;
+    float x[D], s1[D], g[(MODE == 0) ? MT : 1];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { x[k] = (iok && k < d) ? __ldg(X + i * ldx + k) : 0.f; s1[k] = 0.f; }
+    if (MODE == 0) {
+#pragma unroll
+        for (int c = 0; c < MT; ++c) g[c] = (iok && c < m) ? __ldg(G + i * ldg + c) : 0.f;
+    }
+    float s0 = 0.f, s2 = 0.f;
+
+    const int64_t j_begin = (int64_t)blockIdx.y * cols_per_split;
+    const int64_t j_end = (j_begin + cols_per_split < M) ? j_begin + cols_per_split : M;
+    for (int64_t j0 = j_begin; j0 < j_end; j0 += KG_TJ) {
+        __syncthreads();
+        // ---- stage the tile ----
+        for (int idx = tid; idx < KG_TJ * D; idx += KG_ROWS) {
+            const int jj = idx / D, k = idx % D;
+            const int64_t j = j0 + jj;
+            sY[jj][k] = (j < j_end && k < d) ? __ldg(Y + j * ldy + k) : 0.f;
+        }
+        if (MODE == 0) {
+            for (int idx = tid; idx < KG_TJ * MT; idx += KG_ROWS) {
+                const int jj = idx / MT, c = idx % MT;
+                const int64_t j = j0 + jj;
+                sA[jj * MT + c] = (j < j_end && c < m) ? __ldg(W + j * ldw + c) : 0.f;
+            }
+        } else {
+            // 128 x 32 block of Gbar: coalesced over j, rows of this CTA; padded row stride 33 -> conflict-free reads
+            const int64_t r0 = (int64_t)blockIdx.x * KG_ROWS;
+            for (int idx = tid; idx < KG_ROWS * KG_TJ; idx += KG_ROWS) {
+                const int rr = idx / KG_TJ, jj = idx % KG_TJ;
+                const int64_t r = r0 + rr, j = j0 + jj;
+                sA[rr * (KG_TJ + 1) + jj] = (r < N && j < j_end) ? __ldg(G + r * ldg + j) : 0.f;
+            }
+        }
+        __syncthreads();
+        const int nj = (int)((j_end - j0 < KG_TJ) ? j_end - j0 : KG_TJ);
+#pragma unroll 2
+        for (int jj = 0; jj < nj; ++jj) {
+            float sq = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float df = x[k] - sY[jj][k];
+                sq = fmaf(df, df, sq);
+            }
+            float a;
+            if (MODE == 0) {
+                a = 0.f;
+#pragma unroll
+                for (int c = 0; c < MT; ++c) a = fmaf(g[c], sA[jj * MT + c], a);
+            } else {
+                a = sA[tid * (KG_TJ + 1) + jj];
+            }
+            // t = a * (K / nconst) * {1 | 1/r | u / r^2}
+            float t;
+            if (PM == PM_SQEXP) {
+                t = a * ex2_approx(sq * ep.c);
+            } else if (PM == PM_LAPLACE) {
+                const float r = sqrt_approx(sq);
+                t = (sq > 0.f) ? a * ex2_approx(r * ep.c) / r : 0.f;
+            } else {
+                const float u = ex2_approx(ep.hp * lg2_approx(sq * ep.c));     // (s r)^p
+                t = (sq > 0.f) ? a * ex2_approx(u * -kLog2e) * u / sq : 0.f;
+            }
+            s0 += t;
+            s2 = fmaf(t, sq, s2);
+#pragma unroll
+            for (int k = 0; k < D; ++k) s1[k] = fmaf(t, sY[jj][k], s1[k]);
+        }
+    }
+    if (iok) {
+        float* dst = part + ((int64_t)blockIdx.y * N + i) * stride;
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            if (k < d) dst[k] = fmaf(-x[k], s0, s1[k]);      // sum_j t (y_j - x_i)
+        dst[d] = s0;
+        dst[d + 1] = s2;
+    }
+}
+
+// gX[i, k] = fac * sum_split part[split][i][k];  gs_rows[i] = -(fac / s) * sum_split part[split][i][d + 1]
+__global__ void kgrad_finalize_kernel(const float* __restrict__ part, int nsplit, int64_t N, int d, int stride, float fac,
+                                      float fac_s, float* __restrict__ gX, int64_t ldgx, float* __restrict__ gs_rows) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = idx / (d + 1);
+    const int k = (int)(idx % (d + 1));
+    if (i >= N) return;
+    float acc = 0.f;
+    for (int s = 0; s < nsplit; ++s) acc += part[((int64_t)s * N + i) * stride + (k < d ? k : d + 1)];
+    if (k < d) gX[i * ldgx + k] = fac * acc;
+    else if (gs_rows) gs_rows[i] = fac_s * acc;
+}
+
+template <int D, int MT, int MODE, int PM>
+int kg_launch(dim3 grid, cudaStream_t st, const float* X, int64_t ldx, const float* Y, int64_t ldy, int d, const float* W,
+              int64_t ldw, const float* G, int64_t ldg, int m, int64_t N, int64_t M, int64_t cps, const EpiParams& ep,
+              float* part, int stride) {
+    kgrad_kernel<D, MT, MODE, PM><<<grid, KG_ROWS, 0, st>>>(X, ldx, Y, ldy, d, W, ldw, G, ldg, m, N, M, cps, ep, part, stride);
+    JRK_LAUNCHED();
+    return JRK_OK;
+}
+
+int kg_sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+struct KgPlan {
+    int nsplit;
+    int64_t cols_per_split;
+};
+KgPlan kg_plan(int64_t N, int64_t M) {
+    const int64_t nblk = (N + KG_ROWS - 1) / KG_ROWS;
+    int64_t want = ((int64_t)kg_sm_count() * 4 + nblk - 1) / nblk;       // ~4 CTAs per SM in flight
+    const int64_t max_split = (M + 4 * KG_TJ - 1) / (4 * KG_TJ);          // at least 4 tiles per split
+    if (want > max_split) want = max_split;
+    if (want > 1024) want = 1024;
+    if (want < 1) want = 1;
+    KgPlan p;
+    p.cols_per_split = ((M + want - 1) / want + KG_TJ - 1) / KG_TJ * KG_TJ;
+    p.nsplit = (int)((M + p.cols_per_split - 1) / p.cols_per_split);
+    return p;
+}
+
+}  // namespace
+
+size_t kgrad_workspace_bytes(int64_t N, int64_t M, int d) {
+    const KgPlan p = kg_plan(N, M);
+    return align256((size_t)p.nsplit * (size_t)N * (size_t)(d + 2) * 4) + 512;
+}
+
+// mode 0: K@W cotangent (W: M x m, G: N x m);  mode 1: Gram cotangent (G = Gbar: N x M, W unused, m = 0)
+int kgrad(int mode, const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, int64_t N,
+          int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float scale,
+          float power, float nconst, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (d > 64) return fail(JRK_ERR_UNSUPPORTED, "kgrad: d = %d > 64 is not supported by the fused backward kernel", d);
+    if (g_extra_kind.kind != 0) return fail(JRK_ERR_UNSUPPORTED, "kgrad: GenGauss kernels only");
+    const EpiParams ep = make_epi(scale, power, nconst);
+    const int pm = pick_pmode(power);
+    const KgPlan p = kg_plan(N, M);
+    Scratch scr(workspace, workspace_bytes, st);
+    JRK_CUDA_OK(scr.reserve(kgrad_workspace_bytes(N, M, d)));
+    const int stride = d + 2;
+    float* part = scr.take<float>((size_t)p.nsplit * N * stride);
+    const double s = (double)scale;
+    const float fac = (float)((double)nconst * (pm == PM_SQEXP ? 2.0 * s * s : pm == PM_LAPLACE ? s : (double)power));
+    const float fac_s = (float)(-(double)fac / s);
+    const int64_t nblk = (N + KG_ROWS - 1) / KG_ROWS;
+    if (nblk > 2147483647LL) return fail(JRK_ERR_UNSUPPORTED, "kgrad: too many rows");
+    dim3 grid((unsigned)nblk, (unsigned)p.nsplit);
+    const int D = d <= 8 ? 8 : d <= 16 ? 16 : d <= 32 ? 32 : 64;
+
+    if (mode == 0 && m > 32)   // (the caller splits wide G / W into column blocks: the gradient is additive over them)
+        return fail(JRK_ERR_UNSUPPORTED, "kgrad: m = %d > 32 is not supported by the fused backward kernel", m);
+    const int MT = m <= 4 ? 4 : m <= 16 ? 16 : 32;
+    int rc;
+#define KG_GO(D_, MT_, MODE_, PM_) \
+    rc = kg_launch<D_, MT_, MODE_, PM_>(grid, st, X, ldx, Y, ldy, d, W, ldw, G, ldg, m, N, M, p.cols_per_split, ep, part, stride)
+#define KG_MT(D_, PM_)                                   \
+    do {                                                 \
+        if (mode == 1) KG_GO(D_, 4, 1, PM_);             \
+        else if (MT == 4) KG_GO(D_, 4, 0, PM_);          \
+        else if (MT == 16) KG_GO(D_, 16, 0, PM_);        \
+        else KG_GO(D_, 32, 0, PM_);                      \
+    } while (0)
+#define KG_D(PM_)                                        \
+    do {                                                 \
+        if (D == 8) KG_MT(8, PM_);                       \
+        else if (D == 16) KG_MT(16, PM_);                \
+        else if (D == 32) KG_MT(32, PM_);                \
+        else KG_MT(64, PM_);                             \
+    } while (0)
+    if (pm == PM_SQEXP) KG_D(PM_SQEXP);
+    else if (pm == PM_LAPLACE) KG_D(PM_LAPLACE);
+    else KG_D(PM_GENERAL);
+#undef KG_D
+#undef KG_MT
+#undef KG_GO
+    if (rc) return rc;
+    const int64_t tot = N * (d + 1);
+    kgrad_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(part, p.nsplit, N, d, stride, fac, fac_s, gX, ldgx, gs_rows);
+    JRK_LAUNCHED();
+    return JRK_OK;
+}
+
+}  // namespace jrk

@@ -410,6 +410,36 @@ RTOL = 1e-5
 ATOL = 1e-6
 
 
+def gengauss_vjp_truth64(X, Y, A, s, power: float, nconst=None):
+    """float64 vector-Jacobian product of K = nconst exp(-(s |x - y|)^p) with cotangent A = dL/dK (N x M):
+    returns (dL/dX, dL/dY, dL/ds at fixed nconst, sum_j |a_ij dK_ij/dx_i| as the accumulation magnitude for tolerances).
+    This is what jax.grad derives from the reference chain (kern/rbf.py:104-105 over kern/util.py:115), written out:
+    dK/dx_i = -K p s^p r^(p-2) (x_i - y_j),  dK/ds = -K p s^(p-1) r^p;  pairs at r = 0 contribute nothing."""
+    s = np.asarray(s, dtype=f32)
+    assert s.size == 1
+    sv = float(s.reshape(()))
+    if nconst is None:
+        nconst = gengauss_nconst_ref32(s, power)
+    nc = float(np.asarray(nconst, dtype=np.float64).reshape(-1)[0])
+    p = float(f32(power))
+    X64, Y64 = _as2d_f32(X).astype(np.float64), _as2d_f32(Y).astype(np.float64)
+    A = np.asarray(A, dtype=np.float64)
+    diff = X64[:, None, :] - Y64[None, :, :]                    # N x M x d
+    sq = (diff ** 2).sum(-1)
+    r = np.sqrt(sq)
+    K = nc * np.exp(-np.power(sv * r, p))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        phi = np.where(sq > 0, K * p * sv ** p * np.power(r, p - 2.0), 0.0)
+    T = A * phi
+    gX = -(T[:, :, None] * diff).sum(1)
+    gY = (T[:, :, None] * diff).sum(0)
+    gs = -(A * K * p * sv ** (p - 1.0) * np.power(r, p)).sum()
+    mag_x = (np.abs(T)[:, :, None] * np.abs(diff)).sum(1)
+    mag_y = (np.abs(T)[:, :, None] * np.abs(diff)).sum(0)
+    mag_s = (np.abs(A) * K * p * sv ** (p - 1.0) * np.power(r, p)).sum()
+    return gX, gY, gs, (mag_x, mag_y, mag_s)
+
+
 def within_tol(got, truth, rtol=RTOL, atol=ATOL) -> np.ndarray:
     got = np.asarray(got, dtype=np.float64)
     truth = np.asarray(truth, dtype=np.float64)

@@ -1,0 +1,109 @@
+"""Fused backward kernels (csrc/kgrad.cu: jrk_kmatw_grad_f32 / jrk_gram_grad_f32) and the torch.autograd functions
+over them (jaxrk_b200/autograd.py) against the float64 analytic oracle.  SURVEY.md §8f rank 2."""
+import numpy as np
+import pytest
+import torch
+
+from jaxrk_b200 import _native as nat
+from jaxrk_b200 import autograd as ag
+from oracle import jaxrk_oracle as orc
+from gpu_util import cu, f32, gauss, kparams
+
+pytestmark = pytest.mark.gpu
+RT, AT = 2e-5, 2e-6      # gradient sums are judged against the magnitude of what was accumulated
+
+
+def _check(got, want, mag, what):
+    got = np.asarray(got, np.float64)
+    err = np.abs(got - want)
+    lim = AT + RT * mag
+    assert (err <= lim).all(), f"{what}: worst err {err.max():.3e}, limit there {np.broadcast_to(lim, err.shape).flat[err.argmax()]:.3e}"
+
+
+@pytest.mark.parametrize("kname", ["sqexp", "laplace", "gg15", "gg05"])
+@pytest.mark.parametrize("N,M,d,m", [(300, 517, 16, 16), (129, 64, 3, 1), (1000, 33, 40, 5), (64, 2100, 8, 32)])
+def test_kmatw_grad_against_oracle(kname, N, M, d, m):
+    X, Y, W, G = gauss(0, N, d), gauss(1, M, d), gauss(2, M, m), gauss(3, N, m)
+    s, scale, p, nconst = kparams(kname, np.sqrt(d) * 0.9)
+    A = G.astype(np.float64) @ W.astype(np.float64).T
+    gX, gY, gs, (mx, my, ms) = orc.gengauss_vjp_truth64(X, Y, A, s, p, nconst=nconst)
+    # |a_ij| <= sum_c |G_ic W_jc|: the accumulated magnitude of the fused kernel includes the m-term dot product
+    Aabs = np.abs(G).astype(np.float64) @ np.abs(W).astype(np.float64).T
+    _, _, _, (mxa, mya, msa) = orc.gengauss_vjp_truth64(X, Y, Aabs, s, p, nconst=nconst)
+    n0 = nat.launch_count()
+    gx_d, gs_rows = nat.kmatw_grad(cu(X), cu(Y), cu(W), cu(G), scale, p, nconst)
+    assert nat.launch_count() - n0 == 2            # fused pass + fixed-order finalize
+    _check(gx_d.cpu().numpy(), gX, mxa, f"dL/dX {kname}")
+    _check(float(gs_rows.double().sum()), gs, msa, f"dL/dscale {kname}")
+    gy_d, _ = nat.kmatw_grad(cu(Y), cu(X), cu(G), cu(W), scale, p, nconst, want_scale=False)
+    _check(gy_d.cpu().numpy(), gY, mya, f"dL/dY {kname}")
+
+
+@pytest.mark.parametrize("kname", ["sqexp", "laplace", "gg15"])
+@pytest.mark.parametrize("N,M,d", [(300, 517, 16), (130, 70, 2), (257, 1025, 64)])
+def test_gram_grad_against_oracle(kname, N, M, d):
+    X, Y, A = gauss(0, N, d), gauss(1, M, d), gauss(4, N, M)
+    s, scale, p, nconst = kparams(kname, np.sqrt(d) * 1.1)
+    gX, gY, gs, (mx, my, ms) = orc.gengauss_vjp_truth64(X, Y, A, s, p, nconst=nconst)
+    gx_d, gs_rows = nat.gram_grad(cu(X), cu(Y), cu(A), scale, p, nconst)
+    _check(gx_d.cpu().numpy(), gX, mx, f"gram dL/dX {kname}")
+    _check(float(gs_rows.double().sum()), gs, ms, f"gram dL/dscale {kname}")
+    gy_d, _ = nat.gram_grad(cu(Y), cu(X), cu(A.T.copy()), scale, p, nconst, want_scale=False)
+    _check(gy_d.cpu().numpy(), gY, my, f"gram dL/dY {kname}")
+
+
+def test_self_gram_with_coincident_points_has_finite_gradients():
+    X = gauss(5, 200, 6)
+    A = gauss(6, 200, 200)
+    for kname in ("laplace", "gg05", "sqexp"):
+        s, scale, p, nconst = kparams(kname, 2.0)
+        gX, gY, gs, (mx, my, ms) = orc.gengauss_vjp_truth64(X, X, A, s, p, nconst=nconst)
+        gx_d, gs_rows = nat.gram_grad(cu(X), cu(X), cu(A), scale, p, nconst)
+        assert torch.isfinite(gx_d).all() and torch.isfinite(gs_rows).all()
+        _check(gx_d.cpu().numpy(), gX, mx, f"self gram {kname}")
+
+
+@pytest.mark.parametrize("power", [2.0, 1.0, 1.5])
+def test_autograd_functions_match_float64_autograd(power):
+    """End to end: loss(K) and loss(K @ W) differentiated with respect to X, Y, W and the length scale, against torch
+    float64 autograd through the reference's op sequence."""
+    N, M, d, m = 400, 300, 5, 40          # m > 32: the backward runs in two column blocks
+    Xn, Yn, Wn, Cn = gauss(0, N, d), gauss(1, M, d), gauss(2, M, m), gauss(3, N, m)
+    ls0 = 1.7
+
+    def run(dtype, dev, gram_fn, kmatw_fn):
+        X = torch.tensor(Xn, dtype=dtype, device=dev, requires_grad=True)
+        Y = torch.tensor(Yn, dtype=dtype, device=dev, requires_grad=True)
+        W = torch.tensor(Wn, dtype=dtype, device=dev, requires_grad=True)
+        ls = torch.tensor(ls0, dtype=dtype, device=dev, requires_grad=True)
+        C = torch.tensor(Cn, dtype=dtype, device=dev)
+        scale = 1.0 / ls
+        loss = (kmatw_fn(X, Y, W, scale) * C).sum() + (gram_fn(X, Y, scale) ** 2).sum() + gram_fn(X, None, scale).sum()
+        loss.backward()
+        return [float(loss)] + [t.grad.detach().double().cpu().numpy() for t in (X, Y, W, ls)]
+
+    def ref_gram(X, Y, scale):
+        Y = X if Y is None else Y
+        sq = ((X[:, None, :] - Y[None, :, :]) ** 2).sum(-1)
+        r = torch.where(sq > 0, torch.sqrt(torch.where(sq > 0, sq, torch.ones_like(sq))), torch.zeros_like(sq))
+        return ag.gengauss_nconst(scale, power) * torch.exp(-(scale * r) ** power)
+
+    want = run(torch.float64, "cpu", ref_gram, lambda X, Y, W, s: ref_gram(X, Y, s) @ W)
+    got = run(torch.float32, "cuda", lambda X, Y, s: ag.gengauss_gram(X, Y, s, power),
+              lambda X, Y, W, s: ag.gengauss_kmatw(X, Y, W, s, power))
+    assert abs(got[0] - want[0]) <= 1e-5 * abs(want[0]) + 1e-4
+    for g, w, name in zip(got[1:], want[1:], ("X", "Y", "W", "length_scale")):
+        scale_ = np.abs(w).max()
+        assert np.abs(g - w).max() <= 1e-4 * scale_ + 1e-5, (name, np.abs(g - w).max(), scale_)
+
+
+def test_grad_entry_points_validate_arguments():
+    a = cu(gauss(0, 8, 2))
+    with pytest.raises(nat.JrkError) as ei:
+        nat.kmatw_grad(cu(gauss(0, 8, 70)), cu(gauss(1, 8, 70)), cu(gauss(2, 8, 2)), cu(gauss(3, 8, 2)), 1.0, 2.0, 1.0)
+    assert ei.value.code == 3 and "d = 70" in str(ei.value)
+    with pytest.raises(nat.JrkError) as ei:
+        nat.kmatw_grad(a, a, cu(gauss(2, 8, 40)), cu(gauss(3, 8, 40)), 1.0, 2.0, 1.0)
+    assert ei.value.code == 3
+    with pytest.raises(nat.JrkError):
+        nat.gram_grad(a, a, cu(gauss(4, 8, 8)), 1.0, 2.5, 1.0)
