@@ -23,8 +23,11 @@ def _gammaln32(x):
 
 
 class GenGaussKernel(DensityKernel):
-    def __init__(self, dist: ScaledPairwiseDistance):
+    def __init__(self, dist: ScaledPairwiseDistance, scale_tensor=None):
         self.dist = dist
+        # differentiable global scale (0-dim tensor, 1 / length_scale) when the kernel was made from a tensor that
+        # requires grad: the Gram / inner products are then differentiable in it (jaxrk_b200/autograd.py)
+        self.scale_tensor = scale_tensor
         # rbf.py:34, float32 as under jax without x64
         self.nconst = (f32(dist.power) / (f32(2) * dist._get_scale_param()
                                           * np.exp(_gammaln32(1. / dist.power)))).astype(f32)
@@ -33,14 +36,17 @@ class GenGaussKernel(DensityKernel):
     def make(cls, length_scale, shape: float) -> "GenGaussKernel":
         """rbf.py:62-73: scale = 1/length_scale, shape in (0, 2]."""
         assert shape > 0 and shape <= 2
+        scale_t = None
         if isinstance(length_scale, torch.Tensor):
+            if length_scale.requires_grad and length_scale.numel() == 1:
+                scale_t = 1. / length_scale.reshape(())
             length_scale = length_scale.detach().cpu().numpy()
         if isinstance(length_scale, (float, int)):
             s = 1. / float(length_scale)
         else:
             ls = np.asarray(length_scale)
             s = float(1. / ls) if ls.ndim == 0 else (f32(1.) / ls.astype(f32)).astype(f32)
-        return GenGaussKernel(ScaledPairwiseDistance(scaler=SimpleScaler(s), power=shape))
+        return GenGaussKernel(ScaledPairwiseDistance(scaler=SimpleScaler(s), power=shape), scale_tensor=scale_t)
 
     @classmethod
     def make_laplace(cls, length_scale) -> "GenGaussKernel":
@@ -50,6 +56,8 @@ class GenGaussKernel(DensityKernel):
     def make_gauss(cls, length_scale) -> "GenGaussKernel":
         # the reference hard-codes this literal (rbf.py:93); it is not exactly 1/sqrt(2)
         f = 0.70710695
+        if isinstance(length_scale, torch.Tensor) and length_scale.requires_grad and length_scale.numel() == 1:
+            return GenGaussKernel.make(length_scale / f, 2.)
         if isinstance(length_scale, (float, int)):
             return GenGaussKernel.make(float(length_scale) / f, 2.)
         ls = np.asarray(length_scale.detach().cpu().numpy() if isinstance(length_scale, torch.Tensor) else length_scale)
@@ -80,7 +88,20 @@ class GenGaussKernel(DensityKernel):
             nc = torch.from_numpy(self.nconst).to(X.device)
             return nc * torch.exp(-self.dist(X, Y, diag))  # rbf.py:104-105 literally (O(N d) / quirk Q2)
         scale, dim_scale, power, nconst = args
+        if self.wants_grad(X, Y) and dim_scale is None:
+            from .. import autograd as ag
+            if self.scale_tensor is not None:
+                return ag.gengauss_gram(X, Y, self.scale_tensor, power)          # nconst follows the scale
+            return ag.gengauss_gram(X, Y, scale, power, nconst=nconst)
         return nat.gram(X, Y, scale, power, nconst, dim_scale=dim_scale)
+
+    def wants_grad(self, *tensors) -> bool:
+        """True when autograd is recording and one of the tensors -- or this kernel's scale -- requires grad."""
+        if not torch.is_grad_enabled():
+            return False
+        if self.scale_tensor is not None and self.scale_tensor.requires_grad:
+            return True
+        return any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
 
 
 class PeriodicKernel(Kernel):

@@ -129,6 +129,57 @@ def kernel_spec_of(k):
     return nat.KernelSpec(nat.KIND_GENGAUSS, (scale, power, nconst), dim_scale)
 
 
+def _chain_tensors(chain):
+    for r in chain or []:
+        for name in ("prefactors", "linear_map"):
+            t = getattr(r, name, None)
+            if isinstance(t, torch.Tensor):
+                yield t
+
+
+def _reduced_gram_autograd(k, spec, X, fx: Folded, Y, fy: Folded, self_gram: bool) -> torch.Tensor:
+    """The differentiable route (torch.autograd over the fused backward kernels, jaxrk_b200/autograd.py): the K@W
+    contraction stays fused; prefactors, the LinearReduce maps and the row reduces are ordinary torch ops on the small
+    operands, so gradients reach the points, the chain parameters and the kernel's scale."""
+    from .. import autograd as ag
+    scale, power, nconst = spec.kparams
+    st = getattr(k, "scale_tensor", None)
+    s_arg, nc_arg = (st, None) if st is not None else (scale, nconst)
+    skinny = (LINEAR, SUM, MEAN)
+
+    def side(Xa, fa: Folded, Yb, fb: Folded):      # fold_a(K(Xa, Yb)) applied with W = fold_b^T
+        W = _w_of(fb, Xa.device)
+        if fb.pref is not None:
+            W = fb.pref[:, None] * W
+        T = ag.gengauss_kmatw(Xa, Yb, W, s_arg, power, nconst=nc_arg)
+        if fa.pref is not None:
+            T = fa.pref[:, None] * T
+        if fa.kind == LINEAR:
+            return fa.A @ T
+        if fa.kind == SUM:
+            return T.sum(0, keepdim=True)
+        if fa.kind == MEAN:
+            return T.mean(0, keepdim=True)
+        if fa.kind == BALANCED:
+            return BalancedRed(fa.group, fa.average)(T, 0)
+        return T
+
+    if fy.kind in skinny and (fx.kind not in skinny or fy.out_len <= fx.out_len):
+        return side(X, fx, Y, fy)
+    if fx.kind in skinny:
+        return side(Y, fy, X, fx).t()
+    G = ag.gengauss_gram(X, None if self_gram else Y, s_arg, power, nconst=nc_arg)
+    if fx.pref is not None:
+        G = fx.pref[:, None] * G
+    if fy.pref is not None:
+        G = G * fy.pref[None, :]
+    if fx.kind == BALANCED:
+        G = BalancedRed(fx.group, fx.average)(G, 0)
+    if fy.kind == BALANCED:
+        G = BalancedRed(fy.group, fy.average)(G, 1)
+    return G
+
+
 def reduced_gram(k, X, chain_x, Y, chain_y, self_gram: bool = False) -> torch.Tensor:
     """R_X K(X, Y) R_Y^T.  `self_gram` says Y is X (enables the symmetric self-Gram kernel)."""
     dev = X.device
@@ -142,6 +193,12 @@ def reduced_gram(k, X, chain_x, Y, chain_y, self_gram: bool = False) -> torch.Te
     fx = fold_chain(chain_x, X.shape[0], dev)
     fy = fold_chain(chain_y, Y.shape[0], dev)
     skinny = (LINEAR, SUM, MEAN)
+
+    if (gg and dim_scale is None and X.shape[1] <= 64 and hasattr(k, "wants_grad")
+            and k.wants_grad(X, Y, *_chain_tensors(chain_x), *_chain_tensors(chain_y))):
+        out = _reduced_gram_autograd(k, spec, X, fx, Y, fy, self_gram)
+        out = Reduce.apply(out, fx.post, 0)
+        return Reduce.apply(out, fy.post, 1)
 
     if fy.kind in skinny and (fx.kind not in skinny or fy.out_len <= fx.out_len):
         out = _kmatw_side(X, Y, fx, fy, spec)

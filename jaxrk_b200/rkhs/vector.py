@@ -48,8 +48,10 @@ class FiniteVec(Vec):
         if Y is self:  # Cov_solve asks for inner(inp_feat) twice (operator.py:138 and :46): keep it
             key = tuple(id(r) for r in self.reduce)
             if self._inner_cache is None or self._inner_cache[0] != key:
-                self._inner_cache = (key, _lowering.reduced_gram(self.k, self.insp_pts, self.reduce,
-                                                                 self.insp_pts, self.reduce, True))
+                res = _lowering.reduced_gram(self.k, self.insp_pts, self.reduce, self.insp_pts, self.reduce, True)
+                if res.requires_grad:   # part of an autograd graph: not cached (a graph is backpropagated once)
+                    return res
+                self._inner_cache = (key, res)
             return self._inner_cache[1]
         return _lowering.reduced_gram(self.k, self.insp_pts, self.reduce, Y.insp_pts, Y.reduce, self_gram)
 

@@ -80,7 +80,7 @@ def test_autograd_functions_match_float64_autograd(power):
         scale = 1.0 / ls
         loss = (kmatw_fn(X, Y, W, scale) * C).sum() + (gram_fn(X, Y, scale) ** 2).sum() + gram_fn(X, None, scale).sum()
         loss.backward()
-        return [float(loss)] + [t.grad.detach().double().cpu().numpy() for t in (X, Y, W, ls)]
+        return [loss.item()] + [t.grad.detach().double().cpu().numpy() for t in (X, Y, W, ls)]
 
     def ref_gram(X, Y, scale):
         Y = X if Y is None else Y
@@ -107,3 +107,61 @@ def test_grad_entry_points_validate_arguments():
     assert ei.value.code == 3
     with pytest.raises(nat.JrkError):
         nat.gram_grad(a, a, cu(gauss(4, 8, 8)), 1.0, 2.5, 1.0)
+
+
+def test_api_level_gradients_through_finitevec_inner():
+    """jax.grad-style use of the reference-shaped API (examples/Using_FLAX_Optax.ipynb cells 6-10): a loss over
+    FiniteVec.inner / GenGaussKernel.__call__ differentiated with respect to the length scale, the points, prefactors
+    and a LinearReduce map -- against torch float64 autograd through the reference op sequence."""
+    from jaxrk_b200.kern import GenGaussKernel
+    from jaxrk_b200.reduce import BalancedRed, LinearReduce, Mean, Prefactors
+    from jaxrk_b200.rkhs import FiniteVec, inner
+    N, M, d, m = 240, 130, 3, 6
+    Xn, Yn, Pn, An = gauss(0, N, d), gauss(1, M, d), np.abs(gauss(2, N)), gauss(3, m, M)
+
+    def loss_api(dtype, dev, use_api):
+        X = torch.tensor(Xn, dtype=dtype, device=dev, requires_grad=True)
+        Y = torch.tensor(Yn, dtype=dtype, device=dev, requires_grad=True)
+        P = torch.tensor(Pn, dtype=dtype, device=dev, requires_grad=True)
+        A = torch.tensor(An, dtype=dtype, device=dev, requires_grad=True)
+        ls = torch.tensor(1.3, dtype=dtype, device=dev, requires_grad=True)
+        if use_api:
+            k = GenGaussKernel.make_gauss(ls)
+            t1 = inner(FiniteVec(k, X, [Prefactors(P)]), FiniteVec(k, Y, [LinearReduce(A)]))          # N x m  (K@W)
+            t2 = inner(FiniteVec(k, X, [BalancedRed(4, True)]), FiniteVec(k, Y, [Mean()]))            # N/4 x 1
+            t3 = k(X)                                                                                  # self-Gram
+        else:
+            f = 0.70710695
+            s = f / ls
+            def gram(a, b):
+                sq = ((a[:, None, :] - b[None, :, :]) ** 2).sum(-1)
+                return ag.gengauss_nconst(s, 2.0) * torch.exp(-(s * s) * sq)
+            K = gram(X, Y)
+            t1 = (P[:, None] * K) @ A.T
+            t2 = K.reshape(N // 4, 4, M).mean(1).mean(1, keepdim=True)
+            t3 = gram(X, X)
+        loss = (t1 ** 2).sum() + t2.sum() + (t3 ** 2).sum()
+        loss.backward()
+        return [loss.item()] + [t.grad.detach().double().cpu().numpy() for t in (X, Y, P, A, ls)]
+
+    want = loss_api(torch.float64, "cpu", False)
+    n0 = nat.launch_count()
+    got = loss_api(torch.float32, "cuda", True)
+    assert nat.launch_count() - n0 >= 8          # forward and backward both ran in libjaxrk_b200.so
+    assert abs(got[0] - want[0]) <= 2e-5 * abs(want[0])
+    for g, w, name in zip(got[1:], want[1:], ("X", "Y", "prefactors", "linear_map", "length_scale")):
+        scale_ = np.abs(w).max()
+        assert np.abs(g - w).max() <= 1e-4 * scale_ + 1e-6, (name, np.abs(g - w).max(), scale_)
+
+
+def test_no_grad_path_is_unchanged():
+    from jaxrk_b200.kern import GenGaussKernel
+    X = cu(gauss(0, 100, 4))
+    k = GenGaussKernel.make_gauss(1.1)
+    K0 = k(X)
+    Xg = X.clone().requires_grad_(True)
+    with torch.no_grad():
+        K1 = k(Xg)
+    K2 = k(Xg)
+    assert not K1.requires_grad and K2.requires_grad
+    assert torch.equal(K0, K1) and torch.allclose(K0, K2, rtol=1e-6, atol=1e-8)
