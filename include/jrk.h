@@ -64,7 +64,8 @@ extern "C" {
  *   JRK_KIND_PERIODIC     {1/period, length_scale}                      PeriodicKernel    jaxrk/kern/rbf.py:109-154
  *                         k = exp(-2 (sin(pi ||x-y|| / period) / length_scale)^2)
  *   JRK_KIND_THRESHSPIKE  {scale, power, spike, non_spike, threshold}   ThreshSpikeKernel jaxrk/kern/rbf.py:156-206
- *                         k = (scale ||x-y||)^power <= threshold ? spike : non_spike   (power > 0) */
+ *                         k = (scale ||x-y||)^power <= threshold ? spike : non_spike   (power > 0), evaluated as
+ *                         ||x-y||^2 <= (threshold^(1/power) / scale)^2 */
 #define JRK_KIND_GENGAUSS 0
 #define JRK_KIND_PERIODIC 1
 #define JRK_KIND_THRESHSPIKE 2

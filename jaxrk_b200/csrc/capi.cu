@@ -162,7 +162,9 @@ static int parse_kind(const char* fn, int kind, const float* kp, int n, float& s
         if (!(kp[2] > 0.f) || !(std::fabs(kp[3]) < kp[2]) || !(kp[4] >= 0.f))
             return fail(JRK_ERR_INVALID_ARG, "%s: need spike > 0, |non_spike| < spike, threshold >= 0", fn);
         scale = kp[0]; power = kp[1]; nconst = 1.f;
-        ex.kind = kind; ex.a0 = kp[4]; ex.a1 = kp[2]; ex.a2 = kp[3];
+        if (!(kp[0] > 0.f) || !(kp[1] > 0.f)) return fail(JRK_ERR_INVALID_ARG, "%s: scale and power must be positive", fn);
+        const double root = std::pow((double)kp[4], 1.0 / (double)kp[1]) / (double)kp[0];   // threshold on r
+        ex.kind = kind; ex.a0 = (float)(root * root); ex.a1 = kp[2]; ex.a2 = kp[3];
     } else {
         return fail(JRK_ERR_INVALID_ARG, "%s: unknown kernel kind %d", fn, kind);
     }

@@ -111,7 +111,7 @@ struct EpiParams {
     float p;
     // PM_EXTRA
     int kind;      // JRK_KIND_*
-    float a0;      // PERIODIC: 1 / length_scale;  THRESHSPIKE: threshold
+    float a0;      // PERIODIC: 1 / length_scale;  THRESHSPIKE: (threshold^(1/p) / s)^2, the threshold on r^2
     float a1;      // THRESHSPIKE: spike
     float a2;      // THRESHSPIKE: non_spike
 };
@@ -145,20 +145,17 @@ __device__ __forceinline__ float kexp_unnorm(float sq, const EpiParams& e) {
     } else {
         if (e.kind == JRK_KIND_PERIODIC) {
             // distance in periods; sin(pi t) has period 2 in t, so reduce t to [-1, 1] exactly before the MUFU sine
-            // (sin.approx is only accurate on a few periods around 0)
-            const float t = e.s * sqrtf(sq);
+            // (sin.approx is only accurate on a few periods around 0).  3 MUFU per evaluation.
+            const float t = e.s * sqrt_approx(sq);
             const float r = fmaf(-2.f, rintf(0.5f * t), t);
             float sn;
             asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(r * 3.14159265358979323846f));
             const float q = sn * e.a0;
             return ex2_approx(q * q * (-2.f * kLog2e));
         }
-        // ThreshSpike: the same distance expression as jrk_dist_f32, so that K == where(D <= threshold, ...)
-        float dist;
-        if (e.p == 2.f) dist = (e.s * e.s) * sq;
-        else if (e.p == 1.f) dist = e.s * sqrtf(sq);
-        else dist = powf(e.s * sqrtf(sq), e.p);
-        return dist <= e.a0 ? e.a1 : e.a2;
+        // ThreshSpike: (s r)^p <= threshold  <=>  r^2 <= (threshold^(1/p) / s)^2 =: a0 (monotone; computed on the host
+        // in double), so the epilogue is one compare + select and the Gram stays HBM-write-bound
+        return sq <= e.a0 ? e.a1 : e.a2;
     }
 }
 

@@ -40,17 +40,44 @@ kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__
     const int tid = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * KG_ROWS + tid;
     const bool iok = i < N;
-    float x[D], s1[D], g[(MODE == 0) ? MT : 1];
+    // packed FP32x2 over dimension pairs (k, k + 1) and column pairs (c, c + 1): half the issue slots of scalar code
+    f32x2 x2[D / 2], s1[D / 2], g2[(MODE == 0) ? MT / 2 : 1];
 #pragma unroll
-    for (int k = 0; k < D; ++k) { x[k] = (iok && k < d) ? __ldg(X + i * ldx + k) : 0.f; s1[k] = 0.f; }
+    for (int k = 0; k < D / 2; ++k) {
+        const float a0 = (iok && 2 * k < d) ? __ldg(X + i * ldx + 2 * k) : 0.f;
+        const float a1 = (iok && 2 * k + 1 < d) ? __ldg(X + i * ldx + 2 * k + 1) : 0.f;
+        x2[k] = pack2(a0, a1);
+        s1[k] = 0ull;
+    }
     if (MODE == 0) {
 #pragma unroll
-        for (int c = 0; c < MT; ++c) g[c] = (iok && c < m) ? __ldg(G + i * ldg + c) : 0.f;
+        for (int c = 0; c < MT / 2; ++c) {
+            const float a0 = (iok && 2 * c < m) ? __ldg(G + i * ldg + 2 * c) : 0.f;
+            const float a1 = (iok && 2 * c + 1 < m) ? __ldg(G + i * ldg + 2 * c + 1) : 0.f;
+            g2[c] = pack2(a0, a1);
+        }
     }
     float s0 = 0.f, s2 = 0.f;
 
     const int64_t j_begin = (int64_t)blockIdx.y * cols_per_split;
     const int64_t j_end = (j_begin + cols_per_split < M) ? j_begin + cols_per_split : M;
+    // MODE 1: this thread's share of the next 128 x 32 block of Gbar, fetched one tile ahead (the global-load latency
+    // would otherwise be exposed once per tile: only 8 warps are resident per SM)
+    constexpr int PRE = (MODE == 1) ? KG_TJ : 1;
+    float pre[PRE];
+    const int64_t r0 = (int64_t)blockIdx.x * KG_ROWS;
+    auto fetch_gbar = [&](int64_t j0) {
+        if (MODE == 1) {
+#pragma unroll
+            for (int q = 0; q < PRE; ++q) {
+                const int idx = q * KG_ROWS + tid;
+                const int rr = idx / KG_TJ, jj = idx % KG_TJ;
+                const int64_t r = r0 + rr, j = j0 + jj;
+                pre[q] = (r < N && j < j_end) ? __ldg(G + r * ldg + j) : 0.f;
+            }
+        }
+    };
+    fetch_gbar(j_begin);
     for (int64_t j0 = j_begin; j0 < j_end; j0 += KG_TJ) {
         __syncthreads();
         // ---- stage the tile ----
@@ -67,28 +94,47 @@ kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__
             }
         } else {
             // 128 x 32 block of Gbar: coalesced over j, rows of this CTA; padded row stride 33 -> conflict-free reads
-            const int64_t r0 = (int64_t)blockIdx.x * KG_ROWS;
-            for (int idx = tid; idx < KG_ROWS * KG_TJ; idx += KG_ROWS) {
-                const int rr = idx / KG_TJ, jj = idx % KG_TJ;
-                const int64_t r = r0 + rr, j = j0 + jj;
-                sA[rr * (KG_TJ + 1) + jj] = (r < N && j < j_end) ? __ldg(G + r * ldg + j) : 0.f;
+#pragma unroll
+            for (int q = 0; q < PRE; ++q) {
+                const int idx = q * KG_ROWS + tid;
+                sA[(idx / KG_TJ) * (KG_TJ + 1) + (idx % KG_TJ)] = pre[q];
             }
+            if (j0 + KG_TJ < j_end) fetch_gbar(j0 + KG_TJ);
         }
         __syncthreads();
         const int nj = (int)((j_end - j0 < KG_TJ) ? j_end - j0 : KG_TJ);
 #pragma unroll 2
         for (int jj = 0; jj < nj; ++jj) {
-            float sq = 0.f;
+            const ulonglong2* yrow = reinterpret_cast<const ulonglong2*>(&sY[jj][0]);
+            f32x2 y2[D / 2];
+            f32x2 sq2 = 0ull;
 #pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const float df = x[k] - sY[jj][k];
-                sq = fmaf(df, df, sq);
+            for (int k = 0; k < D / 4; ++k) {
+                const ulonglong2 v = yrow[k];
+                y2[2 * k] = v.x;
+                y2[2 * k + 1] = v.y;
             }
+#pragma unroll
+            for (int k = 0; k < D / 2; ++k) {
+                const f32x2 df = sub2(x2[k], y2[k]);
+                sq2 = fma2(df, df, sq2);
+            }
+            float sqa, sqb;
+            unpack2(sq2, sqa, sqb);
+            const float sq = sqa + sqb;
             float a;
             if (MODE == 0) {
-                a = 0.f;
+                const ulonglong2* wrow = reinterpret_cast<const ulonglong2*>(&sA[jj * MT]);
+                f32x2 a2 = 0ull;
 #pragma unroll
-                for (int c = 0; c < MT; ++c) a = fmaf(g[c], sA[jj * MT + c], a);
+                for (int c = 0; c < MT / 4; ++c) {
+                    const ulonglong2 v = wrow[c];
+                    a2 = fma2(g2[2 * c], v.x, a2);
+                    a2 = fma2(g2[2 * c + 1], v.y, a2);
+                }
+                float aa, ab;
+                unpack2(a2, aa, ab);
+                a = aa + ab;
             } else {
                 a = sA[tid * (KG_TJ + 1) + jj];
             }
@@ -105,15 +151,21 @@ kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__
             }
             s0 += t;
             s2 = fmaf(t, sq, s2);
+            const f32x2 t2 = pack2(t, t);
 #pragma unroll
-            for (int k = 0; k < D; ++k) s1[k] = fmaf(t, sY[jj][k], s1[k]);
+            for (int k = 0; k < D / 2; ++k) s1[k] = fma2(t2, y2[k], s1[k]);
         }
     }
     if (iok) {
         float* dst = part + ((int64_t)blockIdx.y * N + i) * stride;
 #pragma unroll
-        for (int k = 0; k < D; ++k)
-            if (k < d) dst[k] = fmaf(-x[k], s0, s1[k]);      // sum_j t (y_j - x_i)
+        for (int k = 0; k < D / 2; ++k) {                     // sum_j t (y_j - x_i)
+            float xa, xb, sa, sb;
+            unpack2(x2[k], xa, xb);
+            unpack2(s1[k], sa, sb);
+            if (2 * k < d) dst[2 * k] = fmaf(-xa, s0, sa);
+            if (2 * k + 1 < d) dst[2 * k + 1] = fmaf(-xb, s0, sb);
+        }
         dst[d] = s0;
         dst[d + 1] = s2;
     }

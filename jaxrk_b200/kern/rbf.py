@@ -130,7 +130,8 @@ class PeriodicKernel(Kernel):
 
 class ThreshSpikeKernel(Kernel):
     """`spike` where the scaled distance is <= threshold, else `non_spike` -- drop-in for jaxrk/kern/rbf.py:156-206
-    (jrk_gram_kind_f32, JRK_KIND_THRESHSPIKE: the comparison runs on the same distance expression as jrk_dist_f32)."""
+    (jrk_gram_kind_f32, JRK_KIND_THRESHSPIKE: the comparison runs on the squared distance against the equivalent
+    threshold, one compare + select per entry)."""
 
     def __init__(self, dist: ScaledPairwiseDistance, spike: float, non_spike: float, threshold: float):
         spike, non_spike, threshold = float(spike), float(non_spike), float(threshold)

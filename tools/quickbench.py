@@ -1,5 +1,5 @@
 """Kernel-only timings of the C-ABI entry points (CUDA events, resident inputs).
-Usage: python tools/quickbench.py [gram|kmatw|groupsum|all]   -> JSON lines on stdout."""
+Usage: python tools/quickbench.py [gram|kmatw|groupsum|grad|siblings|all]   -> JSON lines on stdout."""
 import json
 import sys
 
@@ -80,6 +80,39 @@ def bench_groupsum():
                       "fma_frac": ev * (2 * d + 2) / FMA}), flush=True)
 
 
+def bench_grad():
+    """Fused backward kernels: pairs/s and the FP32-pipe fraction (3d + m + 8 lane-ops per pair, kgrad.cu)."""
+    for (N, M, d, m) in [(131072, 131072, 16, 16), (131072, 131072, 8, 1), (65536, 131072, 32, 16), (32768, 131072, 64, 16)]:
+        X, Y, W, G = randn(0, N, d), randn(1, M, d), randn(2, M, m), randn(3, N, m)
+        for power in (2.0, 1.0, 1.5):
+            s, p, nc = kp(power, d)
+            best, med = timeit(lambda: nat.kmatw_grad(X, Y, W, G, s, p, nc), reps=3, warm=1)
+            ev = N * M / best
+            print(json.dumps({"op": "kmatw_grad", "N": N, "M": M, "d": d, "m": m, "power": power, "ms": best * 1e3,
+                              "pairs_per_s": ev, "fma_frac": ev * (3 * d + m + 8) / FMA}), flush=True)
+    for (N, M, d) in [(32768, 32768, 16), (32768, 32768, 64)]:
+        X, Y, Gb = randn(0, N, d), randn(1, M, d), randn(4, N, M)
+        s, p, nc = kp(2.0, d)
+        best, med = timeit(lambda: nat.gram_grad(X, Y, Gb, s, p, nc), reps=3, warm=1)
+        ev = N * M / best
+        print(json.dumps({"op": "gram_grad", "N": N, "M": M, "d": d, "power": 2.0, "ms": best * 1e3, "pairs_per_s": ev,
+                          "hbm_read_frac": 4 * ev / HBM, "fma_frac": ev * (3 * d + 8) / FMA}), flush=True)
+
+
+def bench_siblings():
+    """PeriodicKernel / ThreshSpikeKernel Grams on the direct kernel (HBM-write roofline, 4 B per evaluation)."""
+    for (N, M, d) in [(32768, 32768, 1), (32768, 32768, 8)]:
+        X, Y = randn(0, N, d), randn(1, M, d)
+        for name, spec in (("periodic", nat.KernelSpec(nat.KIND_PERIODIC, (0.5, 1.0))),
+                           ("threshspike", nat.KernelSpec(nat.KIND_THRESHSPIKE, (1.0, 1.0, 1.0, 0.1, 1.5)))):
+            K = torch.empty((N, M), device=dev, dtype=torch.float32)
+            best, med = timeit(lambda: nat.gram_spec(X, Y, spec, out=K))
+            ev = N * M / best
+            print(json.dumps({"op": "gram_" + name, "N": N, "M": M, "d": d, "ms": best * 1e3, "evals_per_s": ev,
+                              "hbm_frac": 4 * ev / HBM}), flush=True)
+            del K
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gram", "all"):
@@ -90,3 +123,7 @@ if __name__ == "__main__":
         bench_kmatw()
     if what in ("groupsum", "all"):
         bench_groupsum()
+    if what in ("grad", "all"):
+        bench_grad()
+    if what in ("siblings", "all"):
+        bench_siblings()
