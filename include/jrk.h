@@ -161,7 +161,8 @@ int jrk_dist_diag_f32(const float *X, const float *Y, float *out, int64_t N, int
                       int64_t ldx, int64_t ldy, float scale, const float *dim_scale, float power, void *stream);
 
 /* 1 when jrk_kmatw_f32 would run both contractions of this problem on the tensor cores (kmatw_tc.cu: d <= 32,
- * m <= 16, no per-dimension scale, row_reduce NONE, large N and M, JRK_KMATW_TC != "0"), else 0 (FP32-pipe kernel).
+ * m <= 16, no per-dimension scale, row_reduce NONE / SUM / MEAN, large N and M, JRK_KMATW_TC != "0"), else 0
+ * (FP32-pipe kernel).
  * Introspection only (bench.py picks the roofline by it); results agree within the documented tolerance. */
 int jrk_kmatw_uses_tensor_cores(int64_t N, int64_t M, int d, int m, int has_dim_scale, int row_reduce);
 

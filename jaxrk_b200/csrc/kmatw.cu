@@ -36,7 +36,7 @@ bool kmatw_tc_eligible(int64_t N, int64_t M, int d, int m, const float* dim_scal
 size_t kmatw_tc_workspace_bytes(int64_t N, int64_t M);
 int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
              int64_t ldy, int64_t ldw, int64_t ldo, float scale, float power, float nconst, const float* row_pref,
-             const float* col_pref, void* workspace, size_t workspace_bytes, cudaStream_t st);
+             const float* col_pref, int row_reduce, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 constexpr int KW_THREADS = 128;
 constexpr int KW_TJ = 128;  // rows of Y / W per stage
@@ -476,7 +476,7 @@ int kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N,
     // both contractions on the tensor cores when the problem is large, narrow and plain (kmatw_tc.cu)
     if (kmatw_uses_tc(N, M, d, m, dim_scale != nullptr, row_reduce))
         return kmatw_tc(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, power, nconst, row_pref, col_pref,
-                        workspace, workspace_bytes, st);
+                        row_reduce, workspace, workspace_bytes, st);
     Scratch scr(workspace, workspace_bytes, st);
     JRK_CUDA_OK(scr.reserve(kmatw_workspace_bytes(N, M, d, m, row_reduce, group)));
     for (int c0 = 0; c0 < m; c0 += 32) {  // wide W: column blocks of 32 (K is recomputed per block)

@@ -616,6 +616,30 @@ __global__ void tc_rownorm_kernel(const float* __restrict__ A, int64_t rows, int
     if ((threadIdx.x & 31) == 0 && mx == mx) atomicMax(gmax, __float_as_uint(mx));
 }
 
+// Sum / Mean over rows of T (N x 16, dense), deterministic: per-chunk partial sums, then one thread per column.
+__global__ void tc_rowsum_kernel(const float* __restrict__ T, int64_t N, int64_t chunk, float* __restrict__ part) {
+    __shared__ float red[16][TC_MT];
+    const int c = threadIdx.x & 15, rl = threadIdx.x >> 4;          // 16 row lanes x 16 columns
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = (r0 + chunk < N) ? r0 + chunk : N;
+    float a = 0.f;
+    for (int64_t r = r0 + rl; r < r1; r += 16) a += T[r * TC_MT + c];
+    red[rl][c] = a;
+    __syncthreads();
+    if (rl == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) s += red[q][c];
+        part[(int64_t)blockIdx.x * TC_MT + c] = s;
+    }
+}
+__global__ void tc_rowsum_final_kernel(const float* __restrict__ part, int64_t nchunks, float scale, float* __restrict__ out, int m) {
+    const int c = threadIdx.x;
+    if (c >= m) return;
+    float s = 0.f;
+    for (int64_t q = 0; q < nchunks; ++q) s += part[q * TC_MT + c];
+    out[c] = scale * s;
+}
+
 template <int PM>
 int tc_launch(const TcParams& P, const EpiParams& ep, cudaStream_t st) {
     auto kern = kmatw_tc_kernel<PM>;
@@ -630,20 +654,24 @@ int tc_launch(const TcParams& P, const EpiParams& ep, cudaStream_t st) {
 
 bool kmatw_tc_eligible(int64_t N, int64_t M, int d, int m, const float* dim_scale, int row_reduce, float nconst) {
     (void)nconst;
-    if (dim_scale || row_reduce != JRK_REDUCE_NONE) return false;
+    // Sum / Mean over rows: the N x m result goes to scratch and is reduced in a fixed order (tc_rowsum_kernel)
+    if (dim_scale || !(row_reduce == JRK_REDUCE_NONE || row_reduce == JRK_REDUCE_SUM || row_reduce == JRK_REDUCE_MEAN)) return false;
     if (d < 1 || d > TC_DP || m < 1 || m > TC_MT) return false;
     // enough row blocks to fill the machine and enough columns to amortise the pre-pass
     return N >= (int64_t)TC_BM * 64 && M >= 4096 && M <= ((int64_t)1 << 30) && N <= ((int64_t)1 << 36);
 }
 
+constexpr int64_t TC_RS_CHUNK = 1024;    // rows per partial sum of the Sum / Mean reduction
+
 size_t kmatw_tc_workspace_bytes(int64_t N, int64_t M) {
     const int64_t n_tiles = (M + TC_NT - 1) / TC_NT;
-    return align256((size_t)n_tiles * tc_image(TC_DP).bytes) + align256((size_t)N * 4) + align256((size_t)M * 4) + 1024;
+    const size_t reduce_bytes = align256((size_t)N * TC_MT * 4) + align256((size_t)((N + TC_RS_CHUNK - 1) / TC_RS_CHUNK) * TC_MT * 4);
+    return reduce_bytes + align256((size_t)n_tiles * tc_image(TC_DP).bytes) + align256((size_t)N * 4) + align256((size_t)M * 4) + 1024;
 }
 
 int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
              int64_t ldy, int64_t ldw, int64_t ldo, float scale, float power, float nconst, const float* row_pref,
-             const float* col_pref, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+             const float* col_pref, int row_reduce, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     Scratch scr(workspace, workspace_bytes, st);
     JRK_CUDA_OK(scr.reserve(kmatw_tc_workspace_bytes(N, M)));
     const int64_t n_tiles = (M + TC_NT - 1) / TC_NT;
@@ -652,6 +680,10 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     float* xn = scr.take<float>((size_t)N);
     float* yn_all = scr.take<float>((size_t)M);
     unsigned* nmax = scr.take<unsigned>(2);
+    const bool reduce_rows = row_reduce == JRK_REDUCE_SUM || row_reduce == JRK_REDUCE_MEAN;
+    const int64_t nchunks = (N + TC_RS_CHUNK - 1) / TC_RS_CHUNK;
+    float* Tbuf = reduce_rows ? scr.take<float>((size_t)N * TC_MT) : nullptr;
+    float* rpart = reduce_rows ? scr.take<float>((size_t)nchunks * TC_MT) : nullptr;
 
     EpiParams ep = make_epi(scale, power, nconst);
     const int pm = pick_pmode(power);
@@ -675,7 +707,7 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     }
     TcParams P;
     P.X = X; P.ldx = ldx; P.d = d; P.Y = Y; P.ldy = ldy; P.xn = xn; P.img = img; P.L = L; P.row_pref = row_pref;
-    P.out = out; P.ldo = ldo; P.m = m; P.N = N; P.M = M;
+    P.out = reduce_rows ? Tbuf : out; P.ldo = reduce_rows ? TC_MT : ldo; P.m = reduce_rows ? TC_MT : m; P.N = N; P.M = M;
     P.n_tiles = (int)n_tiles;
     P.n_units = (int)((N + TC_BM - 1) / TC_BM);
     P.ksteps = (d + 7) / 8;
@@ -685,9 +717,16 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     // from the device-side maxima of the pre-pass (no host synchronisation)
     P.check = 0;
     P.nmax = nmax;
-    if (pm == PM_SQEXP) return tc_launch<PM_SQEXP>(P, ep, st);
-    if (pm == PM_LAPLACE) return tc_launch<PM_LAPLACE>(P, ep, st);
-    return tc_launch<PM_GENERAL>(P, ep, st);
+    int rc;
+    if (pm == PM_SQEXP) rc = tc_launch<PM_SQEXP>(P, ep, st);
+    else if (pm == PM_LAPLACE) rc = tc_launch<PM_LAPLACE>(P, ep, st);
+    else rc = tc_launch<PM_GENERAL>(P, ep, st);
+    if (rc || !reduce_rows) return rc;
+    tc_rowsum_kernel<<<(unsigned)nchunks, 256, 0, st>>>(Tbuf, N, TC_RS_CHUNK, rpart);
+    JRK_LAUNCHED();
+    tc_rowsum_final_kernel<<<1, 32, 0, st>>>(rpart, nchunks, row_reduce == JRK_REDUCE_MEAN ? 1.f / (float)N : 1.f, out, m);
+    JRK_LAUNCHED();
+    return JRK_OK;
 }
 
 }  // namespace jrk

@@ -131,5 +131,84 @@ class FiniteVec(Vec):
         return inner(self, FiniteVec(self.k, argument, []))
 
 
+class _ProductSqExp:
+    """The product of two squared-exponential GenGauss kernels on the column blocks of concatenated, pre-scaled
+    inputs: exp(-sR^2 |xR - yR|^2) exp(-sL^2 |xL - yL|^2) = exp(-|[sR xR, sL xL] - [sR yR, sL yL]|^2) -- again a
+    GenGauss kernel (scale 1, power 2), so CombVec products run through the fused kernels instead of two materialised
+    Grams."""
+
+    def __init__(self, nconst: float):
+        self._nconst = float(nconst)
+
+    def kernel_args(self):
+        return 1.0, None, 2.0, self._nconst
+
+
+def _is_product(op) -> bool:
+    import operator
+    import numpy as np
+    return op in (operator.mul, torch.mul, torch.multiply, np.multiply)
+
+
+class CombVec(Vec):
+    """Elementwise combination (e.g. product) of two vectors' Gram matrices, then a reduce chain -- drop-in for
+    jaxrk/rkhs/vector.py:227-268.  inner = reduce_0(reduce_1(operation(vR.inner(Y.vR), vL.inner(Y.vL)))).
+    When the operation is a product and both factors are plain FiniteVecs over squared-exponential kernels, the
+    combined Gram is itself a squared-exponential Gram on concatenated inputs (_ProductSqExp) and the whole inner
+    product, reduce chain included, is lowered onto ONE fused kernel call; otherwise the two (reduced) Grams are
+    computed by the fused kernels and combined with `operation`."""
+
+    def __init__(self, vR, vL, operation, reduce: List[Reduce] = []):
+        assert len(vR) == len(vL)
+        self.vR, self.vL = vR, vL
+        self.reduce = [] if reduce is None else reduce
+        self.operation = operation
+        self.__len = Reduce.final_len(len(self.vR), self.reduce)
+
+    def reduce_gram(self, gram, axis=0):
+        return Reduce.apply(gram, self.reduce, axis)
+
+    def _fusable_with(self, Y) -> bool:
+        def plain_sqexp(v):
+            if not isinstance(v, FiniteVec) or v.reduce or not hasattr(v.k, "kernel_args"):
+                return False
+            a = v.k.kernel_args()
+            return a is not None and a[1] is None and a[2] == 2.0
+        return (_is_product(self.operation) and all(plain_sqexp(v) for v in (self.vR, self.vL, Y.vR, Y.vL))
+                and self.vR.k is Y.vR.k and self.vL.k is Y.vL.k)
+
+    def _concat(self):
+        (sR, _, _, ncR), (sL, _, _, ncL) = self.vR.k.kernel_args(), self.vL.k.kernel_args()
+        return torch.cat([sR * self.vR.insp_pts, sL * self.vL.insp_pts], 1), ncR * ncL
+
+    def inner(self, Y: "CombVec" = None, full=True):
+        if Y is None:
+            Y = self
+        else:
+            assert Y.operation == self.operation
+        if self._fusable_with(Y):
+            Xc, nc = self._concat()
+            Yc = Xc if Y is self else Y._concat()[0]
+            return _lowering.reduced_gram(_ProductSqExp(nc), Xc, self.reduce, Yc, Y.reduce, Y is self)
+        G = self.operation(self.vR.inner(Y.vR), self.vL.inner(Y.vL))
+        return self.reduce_gram(Y.reduce_gram(G, 1), 0)
+
+    def extend_reduce(self, r: List[Reduce]) -> "CombVec":
+        if r is None or len(r) == 0:
+            return self
+        _r = copy(self.reduce)
+        _r.extend(r)
+        return CombVec(self.vR, self.vL, self.operation, _r)
+
+    def centered(self) -> "CombVec":
+        return self.extend_reduce([Center()])
+
+    def __len__(self):
+        return self.__len
+
+    def updated(self, prefactors):
+        raise NotImplementedError()
+
+
 def inner(X, Y=None, full=True):
     return X.inner(Y, full)

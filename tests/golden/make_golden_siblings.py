@@ -77,6 +77,21 @@ def main():
     Xb = X[:36]
     out["inner_periodic_balanced"] = onp.asarray(inner(FiniteVec(k, Xb, [BalancedRed(4, True)]), FiniteVec(k, Y, [LinearReduce(A)])), F32)
 
+    # ---- CombVec (jaxrk/rkhs/vector.py:227-268): product of two vectors' Grams, then a reduce chain ----
+    import operator
+    from jaxrk.rkhs import CombVec
+    kg1, kg2, kl = GenGaussKernel.make_gauss(1.3), GenGaussKernel.make_gauss(0.8), GenGaussKernel.make_laplace(1.1)
+    XR, XL = (rng.randn(24, 2)).astype(F32), (rng.randn(24, 3)).astype(F32)
+    YR, YL = (rng.randn(18, 2)).astype(F32), (rng.randn(18, 3)).astype(F32)
+    B = rng.randn(5, 18).astype(F32)
+    out.update(comb_XR=XR, comb_XL=XL, comb_YR=YR, comb_YL=YL, comb_B=B)
+    for name, (ka, kb) in {"gg": (kg1, kg2), "gl": (kg1, kl)}.items():
+        cx = CombVec(FiniteVec(ka, XR, []), FiniteVec(kb, XL, []), operator.mul, [BalancedRed(3, True)])
+        cy = CombVec(FiniteVec(ka, YR, []), FiniteVec(kb, YL, []), operator.mul, [LinearReduce(B)])
+        out[f"comb_{name}_xy"] = onp.asarray(cx.inner(cy), F32)
+        out[f"comb_{name}_xx"] = onp.asarray(cx.inner(), F32)
+        out[f"comb_{name}_len"] = onp.array([len(cx), len(cy)])
+
     path = os.path.join(HERE, "reference_siblings.npz")
     onp.savez_compressed(path, **out)
     print("wrote", path, len(out), "arrays")

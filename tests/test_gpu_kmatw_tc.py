@@ -121,3 +121,29 @@ def test_tc_factored_sqexp_path_regimes(ls_factor, expect, force, monkeypatch):
     assert_kmatw_close(G.cpu().numpy()[rows], truth, bound, f"tc sqexp {expect}, generic epilogue")
     b = torch.from_numpy(bound.max(0)).to(T.device).float()
     assert ((T - G).abs() <= 2e-6 + 2e-5 * b).all()
+
+
+@pytest.mark.parametrize("kname", ["sqexp", "laplace"])
+@pytest.mark.parametrize("rr", [nat.REDUCE_SUM, nat.REDUCE_MEAN])
+def test_tc_path_with_sum_and_mean_over_rows(kname, rr, force):
+    """Sum / Mean (jaxrk/reduce/base.py:132-150) folded behind the tensor-core kernel: the mean embedding evaluated at
+    M points, 1 x m, reduced in a fixed order."""
+    N, M, d, m = 16384 + 300, 8192 + 17, 16, 7
+    X, Y, W = gauss(0, N, d), gauss(1, M, d), gauss(2, M, m)
+    rp = np.random.RandomState(3).rand(N).astype(f32)
+    s, scale, p, nconst = kparams(kname, np.sqrt(d))
+    assert nat.lib().jrk_kmatw_uses_tensor_cores(N, M, d, m, 0, rr) == 1
+    force(True)
+    T = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst, row_pref=rp, row_reduce=rr)
+    T2 = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst, row_pref=rp, row_reduce=rr)
+    force(False)
+    F = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst, row_pref=rp, row_reduce=rr)
+    assert tuple(T.shape) == (1, m) and torch.equal(T, T2)          # deterministic
+    rows = np.arange(N)
+    G = orc.gengauss_gram_truth64(X, Y, s, p) * rp.astype(np.float64)[:, None]
+    truth = (G @ W.astype(np.float64)).sum(0, keepdims=True)
+    bound = (np.abs(G) @ np.abs(W.astype(np.float64))).sum(0, keepdims=True)
+    if rr == nat.REDUCE_MEAN:
+        truth, bound = truth / N, bound / N
+    assert_kmatw_close(T.cpu().numpy(), truth, bound, f"tc {kname} reduce {rr}")
+    assert_kmatw_close(F.cpu().numpy(), truth, bound, f"fp32 {kname} reduce {rr}")

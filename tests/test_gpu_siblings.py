@@ -171,3 +171,28 @@ def test_kind_entry_points_validate_arguments():
     K1 = nat.gram_spec(a, None, nat.KernelSpec(nat.KIND_GENGAUSS, (s, p, nc)))
     K2 = nat.gram(a, None, s, p, nc)
     assert torch.equal(K1, K2)
+
+
+def test_combvec_product_of_grams():
+    """CombVec.inner (jaxrk/rkhs/vector.py:242-247) against the reference's own outputs: the product of two
+    squared-exponential Grams runs as ONE fused call on concatenated inputs, a Gauss x Laplace product as two."""
+    import operator
+    from jaxrk_b200.rkhs import CombVec
+    kg1, kg2, kl = GenGaussKernel.make_gauss(1.3), GenGaussKernel.make_gauss(0.8), GenGaussKernel.make_laplace(1.1)
+    XR, XL, YR, YL, B = (cu(G[n]) for n in ("comb_XR", "comb_XL", "comb_YR", "comb_YL", "comb_B"))
+    for name, (ka, kb), launches in (("gg", (kg1, kg2), 1), ("gl", (kg1, kl), 2)):
+        cx = CombVec(FiniteVec(ka, XR, []), FiniteVec(kb, XL, []), operator.mul, [BalancedRed(3, True)])
+        cy = CombVec(FiniteVec(ka, YR, []), FiniteVec(kb, YL, []), operator.mul, [LinearReduce(B)])
+        assert [len(cx), len(cy)] == list(G[f"comb_{name}_len"])
+        n0 = nat.launch_count()
+        got = cx.inner(cy).cpu().numpy()
+        n1 = nat.launch_count() - n0
+        assert (n1 <= 5) if launches == 1 else (n1 >= 2), n1      # fused: K@W (+ operand packing / finalize); else two Grams
+        want = G[f"comb_{name}_xy"]
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 2e-6 + 3e-5 * np.abs(want).max(), name
+        gxx = cx.inner().cpu().numpy()
+        wxx = G[f"comb_{name}_xx"]
+        # (the reference misses truth on self-Gram diagonals for p < 2: up to 1.2e-4 there, SURVEY.md §7)
+        assert np.abs(gxx - wxx).max() <= (2e-6 if name == "gg" else 2e-4) + 3e-5 * np.abs(wxx).max(), name
+    assert len(cx.extend_reduce([Sum()])) == 1 and len(cx.centered()) == len(cx)
