@@ -54,6 +54,7 @@ if what in ("cfg5", "all"):
     N, T, d, m = 32768, 1 << 20, 16, 16
     X = randn(2, N, d)
     k = GenGaussKernel.make_gauss(float(np.sqrt(d)))
+    inner(FiniteVec(k, X))                     # warm-up (module load, allocator); a fresh FiniteVec is not cached
     inp = FiniteVec(k, X)
     Gm, t_gram = timed(lambda: inner(inp))
     print(json.dumps({"config": "cfg5-gram", "N": N, "d": d, "seconds": t_gram, "evals_per_s": N * N / t_gram,
@@ -62,6 +63,7 @@ if what in ("cfg5", "all"):
     print(json.dumps({"config": "cfg5-solve (library path, not hot)", "seconds": t_solve}), flush=True)
     Xt = randn(3, T, d)
     W = randn(4, m, N)
+    inner(FiniteVec(k, Xt[:16384]), FiniteVec(k, X, [LinearReduce(W)]))     # warm-up
     out, t_apply = timed(lambda: inner(FiniteVec(k, Xt), FiniteVec(k, X, [LinearReduce(W)])))
     print(json.dumps({"config": "cfg5-apply", "T": T, "N": N, "m": m, "out": list(out.shape), "seconds": t_apply,
                       "evals_per_s": T * N / t_apply, "fp32_pipe_frac": T * N / t_apply * (2 * d + m + 2) / 3.69e13}), flush=True)
