@@ -25,6 +25,7 @@ done by libjaxrk_b200.so.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -114,6 +115,12 @@ def _kmatw_side(X, Y, fx: Folded, fy: Folded, spec) -> torch.Tensor:
         T = nat.kmatw_spec(X, Y, W, spec, row_pref=fx.pref, col_pref=fy.pref)
         return fx.A @ T  # (mx x N) @ (N x my): small dense GEMM, stays in the library path
     rr, group = _row_reduce_of(fx)
+    if (fx.kind == BALANCED and spec.kind == nat.KIND_GENGAUSS and spec.dim_scale is None
+            and nat.lib().jrk_kmatw_uses_tensor_cores(X.shape[0], Y.shape[0], X.shape[1], W.shape[1], 0, 0)):
+        # grouped row sums on a large, narrow problem: both contractions on the tensor cores (which write N x m),
+        # the groups are summed on that small result
+        T = nat.kmatw_spec(X, Y, W, spec, row_pref=fx.pref, col_pref=fy.pref)
+        return BalancedRed(fx.group, fx.average)(T, 0)
     return nat.kmatw_spec(X, Y, W, spec, row_pref=fx.pref, col_pref=fy.pref, row_reduce=rr, group=group)
 
 
@@ -180,6 +187,37 @@ def _reduced_gram_autograd(k, spec, X, fx: Folded, Y, fy: Folded, self_gram: boo
     return G
 
 
+def _groupsum_tensor(X, Y, fx: Folded, fy: Folded, scale, power, nconst, self_gram: bool) -> torch.Tensor:
+    """BalancedRed on both axes through the tensor-core K@W kernel: for 16 column groups at a time,
+    T = K(X, Y[groups]) @ (group indicator, M_chunk x 16) -- both contractions on tcgen05 (csrc/kmatw_tc.cu) -- and the
+    row groups are summed on the small N x 16 result.  For the self inner product only the blocks on and below the
+    diagonal are computed and mirrored, so the result is exactly symmetric (jaxrk/utilities/gram.py:18 asserts it).
+    Measured at BASELINE configs[3] (4.19M points, d = 32, 1024 x 1024 groups): see DESIGN.md."""
+    dev = X.device
+    gx, gy = fx.group, fy.group
+    na, nb = X.shape[0] // gx, Y.shape[0] // gy
+    out = torch.empty((na, nb), dtype=torch.float32, device=dev)
+    GB = 16
+    ind = torch.zeros((GB * gy, GB), dtype=torch.float32, device=dev)
+    for q in range(GB):
+        ind[q * gy:(q + 1) * gy, q] = 1.0
+    sym = self_gram and gx == gy and fx.pref is fy.pref
+    for b0 in range(0, nb, GB):
+        nbk = min(GB, nb - b0)
+        a0 = b0 if sym else 0                         # symmetric: rows from the diagonal block downwards
+        Xs = X[a0 * gx:]
+        T = nat.kmatw(Xs, Y[b0 * gy:(b0 + nbk) * gy], ind[:nbk * gy, :nbk], scale, power, nconst,
+                      row_pref=None if fx.pref is None else fx.pref[a0 * gx:],
+                      col_pref=None if fy.pref is None else fy.pref[b0 * gy:(b0 + nbk) * gy])
+        blk = T.reshape(na - a0, gx, nbk).sum(1)      # (row groups) x nbk, fixed summation order
+        out[a0:, b0:b0 + nbk] = blk
+        if sym:
+            d_ = torch.tril(blk[:nbk])                # diagonal block: keep the lower triangle, mirror it
+            out[b0:b0 + nbk, b0:b0 + nbk] = d_ + torch.tril(d_, -1).T
+            out[b0:b0 + nbk, b0 + nbk:] = blk[nbk:].T
+    return out
+
+
 def reduced_gram(k, X, chain_x, Y, chain_y, self_gram: bool = False) -> torch.Tensor:
     """R_X K(X, Y) R_Y^T.  `self_gram` says Y is X (enables the symmetric self-Gram kernel)."""
     dev = X.device
@@ -204,6 +242,12 @@ def reduced_gram(k, X, chain_x, Y, chain_y, self_gram: bool = False) -> torch.Te
         out = _kmatw_side(X, Y, fx, fy, spec)
     elif fx.kind in skinny:
         out = _kmatw_side(Y, X, fy, fx, spec).t()
+    elif (gg and fx.kind == BALANCED and fy.kind == BALANCED and dim_scale is None and 12 <= X.shape[1] <= 32
+          and X.shape[0] * fy.group * 16 >= (1 << 30) and os.environ.get("JRK_GROUPSUM_TC", "1") != "0"
+          and nat.lib().jrk_kmatw_uses_tensor_cores(X.shape[0] // 2, 16 * fy.group, X.shape[1], 16, 0, 0)):
+        out = _groupsum_tensor(X, Y, fx, fy, scale, power, nconst, self_gram)
+        if fx.average or fy.average:
+            out = out * (1.0 / ((fx.group if fx.average else 1) * (fy.group if fy.average else 1)))
     elif gg and fx.kind == BALANCED and fy.kind == BALANCED and fx.group % 128 == 0:
         out = nat.gram_groupsum(X, None if self_gram else Y, scale, power, nconst, fx.group, fy.group,
                                 False, dim_scale=dim_scale, row_pref=fx.pref, col_pref=fy.pref)

@@ -158,3 +158,42 @@ def test_config5_shape_cdo_apply_reduced():
     assert torch.allclose(res.reduce[-1].linear_map, lin.T, rtol=1e-5, atol=1e-6)
     ev = res(R)
     assert tuple(ev.shape) == (T, 64) and torch.isfinite(ev).all()
+
+
+def test_balanced_inner_through_the_tensor_core_route(monkeypatch):
+    """BalancedRed on both vectors on a large problem: 16 column groups at a time through the tensor-core K@W kernel
+    (rkhs/_lowering.py: _groupsum_tensor) -- against the FP32 group-sum kernel and the float64 oracle; the self inner
+    product must stay exactly symmetric."""
+    import numpy as np
+    from jaxrk_b200 import _native as nat
+    from jaxrk_b200.kern import GenGaussKernel
+    from jaxrk_b200.reduce import BalancedRed, Prefactors
+    from jaxrk_b200.rkhs import FiniteVec, inner
+    from oracle import jaxrk_oracle as orc
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    N, M, d, gx, gy = 65536, 40960, 16, 512, 1024
+    X, Y = torch.randn(N, d, generator=g, device=dev), torch.randn(M, d, generator=g, device=dev)
+    P = torch.rand(N, generator=g, device=dev)
+    k = GenGaussKernel.make_gauss(4.0)
+    scale, _, power, nconst = k.kernel_args()
+    s = orc.simple_scaler_s(orc.gauss_length_scale(4.0))
+    vx = FiniteVec(k, X, [Prefactors(P), BalancedRed(gx, True)])
+    vy = FiniteVec(k, Y, [BalancedRed(gy, False)])
+    A = inner(vx, vy)
+    S = FiniteVec(k, X, [BalancedRed(gy, True)]).inner()
+    monkeypatch.setenv("JRK_GROUPSUM_TC", "0")
+    A0 = inner(vx, vy)
+    S0 = FiniteVec(k, X, [BalancedRed(gy, True)]).inner()
+    assert tuple(A.shape) == (N // gx, M // gy) and tuple(S.shape) == (N // gy, N // gy)
+    assert torch.allclose(A, A0, rtol=2e-5, atol=1e-6) and torch.allclose(S, S0, rtol=2e-5, atol=1e-7)
+    assert torch.equal(S, S.T)
+    for a, b in ((0, 0), (5, 39), (127, 17)):
+        Xa, Yb = X[a * gx:(a + 1) * gx].cpu().numpy(), Y[b * gy:(b + 1) * gy].cpu().numpy()
+        Pa = P[a * gx:(a + 1) * gx].cpu().numpy().astype(np.float64)
+        truth = (orc.gengauss_gram_truth64(Xa, Yb, s, power, nconst=nconst) * Pa[:, None]).sum() / gx
+        assert abs(float(A[a, b]) - truth) <= 1e-6 + 1e-5 * abs(truth)
+    for a, b in ((3, 3), (40, 7)):
+        Xa, Xb = X[a * gy:(a + 1) * gy].cpu().numpy(), X[b * gy:(b + 1) * gy].cpu().numpy()
+        truth = orc.gengauss_gram_truth64(Xa, Xb, s, power, nconst=nconst).mean()
+        assert abs(float(S[a, b]) - truth) <= 1e-6 + 1e-5 * abs(truth)
