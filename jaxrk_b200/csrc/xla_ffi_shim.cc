@@ -60,6 +60,63 @@ static ffi::Error KmatwImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, 
                                   scale, nullptr, power, nconst, nullptr, nullptr, row_reduce, group, ws, wsb, stream));
 }
 
+// (gX, gs_rows) = VJP of out = K(X, Y) W with cotangent G: the backward rule of a jax.custom_vjp around jrk_kmatw_f32_ffi
+// (INTEGRATION.md); dL/dY is the same handler called with (Y, X, G, W), dL/dW = jrk_kmatw_f32_ffi(Y, X, G).
+static ffi::Error KmatwGradImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, ffi::Buffer<ffi::F32> x,
+                                ffi::Buffer<ffi::F32> y, ffi::Buffer<ffi::F32> w, ffi::Buffer<ffi::F32> g, float scale,
+                                float power, float nconst, ffi::ResultBuffer<ffi::F32> gx, ffi::ResultBuffer<ffi::F32> gs_rows) {
+    const auto xd = x.dimensions(), yd = y.dimensions(), wd = w.dimensions(), gd = g.dimensions();
+    if (xd.size() != 2 || yd.size() != 2 || wd.size() != 2 || gd.size() != 2 || xd[1] != yd[1] || wd[0] != yd[0] ||
+        gd[0] != xd[0] || gd[1] != wd[1])
+        return ffi::Error::InvalidArgument("X: N x d, Y: M x d, W: M x m, G: N x m expected");
+    const int64_t N = xd[0], M = yd[0];
+    const int d = (int)xd[1], m = (int)wd[1];
+    const size_t wsb = jrk_grad_workspace_bytes(N, M, d);
+    auto a = scratch.Allocate(wsb);
+    if (!a.has_value()) return ffi::Error::Internal("jrk_kmatw_grad_f32: scratch allocation failed");
+    return to_error(jrk_kmatw_grad_f32(x.typed_data(), y.typed_data(), w.typed_data(), g.typed_data(), gx->typed_data(),
+                                       gs_rows->typed_data(), N, M, d, m, d, d, m, m, d, scale, power, nconst, *a, wsb, stream));
+}
+
+// K = kernel(X, Y) for any family of the distance front-end (JRK_KIND_*): PeriodicKernel / ThreshSpikeKernel
+static ffi::Error GramKindImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> x, ffi::Buffer<ffi::F32> y, int32_t kind, float p0,
+                               float p1, float p2, float p3, float p4, ffi::ResultBuffer<ffi::F32> k) {
+    const auto xd = x.dimensions(), yd = y.dimensions();
+    if (xd.size() != 2 || yd.size() != 2 || xd[1] != yd[1]) return ffi::Error::InvalidArgument("X, Y must be N x d, M x d");
+    const float kp[5] = {p0, p1, p2, p3, p4};
+    return to_error(jrk_gram_kind_f32(x.typed_data(), y.typed_data(), k->typed_data(), xd[0], yd[0], (int)xd[1], xd[1], xd[1],
+                                      yd[0], kind, kp, 5, nullptr, JRK_PATH_AUTO, nullptr, 0, stream));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(jrk_kmatw_grad_f32_ffi, KmatwGradImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<float>("scale")
+                                  .Attr<float>("power")
+                                  .Attr<float>("nconst")
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>(),
+                              {ffi::Traits::kCmdBufferCompatible});
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(jrk_gram_kind_f32_ffi, GramKindImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("kind")
+                                  .Attr<float>("p0")
+                                  .Attr<float>("p1")
+                                  .Attr<float>("p2")
+                                  .Attr<float>("p3")
+                                  .Attr<float>("p4")
+                                  .Ret<ffi::Buffer<ffi::F32>>(),
+                              {ffi::Traits::kCmdBufferCompatible});
+
 XLA_FFI_DEFINE_HANDLER_SYMBOL(jrk_gram_f32_ffi, GramImpl,
                               ffi::Ffi::Bind()
                                   .Ctx<ffi::PlatformStream<cudaStream_t>>()
