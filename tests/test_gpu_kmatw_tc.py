@@ -128,7 +128,7 @@ def test_tc_factored_sqexp_path_regimes(ls_factor, expect, force, monkeypatch):
 def test_tc_path_with_sum_and_mean_over_rows(kname, rr, force):
     """Sum / Mean (jaxrk/reduce/base.py:132-150) folded behind the tensor-core kernel: the mean embedding evaluated at
     M points, 1 x m, reduced in a fixed order."""
-    N, M, d, m = 16384 + 300, 8192 + 17, 16, 7
+    N, M, d, m = 8192 + 300, 4096 + 17, 16, 7
     X, Y, W = gauss(0, N, d), gauss(1, M, d), gauss(2, M, m)
     rp = np.random.RandomState(3).rand(N).astype(f32)
     s, scale, p, nconst = kparams(kname, np.sqrt(d))

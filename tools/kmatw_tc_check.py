@@ -36,6 +36,10 @@ if len(_s.argv) > 1 and _s.argv[1] == "dbg":
 if len(_s.argv) > 1 and _s.argv[1] == "fast1":
     run(131072, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
     _s.exit(0)
+if len(_s.argv) > 1 and _s.argv[1] == "var":
+    for v in _s.argv[2:]:
+        os.environ["JRK_TC_VAR"] = v; print("VAR", v, end=": "); run(131072, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
+    _s.exit(0)
 if len(_s.argv) > 1 and _s.argv[1] == "fast":
     for f in ("1", "0"):
         os.environ["JRK_TC_FAST"] = f; print("JRK_TC_FAST", f)
