@@ -1,0 +1,6 @@
+// Instantiations of the fused K@W FP32-pipe kernel (kmatw_kernel.cuh) for epilogue mode PM_GENERAL.
+#include "kmatw_kernel.cuh"
+
+namespace jrk {
+JRK_KMATW_DEFINE_DISPATCH(PM_GENERAL)
+}  // namespace jrk
