@@ -96,7 +96,7 @@ __global__ void tf_norm_kernel(const float* __restrict__ A, int64_t rows, int64_
     }
 }
 
-inline int tf_dp(int d) { return d <= 64 ? 64 : d <= 96 ? 96 : 128; }
+inline int tf_dp(int d) { return d <= 32 ? 32 : d <= 64 ? 64 : d <= 96 ? 96 : 128; }
 inline bool tf_usable_in_place(const float* A, int64_t lda, int d, int DP, const float* dim_scale) {
     return !dim_scale && d == DP && lda == DP && ((uintptr_t)A % 16 == 0);
 }

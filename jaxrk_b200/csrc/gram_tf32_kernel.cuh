@@ -1,4 +1,4 @@
-// Kernel (a2): materialised Gram for 64 <= d <= 128 by the compensated 3xTF32 expansion on the
+// Kernel (a2): materialised Gram for d <= 128 (columns padded to 32 / 64 / 96 / 128) by the compensated 3xTF32 expansion on the
 // 5th-generation tensor cores (tcgen05.mma, operands and accumulators in TMEM).
 //
 // Replaces, for wide inputs, the same reference chain as gram_direct.cu:
@@ -483,7 +483,7 @@ int tf_launch(const float* Ximg, const float* Xp, const float* Yp, const float* 
 }
 
 // Row-tile height of the X tile images for (DP, nacc): must match the dispatch table below.
-inline int tf_nt(int DP, int nacc) { return (DP == 64 || (DP == 96 && nacc == 2)) ? 64 : 32; }
+inline int tf_nt(int DP, int nacc) { return (DP <= 64 || (DP == 96 && nacc == 2)) ? 64 : 32; }
 
 // One translation unit per epilogue mode (gram_tf32_pm{0,1,2}.cu) instantiates this.
 //   nacc 3 = symmetric accumulation (self-Gram), 2 = X != Y (frees TMEM: NT = 64 also for DP = 96)
@@ -497,10 +497,12 @@ int tf_run_pm(int DP, int nacc, const float* Ximg, const float* Xp, const float*
                        const float* yn, float* K, int64_t N, int64_t M, int64_t ldk, const EpiParams& ep,           \
                        const TfEpi& te, cudaStream_t st) {                                                          \
         if (nacc == 3) {                                                                                            \
+            if (DP == 32) return tf_launch<32, 64, PM_, 3>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);         \
             if (DP == 64) return tf_launch<64, 64, PM_, 3>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);         \
             if (DP == 96) return tf_launch<96, 32, PM_, 3>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);         \
             return tf_launch<128, 32, PM_, 3>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);                      \
         }                                                                                                           \
+        if (DP == 32) return tf_launch<32, 64, PM_, 2>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);             \
         if (DP == 64) return tf_launch<64, 64, PM_, 2>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);             \
         if (DP == 96) return tf_launch<96, 64, PM_, 2>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);             \
         return tf_launch<128, 32, PM_, 2>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);                          \
