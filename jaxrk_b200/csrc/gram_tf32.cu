@@ -1,4 +1,6 @@
 // Host side of kernel (a2) (gram_tf32_kernel.cuh): operand packing, the row-norm pre-pass and dispatch.
+#include <cstdlib>
+
 #include "gram_tf32_kernel.cuh"
 
 namespace jrk {
@@ -65,6 +67,34 @@ __global__ void tf_split_kernel(const float* __restrict__ Xp, int64_t rows, int6
     *reinterpret_cast<uint4*>(base + (size_t)NT * DP * 4 + off) = l;
 }
 
+// The same for fp16 operands (H16 kernels): rows normalised by 2^-ex (ex from the pre-pass maximum, on the device),
+// hi = fp16(x), lo' = fp16((x - hi) 2^11); a 128-byte k-chunk holds 64 values, one thread per 16-byte piece (8 values).
+__global__ void tf_split_h16_kernel(const float* __restrict__ Xp, int64_t rows, int64_t rows_padded, int DP, int NT,
+                                    unsigned char* __restrict__ img, const unsigned* __restrict__ nmax_x, float inv_abs_mult) {
+    const int cpr = DP / 8;                                  // 16-byte pieces per row
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows_padded * cpr) return;
+    const float sx = pow2i(-h16_exp(__uint_as_float(__ldg(nmax_x)) * inv_abs_mult));
+    const int64_t row = idx / cpr;
+    const int piece = (int)(idx % cpr), kc = piece >> 3, c = piece & 7;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (row < rows) {
+        v0 = __ldg(reinterpret_cast<const float4*>(Xp + row * DP) + 2 * piece);
+        v1 = __ldg(reinterpret_cast<const float4*>(Xp + row * DP) + 2 * piece + 1);
+    }
+    uint4 h, l;
+    split_h16_pair(v0.x * sx, v0.y * sx, h.x, l.x);
+    split_h16_pair(v0.z * sx, v0.w * sx, h.y, l.y);
+    split_h16_pair(v1.x * sx, v1.y * sx, h.z, l.z);
+    split_h16_pair(v1.z * sx, v1.w * sx, h.w, l.w);
+    const int64_t t = row / NT;
+    const int r = (int)(row % NT);
+    unsigned char* base = img + (size_t)t * 2 * NT * DP * 2;
+    const int off = kc * NT * 128 + r * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(base + off) = h;
+    *reinterpret_cast<uint4*>(base + (size_t)NT * DP * 2 + off) = l;
+}
+
 // out[r] = mult * |row r|^2 + add (0 for padded rows) -- ONE function for X and Y, so the norms are role
 // independent (bitwise symmetric self-Gram).  One warp per row: 16-byte chunks, xor-shuffle tree.  The block's
 // largest |mult| |row|^2 goes to *gmax by atomicMax on the (non-negative) float's bit pattern.
@@ -96,7 +126,14 @@ __global__ void tf_norm_kernel(const float* __restrict__ A, int64_t rows, int64_
     }
 }
 
-inline int tf_dp(int d) { return d <= 32 ? 32 : d <= 64 ? 64 : d <= 96 ? 96 : 128; }
+// d <= 32: tf32 operands padded to 32 columns; above: fp16 hi / lo operands padded to 64 / 128 (JRK_GRAM_H16=0: tf32,
+// padded to 64, d <= 64 only -- kept for A/B comparison)
+inline bool tf_use_h16(int d) {
+    if (d <= 32) return false;
+    const char* e = getenv("JRK_GRAM_H16");
+    return !(e && e[0] == '0' && d <= 64);
+}
+inline int tf_dp(int d) { return d <= 32 ? 32 : d <= 64 ? 64 : 128; }
 inline bool tf_usable_in_place(const float* A, int64_t lda, int d, int DP, const float* dim_scale) {
     return !dim_scale && d == DP && lda == DP && ((uintptr_t)A % 16 == 0);
 }
@@ -186,17 +223,25 @@ int gram_tf32x3(const float* X, const float* Y, float* K, int64_t N, int64_t M, 
 
     const int nacc = same ? 3 : 2;
 
-    // tf32 hi / lo tile images of X (pre-swizzled; one bulk copy per tile in the main kernel)
-    const int NT = tf_nt(DP, nacc);
+    // hi / lo tile images of X (pre-swizzled; one bulk copy per tile in the main kernel)
+    const int h16 = tf_use_h16(d) ? 1 : 0;
+    const int NT = tf_nt(DP, nacc, h16);
+    te.inv_abs_mult = 1.f / fabsf(mult);
+    te.d_used = d;
     float* ximg = scr.take<float>((size_t)Np * DP * 2);
-    {
+    if (h16) {
+        const int64_t tot = Np * (DP / 8);
+        tf_split_h16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Xp, N, Np, DP, NT, reinterpret_cast<unsigned char*>(ximg),
+                                                                           nmax, te.inv_abs_mult);
+        JRK_LAUNCHED();
+    } else {
         const int64_t tot = Np * (DP / 4);
         tf_split_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Xp, N, Np, DP, NT, ximg);
         JRK_LAUNCHED();
     }
-    if (pm == PM_SQEXP) return tf_run_pm<PM_SQEXP>(DP, nacc, ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
-    if (pm == PM_LAPLACE) return tf_run_pm<PM_LAPLACE>(DP, nacc, ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
-    return tf_run_pm<PM_GENERAL>(DP, nacc, ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
+    if (pm == PM_SQEXP) return tf_run_pm<PM_SQEXP>(DP, nacc, h16, ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
+    if (pm == PM_LAPLACE) return tf_run_pm<PM_LAPLACE>(DP, nacc, h16, ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
+    return tf_run_pm<PM_GENERAL>(DP, nacc, h16, ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);
 }
 
 }  // namespace jrk

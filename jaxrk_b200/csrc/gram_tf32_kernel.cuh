@@ -45,6 +45,8 @@
 // relative accuracy.  For p = 2 the test is skipped when the pre-pass finds
 // s^2 log2(e) (max|x|^2 + max|y|^2) <= 4, where the expansion error is < 1.4e-6 relative.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace jrk {
@@ -58,10 +60,16 @@ constexpr int S_OP = 3;           // operand stages (hi + lo images of one X til
 constexpr float TF_TAU = 1.0f / 64.0f;
 constexpr float TF_SKIP_BOUND = 4.0f;   // |c| (max|x|^2 + max|y|^2) below which the p = 2 near-zero test is skipped
 
-template <int DP, int NT, int NACC>
+// H16: operands as fp16 hi / lo pairs (kind::f16, K = 16 per MMA) instead of tf32 (K = 8): the same 11 + 11 significant
+// bits per value, HALF the MMAs and half the operand bytes.  The inputs are normalised by powers of two (2^-ex, 2^-ey
+// from the pre-pass maxima, so every element is <= 1 in magnitude), lo is stored scaled by 2^11 (full fp16 precision
+// again) and the cross-term accumulator is folded in with 2^-11:  x.y = 2^(ex+ey) (c1 + 2^-11 c2).
+template <int DP, int NT, int NACC, bool H16 = false>
 struct TfCfg {
-    static constexpr int KC = DP / 32;                    // 128-byte k-chunks per row
-    static constexpr int HALF_BYTES = NT * DP * 4;        // one swizzled image (hi or lo)
+    static constexpr int EB = H16 ? 2 : 4;                // bytes per operand element
+    static constexpr int KC = DP * EB / 128;              // 128-byte k-chunks per row
+    static constexpr int ACOLS = DP * EB / 4;             // TMEM columns of one half (hi or lo) of the A operand
+    static constexpr int HALF_BYTES = NT * DP * EB;       // one swizzled image (hi or lo)
     static constexpr int STAGE_BYTES = 2 * HALF_BYTES;    // what one cp.async.bulk brings
     static constexpr int OFF_OP = 0;
     static constexpr int OFF_BAR = OFF_OP + S_OP * STAGE_BYTES;
@@ -69,10 +77,10 @@ struct TfCfg {
     static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
     static constexpr int BYTES = OFF_TMEM_SLOT + 16;
     static constexpr int DYN_BYTES = BYTES + 1024;        // slack to align the base to 1024 B
-    static constexpr int ACC_COL0 = 2 * DP;               // first accumulator column
-    static_assert(DP % 32 == 0 && DP <= 128 && NT % 16 == 0, "unsupported tile");
+    static constexpr int ACC_COL0 = 2 * ACOLS;            // first accumulator column
+    static_assert((DP * EB) % 128 == 0 && DP <= 128 && NT % 16 == 0, "unsupported tile");
     static_assert(HALF_BYTES % 1024 == 0, "swizzled images must be 1024 B aligned");
-    static_assert(2 * DP + 2 * NACC * NT <= 512, "TMEM budget");
+    static_assert(2 * ACOLS + 2 * NACC * NT <= 512, "TMEM budget");
     static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -83,7 +91,24 @@ struct TfEpi {
     float add;     // PM_SQEXP: log2(nconst), folded into the exponent through xs / ys;  otherwise 0
     float w0;      // refinement threshold for w = u - tau (xs + ys): PM_SQEXP add (1 - tau), else 0
     const unsigned* norm_max;   // [2]: bit patterns of max |mult| |x|^2 and max |mult| |y|^2 (pre-pass atomicMax)
+    float inv_abs_mult;         // 1 / |mult|: norm_max * inv_abs_mult = max |row|^2 (H16 normalisation)
+    int d_used;                 // columns that are not zero padding (k-steps beyond them are skipped)
 };
+
+// smallest e with 2^e >= sqrt(v)  (v >= 0): the power-of-two normalisation of the fp16 operands
+__device__ __forceinline__ int h16_exp(float v) {
+    int e;
+    frexpf(v, &e);                 // v = m 2^e, m in [0.5, 1)  =>  2^e > v
+    return (e + 1) >> 1;           // ceil(e / 2)
+}
+__device__ __forceinline__ float pow2i(int e) { return __int_as_float((127 + e) << 23); }
+// fp16 hi / lo' split of a normalised value (|x| <= 1): hi = fp16(x), lo' = fp16((x - hi) 2^11); packed pairs
+__device__ __forceinline__ void split_h16_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    const __half l0 = __float2half_rn((x0 - __half2float(h0)) * 2048.f), l1 = __float2half_rn((x1 - __half2float(h1)) * 2048.f);
+    hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+}
 
 // ---------------------------------------------------------------------------------
 // tcgen05 / TMEM primitives (inline PTX)
@@ -106,6 +131,18 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the same with fp16 operands (kind::f16): K = 16
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -201,13 +238,13 @@ __device__ __forceinline__ void st_global_cs(float* p, float v) {
 // ---------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------
-template <int DP, int NT, int PM, int NACC>
+template <int DP, int NT, int PM, int NACC, bool H16>
 __global__ void __launch_bounds__(TF_THREADS, 1)
 gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, const float* __restrict__ Yp,
                  const float* __restrict__ xn,
                  const float* __restrict__ yn, float* __restrict__ K, int64_t N, int64_t M, int64_t ldk,
-                 EpiParams ep, TfEpi te, int n_it, int tpu, int n_jb, int n_units) {
-    using C = TfCfg<DP, NT, NACC>;
+                 EpiParams ep, TfEpi te, int n_it, int tpu, int n_jb, int n_units, int ksteps) {
+    using C = TfCfg<DP, NT, NACC, H16>;
     extern __shared__ unsigned char tf_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tf_smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -256,7 +293,9 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
         // uniform registers; only the tcgen05 instructions themselves are predicated to one elected lane.
         // (Issuing from inside an `if (lane == 0)` region makes the compiler wrap every MMA in an ELECT / R2UR
         // waterfall loop -- ~13 instructions per MMA on the critical path.)
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TF_BM >> 4) << 24);
+        // instruction descriptor: FP32 accumulate; operand format tf32 (2) or fp16 (0); N, M
+        constexpr uint32_t fmt = H16 ? 0u : 2u;
+        constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TF_BM >> 4) << 24);
         const uint32_t op_base = smem_u32(smem + C::OFF_OP);
         uint32_t tc = 0, uc = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
@@ -271,16 +310,20 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
                 const uint64_t dl0 = make_b_desc(op_base + q * C::STAGE_BYTES + C::HALF_BYTES);
                 const uint32_t acc = C::ACC_COL0 + a * NACC * NT;      // TMEM base is 0 (checked at start-up)
                 if (elect_one()) {
-#pragma unroll
-                    for (int kc = 0; kc < C::KC; ++kc) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint32_t k = kc * 4 + ks;
-                            const uint64_t off = (uint64_t)((kc * NT * 128 + ks * 32) >> 4);   // start-address field
+                    // one k-step = 32 bytes of a row (8 tf32 or 16 fp16 values); k-steps that hold only zero padding
+                    // are not issued (d = 16 padded to 32 columns: 6 instead of 12 MMAs)
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t off = (uint64_t)(((k >> 2) * NT * 128 + (k & 3) * 32) >> 4);   // start-address field
+                        if (H16) {
+                            mma_f16_ts(acc, k * 8, dh0 + off, idesc, k);                        // hi_y . hi_x
+                            mma_f16_ts(acc + NT, k * 8, dl0 + off, idesc, k);                   // hi_y . lo_x
+                            if (NACC == 3) mma_f16_ts(acc + 2 * NT, C::ACOLS + k * 8, dh0 + off, idesc, k);  // lo_y . hi_x
+                            else mma_f16_ts(acc + NT, C::ACOLS + k * 8, dh0 + off, idesc, 1u);
+                        } else {
                             mma_tf32_ts(acc, k * 8, dh0 + off, idesc, k);                       // hi_y . hi_x
                             mma_tf32_ts(acc + NT, k * 8, dl0 + off, idesc, k);                  // hi_y . lo_x
-                            if (NACC == 3) mma_tf32_ts(acc + 2 * NT, DP + k * 8, dh0 + off, idesc, k);  // lo_y . hi_x
-                            else mma_tf32_ts(acc + NT, DP + k * 8, dh0 + off, idesc, 1u);       // same accumulator
+                            if (NACC == 3) mma_tf32_ts(acc + 2 * NT, C::ACOLS + k * 8, dh0 + off, idesc, k);  // lo_y . hi_x
+                            else mma_tf32_ts(acc + NT, C::ACOLS + k * 8, dh0 + off, idesc, 1u);  // same accumulator
                         }
                     }
                     tc_commit(&op_empty[q]);   // operand stage may be refilled
@@ -307,8 +350,26 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
             const int it0 = (u / n_jb) * tpu, it1 = min(it0 + tpu, n_it);
             const int64_t j = (int64_t)jb * TF_BM + jl;
             const bool jok = j < M;
-            // ---- park this unit's Y block in TMEM as tf32 hi / lo (16-column items dealt to the G groups) ----
+            // ---- park this unit's Y block in TMEM as hi / lo operands (16-column items dealt to the G groups) ----
             const float* yrow = Yp + (jok ? j : 0) * DP;
+            if (H16) {
+                // 32 values -> 16 packed columns per item; normalised by 2^-ey
+                const float sy = pow2i(-h16_exp(__uint_as_float(__ldg(te.norm_max + 1)) * te.inv_abs_mult));
+#pragma unroll
+                for (int item = 0; item < DP / 32; ++item) {
+                    if ((item % G) != ch) continue;
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (jok) v = __ldg(reinterpret_cast<const float4*>(yrow + item * 32 + cc * 4));
+                        split_h16_pair(v.x * sy, v.y * sy, hi[cc * 2], lo[cc * 2]);
+                        split_h16_pair(v.z * sy, v.w * sy, hi[cc * 2 + 1], lo[cc * 2 + 1]);
+                    }
+                    tmem_st16(tmem_base + lane_addr + item * 16, hi);
+                    tmem_st16(tmem_base + lane_addr + C::ACOLS + item * 16, lo);
+                }
+            } else {
 #pragma unroll
             for (int kc = 0; kc < C::KC; ++kc) {
 #pragma unroll
@@ -325,8 +386,9 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
                         split_tf32(v.w, hi[cc * 4 + 3], lo[cc * 4 + 3]);
                     }
                     tmem_st16(tmem_base + lane_addr + kc * 32 + half * 16, hi);
-                    tmem_st16(tmem_base + lane_addr + DP + kc * 32 + half * 16, lo);
+                    tmem_st16(tmem_base + lane_addr + C::ACOLS + kc * 32 + half * 16, lo);
                 }
+            }
             }
             tmem_st_wait();
             tc_fence_before();
@@ -334,7 +396,13 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
             if (lane == 0) mbar_arrive(a_ready);
             const float ys = jok ? __ldg(yn + j) : 0.f;   // (scaled) |y_j|^2 + half of the folded constant
             const f32x2 ys2 = pack2(ys, ys);
-            const f32x2 a2 = pack2(te.a, te.a), ntau2 = pack2(-TF_TAU, -TF_TAU);
+            // H16: x.y = 2^(ex+ey) (c1 + 2^-11 cross): the power of two rides in `a`
+            float a_eff = te.a;
+            if (H16)
+                a_eff *= pow2i(h16_exp(__uint_as_float(__ldg(te.norm_max)) * te.inv_abs_mult) +
+                               h16_exp(__uint_as_float(__ldg(te.norm_max + 1)) * te.inv_abs_mult));
+            const f32x2 a2 = pack2(a_eff, a_eff), ntau2 = pack2(-TF_TAU, -TF_TAU);
+            const f32x2 lo_w2 = pack2(1.f / 2048.f, 1.f / 2048.f);
 
             // ---- tiles of this unit ----
             // (scaled) |x_i|^2 of this warp's rows: uniform 16-byte loads, software-pipelined one tile ahead -- loaded
@@ -369,7 +437,8 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
                     for (int i = 0; i < LC / 2; ++i) {
                         f32x2 cross = pack2(c2[2 * i], c2[2 * i + 1]);
                         if (NACC == 3) cross = add2(cross, pack2(c3[2 * i], c3[2 * i + 1]));   // symmetric in the two terms
-                        dot2[g * (LC / 2) + i] = add2(pack2(c1[2 * i], c1[2 * i + 1]), cross);
+                        dot2[g * (LC / 2) + i] = H16 ? fma2(cross, lo_w2, pack2(c1[2 * i], c1[2 * i + 1]))
+                                                     : add2(pack2(c1[2 * i], c1[2 * i + 1]), cross);
                     }
                 }
                 tc_fence_before();
@@ -455,11 +524,11 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
 
 int tf_sm_count();
 
-template <int DP, int NT, int PM, int NACC>
+template <int DP, int NT, int PM, int NACC, bool H16 = false>
 int tf_launch(const float* Ximg, const float* Xp, const float* Yp, const float* xn, const float* yn, float* K, int64_t N,
               int64_t M, int64_t ldk, const EpiParams& ep, const TfEpi& te, cudaStream_t st) {
-    using C = TfCfg<DP, NT, NACC>;
-    auto kern = gram_tf32_kernel<DP, NT, PM, NACC>;
+    using C = TfCfg<DP, NT, NACC, H16>;
+    auto kern = gram_tf32_kernel<DP, NT, PM, NACC, H16>;
     JRK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::DYN_BYTES));
     const int grid_max = tf_sm_count();
     const int64_t n_it = (N + NT - 1) / NT, n_jb = (M + TF_BM - 1) / TF_BM;
@@ -476,36 +545,41 @@ int tf_launch(const float* Ximg, const float* Xp, const float* Yp, const float* 
     if (n_units > 2147483647LL || n_it > 2147483647LL)
         return fail(JRK_ERR_UNSUPPORTED, "gram_tf32x3: problem too large (%lld units)", (long long)n_units);
     const int grid = (int)(grid_max < n_units ? grid_max : n_units);
+    const int per_step = H16 ? 16 : 8;
+    int ksteps = (te.d_used + per_step - 1) / per_step;
+    if (ksteps < 1 || ksteps > C::KC * 4) ksteps = C::KC * 4;
     kern<<<grid, TF_THREADS, C::DYN_BYTES, st>>>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, (int)n_it, (int)tpu, (int)n_jb,
-                                                 (int)n_units);
+                                                 (int)n_units, ksteps);
     JRK_LAUNCHED();
     return JRK_OK;
 }
 
-// Row-tile height of the X tile images for (DP, nacc): must match the dispatch table below.
-inline int tf_nt(int DP, int nacc) { return (DP <= 64 || (DP == 96 && nacc == 2)) ? 64 : 32; }
+// Row-tile height of the X tile images for (DP, nacc, h16): must match the dispatch table below.
+inline int tf_nt(int DP, int nacc, int h16) { return (h16 || DP <= 64) ? 64 : 32; }
 
 // One translation unit per epilogue mode (gram_tf32_pm{0,1,2}.cu) instantiates this.
-//   nacc 3 = symmetric accumulation (self-Gram), 2 = X != Y (frees TMEM: NT = 64 also for DP = 96)
+//   nacc 3 = symmetric accumulation (self-Gram), 2 = X != Y;  h16: fp16 operands (DP 64 / 128), else tf32 (DP 32 / 64)
 template <int PM>
-int tf_run_pm(int DP, int nacc, const float* Ximg, const float* Xp, const float* Yp, const float* xn, const float* yn,
-              float* K, int64_t N, int64_t M, int64_t ldk, const EpiParams& ep, const TfEpi& te, cudaStream_t st);
+int tf_run_pm(int DP, int nacc, int h16, const float* Ximg, const float* Xp, const float* Yp, const float* xn,
+              const float* yn, float* K, int64_t N, int64_t M, int64_t ldk, const EpiParams& ep, const TfEpi& te,
+              cudaStream_t st);
 
+#define JRK_TF_ARGS Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st
 #define JRK_TF32_DEFINE_RUN_PM(PM_)                                                                                  \
     template <>                                                                                                     \
-    int tf_run_pm<PM_>(int DP, int nacc, const float* Ximg, const float* Xp, const float* Yp, const float* xn,      \
-                       const float* yn, float* K, int64_t N, int64_t M, int64_t ldk, const EpiParams& ep,           \
-                       const TfEpi& te, cudaStream_t st) {                                                          \
-        if (nacc == 3) {                                                                                            \
-            if (DP == 32) return tf_launch<32, 64, PM_, 3>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);         \
-            if (DP == 64) return tf_launch<64, 64, PM_, 3>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);         \
-            if (DP == 96) return tf_launch<96, 32, PM_, 3>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);         \
-            return tf_launch<128, 32, PM_, 3>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);                      \
+    int tf_run_pm<PM_>(int DP, int nacc, int h16, const float* Ximg, const float* Xp, const float* Yp,              \
+                       const float* xn, const float* yn, float* K, int64_t N, int64_t M, int64_t ldk,               \
+                       const EpiParams& ep, const TfEpi& te, cudaStream_t st) {                                     \
+        if (h16) {                                                                                                  \
+            if (DP == 64) return nacc == 3 ? tf_launch<64, 64, PM_, 3, true>(JRK_TF_ARGS)                           \
+                                           : tf_launch<64, 64, PM_, 2, true>(JRK_TF_ARGS);                          \
+            if (DP == 128) return nacc == 3 ? tf_launch<128, 64, PM_, 3, true>(JRK_TF_ARGS)                         \
+                                            : tf_launch<128, 64, PM_, 2, true>(JRK_TF_ARGS);                        \
+        } else {                                                                                                    \
+            if (DP == 32) return nacc == 3 ? tf_launch<32, 64, PM_, 3>(JRK_TF_ARGS) : tf_launch<32, 64, PM_, 2>(JRK_TF_ARGS); \
+            if (DP == 64) return nacc == 3 ? tf_launch<64, 64, PM_, 3>(JRK_TF_ARGS) : tf_launch<64, 64, PM_, 2>(JRK_TF_ARGS); \
         }                                                                                                           \
-        if (DP == 32) return tf_launch<32, 64, PM_, 2>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);             \
-        if (DP == 64) return tf_launch<64, 64, PM_, 2>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);             \
-        if (DP == 96) return tf_launch<96, 64, PM_, 2>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);             \
-        return tf_launch<128, 32, PM_, 2>(Ximg, Xp, Yp, xn, yn, K, N, M, ldk, ep, te, st);                          \
+        return fail(JRK_ERR_UNSUPPORTED, "gram tensor path: no kernel for DP = %d, h16 = %d", DP, h16);             \
     }
 
 }  // namespace tf32
