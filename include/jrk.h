@@ -47,7 +47,7 @@ extern "C" {
 #define JRK_ERR_UNSUPPORTED 3   /* valid request this build cannot serve       */
 
 /* distance path of jrk_gram_f32 */
-#define JRK_PATH_AUTO 0    /* 3xTF32 tcgen05 for d >= 64, and for 16 <= d < 64 when N*M >= 2^24; else direct */
+#define JRK_PATH_AUTO 0    /* tcgen05 (3-product hi/lo split) for d >= 64, and for 12 <= d < 64 when N*M >= 2^24; else direct */
 #define JRK_PATH_DIRECT 1  /* FP32 direct differencing (sum_k (x_k - y_k)^2)  */
 #define JRK_PATH_TF32X3 2  /* compensated 3xTF32 expansion on tcgen05/TMEM    */
 

@@ -59,14 +59,15 @@ static int have_device(const char* fn) {
     return JRK_OK;
 }
 
-// AUTO: the tcgen05 3xTF32 path for d >= 64 (where the distance is a dense contraction), and -- measured on B200,
-// tools/small_d_paths.py -- also for 16 <= d < 64 once the Gram is large (>= 2^24 entries): padded to 64 columns it
-// stays HBM-write-bound (3.7 ms at 65536^2) while direct differencing is FP32-bound (6.1 / 10.3 / 14.3 ms at
-// d = 16 / 32 / 48).  Small problems and d < 16 use direct differencing (one launch, exact diagonal).
+// AUTO: the tcgen05 path for d >= 64 (where the distance is a dense contraction), and -- measured on B200,
+// tools/small_d_paths.py -- also for 12 <= d < 64 once the Gram is large (>= 2^24 entries): it stays HBM-write-bound
+// (3.1 ms at 65536^2) while direct differencing is FP32-bound (5.1 / 6.0 / 10.3 / 14.3 ms at d = 12 / 16 / 32 / 48).
+// Small problems and d < 12 use direct differencing (one launch, exact diagonal; at d <= 4 it writes 6.6 TB/s, and the
+// tensor path would spend its time in the near-coincident refinement that low-dimensional data triggers all the time).
 static int resolve_gram_path(int path, int d, int64_t N, int64_t M) {
     if (path != JRK_PATH_AUTO) return path;
     if (d >= 64) return JRK_PATH_TF32X3;
-    if (d >= 16 && N * M >= ((int64_t)1 << 24)) return JRK_PATH_TF32X3;
+    if (d >= 12 && N * M >= ((int64_t)1 << 24)) return JRK_PATH_TF32X3;
     return JRK_PATH_DIRECT;
 }
 
