@@ -201,3 +201,35 @@ def test_invalid_arguments_raise():
         nat.gram(X, cu(gauss(1, 8, 4)), 1.0, 2.0, 1.0)
     with pytest.raises(TypeError):
         nat.gram(X.double(), None, 1.0, 2.0, 1.0)
+
+
+@pytest.mark.parametrize("d", [33, 64, 100, 128])
+@pytest.mark.parametrize("case", ["huge", "tiny", "mixed_columns", "zero_rows", "offset"])
+def test_fp16_operand_path_is_robust_to_input_magnitudes(d, case):
+    """32 < d <= 128 runs on fp16 hi / lo operands normalised by powers of two taken from the data (gram_tf32_kernel,
+    H16): magnitudes far outside fp16's range, columns of very different scale, zero rows and a large common offset
+    must all stay within tolerance of the float64 truth."""
+    rng = np.random.RandomState(d)
+    N, M = 260, 190
+    X, Y = rng.randn(N, d), rng.randn(M, d)
+    ls = np.sqrt(d)
+    if case == "huge":
+        X, Y, ls = X * 3e4, Y * 3e4, ls * 3e4
+    elif case == "tiny":
+        X, Y, ls = X * 2e-6, Y * 2e-6, ls * 2e-6
+    elif case == "mixed_columns":
+        col = np.where(np.arange(d) % 7 == 0, 50.0, 1e-3)
+        X, Y, ls = X * col, Y * col, 50.0 * np.sqrt(d / 7)
+    elif case == "zero_rows":
+        X[::3] = 0.0
+        Y[5] = 0.0
+    elif case == "offset":
+        X, Y = X + 40.0, Y + 40.0          # |x|^2 >> |x - y|^2: the expansion form is at its worst
+    X, Y = X.astype(f32), Y.astype(f32)
+    for kname in ("sqexp", "laplace"):
+        s, scale, p, nconst = kparams(kname, ls)
+        K = nat.gram(cu(X), cu(Y), scale, p, nconst, path=nat.PATH_TF32X3).cpu().numpy()
+        assert_close_truth(K, orc.gengauss_gram_truth64(X, Y, s, p), f"{case} {kname} d={d}")
+        Ks = nat.gram(cu(X), None, scale, p, nconst, path=nat.PATH_TF32X3).cpu().numpy()
+        assert (Ks == Ks.T).all()
+        assert_close_truth(Ks, orc.gengauss_gram_truth64(X, X, s, p), f"{case} {kname} d={d} self")
