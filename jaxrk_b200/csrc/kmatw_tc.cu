@@ -30,6 +30,7 @@
 // hi_e.hi_w and the two small cross terms go to separate accumulators (8 instead of 24 MMAs per tile on the one
 // that matters).
 // Near-coincident pairs (sq < (|x|^2+|y|^2)/64) are recomputed by FP32 direct differencing, as in the Gram kernel.
+#include <cmath>
 #include <cstdlib>
 #include <type_traits>
 
@@ -64,6 +65,7 @@ static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
 // Byte layout of one tile image.  packed (d <= 16): a Y row is [16 hi | 16 lo] floats in one 128-byte swizzle row.
 struct TcImage {
     int y_lo;      // offset of the lo half relative to the hi half (what the GEMM1 descriptors differ by)
+    int y_lo_h16;  // the same for the fp16 layout of the factored path (hi and lo halves are 32 / 64 bytes per row)
     int w;         // offset of the W^T image: per 32-column k-chunk 16 rows hi then 16 rows lo (2 x TC_WH bytes in all)
     int yn;        // offset of the 64 scaled squared norms
     int bytes;     // image size (multiple of 16)
@@ -74,6 +76,7 @@ inline TcImage tc_image(int d) {
     const bool packed = d <= 16;
     const int ybytes = packed ? TC_NT * 128 : 2 * TC_NT * 128;
     L.y_lo = packed ? 64 : TC_NT * 128;
+    L.y_lo_h16 = packed ? 32 : TC_NT * 128;
     L.w = ybytes;
     L.yn = ybytes + 2 * TC_WH;
     L.bytes = L.yn + TC_NT * 4;
@@ -126,10 +129,26 @@ struct TcParams {
     int check;                             // 1: near-zero refinement always; 0: only if the norm maxima demand it
     const unsigned* nmax;                  // [2] bit patterns of max |mult| |x|^2, max |mult| |y|^2
     int allow_fast;                        // 0 disables the factored p = 2 path (JRK_TC_FAST=0, tests)
+    float inv_abs_mult;                    // 1 / |mult|: nmax * inv_abs_mult = max |row|^2 (fp16 normalisation of GEMM1)
 };
+
+// fp16 hi / lo split WITHOUT rescaling lo (factored path, GEMM1): both parts go into ONE accumulator.  Values are
+// normalised so that |x| <= 16; a lo part below fp16's normal range costs at most 3e-8 absolute per element, which
+// the TC_FAST_BOUND regime turns into < 1.5e-6 in the exponent (d <= 32).
+__device__ __forceinline__ void split_h16u_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+    hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+}
 
 __device__ __forceinline__ bool tc_fast_regime(const unsigned* nmax) {
     return (__uint_as_float(__ldg(nmax)) + __uint_as_float(__ldg(nmax + 1))) <= TC_FAST_BOUND;
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
     uint32_t r[4];
@@ -211,15 +230,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 const uint32_t c1 = TC_COL_S + a * 128, c2 = c1 + 64;
                 if (elect_one()) {
                     if (fast) {
-                        // one accumulator: the small cross terms first, the hi.hi terms last (the accumulator
-                        // truncates, so only the last `ksteps` additions carry a rounding error that matters)
-                        for (int ks = 0; ks < ksteps; ++ks) {
+                        // fp16 hi / lo operands (K = 16 per MMA: half the MMAs of the tf32 form), one accumulator: the
+                        // small cross terms first, the hi.hi terms last (the accumulator truncates, so only the last
+                        // additions carry a rounding error that matters)
+                        constexpr uint32_t idesc1h = (1u << 4) | ((uint32_t)(TC_NT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                        const int ksh = (P.d + 15) >> 4;
+                        const uint64_t dylh = dyh + (uint64_t)(P.L.y_lo_h16 >> 4);
+                        for (int ks = 0; ks < ksh; ++ks) {
                             const uint64_t off = (uint64_t)(ks * 2);
-                            mma_tf32_ts(c1, TC_COL_X + ks * 8, dyl + off, idesc1, ks);            // hi_x . lo_y
-                            mma_tf32_ts(c1, TC_COL_X + TC_DP + ks * 8, dyh + off, idesc1, 1u);    // lo_x . hi_y
+                            mma_f16_ts(c1, TC_COL_X + ks * 8, dylh + off, idesc1h, ks);            // hi_x . lo_y
+                            mma_f16_ts(c1, TC_COL_X + TC_DP + ks * 8, dyh + off, idesc1h, 1u);    // lo_x . hi_y
                         }
-                        for (int ks = 0; ks < ksteps; ++ks)
-                            mma_tf32_ts(c1, TC_COL_X + ks * 8, dyh + (uint64_t)(ks * 2), idesc1, 1u);   // hi_x . hi_y
+                        for (int ks = 0; ks < ksh; ++ks)
+                            mma_f16_ts(c1, TC_COL_X + ks * 8, dyh + (uint64_t)(ks * 2), idesc1h, 1u);   // hi_x . hi_y
                     } else {
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint64_t off = (uint64_t)(ks * 2);
@@ -293,16 +316,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
             const int64_t i = (int64_t)u * TC_BM + quad * 32 + lane;
             const bool iok = i < P.N;
             const float* xrow = P.X + (iok ? i : 0) * P.ldx;
+            // park the X block as fp16 hi / lo, normalised by 2^-ex (the Y image carries a 2^ex): 16 values -> 8 packed
+            // columns per column group
             if (cg * 16 < P.d) {
-                uint32_t hi[16], lo[16];
+                const float sx = pow2i(-h16_exp(__uint_as_float(__ldg(P.nmax)) * P.inv_abs_mult));
+                uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int kk = cg * 16 + k;
-                    const float v = (iok && kk < P.d) ? __ldg(xrow + kk) : 0.f;
-                    split_tf32(v, hi[k], lo[k]);
+                for (int k = 0; k < 8; ++k) {
+                    const int kk = cg * 16 + 2 * k;
+                    const float v0 = (iok && kk < P.d) ? __ldg(xrow + kk) : 0.f;
+                    const float v1 = (iok && kk + 1 < P.d) ? __ldg(xrow + kk + 1) : 0.f;
+                    split_h16u_pair(v0 * sx, v1 * sx, hi[k], lo[k]);
                 }
-                tmem_st16(lane_base + TC_COL_X + cg * 16, hi);
-                tmem_st16(lane_base + TC_COL_X + TC_DP + cg * 16, lo);
+                tmem_st8(lane_base + TC_COL_X + cg * 8, hi);
+                tmem_st8(lane_base + TC_COL_X + TC_DP + cg * 8, lo);
                 tmem_st_wait();
             }
             tc_fence_before();
@@ -539,7 +566,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
 __global__ void tc_pack_kernel(const float* __restrict__ Y, int64_t M, int d, int64_t ldy, const float* __restrict__ W,
                                int m, int64_t ldw, const float* __restrict__ col_pref, int n_tiles, float mult,
                                TcImage L, unsigned char* __restrict__ img, int fast_ok, float a,
-                               const float* __restrict__ yn_all, const unsigned* __restrict__ nmax) {
+                               const float* __restrict__ yn_all, const unsigned* __restrict__ nmax, float inv_abs_mult) {
     const bool fast = fast_ok && tc_fast_regime(nmax);
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int ypt = TC_NT * L.ypieces;            // Y pieces per tile (256 or 512: whole warps)
@@ -571,8 +598,18 @@ __global__ void tc_pack_kernel(const float* __restrict__ Y, int64_t M, int d, in
         if (L.ypieces == 8) q += __shfl_xor_sync(0xffffffffu, q, 4);
         if (c == 0) reinterpret_cast<float*>(base + L.yn)[r] = mult * q;
         if (fast) {
-#pragma unroll
-            for (int q2 = 0; q2 < 4; ++q2) v[q2] *= a;
+            // factored path: y'' = a y 2^ex as fp16 hi / lo (ex normalises X to |x| <= 1, so S = x~ . y'' is the
+            // exponent itself); 4 values = 8 bytes per thread, hi at byte 2k of the row, lo 32 bytes further (packed
+            // layout) or in the lo image
+            const float f = a * pow2i(h16_exp(__uint_as_float(__ldg(nmax)) * inv_abs_mult));
+            uint2 h2, l2;
+            split_h16u_pair(v[0] * f, v[1] * f, h2.x, l2.x);
+            split_h16u_pair(v[2] * f, v[3] * f, h2.y, l2.y);
+            const int oh = r * 128 + (((c >> 1) ^ (r & 7)) << 4) + (c & 1) * 8;
+            const int ol = (L.ypieces == 8) ? L.y_lo_h16 + oh : r * 128 + ((((c >> 1) + 2) ^ (r & 7)) << 4) + (c & 1) * 8;
+            *reinterpret_cast<uint2*>(base + oh) = h2;
+            *reinterpret_cast<uint2*>(base + ol) = l2;
+            return;
         }
     } else {         // W^T: row = output column cc, K = j; piece holds 4 consecutive j
         const int pw = p - ypt;
@@ -702,7 +739,7 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
         JRK_LAUNCHED();
         const int64_t tot = n_tiles * (TC_NT * L.ypieces + 256);
         tc_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, col_pref, (int)n_tiles, mult, L, img,
-                                                                      allow_fast, a_scale, yn_all, nmax);
+                                                                      allow_fast, a_scale, yn_all, nmax, 1.f / fabsf(mult));
         JRK_LAUNCHED();
     }
     TcParams P;
@@ -713,6 +750,7 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     P.ksteps = (d + 7) / 8;
     P.a = a_scale;
     P.allow_fast = allow_fast;
+    P.inv_abs_mult = 1.f / fabsf(mult);
     // p = 2: the near-zero test only matters when the norms are large against the length scale; the kernel decides
     // from the device-side maxima of the pre-pass (no host synchronisation)
     P.check = 0;
