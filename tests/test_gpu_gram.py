@@ -203,7 +203,7 @@ def test_invalid_arguments_raise():
         nat.gram(X.double(), None, 1.0, 2.0, 1.0)
 
 
-@pytest.mark.parametrize("d", [33, 64, 100, 128])
+@pytest.mark.parametrize("d", [20, 33, 64, 100, 128])
 @pytest.mark.parametrize("case", ["huge", "tiny", "mixed_columns", "zero_rows", "offset"])
 def test_fp16_operand_path_is_robust_to_input_magnitudes(d, case):
     """32 < d <= 128 runs on fp16 hi / lo operands normalised by powers of two taken from the data (gram_tf32_kernel,
