@@ -52,10 +52,10 @@ constexpr int TC_THREADS = (3 + TC_EW) * 32;
 constexpr int TC_WIN = 2;                                // tiles per O window (128 j); a power of two
 // p = 2 "factored" fast path: taken when |c| (max|x|^2 + max|y|^2) <= TC_FAST_BOUND (decided on the device from
 // the pre-pass maxima).  There K_ij = 2^(c|x_i|^2) . 2^(-2c x_i.y_j) . 2^(c|y_j|^2) with every factor inside
-// [2^-8, 2^8]: the column factor is folded into W and the scale -2c into Y by the pack pre-pass, the row factor is
+// [2^-12, 2^12]: the column factor is folded into W and the scale -2c into Y by the pack pre-pass, the row factor is
 // applied once per output row, and the epilogue is reduced to  e = ex2(S)  (no norms, no near-zero test, one
 // accumulator).  Worst-case relative error of a term: ~4e-7 * bound (3xTF32 + truncating accumulation), < 1e-5.
-constexpr float TC_FAST_BOUND = 8.0f;
+constexpr float TC_FAST_BOUND = 12.0f;
 constexpr int TC_COL_X = 0, TC_COL_S = 64, TC_COL_O = 64 + TC_SS * 128;   // TMEM columns
 constexpr int TC_OFF_BAR = TC_SOP * TC_STAGE;
 constexpr int TC_NBAR = 2 * TC_SOP + 3 * TC_SS + 4 + 1;  // op full/empty, s_full/e_ready/s_empty, o_full/o_empty x2, x_ready

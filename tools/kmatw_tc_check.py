@@ -40,6 +40,26 @@ if len(_s.argv) > 1 and _s.argv[1] == "var":
     for v in _s.argv[2:]:
         os.environ["JRK_TC_VAR"] = v; print("VAR", v, end=": "); run(131072, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
     _s.exit(0)
+if len(_s.argv) > 1 and _s.argv[1] == "edge":
+    # accuracy at the edge of the factored regime: length scales that put |c| (max|x|^2 + max|y|^2) near the bound
+    for f in (1.0, 0.8, 0.7, 0.62, 0.6):
+        N, M, d, m = 16384, 65536, 16, 16
+        X = torch.randn(N, d, generator=g, device=dev); Y = torch.randn(M, d, generator=g, device=dev)
+        s = float(0.70710695 / (np.sqrt(d) * f)); nc = 0.25
+        c = s * s * 1.4426950408889634
+        bnd = c * float((X * X).sum(1).max() + (Y * Y).sum(1).max())
+        for positive in (True, False):
+            W = torch.rand(M, m, generator=g, device=dev) if positive else torch.randn(M, m, generator=g, device=dev)
+            os.environ["JRK_KMATW_TC"] = "1"
+            for fast in ("1", "0"):
+                os.environ["JRK_TC_FAST"] = fast
+                A = nat.kmatw(X, Y, W, s, 2.0, nc); torch.cuda.synchronize()
+                rows = torch.arange(0, N, N // 64, device=dev)[:64]
+                Kt = nc * torch.exp(-(s * torch.cdist(X[rows].double(), Y.double())) ** 2)
+                T = Kt @ W.double(); bound = Kt @ W.double().abs()
+                ea = ((A[rows].double() - T).abs() / (1e-6 + 1e-5 * bound)).max().item()
+                print(f"f={f} bound={bnd:.2f} positive={positive} fast={fast}: err/lim {ea:.3f}", flush=True)
+    _s.exit(0)
 if len(_s.argv) > 1 and _s.argv[1] == "fast":
     for f in ("1", "0"):
         os.environ["JRK_TC_FAST"] = f; print("JRK_TC_FAST", f)
