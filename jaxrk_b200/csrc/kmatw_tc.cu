@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_SOP; ++s) { mbar_init(&op_full[s], 1); mbar_init(&op_empty[s], 1); }
         for (int s = 0; s < TC_SS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&e_ready[s], TC_EW); mbar_init(&s_empty[s], 1); }
-        // the O windows are folded by the 4 warps of column group 0 (generic path) or by all 16 warps (fast path)
-        for (int s = 0; s < 2; ++s) { mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], fast ? TC_EW : 4); }
+        // every epilogue warp folds its own 4 + 4 columns of an O window
+        for (int s = 0; s < 2; ++s) { mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], TC_EW); }
         mbar_init(x_ready, TC_EW);
         fence_mbar_init();
     }
@@ -433,23 +433,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
             if (lane == 0) mbar_arrive(x_ready);
             const float xs = iok ? __ldg(P.xn + i) : 0.f;
             const f32x2 xs2 = pack2(xs, xs);
-            float oacc[TC_MT];
-#pragma unroll
-            for (int c = 0; c < TC_MT; ++c) oacc[c] = 0.f;
+            float oacc[4] = {0.f, 0.f, 0.f, 0.f};
 
-            auto fold_window = [&]() {   // column group 0 only: O buffers of window wc -> registers
+            auto fold_window = [&]() {   // O buffers of window wc, this warp's 4 + 4 columns -> registers (balanced)
                 const uint32_t ob = wc & 1;
                 bar_wait(b_ofull + ob * 8, (wc >> 1) & 1);
                 tc_fence_after();
-                float o[16], ox[16];
-                tmem_ld16(tmem_base + lane_addr + TC_COL_O + ob * 2 * TC_MT, o);
-                tmem_ld16(tmem_base + lane_addr + TC_COL_O + ob * 2 * TC_MT + TC_MT, ox);
+                float o[4], ox[4];
+                tmem_ld4(tmem_base + lane_addr + TC_COL_O + ob * 2 * TC_MT + cg * 4, o);
+                tmem_ld4(tmem_base + lane_addr + TC_COL_O + ob * 2 * TC_MT + TC_MT + cg * 4, ox);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(b_oempty + ob * 8);
 #pragma unroll
-                for (int c = 0; c < TC_MT; ++c) oacc[c] += o[c] + ox[c];
+                for (int c = 0; c < 4; ++c) oacc[c] += o[c] + ox[c];
                 ++wc;
             };
 
@@ -539,17 +537,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 if (check) tile(t, std::true_type{});
                 else tile(t, std::false_type{});
                 // fold the previous window once its last GEMM2 has been issued (one tile later)
-                if (cg == 0 && t > 0 && (t & (TC_WIN - 1)) == 0) fold_window();
+                if (t > 0 && (t & (TC_WIN - 1)) == 0) fold_window();
             }
-            if (cg == 0) {
-                fold_window();   // the unit's last (possibly partial) window
-                if (iok) {
-                    const float f = ep.nconst * (P.row_pref ? __ldg(P.row_pref + i) : 1.f);
-                    float* dst = P.out + i * P.ldo;
+            fold_window();   // the unit's last (possibly partial) window
+            if (iok) {
+                const float f = ep.nconst * (P.row_pref ? __ldg(P.row_pref + i) : 1.f);
+                float* dst = P.out + i * P.ldo + cg * 4;
 #pragma unroll
-                    for (int c = 0; c < TC_MT; ++c)
-                        if (c < P.m) dst[c] = f * oacc[c];
-                }
+                for (int c = 0; c < 4; ++c)
+                    if (cg * 4 + c < P.m) dst[c] = f * oacc[c];
             }
         }
     }
