@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no built library (it is git-ignored): build it once, in-tree (nvcc cross-compiles without a GPU)
+    lib = os.path.join(ROOT, "jaxrk_b200", "lib", "libjaxrk_b200.so")
+    if not os.path.exists(lib) and os.path.exists("/usr/local/cuda/bin/nvcc"):
+        from jaxrk_b200 import build as _b
+        _b.build()
 
 
 @pytest.fixture(scope="session")
