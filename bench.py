@@ -37,6 +37,10 @@ WORKLOADS = {
     "gram": dict(N=65536, M=65536, d=64, m=0, config="configs[1]: GenGaussKernel Gram N=M=65536 d=64 fp32 materialised"),
     "kmatw": dict(N=1 << 20, M=1 << 20, d=16, m=16, config="configs[2]: fused K(X,Y)@W N=M=2^20 d=16 m=16, never materialised"),
 }
+# north_star's "Gram at N = M = 1M, d = 16": 4.4 TB cannot be materialised, so it is STREAMED: every
+# GPU writes its rows block by block (16384 x 2^20 = 68.7 GB) into one reused buffer; evals/s = N M / time.
+GRAM1M = dict(N=1 << 20, M=1 << 20, d=16, block=16384,
+              config="north_star target: Gram N=M=2^20 d=16, streamed in 16384-row blocks into one reused 68.7 GB buffer")
 POWER = 2.0  # SqExp member of the GenGauss family (make_gauss); other shapes are covered by tools/quickbench.py
 
 
@@ -332,6 +336,50 @@ def run_workload(name, args, torch, nat, dist_ctx, with_cpu):
     return res
 
 
+def run_gram1m(args, torch, nat, dist_ctx):
+    """Streamed Gram N = M = 2^20, d = 16 (kernel-only; there is nowhere to put 4.4 TB, so no e2e leg)."""
+    rank, world, dev = dist_ctx
+    N, M, d, B = GRAM1M["N"], GRAM1M["M"], GRAM1M["d"], GRAM1M["block"]
+    n_local = N // world
+    scale, power, nconst = kernel_params(d)
+    g = torch.Generator(device=dev).manual_seed(300 + rank)
+    X = torch.randn(n_local, d, generator=g, device=dev, dtype=torch.float32)
+    Y = torch.randn(M, d, generator=torch.Generator(device=dev).manual_seed(1), device=dev, dtype=torch.float32)
+    out = torch.empty((B, M), dtype=torch.float32, device=dev)
+
+    def step():
+        for r in range(0, n_local, B):
+            nat.gram(X[r:r + B], Y, scale, power, nconst, out=out[:min(B, n_local - r)])
+
+    nat.gram(X[:B], Y, scale, power, nconst, out=out)      # warm-up (one block)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        torch.distributed.barrier()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    l0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    launches = nat.launch_count() - l0
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+    t_local = float(t.item())
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    hbm, hbm_src, _ = peaks()
+    achieved = 4.0 * n_local * M / t_local / 1e9
+    return {"value": float(N) * M / float(t.item()), "ms_per_step": float(t.item()) * 1e3, "steps": 1, "scaling": "strong",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": None, "peak_source": hbm_src + " (sustained for seconds: the power cap applies)",
+                         "algorithmic_bytes_per_step": 4.0 * n_local * M},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "config": {"workload": GRAM1M["config"], "rows_per_gpu": n_local, "M": M, "d": d, "block_rows": B,
+                       "l2": "every block (68.7 GB) is far larger than L2"}}
+
+
 def run_b200(args):
     import torch
     from jaxrk_b200 import _native as nat
@@ -354,6 +402,11 @@ def run_b200(args):
             also["kmatw_cfg3"] = run_workload("kmatw", args, torch, nat, ctx, with_cpu=(world == 1))
         except Exception as e:  # noqa: BLE001  (the headline line must still print)
             also["kmatw_cfg3"] = {"error": repr(e)}
+        try:
+            torch.cuda.empty_cache()
+            also["gram_1m_d16_streamed"] = run_gram1m(args, torch, nat, ctx)
+        except Exception as e:  # noqa: BLE001
+            also["gram_1m_d16_streamed"] = {"error": repr(e)}
     if rank == 0:
         line = {"metric": "kernel_evals_per_s", "value": main["value"], "unit": "evals/s", "n_gpus": world,
                 "steps": main["steps"], "warmup": main["warmup"], "ms_per_step": main["ms_per_step"],
