@@ -4,7 +4,6 @@ Scale parameters live on the HOST as float32 numpy arrays (they are kernel-launc
 scalars, never device data), with the shapes the reference uses: (1, 1) for a global
 scale, (1, d) for per-dimension scales (util.py:34-50).
 """
-from abc import ABC, abstractmethod
 from typing import Union
 
 import numpy as np
@@ -16,29 +15,30 @@ from .._array import as2d, asarray
 f32 = np.float32
 
 
-class Scaler(ABC):
-    @abstractmethod
+class Scaler:
+    """Interface of the input / distance scalers (jaxrk/kern/util.py:11-31): `scaler(inp)`, the scale `scale()` it
+    multiplies by and its reciprocal `inv()` -- both float32 numpy arrays held on the host."""
+
     def __call__(self, inp):
-        raise NotImplementedError()
+        raise NotImplementedError(type(self).__name__ + " does not scale")
 
-    @abstractmethod
-    def inv(self):
-        raise NotImplementedError()
-
-    @abstractmethod
     def scale(self):
         raise NotImplementedError()
+
+    def inv(self):
+        return (f32(1.) / self.scale()).astype(f32)
 
 
 class NoScaler(Scaler):
+    """Scale 1: the input passes through untouched."""
+
+    _ONE = np.ones(1, f32)
+
     def __call__(self, inp):
         return inp
 
-    def inv(self):
-        return np.ones(1, f32)
-
     def scale(self):
-        return np.ones(1, f32)
+        return self._ONE
 
 
 class SimpleScaler(Scaler):
@@ -57,9 +57,6 @@ class SimpleScaler(Scaler):
                 assert scale.ndim == 2 and scale.shape[0] == 1
         assert np.all(scale > 0.)
         self.s = scale
-
-    def inv(self):
-        return (f32(1.) / self.s).astype(f32)
 
     def scale(self):
         return self.s
