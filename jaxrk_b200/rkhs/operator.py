@@ -37,23 +37,30 @@ class FiniteOp(LinOp):
         return len(self.inp_feat) * len(self.outp_feat)
 
     def __matmul__(self, right_inp):
-        if isinstance(right_inp, FiniteOp):  # Op1 @ Op2  (operator.py:34-40)
-            matr = self.inp_feat.inner(right_inp.outp_feat) @ right_inp.matr
-            if self.matr is not None:
-                matr = self.matr @ matr
-            return FiniteOp(right_inp.inp_feat, self.outp_feat, matr)
+        """op @ op composes (operator.py:34-40); op @ vec / op @ points applies the operator (operator.py:42-56)."""
+        if isinstance(right_inp, FiniteOp):
+            return self._compose(right_inp)
         if _is_array(right_inp):
             right_inp = FiniteVec(self.inp_feat.k, torch.atleast_2d(asarray(right_inp)))
-        # Op @ vec  (operator.py:44-56)
-        lin_LinOp = inner(self.inp_feat, right_inp)
+        return self._apply_to(right_inp)
+
+    def _compose(self, other: "FiniteOp") -> "FiniteOp":
+        # (self.matr) . <inp_feat, other.outp_feat> . (other.matr): the middle factor is a fused inner product
+        core = self.inp_feat.inner(other.outp_feat) @ other.matr
+        return FiniteOp(other.inp_feat, self.outp_feat, core if self.matr is None else self.matr @ core)
+
+    def _apply_to(self, vec) -> FiniteVec:
+        # coefficients over the output features: matr . <inp_feat, vec>  (len(outp_feat) x len(vec)); the inner
+        # product is the hot part (fused Gram / K@W), the small dense products stay on the library path
+        coeff = inner(self.inp_feat, vec)
         if self.matr is not None:
-            lin_LinOp = self.matr @ lin_LinOp
+            coeff = self.matr @ coeff
         if self._normalize:
-            lin_LinOp = lin_LinOp / lin_LinOp.sum(1, keepdim=True)
-        lr = LinearReduce(lin_LinOp.T)
-        if len(right_inp) != 1:
-            return self.outp_feat.extend_reduce([lr])
-        return self.outp_feat.extend_reduce([lr, Sum()])
+            coeff = coeff / coeff.sum(1, keepdim=True)
+        chain = [LinearReduce(coeff.T)]
+        if len(vec) == 1:
+            chain.append(Sum())
+        return self.outp_feat.extend_reduce(chain)
 
     def inner(self, Y=None, full=True):
         if Y is None:
