@@ -29,10 +29,6 @@ def run(N, M, d, m, p, positive=False, timing=False):
         msg += f" | tc {ta:.2f} ms ({N*M/ta/1e6:.0f} Gpairs/s)  fp32 {tb:.2f} ms ({N*M/tb/1e6:.0f} Gpairs/s)"
     print(msg, flush=True)
 import sys as _s
-if len(_s.argv) > 1 and _s.argv[1] == "dbg":
-    for w in ("0", "4", "8", "1", "2", "3", "11", "27", "31"):
-        os.environ["JRK_TC_DBG"] = w; print("DBG", w, end=": "); run(131072, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
-    _s.exit(0)
 if len(_s.argv) > 1 and _s.argv[1] == "fast1":
     run(131072, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
     _s.exit(0)
