@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
             };
 
             // one tile: S -> e for this warp's 32 rows x 16 columns
-            auto tile = [&](int t, auto chk) {
+            auto tile = [&](int t, auto chk, uint32_t st, uint32_t st_ph, uint32_t sa, uint32_t sa_ph) {
                 constexpr bool CHECK = decltype(chk)::value;
                 // the tile's (scaled) |y_j|^2 arrived with the operand image: observe the TMA completion, then
                 // broadcast 16-byte reads from shared memory (the stage is released only after GEMM2 of this tile)
@@ -546,16 +546,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(b_eready + sa * 8);
+            };
+            auto tile_dyn = [&](int t) {       // stage indices in registers
+                if (check) tile(t, std::true_type{}, st, st_ph, sa, sa_ph);
+                else tile(t, std::false_type{}, st, st_ph, sa, sa_ph);
                 if (++st == TC_SOP) { st = 0; st_ph ^= 1; }
                 if (++sa == TC_SS) { sa = 0; sa_ph ^= 1; }
-            };
-
-            for (int t = 0; t < T; ++t) {
-                if (check) tile(t, std::true_type{});
-                else tile(t, std::false_type{});
                 // fold the previous window once its last GEMM2 has been issued (one tile later)
                 if (t > 0 && (t & (TC_WIN - 1)) == 0) fold_window();
+            };
+            // as in the factored path: once the operand stage is 0 (then the S / e stage is 0 too: TC_SOP is a multiple
+            // of TC_SS), TC_SOP tiles per iteration with both stages as compile-time constants
+            static_assert(TC_SOP % TC_SS == 0, "stage periods");
+            int t = 0;
+            for (; t < T && st != 0; ++t) tile_dyn(t);
+            for (; t + TC_SOP <= T; t += TC_SOP) {
+#pragma unroll
+                for (int k = 0; k < TC_SOP; ++k) {
+                    const uint32_t sap = sa_ph ^ (uint32_t)((k / TC_SS) & 1);
+                    if (check) tile(t + k, std::true_type{}, (uint32_t)k, st_ph, (uint32_t)(k % TC_SS), sap);
+                    else tile(t + k, std::false_type{}, (uint32_t)k, st_ph, (uint32_t)(k % TC_SS), sap);
+                    if (t + k > 0 && ((t + k) & (TC_WIN - 1)) == 0) fold_window();
+                }
+                st_ph ^= 1;
+                if ((TC_SOP / TC_SS) & 1) sa_ph ^= 1;
             }
+            for (; t < T; ++t) tile_dyn(t);
             fold_window();   // the unit's last (possibly partial) window
             if (iok) {
                 const float f = ep.nconst * (P.row_pref ? __ldg(P.row_pref + i) : 1.f);
