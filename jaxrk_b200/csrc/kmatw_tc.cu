@@ -230,13 +230,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 const uint64_t dyh = dbase + (uint64_t)((s * TC_STAGE) >> 4), dyl = dyh + y_lo;
                 const uint32_t c1 = TC_COL_S + a * 128, c2 = c1 + 64;
                 if (elect_one()) {
+                    // fp16 hi / lo operands (K = 16 per MMA: half the MMAs of the tf32 form)
+                    constexpr uint32_t idesc1h = (1u << 4) | ((uint32_t)(TC_NT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                    const int ksh = (P.d + 15) >> 4;
+                    const uint64_t dylh = dyh + (uint64_t)(P.L.y_lo_h16 >> 4);
                     if (fast) {
-                        // fp16 hi / lo operands (K = 16 per MMA: half the MMAs of the tf32 form), one accumulator: the
-                        // small cross terms first, the hi.hi terms last (the accumulator truncates, so only the last
-                        // additions carry a rounding error that matters)
-                        constexpr uint32_t idesc1h = (1u << 4) | ((uint32_t)(TC_NT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-                        const int ksh = (P.d + 15) >> 4;
-                        const uint64_t dylh = dyh + (uint64_t)(P.L.y_lo_h16 >> 4);
+                        // one accumulator: the small cross terms first, the hi.hi terms last (the accumulator
+                        // truncates, so only the last additions carry a rounding error that matters)
                         for (int ks = 0; ks < ksh; ++ks) {
                             const uint64_t off = (uint64_t)(ks * 2);
                             mma_f16_ts(c1, TC_COL_X + ks * 8, dylh + off, idesc1h, ks);            // hi_x . lo_y
@@ -245,11 +245,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                         for (int ks = 0; ks < ksh; ++ks)
                             mma_f16_ts(c1, TC_COL_X + ks * 8, dyh + (uint64_t)(ks * 2), idesc1h, 1u);   // hi_x . hi_y
                     } else {
-                        for (int ks = 0; ks < ksteps; ++ks) {
+                        // generic epilogue: the same fp16 operands with lo' = lo 2^11 (full precision at any
+                        // magnitude), cross terms in their own accumulator, folded in with 2^-11 by the epilogue
+                        for (int ks = 0; ks < ksh; ++ks) {
                             const uint64_t off = (uint64_t)(ks * 2);
-                            mma_tf32_ts(c1, TC_COL_X + ks * 8, dyh + off, idesc1, ks);            // hi_x . hi_y
-                            mma_tf32_ts(c2, TC_COL_X + ks * 8, dyl + off, idesc1, ks);            // hi_x . lo_y
-                            mma_tf32_ts(c2, TC_COL_X + TC_DP + ks * 8, dyh + off, idesc1, 1u);    // lo_x . hi_y
+                            mma_f16_ts(c1, TC_COL_X + ks * 8, dyh + off, idesc1h, ks);            // hi_x . hi_y
+                            mma_f16_ts(c2, TC_COL_X + ks * 8, dylh + off, idesc1h, ks);           // hi_x . lo'_y
+                            mma_f16_ts(c2, TC_COL_X + TC_DP + ks * 8, dyh + off, idesc1h, 1u);    // lo'_x . hi_y
                         }
                     }
                     tc_commit_addr(b_sfull + a * 8);
@@ -413,7 +415,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
         const int quad = warp & 3;                          // TMEM lane quarter this warp may touch
         const int cg = e >> 2;                              // 16-column group of the tile
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const f32x2 a2 = pack2(P.a, P.a), ntau2 = pack2(-TF_TAU, -TF_TAU);
+        // x.y = 2^(ex+ey) (c1 + 2^-11 c2): the power of two rides in `a`
+        const float a_eff = P.a * pow2i(h16_exp(__uint_as_float(__ldg(P.nmax)) * P.inv_abs_mult) +
+                                        h16_exp(__uint_as_float(__ldg(P.nmax + 1)) * P.inv_abs_mult));
+        const f32x2 a2 = pack2(a_eff, a_eff), ntau2 = pack2(-TF_TAU, -TF_TAU), low2 = pack2(1.f / 2048.f, 1.f / 2048.f);
         // shared-window base in an opaque register (otherwise the address conversion is rematerialised per tile)
         uint32_t sbase;
         asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));
@@ -431,18 +436,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
             const int64_t i = (int64_t)u * TC_BM + quad * 32 + lane;
             const bool iok = i < P.N;
             const float* xrow = P.X + (iok ? i : 0) * P.ldx;
-            // ---- park the X block in TMEM as tf32 hi / lo: column groups 0 and 1 take 16 columns each ----
+            // ---- park the X block in TMEM as fp16 hi / lo' (normalised by 2^-ex, lo' = lo 2^11): column groups 0 and 1
+            // take 16 values = 8 packed columns each ----
             // (every GEMM1 that read the previous block has completed: this warp waited for the last s_full)
             if (cg * 16 < P.d) {
-                uint32_t hi[16], lo[16];
+                const float sx = pow2i(-h16_exp(__uint_as_float(__ldg(P.nmax)) * P.inv_abs_mult));
+                uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int kk = cg * 16 + k;
-                    const float v = (iok && kk < P.d) ? __ldg(xrow + kk) : 0.f;
-                    split_tf32(v, hi[k], lo[k]);
+                for (int k = 0; k < 8; ++k) {
+                    const int kk = cg * 16 + 2 * k;
+                    const float v0 = (iok && kk < P.d) ? __ldg(xrow + kk) : 0.f;
+                    const float v1 = (iok && kk + 1 < P.d) ? __ldg(xrow + kk + 1) : 0.f;
+                    split_h16_pair(v0 * sx, v1 * sx, hi[k], lo[k]);
                 }
-                tmem_st16(tmem_base + lane_addr + TC_COL_X + cg * 16, hi);
-                tmem_st16(tmem_base + lane_addr + TC_COL_X + TC_DP + cg * 16, lo);
+                tmem_st8(tmem_base + lane_addr + TC_COL_X + cg * 8, hi);
+                tmem_st8(tmem_base + lane_addr + TC_COL_X + TC_DP + cg * 8, lo);
                 tmem_st_wait();
             }
             tc_fence_before();
@@ -489,8 +497,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const f32x2 t01 = add2(pack2(yv[g].x, yv[g].y), xs2), t23 = add2(pack2(yv[g].z, yv[g].w), xs2);
-                    const f32x2 d01 = add2(pack2(c1[4 * g], c1[4 * g + 1]), pack2(c2[4 * g], c2[4 * g + 1]));
-                    const f32x2 d23 = add2(pack2(c1[4 * g + 2], c1[4 * g + 3]), pack2(c2[4 * g + 2], c2[4 * g + 3]));
+                    const f32x2 d01 = fma2(pack2(c2[4 * g], c2[4 * g + 1]), low2, pack2(c1[4 * g], c1[4 * g + 1]));
+                    const f32x2 d23 = fma2(pack2(c2[4 * g + 2], c2[4 * g + 3]), low2, pack2(c1[4 * g + 2], c1[4 * g + 3]));
                     const f32x2 u01 = fma2(d01, a2, t01), u23 = fma2(d23, a2, t23);
                     unpack2(u01, uu[4 * g], uu[4 * g + 1]);
                     unpack2(u23, uu[4 * g + 2], uu[4 * g + 3]);
@@ -626,14 +634,20 @@ __global__ void tc_pack_kernel(const float* __restrict__ Y, int64_t M, int d, in
         q += __shfl_xor_sync(0xffffffffu, q, 2);
         if (L.ypieces == 8) q += __shfl_xor_sync(0xffffffffu, q, 4);
         if (c == 0) reinterpret_cast<float*>(base + L.yn)[r] = mult * q;
-        if (fast) {
-            // factored path: y'' = a y 2^ex as fp16 hi / lo (ex normalises X to |x| <= 1, so S = x~ . y'' is the
-            // exponent itself); 4 values = 8 bytes per thread, hi at byte 2k of the row, lo 32 bytes further (packed
-            // layout) or in the lo image
-            const float f = a * pow2i(h16_exp(__uint_as_float(__ldg(nmax)) * inv_abs_mult));
+        {
+            // fp16 hi / lo image: 4 values = 8 bytes per thread, hi at byte 2k of the row, lo 32 bytes further (packed
+            // layout) or in the lo image.  Factored path: y'' = a y 2^ex with lo unscaled (ex normalises X to |x| <= 1,
+            // so S = x~ . y'' is the exponent itself).  Generic path: y 2^-ey with lo' = lo 2^11.
             uint2 h2, l2;
-            split_h16u_pair(v[0] * f, v[1] * f, h2.x, l2.x);
-            split_h16u_pair(v[2] * f, v[3] * f, h2.y, l2.y);
+            if (fast) {
+                const float f = a * pow2i(h16_exp(__uint_as_float(__ldg(nmax)) * inv_abs_mult));
+                split_h16u_pair(v[0] * f, v[1] * f, h2.x, l2.x);
+                split_h16u_pair(v[2] * f, v[3] * f, h2.y, l2.y);
+            } else {
+                const float f = pow2i(-h16_exp(__uint_as_float(__ldg(nmax + 1)) * inv_abs_mult));
+                split_h16_pair(v[0] * f, v[1] * f, h2.x, l2.x);
+                split_h16_pair(v[2] * f, v[3] * f, h2.y, l2.y);
+            }
             const int oh = r * 128 + (((c >> 1) ^ (r & 7)) << 4) + (c & 1) * 8;
             const int ol = (L.ypieces == 8) ? L.y_lo_h16 + oh : r * 128 + ((((c >> 1) + 2) ^ (r & 7)) << 4) + (c & 1) * 8;
             *reinterpret_cast<uint2*>(base + oh) = h2;
