@@ -1,36 +1,37 @@
 // Kernel (b'): fused, never-materialised K(X, Y) @ W with BOTH contractions on the tensor cores (tcgen05),
-// for d <= 32 and m <= 16 on large problems.
+// for d <= 32 and m <= 16 on large problems (row reduce none / Sum / Mean).
 //
 // Replaces the same reference code as kmatw.cu -- FiniteVec.inner (jaxrk/rkhs/vector.py:62-75) with a
 // LinearReduce / Sum / Mean on the Y side (jaxrk/reduce/lincomb.py:137-140, reduce/base.py:132-150), the inner()
 // of FiniteOp.__matmul__ (jaxrk/rkhs/operator.py:46) -- and computes the same numbers; what changes is where the
 // arithmetic runs.  kmatw.cu is bound by the FP32 pipe (2d + m + 2 lane-operations per pair).  Here
-//   GEMM1   S = x.y   by 3xTF32 (hi.hi + hi.lo + lo.hi), X block resident in TMEM (A), Y tiles in shared memory (B)
-//   epilogue           e = exp2(a S + xs_i + ys_j), split into tf32 hi / lo, written back over S in TMEM
-//   GEMM2   O += e.W   by 3xTF32, A = e from TMEM, B = W^T tiles in shared memory, O accumulates in TMEM
-// so a pair costs ~10 issued instructions and one MUFU instead of ~33 instructions: the kernel is bound by the
-// MUFU / issue rate, not by FP32 FMAs (DESIGN.md "Rooflines").
+//   GEMM1   S = x.y    3 products of fp16 hi / lo operands (kind::f16, K = 16), X block resident in TMEM (A operand),
+//                      64-row Y tiles in shared memory (B)
+//   epilogue           e = exp2(...) split into tf32 hi / lo, written back over S in TMEM
+//   GEMM2   O += e.W   3xTF32, A = e from TMEM, B = W^T tiles in shared memory, O accumulates in TMEM
+// so a pair costs ~5 issued instructions and one MUFU instead of ~33 instructions.
 //
-// A pre-pass writes, per 64-row tile of Y, one contiguous image [Y hi, Y lo | W^T hi | W^T lo | 64 scaled |y|^2] in the
-// K-major 128B-swizzled layout of the UMMA descriptor, so a tile arrives with one cp.async.bulk.  For d <= 16 the
-// hi and lo halves of a Y row share one 128-byte swizzle row (16.25 KB per tile), else they are separate (24.25 KB).
-// The first version of this kernel gave each CTA one 128-row block of X and was bound by the L2 -> SM operand
-// stream (24 KB per 8192 pairs = 7.2 TB/s chip-wide; measured 58 ms of 89 with the MMAs and the epilogue switched
-// off).  So a CTA now owns TWO 128-row blocks that share every tile image (half the L2 bytes per pair): the
-// S / e stage of block r is TMEM stage r, epilogue group r (8 warps) owns block r, and the two groups alternate
-// naturally -- while group 0 converts tile t of block 0, the tensor core runs GEMM1 of block 1 / GEMM2 of block 0.
-// Persistent CTAs, one per SM; 18 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-17
-// epilogue (TMEM lane = row i; 32 columns j per warp and tile, in two 16-column chunks).
-// TMEM columns: X of block r [r*64, +64) = hi [32) lo [32) | S / e of block r [128 + r*128, +128) = {c1, c2} -> {e hi, e lo}
-//               | O of block r, buffer b [384 + r*64 + b*32, +32) = {main [16), cross [16)}.
+// A pre-pass (tc_rownorm_kernel x 2, tc_pack_kernel) writes, per 64-row tile of Y, one contiguous image
+// [Y hi, Y lo (fp16) | per 32-column k-chunk: W^T hi, W^T lo (tf32) | 64 scaled |y|^2] in the K-major 128B-swizzled
+// layout of the UMMA descriptor, so a tile arrives with one cp.async.bulk.
+// Persistent CTAs, one per SM, one 128-row block of X per work unit; 19 warps: warp 0 TMA producer, warp 1 GEMM1 issuer
+// (+ TMEM allocation), warp 2 GEMM2 issuer, warps 3-18 epilogue (TMEM lane = row i; warp = lane quarter x 16-column
+// group).  TMEM columns: X [0, 64) = hi [32) lo [32) | TC_SS = 3 in-place S / e stages [64 + s*128, +128) =
+// {c1, c2} -> {e hi, e lo} | two O windows [448 + b*32, +32) = {main [16), cross [16)}.
+//
+// Two epilogues (see TC_FAST_BOUND): the FACTORED p = 2 path (scale folded into the Y image, 2^(c|y|^2) into W,
+// 2^(c|x|^2) applied once per row, one accumulator, e = ex2(S)) and the GENERIC one (any p, any norms: u = a S + xs +
+// ys from two accumulators, near-coincident pairs -- sq < (|x|^2+|y|^2)/64 -- recomputed by FP32 direct differencing
+// as in the Gram kernel).  Both loops are unrolled by the stage period so that barrier / TMEM addresses are immediates.
+//
 // The tensor core's accumulation is not round-to-nearest: for all-positive sums the error grows with the number of
-// MMAs that add into one accumulator (measured: 4.8x the tolerance with 64-tile windows, 0.5x with 1-4 tiles).
-// So (i) O accumulates in TMEM across a window of TC_WIN tiles only (measured, all-positive W, M = 2^20: 0.50 of the
-// tolerance with 2 tiles, 0.53 with 4, 0.60 with 8 -- and 46.2 / 45.4 ms instead of 48.7: TC_WIN = 4); the epilogue then folds the window into FP32
-// registers (round to nearest) while the next window accumulates in the second O buffer, and (ii) the large term
-// hi_e.hi_w and the two small cross terms go to separate accumulators (8 instead of 24 MMAs per tile on the one
-// that matters).
-// Near-coincident pairs (sq < (|x|^2+|y|^2)/64) are recomputed by FP32 direct differencing, as in the Gram kernel.
+// MMAs that add into one accumulator (measured: 4.8x the tolerance with 64-tile windows).  So (i) O accumulates in
+// TMEM across a window of TC_WIN tiles only (measured, all-positive W, M = 2^20: 0.50 of the tolerance with 2 tiles,
+// 0.53 with 4, 0.60 with 8; 48.7 / 46.2 / 45.4 ms: TC_WIN = 4); the epilogue then folds the window into FP32 registers
+// (round to nearest) while the next window accumulates in the second O buffer, and (ii) the large term hi_e.hi_w and
+// the small cross terms go to separate accumulators; GEMM2 pairs hi_e with [W^T hi ; W^T lo] in ONE N = 32 MMA
+// (an MMA of N <= 32 costs ~20 clk whatever N is) plus lo_e x W^T hi.
+// What was measured on the way (ten variants that did not help, and the ones that did) is in profiles/README.md.
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
