@@ -1,12 +1,13 @@
-// Kernel (a2): materialised Gram for d <= 128 (columns padded to 32 / 64 / 96 / 128) by the compensated 3xTF32 expansion on the
-// 5th-generation tensor cores (tcgen05.mma, operands and accumulators in TMEM).
+// Kernel (a2): materialised Gram for d <= 128 by the compensated three-product expansion on the 5th-generation tensor
+// cores (tcgen05.mma, operands and accumulators in TMEM): tf32 hi / lo operands (columns padded to 32) for d <= 16,
+// fp16 hi / lo' operands (kind::f16, K = 16: half the MMAs and operand bytes; padded to 64 / 128) above -- see TfCfg.
 //
 // Replaces, for wide inputs, the same reference chain as gram_direct.cu:
 //   sqeucldist_simple (jaxrk/utilities/eucldist.py:10-18)  sq = |x|^2 + |y|^2 - 2 x.y   <- the GEMM
 //   eucldist (:37-48), ScaledPairwiseDistance (jaxrk/kern/util.py:107-116),
 //   GenGaussKernel.__call__ (jaxrk/kern/rbf.py:104-105)                                  <- the epilogue
 // Here the distance really is a dense contraction, so x.y goes to the tensor cores; FP32
-// accuracy is recovered by splitting every operand into tf32 "hi" and "lo" parts,
+// accuracy is recovered by splitting every operand into "hi" and "lo" parts of 11 significant bits each,
 //   x.y ~= hi_x.hi_y + hi_x.lo_y + lo_x.hi_y          (three tcgen05.mma per k-step),
 // and the kernel is bound by the HBM write of the N x M result (DESIGN.md "Rooflines").
 //
@@ -15,9 +16,9 @@
 // X (output rows i).  An accumulator lane therefore runs along the contiguous output
 // dimension: a warp's 32 lanes hold 32 consecutive floats of one output row.
 //
-// A pre-pass kernel (gram_tf32.cu: tf_split_kernel) splits X once into tf32 hi / lo tile images that are
-// already in the K-major 128B-swizzled layout the UMMA shared-memory descriptor expects, one contiguous
-// 2 x NT x DP x 4 byte block per tile, so the main kernel needs no in-SM conversion pass: a tile arrives
+// A pre-pass kernel (gram_tf32.cu: tf_split_kernel / tf_split_h16_kernel) splits X once into hi / lo tile images that
+// are already in the K-major 128B-swizzled layout the UMMA shared-memory descriptor expects, one contiguous
+// 2 x NT x DP x {4 | 2} byte block per tile, so the main kernel needs no in-SM conversion pass: a tile arrives
 // with ONE cp.async.bulk and is consumed by the tensor core directly.  (A first version converted raw FP32
 // tiles inside the SM with four extra warps; knock-out timing showed the stages contending for the
 // 128 B/clk shared-memory / L1 data pipe -- TMA fill 16 KB + converter 48 KB + MMA operand reads 48 KB +
@@ -34,7 +35,9 @@
 //               At the start of every work unit the same warps load their Y rows, split them
 //               and park hi / lo in TMEM (tcgen05.st): the A operand is read from TMEM, which
 //               keeps it off the shared-memory port.
-// TMEM (512 columns): [0, DP) A hi | [DP, 2DP) A lo | 2 stages x NACC accumulators x NT columns.
+// TMEM (512 columns): A hi | A lo (DP columns each for tf32, DP / 2 for packed fp16) | 2 stages x NACC accumulators x NT
+// columns.  The kernel is power-limited (~1000 W): k-steps that hold only zero padding are not issued, and the fp16
+// form exists because halving the MMAs took cfg2 from 3.86 to 3.40 ms (profiles/README.md).
 //   NACC = 3 (self-Gram): hi.hi, hi.lo and lo.hi go to separate accumulators and are combined as
 //            c1 + (c2 + c3); with the split and the norms being role-independent functions,
 //            K(X, X) is bitwise symmetric (jaxrk/utilities/gram.py:18 asserts G == G.T).
