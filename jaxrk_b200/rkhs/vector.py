@@ -127,6 +127,22 @@ class FiniteVec(Vec):
             self._raw_gram_cache = self.k(self.insp_pts)
         return self._raw_gram_cache
 
+    def point_representant(self, method: str = "inspace_point", keepdims: bool = False):
+        """An input-space point standing for each element (vector.py:161-174): the support point whose feature is
+        nearest in RKHS norm ("inspace_point"; the Grams come from the fused kernels), or the mean ("mean")."""
+        from ..utilities.gram import gram_projection
+        if method == "inspace_point":
+            assert isinstance(self.reduce[-1], (Prefactors, LinearReduce))
+            G_orig_repr = Reduce.apply(self._raw_gram, self.reduce, 1)
+            idx = gram_projection(G_orig_repr, Reduce.apply(G_orig_repr, self.reduce, 0), self._raw_gram,
+                                  method="representer").reshape(-1)
+            rval = self.insp_pts[idx, :]
+        elif method == "mean":
+            rval = self.get_mean_var(keepdims=keepdims)[0]
+        else:
+            assert False, "No known method selected for point_representant"
+        return rval if keepdims else rval.squeeze()
+
     def __call__(self, argument):
         return inner(self, FiniteVec(self.k, argument, []))
 

@@ -4,21 +4,9 @@ utilities/gram.py:8-23)."""
 import torch
 
 from .eucldist import eucldist
+from .gram import rkhs_gram_cdist
 
 __all__ = ["dist", "rkhs_cdist", "rkhs_gram_cdist"]
-
-
-def rkhs_gram_cdist(G_ab, G_a=None, G_b=None, power: float = 2.):
-    """utilities/gram.py:8-23: ||a_i - b_j||_H^power from Gram matrices.  For a single
-    Gram the reference asserts exact symmetry (gram.py:18); the self-Gram kernel
-    guarantees it bitwise."""
-    if G_a is None or G_b is None:
-        assert G_ab.shape[0] == G_ab.shape[1] and bool(torch.all(G_ab == G_ab.T))
-        da = db = torch.diagonal(G_ab)
-    else:
-        da, db = torch.diagonal(G_a), torch.diagonal(G_b)
-    sq = da[:, None] + db[None, :] - 2 * G_ab
-    return sq if power == 2 else torch.pow(sq, power / 2.)
 
 
 def rkhs_cdist(a, b=None, power: float = 2.):

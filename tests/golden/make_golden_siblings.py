@@ -92,6 +92,26 @@ def main():
         out[f"comb_{name}_xx"] = onp.asarray(cx.inner(), F32)
         out[f"comb_{name}_len"] = onp.array([len(cx), len(cy)])
 
+    # ---- Gram-based utilities (jaxrk/utilities/gram.py) and FiniteVec.point_representant (rkhs/vector.py:161-174) ----
+    from jaxrk.utilities.gram import (rkhs_gram_cdist, rkhs_gram_cdist_ignore_const, choose_representer,
+                                      choose_representer_from_gram, gram_projection)
+    kq = GenGaussKernel.make_gauss(0.9)
+    Gxx, Gyy, Gxy = kq(X), kq(Y), kq(X, Y)
+    out["util_cdist_xy"] = onp.asarray(rkhs_gram_cdist(Gxy, Gxx, Gyy), F32)
+    out["util_cdist_xy_p1"] = onp.asarray(rkhs_gram_cdist(Gxy, Gxx, Gyy, power=1.), F32)
+    out["util_cdist_ignore"] = onp.asarray(rkhs_gram_cdist_ignore_const(Gxy, Gyy), F32)
+    fac = rng.rand(37).astype(F32)
+    fac /= fac.sum()
+    out["util_factors"] = fac
+    out["util_representer"] = onp.array([int(choose_representer(X, fac, kq)), int(choose_representer_from_gram(Gxx, fac))])
+    out["util_projection"] = onp.asarray(gram_projection(Gxy, Gyy, Gxx), onp.int64)   # 37 representers x 29 originals
+    A2 = rng.rand(3, 37).astype(F32)
+    A2 /= A2.sum(1, keepdims=True)
+    out["util_A2"] = A2
+    vec = FiniteVec(kq, X, [LinearReduce(A2)])
+    out["util_point_repr"] = onp.asarray(vec.point_representant("inspace_point", keepdims=True), F32)
+    out["util_point_mean"] = onp.asarray(vec.point_representant("mean", keepdims=True), F32)
+
     path = os.path.join(HERE, "reference_siblings.npz")
     onp.savez_compressed(path, **out)
     print("wrote", path, len(out), "arrays")

@@ -197,3 +197,23 @@ def test_balanced_inner_through_the_tensor_core_route(monkeypatch):
         Xa, Xb = X[a * gy:(a + 1) * gy].cpu().numpy(), X[b * gy:(b + 1) * gy].cpu().numpy()
         truth = orc.gengauss_gram_truth64(Xa, Xb, s, power, nconst=nconst).mean()
         assert abs(float(S[a, b]) - truth) <= 1e-6 + 1e-5 * abs(truth)
+
+
+def test_gram_utilities_and_point_representant_on_the_gpu():
+    """jaxrk/utilities/gram.py and FiniteVec.point_representant over Grams from the fused kernels, against outputs of
+    the reference's own code (tests/golden/reference_siblings.npz)."""
+    import os
+    from jaxrk_b200.utilities import choose_representer, gram_projection, rkhs_gram_cdist, rkhs_gram_cdist_ignore_const
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_siblings.npz"))
+    X, Y = g["X"], g["Y"]
+    kq = GenGaussKernel.make_gauss(0.9)
+    Gxx, Gyy, Gxy = kq(X), kq(Y), kq(X, Y)
+    np.testing.assert_allclose(rkhs_gram_cdist(Gxy, Gxx, Gyy).cpu().numpy(), g["util_cdist_xy"], rtol=3e-5, atol=3e-6)
+    np.testing.assert_allclose(rkhs_gram_cdist_ignore_const(Gxy, Gyy).cpu().numpy(), g["util_cdist_ignore"], rtol=3e-5, atol=3e-6)
+    assert choose_representer(X, g["util_factors"], kq) == int(g["util_representer"][0])
+    assert (gram_projection(Gxy, Gyy, Gxx).cpu().numpy() == g["util_projection"]).all()
+    vec = FiniteVec(kq, X, [LinearReduce(g["util_A2"])])
+    np.testing.assert_allclose(vec.point_representant("inspace_point", keepdims=True).cpu().numpy(), g["util_point_repr"], rtol=1e-6)
+    np.testing.assert_allclose(vec.point_representant("mean", keepdims=True).cpu().numpy(), g["util_point_mean"], rtol=3e-5, atol=1e-6)
+    d = rkhs_gram_cdist(Gxx)
+    assert torch.equal(d, d.T) and float(torch.diagonal(d).abs().max()) == 0.0

@@ -267,3 +267,29 @@ def test_combvec_lowering_against_reference_outputs():
         np.testing.assert_allclose(got, g[f"comb_{name}_xy"], rtol=3e-5, atol=3e-6)
         # the reference misses truth on self-Gram diagonals for p < 2: up to 1.2e-4 there
         np.testing.assert_allclose(cx.inner().numpy(), g[f"comb_{name}_xx"], rtol=3e-5, atol=3e-6 if name == "gg" else 2e-4)
+
+
+def test_gram_utilities_and_point_representant_against_reference_outputs():
+    """jaxrk/utilities/gram.py (RKHS distances from Grams, representer choice) and FiniteVec.point_representant
+    (rkhs/vector.py:161-174) against outputs of the reference's own code."""
+    import os
+    from jaxrk_b200.utilities import (choose_representer, choose_representer_from_gram, gram_projection, rkhs_gram_cdist,
+                                      rkhs_gram_cdist_ignore_const)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_siblings.npz"))
+    X, Y = g["X"], g["Y"]
+    kq = GenGaussKernel.make_gauss(0.9)
+    Gxx, Gyy, Gxy = kq(X), kq(Y), kq(X, Y)
+    np.testing.assert_allclose(rkhs_gram_cdist(Gxy, Gxx, Gyy).numpy(), g["util_cdist_xy"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(rkhs_gram_cdist(Gxy, Gxx, Gyy, power=1.).clamp_min(0).numpy(), np.nan_to_num(g["util_cdist_xy_p1"]), rtol=1e-3, atol=2e-3)
+    np.testing.assert_allclose(rkhs_gram_cdist_ignore_const(Gxy, Gyy).numpy(), g["util_cdist_ignore"], rtol=2e-5, atol=2e-6)
+    fac = g["util_factors"]
+    assert [choose_representer(X, fac, kq), choose_representer_from_gram(Gxx, fac)] == list(g["util_representer"])
+    assert (gram_projection(Gxy, Gyy, Gxx).numpy() == g["util_projection"]).all()
+    with pytest.raises(NotImplementedError):
+        gram_projection(Gxy, Gyy, Gxx, method="pos_proj")
+    vec = FiniteVec(kq, X, [LinearReduce(g["util_A2"])])
+    np.testing.assert_allclose(vec.point_representant("inspace_point", keepdims=True).numpy(), g["util_point_repr"], rtol=1e-6)
+    np.testing.assert_allclose(vec.point_representant("mean", keepdims=True).numpy(), g["util_point_mean"], rtol=2e-5, atol=1e-6)
+    # a single (self) Gram must be exactly symmetric, as the reference asserts (utilities/gram.py:18)
+    d = rkhs_gram_cdist(Gxx)
+    assert torch.equal(d, d.T) and float(torch.diagonal(d).abs().max()) == 0.0
