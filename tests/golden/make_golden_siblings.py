@@ -112,6 +112,20 @@ def main():
     out["util_point_repr"] = onp.asarray(vec.point_representant("inspace_point", keepdims=True), F32)
     out["util_point_mean"] = onp.asarray(vec.point_representant("mean", keepdims=True), F32)
 
+    # ---- GP regression (jaxrk/gp.py) over FiniteVec.inner ----
+    from jaxrk.gp import GP
+    kgp = GenGaussKernel.make_gauss(0.8)
+    xtr = onp.linspace(0., 6., 24).reshape(-1, 1).astype(F32)
+    ytr = (onp.sin(xtr) + 0.1 * rng.randn(24, 1)).astype(F32)
+    xte = onp.linspace(0.3, 5.7, 10).reshape(-1, 1).astype(F32)
+    yte = onp.sin(xte).astype(F32)
+    out.update(gp_xtr=xtr, gp_ytr=ytr.copy(), gp_xte=xte, gp_yte=yte)
+    gp = GP(FiniteVec(kgp, xtr, []), ytr.copy(), 0.1, 1.3, 0.2)
+    mu, var = gp.predict(FiniteVec(kgp, xte, []))
+    out["gp_mu"], out["gp_var"] = onp.asarray(mu, F32), onp.asarray(var, F32)
+    out["gp_ml"] = onp.asarray(gp.marginal_likelihood(), onp.float64).reshape(1)
+    out["gp_ppl"] = onp.asarray(gp.post_pred_likelihood(FiniteVec(kgp, xte, []), yte)[2], onp.float64).reshape(1)
+
     path = os.path.join(HERE, "reference_siblings.npz")
     onp.savez_compressed(path, **out)
     print("wrote", path, len(out), "arrays")

@@ -217,3 +217,18 @@ def test_gram_utilities_and_point_representant_on_the_gpu():
     np.testing.assert_allclose(vec.point_representant("mean", keepdims=True).cpu().numpy(), g["util_point_mean"], rtol=3e-5, atol=1e-6)
     d = rkhs_gram_cdist(Gxx)
     assert torch.equal(d, d.T) and float(torch.diagonal(d).abs().max()) == 0.0
+
+
+def test_gp_regression_on_the_gpu():
+    """jaxrk/gp.py over the fused Gram kernels, against the reference's own outputs."""
+    import os
+    from jaxrk_b200.gp import GP
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_siblings.npz"))
+    k = GenGaussKernel.make_gauss(0.8)
+    n0 = nat.launch_count()
+    gp = GP(FiniteVec(k, g["gp_xtr"], []), g["gp_ytr"], 0.1, 1.3, 0.2)
+    mu, var = gp.predict(FiniteVec(k, g["gp_xte"], []))
+    assert nat.launch_count() - n0 >= 3
+    np.testing.assert_allclose(mu.cpu().numpy(), g["gp_mu"], rtol=3e-4, atol=3e-4)
+    np.testing.assert_allclose(var.cpu().numpy(), g["gp_var"], rtol=3e-3, atol=3e-4)
+    assert abs(float(gp.marginal_likelihood()) - float(g["gp_ml"][0])) <= 3e-3 * abs(float(g["gp_ml"][0])) + 3e-3

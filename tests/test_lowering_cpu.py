@@ -293,3 +293,19 @@ def test_gram_utilities_and_point_representant_against_reference_outputs():
     # a single (self) Gram must be exactly symmetric, as the reference asserts (utilities/gram.py:18)
     d = rkhs_gram_cdist(Gxx)
     assert torch.equal(d, d.T) and float(torch.diagonal(d).abs().max()) == 0.0
+
+
+def test_gp_regression_against_reference_outputs():
+    """jaxrk/gp.py:6-33 over FiniteVec.inner: posterior mean / covariance, marginal and predictive likelihood against the
+    reference's own outputs (float32 Cholesky on both sides: loose on the small posterior covariance entries)."""
+    import os
+    from jaxrk_b200.gp import GP
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_siblings.npz"))
+    k = GenGaussKernel.make_gauss(0.8)
+    gp = GP(FiniteVec(k, g["gp_xtr"], []), g["gp_ytr"], 0.1, 1.3, 0.2)
+    mu, var = gp.predict(FiniteVec(k, g["gp_xte"], []))
+    np.testing.assert_allclose(mu.numpy(), g["gp_mu"], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(var.numpy(), g["gp_var"], rtol=2e-3, atol=2e-4)
+    assert abs(float(gp.marginal_likelihood()) - float(g["gp_ml"][0])) <= 2e-3 * abs(float(g["gp_ml"][0])) + 2e-3
+    ppl = gp.post_pred_likelihood(FiniteVec(k, g["gp_xte"], []), g["gp_yte"])[2]
+    assert abs(float(ppl) - float(g["gp_ppl"][0])) <= 2e-2 * abs(float(g["gp_ppl"][0])) + 5e-2
