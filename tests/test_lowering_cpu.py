@@ -309,3 +309,75 @@ def test_gp_regression_against_reference_outputs():
     assert abs(float(gp.marginal_likelihood()) - float(g["gp_ml"][0])) <= 2e-3 * abs(float(g["gp_ml"][0])) + 2e-3
     ppl = gp.post_pred_likelihood(FiniteVec(k, g["gp_xte"], []), g["gp_yte"])[2]
     assert abs(float(ppl) - float(g["gp_ppl"][0])) <= 2e-2 * abs(float(g["gp_ppl"][0])) + 5e-2
+
+
+def _fake_vjp(X, Y, A, scale, power, nconst):
+    gX, gY, gs, _ = orc.gengauss_vjp_truth64(_np(X).astype(f32), _np(Y).astype(f32), A, np.array([[scale]], f32), power, nconst=nconst)
+    return gX
+
+
+def fake_kmatw_grad(X, Y, W, G, scale, power, nconst, want_scale=True):
+    CALLS.append("kmatw_grad")
+    A = _np(G) @ _np(W).T
+    Xn, Yn = _np(X).astype(f32), _np(Y).astype(f32)
+    s = np.array([[scale]], f32)
+    gX, _, _, _ = orc.gengauss_vjp_truth64(Xn, Yn, A, s, power, nconst=nconst)
+    gs_rows = None
+    if want_scale:   # per-row contributions to dL/dscale: finite rows of the analytic formula
+        sq = ((Xn[:, None, :].astype(np.float64) - Yn[None, :, :].astype(np.float64)) ** 2).sum(-1)
+        r = np.sqrt(sq)
+        p = float(f32(power))
+        K = nconst * np.exp(-np.power(float(scale) * r, p))
+        gs_rows = torch.from_numpy((-(A * K * p * float(scale) ** (p - 1.0) * np.power(r, p)).sum(1)).astype(f32))
+    return torch.from_numpy(gX.astype(f32)), gs_rows
+
+
+def fake_gram_grad(X, Y, Gbar, scale, power, nconst, want_scale=True):
+    CALLS.append("gram_grad")
+    ones = torch.eye(Gbar.shape[1], dtype=torch.float32)
+    return fake_kmatw_grad(X, Y, ones, Gbar, scale, power, nconst, want_scale)
+
+
+def test_autograd_plumbing_on_cpu_with_oracle_backed_kernels(monkeypatch):
+    """The differentiable route of the lowering (rkhs/_lowering.py: _reduced_gram_autograd over jaxrk_b200/autograd.py):
+    which backward entry points are called with which operands, the chain rule through prefactors / LinearReduce maps /
+    row reduces / nconst(scale).  The four native calls are oracle-backed stand-ins here; the result is compared with
+    torch float64 autograd through the reference's op sequence."""
+    from jaxrk_b200 import autograd as ag
+    monkeypatch.setattr(nat, "kmatw_grad", fake_kmatw_grad)
+    monkeypatch.setattr(nat, "gram_grad", fake_gram_grad)
+    rng = np.random.RandomState(5)
+    N, M, d, m = 40, 28, 3, 5
+    Xn, Yn, Pn, An = rng.randn(N, d).astype(f32), rng.randn(M, d).astype(f32), rng.rand(N).astype(f32), rng.randn(m, M).astype(f32)
+
+    def run(dtype, use_api):
+        X = torch.tensor(Xn, dtype=dtype, requires_grad=True)
+        Y = torch.tensor(Yn, dtype=dtype, requires_grad=True)
+        P = torch.tensor(Pn, dtype=dtype, requires_grad=True)
+        A = torch.tensor(An, dtype=dtype, requires_grad=True)
+        ls = torch.tensor(1.3, dtype=dtype, requires_grad=True)
+        if use_api:
+            k = GenGaussKernel.make_gauss(ls)
+            t1 = inner(FiniteVec(k, X, [Prefactors(P)]), FiniteVec(k, Y, [LinearReduce(A)]))
+            t2 = inner(FiniteVec(k, X, [BalancedRed(4, True)]), FiniteVec(k, Y, [Mean()]))
+            t3 = k(X)
+        else:
+            s = 0.70710695 / ls
+            def gram(a, b):
+                sq = ((a[:, None, :] - b[None, :, :]) ** 2).sum(-1)
+                return ag.gengauss_nconst(s, 2.0) * torch.exp(-(s * s) * sq)
+            K = gram(X, Y)
+            t1 = (P[:, None] * K) @ A.T
+            t2 = K.reshape(N // 4, 4, M).mean(1).mean(1, keepdim=True)
+            t3 = gram(X, X)
+        loss = (t1 ** 2).sum() + t2.sum() + (t3 ** 2).sum()
+        loss.backward()
+        return [loss.item()] + [t.grad.detach().double().numpy() for t in (X, Y, P, A, ls)]
+
+    want = run(torch.float64, False)
+    CALLS.clear()
+    got = run(torch.float32, True)
+    assert "kmatw_grad" in CALLS and "gram_grad" in CALLS and "kmatw" in CALLS and "gram" in CALLS
+    assert abs(got[0] - want[0]) <= 1e-4 * abs(want[0])
+    for gv, wv, name in zip(got[1:], want[1:], ("X", "Y", "prefactors", "linear_map", "length_scale")):
+        assert np.abs(gv - wv).max() <= 2e-4 * np.abs(wv).max() + 1e-6, (name, np.abs(gv - wv).max())
