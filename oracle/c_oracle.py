@@ -33,6 +33,17 @@ class COracle:
         f.restype, f.argtypes = c_double, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                            c_int, c_float, c_float, c_float]
 
+        f = lib.orc_periodic_truth64
+        f.restype, f.argtypes = None, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_float, c_void_p]
+        f = lib.orc_threshspike_truth64
+        f.restype, f.argtypes = None, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_float, c_float, c_float,
+                                       c_float, c_void_p, c_void_p]
+        f = lib.orc_dist_diag_truth64
+        f.restype, f.argtypes = None, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p]
+        f = lib.orc_vjp_truth64
+        f.restype, f.argtypes = None, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_float, c_float,
+                                       c_void_p, c_void_p]
+
     @staticmethod
     def _p(a):
         return None if a is None else c_void_p(a.ctypes.data)
@@ -78,6 +89,36 @@ class COracle:
         pj = None if pj is None else self._f(pj)
         return float(self.lib.orc_blocksum_truth64(self._p(X), self._p(Y), self._p(pi), self._p(pj), i0, i1, j0, j1,
                                                    X.shape[1], s, p, nconst))
+
+
+    def periodic_truth64(self, X, Y, s, inv_ls):
+        X, Y = self._f(X), self._f(Y)
+        out = np.empty((X.shape[0], Y.shape[0]), np.float64)
+        self.lib.orc_periodic_truth64(self._p(X), self._p(Y), X.shape[0], Y.shape[0], X.shape[1], s, inv_ls, self._p(out))
+        return out
+
+    def threshspike_truth64(self, X, Y, s, p, spike, non_spike, threshold):
+        X, Y = self._f(X), self._f(Y)
+        out = np.empty((X.shape[0], Y.shape[0]), np.float64)
+        margin = np.empty_like(out)
+        self.lib.orc_threshspike_truth64(self._p(X), self._p(Y), X.shape[0], Y.shape[0], X.shape[1], s, p, spike, non_spike,
+                                         threshold, self._p(out), self._p(margin))
+        return out, margin
+
+    def dist_diag_truth64(self, X, Y, s, p):
+        X, Y = self._f(X), self._f(Y)
+        out = np.empty((X.shape[0],), np.float64)
+        self.lib.orc_dist_diag_truth64(self._p(X), self._p(Y), X.shape[0], X.shape[1], s, p, self._p(out))
+        return out
+
+    def vjp_truth64(self, X, Y, A, s, p, nconst):
+        X, Y = self._f(X), self._f(Y)
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        gX = np.empty((X.shape[0], X.shape[1]), np.float64)
+        gs = np.zeros((1,), np.float64)
+        self.lib.orc_vjp_truth64(self._p(X), self._p(Y), self._p(A), X.shape[0], Y.shape[0], X.shape[1], s, p, nconst,
+                                 self._p(gX), self._p(gs))
+        return gX, float(gs[0])
 
 
 def load() -> COracle:

@@ -136,4 +136,80 @@ double orc_blocksum_truth64(const float *X, const float *Y, const float *pi, con
     return tot;
 }
 
-int orc_abi_version(void) { return 1; }
+/* ---- sibling kernels on the same distance front-end and the diag branch (widened rows) ---- */
+
+/* PeriodicKernel (kern/rbf.py:152-154 over ScaledPairwiseDistance(SimpleScaler(1/period), power = 1), rbf.py:120):
+ * exp(-2 (sin(pi * s * |x - y|) / ls)^2), float64 on the float32 inputs; inv_ls is the float32 value 1 / ls. */
+void orc_periodic_truth64(const float *X, const float *Y, int64_t N, int64_t M, int d, float s, float inv_ls,
+                          double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i)
+        for (int64_t j = 0; j < M; ++j) {
+            double sq = 0.0;
+            for (int k = 0; k < d; ++k) {
+                double diff = (double)X[i * d + k] - (double)Y[j * d + k];
+                sq += diff * diff;
+            }
+            double q = sin(3.14159265358979323846 * (double)s * sqrt(sq)) * (double)inv_ls;
+            out[i * M + j] = exp(-2.0 * q * q);
+        }
+}
+
+/* ThreshSpikeKernel (kern/rbf.py:203-206): where((s |x - y|)^p <= threshold, spike, non_spike); margin (nullable)
+ * receives |dist - threshold| so that undecidable entries can be excluded from parity. */
+void orc_threshspike_truth64(const float *X, const float *Y, int64_t N, int64_t M, int d, float s, float p,
+                             float spike, float non_spike, float threshold, double *out, double *margin)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i)
+        for (int64_t j = 0; j < M; ++j) {
+            double sq = 0.0;
+            for (int k = 0; k < d; ++k) {
+                double diff = (double)X[i * d + k] - (double)Y[j * d + k];
+                sq += diff * diff;
+            }
+            double dist = pow((double)s * sqrt(sq), (double)p);
+            out[i * M + j] = dist <= (double)threshold ? (double)spike : (double)non_spike;
+            if (margin) margin[i * M + j] = fabs(dist - (double)threshold);
+        }
+}
+
+/* diag = True branch of ScaledPairwiseDistance.__call__ (kern/util.py:112-113): gs * sum_k |x_ik - y_ik|^p. */
+void orc_dist_diag_truth64(const float *X, const float *Y, int64_t N, int d, float s, float p, double *out)
+{
+    for (int64_t i = 0; i < N; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < d; ++k) acc += pow(fabs((double)X[i * d + k] - (double)Y[i * d + k]), (double)p);
+        out[i] = (double)s * acc;
+    }
+}
+
+/* Vector-Jacobian product of K = nconst exp(-(s |x - y|)^p) with cotangent A (N x M), what jax.grad derives from
+ * kern/rbf.py:104-105 over kern/util.py:115:  gX[i] = -sum_j A_ij K_ij p s^p r^(p-2) (x_i - y_j),
+ * gs = -sum_ij A_ij K_ij p s^(p-1) r^p; pairs at r = 0 contribute nothing.  gX is N x d, gs one double. */
+void orc_vjp_truth64(const float *X, const float *Y, const double *A, int64_t N, int64_t M, int d, float s, float p,
+                     float nconst, double *gX, double *gs)
+{
+    double tot = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : tot)
+    for (int64_t i = 0; i < N; ++i) {
+        for (int k = 0; k < d; ++k) gX[i * d + k] = 0.0;
+        for (int64_t j = 0; j < M; ++j) {
+            double sq = 0.0;
+            for (int k = 0; k < d; ++k) {
+                double diff = (double)X[i * d + k] - (double)Y[j * d + k];
+                sq += diff * diff;
+            }
+            if (sq <= 0.0) continue;
+            double r = sqrt(sq), K = (double)nconst * exp(-pow((double)s * r, (double)p));
+            double phi = K * (double)p * pow((double)s, (double)p) * pow(r, (double)p - 2.0);
+            double a = A[i * M + j];
+            for (int k = 0; k < d; ++k) gX[i * d + k] -= a * phi * ((double)X[i * d + k] - (double)Y[j * d + k]);
+            tot -= a * K * (double)p * pow((double)s, (double)p - 1.0) * pow(r, (double)p);
+        }
+    }
+    *gs = tot;
+}
+
+int orc_abi_version(void) { return 2; }
