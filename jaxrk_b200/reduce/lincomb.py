@@ -62,3 +62,22 @@ class SparseReduce(Reduce):
     def new_len(self, original_len: int):
         assert self.max_idx + 1 <= original_len
         return len(self.idcs)  # as the reference (lincomb.py:62-64)
+
+    def num_rows(self) -> int:
+        """Rows reduce_first_ax actually produces (one per row of every index array)."""
+        return int(sum(i.shape[0] for i in self.idcs))
+
+    def to_linear_map(self, n: int, device=None) -> torch.Tensor:
+        """The same map as a dense (rows x n) matrix: what rkhs/_lowering.py folds into the fused K@W kernel (as
+        LinearReduce) when it is small enough, so that the Gram need not be materialised."""
+        assert self.max_idx + 1 <= n
+        A = torch.zeros((self.num_rows(), n), dtype=torch.float32, device=device)
+        r0 = 0
+        for idx in self.idcs:
+            g, k = idx.shape
+            if k:
+                rows = torch.arange(r0, r0 + g, device=device)[:, None].expand(g, k).reshape(-1)
+                vals = torch.full((g * k,), (1.0 / k) if self.average else 1.0, dtype=torch.float32, device=device)
+                A.index_put_((rows, idx.reshape(-1).to(device)), vals, accumulate=True)
+            r0 += g
+        return A

@@ -33,9 +33,10 @@ import torch
 
 from .. import _native as nat
 from ..reduce.base import BalancedRed, Mean, Prefactors, Reduce, Sum
-from ..reduce.lincomb import LinearReduce
+from ..reduce.lincomb import LinearReduce, SparseReduce
 
 NONE, SUM, MEAN, BALANCED, LINEAR = "none", "sum", "mean", "balanced", "linear"
+SPARSE_DENSE_LIMIT = 1 << 26      # elements of the dense form of a SparseReduce that may be built (256 MB)
 
 
 @dataclass
@@ -84,6 +85,10 @@ def fold_chain(chain: Optional[List[Reduce]], n: int, dev) -> Folded:
         elif type(r) is LinearReduce:
             assert r.linear_map.shape[1] == n
             f.kind, f.A = LINEAR, r.linear_map.to(dev)
+        elif type(r) is SparseReduce and r.num_rows() * n <= SPARSE_DENSE_LIMIT:
+            # a sparse averaging map small enough to hold densely: folded like a LinearReduce (fused K@W, the Gram is
+            # not materialised); larger ones fall through to the generic route below
+            f.kind, f.A = LINEAR, r.to_linear_map(n, dev)
         else:  # Center, TileView, SparseReduce, user types: not folded
             f.post = chain[idx:]
             break

@@ -232,3 +232,20 @@ def test_gp_regression_on_the_gpu():
     np.testing.assert_allclose(mu.cpu().numpy(), g["gp_mu"], rtol=3e-4, atol=3e-4)
     np.testing.assert_allclose(var.cpu().numpy(), g["gp_var"], rtol=3e-3, atol=3e-4)
     assert abs(float(gp.marginal_likelihood()) - float(g["gp_ml"][0])) <= 3e-3 * abs(float(g["gp_ml"][0])) + 3e-3
+
+
+def test_sparse_reduce_folded_into_the_fused_product_on_the_gpu():
+    """SparseReduce as a dense LinearReduce inside the fused K@W (rkhs/_lowering.py) == the reference's route
+    (materialised Gram, then the gather-mean)."""
+    from jaxrk_b200.reduce import SparseReduce
+    rng = np.random.RandomState(11)
+    X, Y = rng.randn(3000, 5).astype(np.float32), rng.randn(2000, 5).astype(np.float32)
+    idcs = [rng.randint(0, 3000, size=(40, 7)), rng.randint(0, 3000, size=(25, 3))]
+    k = GenGaussKernel.make_laplace(1.4)
+    sr = SparseReduce(idcs, True)
+    n0 = nat.launch_count()
+    got = inner(FiniteVec(k, X, [sr]), FiniteVec(k, Y, [Mean()]))
+    assert nat.launch_count() - n0 <= 5                      # fused K@W (+ operand packing / finalize), no N x M Gram
+    want = sr.reduce_first_ax(k(X, Y)).mean(1, keepdim=True)
+    assert tuple(got.shape) == (65, 1)
+    assert torch.allclose(got, want, rtol=2e-5, atol=1e-7)

@@ -381,3 +381,34 @@ def test_autograd_plumbing_on_cpu_with_oracle_backed_kernels(monkeypatch):
     assert abs(got[0] - want[0]) <= 1e-4 * abs(want[0])
     for gv, wv, name in zip(got[1:], want[1:], ("X", "Y", "prefactors", "linear_map", "length_scale")):
         assert np.abs(gv - wv).max() <= 2e-4 * np.abs(wv).max() + 1e-6, (name, np.abs(gv - wv).max())
+
+
+def test_sparse_reduce_is_folded_into_the_fused_product_when_small():
+    """SparseReduce (jaxrk/reduce/lincomb.py:27-87) as a dense LinearReduce inside the fused K@W: same numbers as the
+    reference's route (materialised Gram, then the gather-mean), without the Gram."""
+    from jaxrk_b200.reduce import SparseReduce
+    rng = np.random.RandomState(11)
+    X, Y = rng.randn(30, 3).astype(f32), rng.randn(22, 3).astype(f32)
+    idcs = [np.array([[0, 5, 7], [1, 2, 29]]), np.array([[3, 3], [4, 9], [10, 11]]), np.zeros((1, 0), dtype=np.int64)]
+    k = GenGaussKernel.make_laplace(1.1)
+    for average in (True, False):
+        sr = SparseReduce(idcs, average)
+        assert sr.num_rows() == 6
+        G = k(X, Y)
+        want = Reduce.apply(sr.reduce_first_ax(G), [Mean()], 1)                 # the reference's route
+        np.testing.assert_allclose((sr.to_linear_map(30) @ G).numpy(), sr.reduce_first_ax(G).numpy(), rtol=1e-6, atol=1e-7)
+        CALLS.clear()
+        got = inner(FiniteVec(k, X, [sr]), FiniteVec(k, Y, [Mean()]))
+        assert CALLS == ["kmatw"], CALLS                                         # fused, no Gram
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-5, atol=1e-6)
+    # too large to hold densely: the generic route (Gram, then Reduce.apply)
+    import jaxrk_b200.rkhs._lowering as lowmod
+    old = lowmod.SPARSE_DENSE_LIMIT
+    lowmod.SPARSE_DENSE_LIMIT = 10
+    try:
+        CALLS.clear()
+        got2 = inner(FiniteVec(k, X, [SparseReduce(idcs, True)]), FiniteVec(k, Y, []))
+        assert CALLS == ["gram"], CALLS
+        np.testing.assert_allclose(got2.numpy(), SparseReduce(idcs, True).reduce_first_ax(k(X, Y)).numpy(), rtol=2e-5, atol=1e-6)
+    finally:
+        lowmod.SPARSE_DENSE_LIMIT = old
