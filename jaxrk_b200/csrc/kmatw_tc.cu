@@ -37,6 +37,7 @@
 #include <type_traits>
 
 #include "gram_tf32_kernel.cuh"
+#include "kmatw_tc2.cuh"
 
 namespace jrk {
 
@@ -52,12 +53,13 @@ constexpr int TC_SOP = 6;
 constexpr int TC_EW = 16;
 constexpr int TC_THREADS = (3 + TC_EW) * 32;
 constexpr int TC_WIN = 4;                                // tiles per O window (128 j); a power of two
-// p = 2 "factored" fast path: taken when |c| (max|x|^2 + max|y|^2) <= TC_FAST_BOUND (decided on the device from
-// the pre-pass maxima).  There K_ij = 2^(c|x_i|^2) . 2^(-2c x_i.y_j) . 2^(c|y_j|^2) with every factor inside
+// p = 2 "factored" fast path: taken when |c| (max|x|^2 + max|y|^2) <= TC_FAST_BOUND (kmatw_tc2.cuh; decided on the
+// device from the pre-pass maxima).  There K_ij = 2^(c|x_i|^2) . 2^(-2c x_i.y_j) . 2^(c|y_j|^2) with every factor inside
 // [2^-12, 2^12]: the column factor is folded into W and the scale -2c into Y by the pack pre-pass, the row factor is
 // applied once per output row, and the epilogue is reduced to  e = ex2(S)  (no norms, no near-zero test, one
 // accumulator).  Worst-case relative error of a term: ~4e-7 * bound (3xTF32 + truncating accumulation), < 1e-5.
-constexpr float TC_FAST_BOUND = 12.0f;
+// By default that regime is served by the second-generation kernel (kmatw_tc2.cu) and this file's kernels return at
+// once when they find themselves in it (allow_fast == 2); JRK_TC_V2=0 keeps it here (allow_fast == 1) for A/B runs.
 constexpr int TC_COL_X = 0, TC_COL_S = 64, TC_COL_O = 64 + TC_SS * 128;   // TMEM columns
 constexpr int TC_OFF_BAR = TC_SOP * TC_STAGE;
 constexpr int TC_NBAR = 2 * TC_SOP + 3 * TC_SS + 4 + 1;  // op full/empty, s_full/e_ready/s_empty, o_full/o_empty x2, x_ready
@@ -130,7 +132,8 @@ struct TcParams {
     float a;                               // PM_SQEXP: -2c; else -2
     int check;                             // 1: near-zero refinement always; 0: only if the norm maxima demand it
     const unsigned* nmax;                  // [2] bit patterns of max |mult| |x|^2, max |mult| |y|^2
-    int allow_fast;                        // 0 disables the factored p = 2 path (JRK_TC_FAST=0, tests)
+    int allow_fast;                        // 0: generic epilogue always (JRK_TC_FAST=0, tests); 1: factored p = 2 path here;
+                                           // 2: the factored regime belongs to kmatw_tc2.cu -- return at once inside it
     float inv_abs_mult;                    // 1 / |mult|: nmax * inv_abs_mult = max |row|^2 (fp16 normalisation of GEMM1)
 };
 
@@ -144,9 +147,7 @@ __device__ __forceinline__ void split_h16u_pair(float x0, float x1, uint32_t& hi
     lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
 }
 
-__device__ __forceinline__ bool tc_fast_regime(const unsigned* nmax) {
-    return (__uint_as_float(__ldg(nmax)) + __uint_as_float(__ldg(nmax + 1))) <= TC_FAST_BOUND;
-}
+__device__ __forceinline__ bool tc_fast_regime(const unsigned* nmax) { return tc2_fast_regime(nmax); }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                  "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // factored p = 2 path?  (warp-uniform, the same decision in every CTA and in the pack pre-pass)
     const bool fast = (PM == PM_SQEXP) && P.allow_fast && tc_fast_regime(P.nmax);
+    if (fast && P.allow_fast == 2) return;      // kmatw_tc2_kernel serves this regime
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_SOP; ++s) { mbar_init(&op_full[s], 1); mbar_init(&op_empty[s], 1); }
         for (int s = 0; s < TC_SS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&e_ready[s], TC_EW); mbar_init(&s_empty[s], 1); }
@@ -606,6 +608,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ Y, int64_t M, int d, in
                                TcImage L, unsigned char* __restrict__ img, int fast_ok, float a,
                                const float* __restrict__ yn_all, const unsigned* __restrict__ nmax, float inv_abs_mult) {
     const bool fast = fast_ok && tc_fast_regime(nmax);
+    if (fast && fast_ok == 2) return;           // kmatw_tc2_pack_kernel writes the image of this regime
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int ypt = TC_NT * L.ypieces;            // Y pieces per tile (256 or 512: whole warps)
     const int per_tile = ypt + 256;
@@ -760,7 +763,7 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     unsigned char* img = scr.take<unsigned char>((size_t)n_tiles * L.bytes);
     float* xn = scr.take<float>((size_t)N);
     float* yn_all = scr.take<float>((size_t)M);
-    unsigned* nmax = scr.take<unsigned>(2);
+    unsigned* nmax = scr.take<unsigned>(4);       // max |c||x|^2, max |c||y|^2, max |W col_pref| (kmatw_tc2.cu)
     const bool reduce_rows = row_reduce == JRK_REDUCE_SUM || row_reduce == JRK_REDUCE_MEAN;
     const int64_t nchunks = (N + TC_RS_CHUNK - 1) / TC_RS_CHUNK;
     float* Tbuf = reduce_rows ? scr.take<float>((size_t)N * TC_MT) : nullptr;
@@ -773,7 +776,9 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     JRK_CUDA_OK(cudaMemsetAsync(nmax, 0, 2 * sizeof(unsigned), st));
     const float a_scale = (pm == PM_SQEXP) ? -2.f * ep.c : -2.f;
     const char* fast_env = getenv("JRK_TC_FAST");
-    const int allow_fast = (pm == PM_SQEXP) && !(fast_env && fast_env[0] == '0');
+    const char* v2_env = getenv("JRK_TC_V2");
+    int allow_fast = (pm == PM_SQEXP) && !(fast_env && fast_env[0] == '0');
+    if (allow_fast && !(v2_env && v2_env[0] == '0')) allow_fast = 2;
     {
         // scaled row norms and their maxima first: the pack kernel and the main kernel both decide from the maxima
         // (on the device, no host synchronisation) whether the factored p = 2 path applies
@@ -785,6 +790,9 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
         tc_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, col_pref, (int)n_tiles, mult, L, img,
                                                                       allow_fast, a_scale, yn_all, nmax, 1.f / fabsf(mult));
         JRK_LAUNCHED();
+        if (allow_fast == 2) {
+            if (int rc2 = kmatw_tc2_pack(Y, W, M, d, m, ldy, ldw, col_pref, ep.c, yn_all, nmax, img, st)) return rc2;
+        }
     }
     TcParams P;
     P.X = X; P.ldx = ldx; P.d = d; P.Y = Y; P.ldy = ldy; P.xn = xn; P.img = img; P.L = L; P.row_pref = row_pref;
@@ -800,6 +808,9 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     P.check = 0;
     P.nmax = nmax;
     int rc;
+    if (allow_fast == 2) {
+        if (int rc2 = kmatw_tc2_apply(X, N, d, ldx, xn, img, M, nmax, ep.c, nconst, row_pref, P.out, P.ldo, P.m, st)) return rc2;
+    }
     if (pm == PM_SQEXP) rc = tc_launch<PM_SQEXP>(P, ep, st);
     else if (pm == PM_LAPLACE) rc = tc_launch<PM_LAPLACE>(P, ep, st);
     else rc = tc_launch<PM_GENERAL>(P, ep, st);

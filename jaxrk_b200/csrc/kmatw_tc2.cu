@@ -1,0 +1,494 @@
+// Kernel (b''): second generation of the fused, never-materialised K(X, Y) @ W on the tensor cores -- the FACTORED
+// p = 2 regime of kmatw_tc.cu (|c| (max|x|^2 + max|y|^2) <= 12, decided on the device), which is where the squared-
+// exponential kernel lives for any sensible length scale, and BASELINE.json configs[2] in particular.
+//
+// Replaces the same reference code as kmatw.cu / kmatw_tc.cu: FiniteVec.inner (jaxrk/rkhs/vector.py:62-75) with a
+// LinearReduce / Sum / Mean on the Y side (jaxrk/reduce/lincomb.py:137-140, reduce/base.py:132-150), i.e. the inner() of
+// FiniteOp.__matmul__ (jaxrk/rkhs/operator.py:46), for GenGaussKernel with power = 2 (jaxrk/kern/rbf.py:84-105).
+//
+//   K_ij = nconst 2^(c|x_i|^2) 2^(-2c x_i.y_j) 2^(c|y_j|^2),  c = -s^2 log2(e) < 0,  every factor inside [2^-12, 2^12]
+//   GEMM1   S = x~ . y''      x~ = x 2^-r (parked in TMEM, fp16 hi / lo),  y'' = -2c y 2^r (tile image, fp16 hi / lo),
+//                              2^-r ~ sqrt(-2c) chosen on the host, so both operands stay below 7 in magnitude and the
+//                              image does not depend on X (a plan can keep it: jrk_kmatw_plan_*)
+//   epilogue e = ex2(S)        ONE MUFU per pair -- the roofline of this kernel -- split into a 16-bit hi / lo pair and
+//                              written back over S in TMEM, packed: 64 FP32 columns become 32 + 32 columns of pairs
+//   GEMM2   O += e . W'        kind::f16 (K = 16 per MMA: 12 MMAs per tile instead of 16 tf32 ones), W' = W col_pref
+//                              2^(c|y|^2) 2^-ew in the tile image as hi / lo
+//   out_i = nconst 2^(c|x_i|^2) row_pref_i 2^ew . O_i
+//
+// What changed against the first generation, and why (profiles/README.md, round 2):
+//  * The 16 epilogue warps no longer share every tile (one 16-column group each): warp k of a TMEM lane quarter owns
+//    the WHOLE quarter (32 rows x 64 columns) of the tiles t = k (mod 4).  The four warps of an SM sub-partition then
+//    work on four different tiles, out of phase, and one of them always has MUFU work ready; before, all four were
+//    released by the same barrier, ran their MUFU bursts together and then idled together on TMEM stores and barriers
+//    (the kernel sat at ~700 clk per 128 x 64 tile against 512 clk of MUFU).
+//  * e is handed to GEMM2 as fp16 operands: e_hi = the leading 11 bits (by truncation, exact), e_lo' = (e - e_hi) 2^11,
+//    against W'_hi and W'_lo' = (W' - W'_hi) 2^11; the cross-term accumulator is folded in with 2^-11.  Half the TMEM
+//    write-back, 8 instead of 16 GEMM2 MMAs per tile, and an S / e stage is 64 columns, so SIX stages fit.  (fp16 hi
+//    with a bf16 lo would not need the scaling, but a kind::f16 MMA with different A and B formats is an illegal
+//    instruction on sm_100a: profiles/microbench/umma_probe.cu.)
+//  * The tile image shrinks from 16.6 KB to 8 KB for d <= 16 (Y hi | Y lo | W' pieces share the 128-byte swizzle rows)
+//    and 12 KB for d <= 32: half the L2 -> SM traffic of the first generation.
+//
+// TMEM columns: X hi [0, 16) lo [16, 32) | three O windows [32 + 32 b, +32) = {main [16) | cross [16)} | six S / e
+// stages [128 + 64 a, +64).  The tensor core's accumulator truncates, so O is accumulated in TMEM over windows of four
+// tiles only and folded into FP32 registers (round to nearest) two windows later; the hi.hi products and the small
+// cross terms use separate accumulators (as in kmatw_tc.cu).
+#include <cmath>
+#include <cstdlib>
+
+#include "gram_tf32_kernel.cuh"
+#include "kmatw_tc2.cuh"
+
+namespace jrk {
+
+using namespace tf32;
+
+namespace {
+
+constexpr int T2_BM = 128, T2_NT = 64, T2_MT = 16;
+constexpr int T2_NS = 6;                      // S / e stages in TMEM (64 columns each)
+constexpr int T2_NOB = 3;                     // O windows in TMEM
+constexpr int T2_WIN = 4;                     // tiles per O window = epilogue warps per lane quarter
+constexpr int T2_LAG = 2;                     // a warp folds window w - T2_LAG after its tile of window w
+constexpr int T2_SOP = 8;                     // operand (tile image) stages in shared memory
+constexpr int T2_STAGE = 12288;               // stage stride: the 12 KB image of 16 < d <= 32
+constexpr int T2_EW = 16;
+constexpr int T2_THREADS = (3 + T2_EW) * 32;
+constexpr int T2_COL_X = 0, T2_COL_XLO = 16, T2_COL_O = 32, T2_COL_S = 128;
+constexpr int T2_OFF_BAR = T2_SOP * T2_STAGE;
+constexpr int T2_NBAR = 2 * T2_SOP + 3 * T2_NS + 2 * T2_NOB + 1;
+constexpr int T2_SMEM = T2_OFF_BAR + T2_NBAR * 8 + 16 + 1024;
+static_assert(T2_COL_S + T2_NS * 64 <= 512 && T2_COL_O + T2_NOB * 32 <= T2_COL_S, "TMEM budget");
+static_assert(T2_SMEM <= 227 * 1024, "shared memory budget");
+static_assert(T2_LAG < T2_NOB, "a window must be folded before its buffer is needed again");
+
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity), "r"(20000u)
+        : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void commit_addr(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+// {hi half <- a, lo half <- b}
+__device__ __forceinline__ uint32_t cvt_f16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b));
+    return r;
+}
+// fp16 hi / lo of a pair WITHOUT rescaling lo (GEMM1 operands: both parts go into one accumulator)
+__device__ __forceinline__ void split_h16u_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    lo = cvt_f16x2(x1 - __half2float(h1), x0 - __half2float(h0));
+}
+// hi / lo' of a pair of W' values: hi = fp16(w), lo' = fp16((w - hi) 2^11)
+__device__ __forceinline__ void split_w_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    lo = cvt_f16x2((x1 - __half2float(h1)) * 2048.f, (x0 - __half2float(h0)) * 2048.f);
+}
+
+struct Tc2Params {
+    const float* X; int64_t ldx; int d;
+    const float* xn;                 // c |x_i|^2
+    const unsigned char* img; int img_bytes; int packed;
+    const float* row_pref;
+    float* out; int64_t ldo; int m;
+    int64_t N;
+    int n_tiles, n_units;
+    const unsigned* nmax;            // [3] bit patterns: max |c||x|^2, max |c||y|^2, max |W col_pref|
+    float x_scale;                   // 2^-r
+    float nconst;
+};
+
+// byte offset (in 16-byte units) of the W' operand of k-step q inside a tile image; the lo operand sits 2048 B further
+__device__ __forceinline__ uint32_t w_off16(int packed, int q) {
+    return packed ? (uint32_t)((q >> 1) * 256 + 4 + 2 * (q & 1)) : (uint32_t)(512 + 2 * q);
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1) kmatw_tc2_kernel(Tc2Params P) {
+    if (!tc2_fast_regime(P.nmax)) return;     // the generic kernel (kmatw_tc.cu) serves the problem
+    extern __shared__ unsigned char t2_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(t2_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_OFF_BAR);
+    uint64_t* op_full = bars;                    // [SOP]  tile image landed
+    uint64_t* op_empty = op_full + T2_SOP;       // [SOP]  GEMM2 of the tile complete
+    uint64_t* s_full = op_empty + T2_SOP;        // [NS]   GEMM1 of the stage complete
+    uint64_t* e_ready = s_full + T2_NS;          // [NS]   the four owner warps wrote e
+    uint64_t* s_empty = e_ready + T2_NS;         // [NS]   GEMM2 of the stage complete
+    uint64_t* o_full = s_empty + T2_NS;          // [NOB]  window complete
+    uint64_t* o_empty = o_full + T2_NOB;         // [NOB]  all 16 warps folded the window
+    uint64_t* x_ready = o_empty + T2_NOB;        // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T2_OFF_BAR + T2_NBAR * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T2_SOP; ++s) { mbar_init(&op_full[s], 1); mbar_init(&op_empty[s], 1); }
+        for (int s = 0; s < T2_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&e_ready[s], 4); mbar_init(&s_empty[s], 1); }
+        for (int s = 0; s < T2_NOB; ++s) { mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], T2_EW); }
+        mbar_init(x_ready, T2_EW);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_512(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tmem_base != 0) __trap();
+
+    const int T = P.n_tiles;
+    if (warp == 0) {
+        // ===================== TMA producer: one image per tile =====================
+        uint32_t tc = 0;
+        const uint32_t bytes = (uint32_t)P.img_bytes;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+            for (int t = 0; t < T; ++t, ++tc) {
+                const int s = tc % T2_SOP;
+                mbar_wait_hint(&op_empty[s], ((tc / T2_SOP) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&op_full[s], bytes);
+                    bulk_g2s(smem + s * T2_STAGE, P.img + (int64_t)t * bytes, bytes, &op_full[s]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== GEMM1 issuer:  S[stage] = x~ . y''  (fp16 hi / lo, one accumulator) =====================
+        constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(T2_NT >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
+        const uint64_t dbase = make_b_desc(smem_u32(smem));
+        const uint32_t b_opfull = smem_u32(op_full), b_sempty = smem_u32(s_empty), b_sfull = smem_u32(s_full), b_xready = smem_u32(x_ready);
+        const int ksh = (P.d + 15) >> 4;
+        const uint64_t y_lo = (uint64_t)(P.packed ? 2 : 4);          // 32 or 64 bytes further inside the rows
+        uint32_t s = 0, s_ph = 0, a = 0, a_ph = 0, uc = 0;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, ++uc) {
+            bar_wait(b_xready, uc & 1);
+            for (int t = 0; t < T; ++t) {
+                bar_wait(b_opfull + s * 8, s_ph);
+                bar_wait(b_sempty + a * 8, a_ph ^ 1);
+                tc_fence_after();
+                const uint64_t dyh = dbase + (uint64_t)((s * T2_STAGE) >> 4), dyl = dyh + y_lo;
+                const uint32_t cs = T2_COL_S + a * 64;
+                if (elect_one()) {
+                    // the small cross terms first, the hi.hi terms last: the accumulator truncates, so only the last
+                    // additions carry a rounding error that matters
+                    for (int ks = 0; ks < ksh; ++ks) {
+                        const uint64_t off = (uint64_t)(ks * 2);
+                        mma_f16_ts(cs, T2_COL_X + ks * 8, dyl + off, idesc1, ks);          // hi_x . lo_y
+                        mma_f16_ts(cs, T2_COL_XLO + ks * 8, dyh + off, idesc1, 1u);        // lo_x . hi_y
+                    }
+                    for (int ks = 0; ks < ksh; ++ks) mma_f16_ts(cs, T2_COL_X + ks * 8, dyh + (uint64_t)(ks * 2), idesc1, 1u);
+                    commit_addr(b_sfull + a * 8);
+                }
+                __syncwarp();
+                if (++s == T2_SOP) { s = 0; s_ph ^= 1; }
+                if (++a == T2_NS) { a = 0; a_ph ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== GEMM2 issuer:  O[window] += e . W'  (16-bit hi / lo operands) =====================
+        constexpr uint32_t id16 = (1u << 4) | ((uint32_t)(T2_MT >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);         // N = 16
+        constexpr uint32_t id32 = (1u << 4) | ((uint32_t)((2 * T2_MT) >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);   // N = 32
+        const uint64_t dbase = make_b_desc(smem_u32(smem));
+        const uint32_t b_opfull = smem_u32(op_full), b_opempty = smem_u32(op_empty), b_sempty = smem_u32(s_empty),
+                       b_eready = smem_u32(e_ready), b_ofull = smem_u32(o_full), b_oempty = smem_u32(o_empty);
+        const int packed = P.packed;
+        uint32_t s = 0, s_ph = 0, a = 0, a_ph = 0, ob = 0, ob_ph = 0;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+            for (int t = 0; t < T; ++t) {
+                const bool win_first = (t & (T2_WIN - 1)) == 0, win_last = ((t & (T2_WIN - 1)) == T2_WIN - 1) || (t == T - 1);
+                if (win_first) bar_wait(b_oempty + ob * 8, ob_ph ^ 1);
+                bar_wait(b_opfull + s * 8, s_ph);
+                bar_wait(b_eready + a * 8, a_ph);
+                tc_fence_after();
+                const uint64_t dw = dbase + (uint64_t)((s * T2_STAGE) >> 4);
+                const uint32_t eh = T2_COL_S + a * 64, oc = T2_COL_O + ob * 32, ox = oc + T2_MT;
+                if (elect_one()) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint64_t dq = dw + (uint64_t)w_off16(packed, q);
+                        const uint32_t acc0 = (win_first && q == 0) ? 0u : 1u;
+                        // an MMA of N <= 32 costs the same whatever N is: e_hi meets [W'_hi ; W'_lo'] (stacked rows) in ONE
+                        // MMA whose 32 result columns are {main | cross}
+                        mma_f16_ts(oc, eh + 16 * q, dq, id32, acc0);                 // e_hi  . [W'_hi ; W'_lo'] -> {main | cross}
+                        mma_f16_ts(ox, eh + 16 * q + 8, dq, id16, 1u);               // e_lo' . W'_hi            -> cross
+                    }
+                    commit_addr(b_sempty + a * 8);      // S / e stage reusable
+                    commit_addr(b_opempty + s * 8);     // operand stage reusable
+                    if (win_last) commit_addr(b_ofull + ob * 8);
+                }
+                __syncwarp();
+                if (win_last) { if (++ob == T2_NOB) { ob = 0; ob_ph ^= 1; } }
+                if (++s == T2_SOP) { s = 0; s_ph ^= 1; }
+                if (++a == T2_NS) { a = 0; a_ph ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (and X loader) =====================
+        // warp k of a lane quarter owns the quarter (32 rows x 64 columns) of the tiles t = k (mod 4)
+        const int e = warp - 3;
+        const int quad = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int k = e >> 2;                      // which tiles; also: which 4 output columns this warp folds
+        uint32_t lane_base;                        // opaque registers: keep address arithmetic out of the loop
+        asm volatile("mov.u32 %0, %1;" : "=r"(lane_base) : "r"(tmem_base + ((uint32_t)(quad * 32) << 16)));
+        uint32_t sbase;
+        asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));
+        const uint32_t b_sfull = sbase + T2_OFF_BAR + 2 * T2_SOP * 8, b_eready = b_sfull + T2_NS * 8,
+                       b_ofull = b_sfull + 3 * T2_NS * 8, b_oempty = b_ofull + T2_NOB * 8, b_xready = b_oempty + T2_NOB * 8;
+        const float lo_w = 1.f / 2048.f;
+        const int nwin = (T + T2_WIN - 1) / T2_WIN;
+        // 2^ew: the power of two that normalises W' (the pack pre-pass divides by it)
+        const float wpow = pow2i(tc2_w_exp(__uint_as_float(__ldg(P.nmax + 2))));
+
+        auto park_x = [&](int u) {
+            // x~ = x 2^-r as fp16 hi / lo (unscaled lo): 16 values -> 8 packed columns; warps 0 and 1 of the quarter
+            const int64_t i = (int64_t)u * T2_BM + quad * 32 + lane;
+            if (k * 16 < P.d) {
+                const bool iok = i < P.N;
+                const float* xrow = P.X + (iok ? i : 0) * P.ldx;
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int kk = k * 16 + 2 * q;
+                    const float v0 = (iok && kk < P.d) ? __ldg(xrow + kk) : 0.f;
+                    const float v1 = (iok && kk + 1 < P.d) ? __ldg(xrow + kk + 1) : 0.f;
+                    split_h16u_pair(v0 * P.x_scale, v1 * P.x_scale, hi[q], lo[q]);
+                }
+                tmem_st8(lane_base + T2_COL_X + k * 8, hi);
+                tmem_st8(lane_base + T2_COL_XLO + k * 8, lo);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(b_xready);
+        };
+
+        uint32_t gt = 0, gw = 0;                   // tiles / windows of the units this CTA has finished
+        int u = blockIdx.x;
+        if (u < P.n_units) park_x(u);
+        for (; u < P.n_units; u += gridDim.x) {
+            float oacc[4] = {0.f, 0.f, 0.f, 0.f};
+            int folded = 0;
+            auto fold = [&]() {                    // window `folded` of this unit: this warp's 4 + 4 columns -> registers
+                const uint32_t w = gw + (uint32_t)folded, ob = w % T2_NOB;
+                bar_wait(b_ofull + ob * 8, (w / T2_NOB) & 1);
+                tc_fence_after();
+                float o[4], ox[4];
+                tmem_ld4(lane_base + T2_COL_O + ob * 32 + k * 4, o);
+                tmem_ld4(lane_base + T2_COL_O + ob * 32 + T2_MT + k * 4, ox);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive(b_oempty + ob * 8);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) oacc[c] += fmaf(ox[c], lo_w, o[c]);
+                ++folded;
+            };
+            for (int t = k; t < T; t += T2_WIN) {
+                const uint32_t g = gt + (uint32_t)t, a = g % T2_NS;
+                bar_wait(b_sfull + a * 8, (g / T2_NS) & 1);
+                tc_fence_after();
+                const uint32_t sc = lane_base + T2_COL_S + a * 64;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    // 16 S columns -> 8 columns of e_hi pairs + 8 columns of e_lo pairs, in place
+                    float sv[16];
+                    tmem_ld16(sc + 16 * q, sv);
+                    tmem_ld_wait();
+                    uint32_t eo[16];
+#pragma unroll
+                    for (int c = 0; c < 16; c += 2) {
+                        const float e0 = ex2_approx(sv[c]), e1 = ex2_approx(sv[c + 1]);
+                        const float h0 = __uint_as_float(__float_as_uint(e0) & 0xFFFFE000u);   // 11 significant bits:
+                        const float h1 = __uint_as_float(__float_as_uint(e1) & 0xFFFFE000u);   // exact in fp16
+                        float l0, l1;
+                        unpack2(mul2(sub2(pack2(e0, e1), pack2(h0, h1)), pack2(2048.f, 2048.f)), l0, l1);   // lo' >= 0
+                        eo[c >> 1] = cvt_f16x2(h1, h0);
+                        eo[8 + (c >> 1)] = cvt_f16x2(l1, l0);
+                    }
+                    tmem_st16(sc + 16 * q, eo);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive(b_eready + a * 8);
+                if (t >= T2_WIN * T2_LAG) fold();
+            }
+            // every GEMM1 of this unit has completed once the last tile's s_full is seen: park the next block of X now,
+            // so that the next unit's GEMM1s overlap the tail of this one
+            const int un = u + gridDim.x;
+            if (un < P.n_units) {
+                const uint32_t g = gt + (uint32_t)(T - 1);
+                bar_wait(b_sfull + (g % T2_NS) * 8, (g / T2_NS) & 1);
+                tc_fence_after();
+                park_x(un);
+            }
+            while (folded < nwin) fold();
+            const int64_t i = (int64_t)u * T2_BM + quad * 32 + lane;
+            if (i < P.N) {
+                const float f = P.nconst * wpow * ex2_approx(__ldg(P.xn + i)) * (P.row_pref ? __ldg(P.row_pref + i) : 1.f);
+                float* dst = P.out + i * P.ldo + k * 4;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (k * 4 + c < P.m) dst[c] = f * oacc[c];
+            }
+            gt += (uint32_t)T;
+            gw += (uint32_t)nwin;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc_512(tmem_base);
+}
+
+// ---- pre-pass: per-tile images, one thread per 16-byte piece (8 fp16 / bf16 values) ----
+//   packed (d <= 16), 8 KB: row r = [Y hi (32 B) | Y lo (32 B) | W' pieces (64 B)] in the 128B-swizzled K-major layout;
+//     the W' operand of k-step q (16 columns x 16 j) sits in rows 32 (q >> 1) + 16 piece + column, bytes 64 + 32 (q & 1)
+//   wide (d <= 32), 12 KB: row r = [Y hi (64 B) | Y lo (64 B)], then 32 rows {W' hi [16) ; W' lo [16)} x 64 j
+__global__ void tc2_pack_kernel(const float* __restrict__ Y, int64_t M, int d, int64_t ldy, const float* __restrict__ W,
+                                int m, int64_t ldw, const float* __restrict__ col_pref, int n_tiles,
+                                unsigned char* __restrict__ img, int img_bytes, int packed, float y_scale,
+                                const float* __restrict__ yn_all, const unsigned* __restrict__ nmax) {
+    if (!tc2_fast_regime(nmax)) return;
+    const int cpt = img_bytes >> 4;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_tiles * cpt) return;
+    const int64_t t = idx / cpt;
+    const int p = (int)(idx % cpt);
+    const int rr = (p >> 3), cph = p & 7;
+    const int r = rr & 63;                       // row inside its region (Y region: 64 rows; wide W region: 32 rows)
+    const int cl = cph ^ (r & 7);                // logical 16-byte chunk of the row
+    const bool wregion = p >= 512;               // wide layout only
+    float v[8];
+    bool is_w, is_lo;
+    if (!wregion && (packed ? cl < 4 : true)) {
+        // ---- Y: 8 consecutive features of row j ----
+        is_w = false;
+        const int half = packed ? 2 : 4;
+        is_lo = cl >= half;
+        const int k0 = 8 * (cl - (is_lo ? half : 0));
+        const int64_t j = t * T2_NT + r;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (j < M && k0 + q < d) ? __ldg(Y + j * ldy + k0 + q) * y_scale : 0.f;
+    } else {
+        // ---- W': 8 consecutive j of output column c ----
+        is_w = true;
+        int c;
+        int64_t j0;
+        if (packed) {
+            const int q = 2 * (r >> 5) + ((cl - 4) >> 1);
+            is_lo = ((r >> 4) & 1) != 0;
+            c = r & 15;
+            j0 = t * T2_NT + 16 * q + 8 * ((cl - 4) & 1);
+        } else {
+            is_lo = (r >> 4) != 0;
+            c = r & 15;
+            j0 = t * T2_NT + 8 * cl;
+        }
+        const float wscale = pow2i(-tc2_w_exp(__uint_as_float(__ldg(nmax + 2))));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t j = j0 + q;
+            float w = 0.f;
+            if (j < M && c < m) {
+                w = __ldg(W + j * ldw + c) * wscale;
+                if (col_pref) w *= __ldg(col_pref + j);
+                w *= ex2_approx(__ldg(yn_all + j));
+            }
+            v[q] = w;
+        }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t hi, lo;
+        if (is_w) split_w_pair(v[2 * q], v[2 * q + 1], hi, lo);
+        else split_h16u_pair(v[2 * q], v[2 * q + 1], hi, lo);
+        o[q] = is_lo ? lo : hi;
+    }
+    *reinterpret_cast<uint4*>(img + t * img_bytes + (int64_t)p * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// *gmax = max_j max_c |W[j, c] col_pref[j]|  (atomicMax on the bit pattern; NaN ignored)
+__global__ void tc2_wmax_kernel(const float* __restrict__ W, int64_t M, int m, int64_t ldw, const float* __restrict__ col_pref,
+                                unsigned* __restrict__ gmax) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float mx = 0.f;
+    if (j < M) {
+        for (int c = 0; c < m; ++c) mx = fmaxf(mx, fabsf(__ldg(W + j * ldw + c)));
+        if (col_pref) mx *= fabsf(__ldg(col_pref + j));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx == mx && mx < 3.0e38f) atomicMax(gmax, __float_as_uint(mx));
+}
+
+}  // namespace
+
+int tc2_image_bytes(int d) { return d <= 16 ? 8192 : 12288; }
+
+// W maximum (nmax[2]) + tile images of the factored regime.  nmax[0..1] (norm maxima) and yn_all must already be
+// enqueued on `st`.  Both kernels return at once outside the factored regime.
+int kmatw_tc2_pack(const float* Y, const float* W, int64_t M, int d, int m, int64_t ldy, int64_t ldw,
+                   const float* col_pref, float c, const float* yn_all, unsigned* nmax, unsigned char* img,
+                   cudaStream_t st) {
+    const int64_t n_tiles = (M + T2_NT - 1) / T2_NT;
+    const int img_bytes = tc2_image_bytes(d);
+    JRK_CUDA_OK(cudaMemsetAsync(nmax + 2, 0, sizeof(unsigned), st));
+    tc2_wmax_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(W, M, m, ldw, col_pref, nmax + 2);
+    JRK_LAUNCHED();
+    const Tc2Scales sc = tc2_scales(c);
+    const int64_t tot = n_tiles * (img_bytes >> 4);
+    tc2_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, col_pref, (int)n_tiles, img, img_bytes,
+                                                                   d <= 16, sc.y_scale, yn_all, nmax);
+    JRK_LAUNCHED();
+    return JRK_OK;
+}
+
+int kmatw_tc2_apply(const float* X, int64_t N, int d, int64_t ldx, const float* xn, const unsigned char* img, int64_t M,
+                    const unsigned* nmax, float c, float nconst, const float* row_pref, float* out, int64_t ldo, int m,
+                    cudaStream_t st) {
+    Tc2Params P;
+    P.X = X; P.ldx = ldx; P.d = d; P.xn = xn; P.img = img; P.img_bytes = tc2_image_bytes(d); P.packed = d <= 16;
+    P.row_pref = row_pref; P.out = out; P.ldo = ldo; P.m = m; P.N = N;
+    P.n_tiles = (int)((M + T2_NT - 1) / T2_NT);
+    P.n_units = (int)((N + T2_BM - 1) / T2_BM);
+    P.nmax = nmax;
+    P.x_scale = tc2_scales(c).x_scale;
+    P.nconst = nconst;
+    const int grid = P.n_units < tf_sm_count() ? P.n_units : tf_sm_count();
+    JRK_CUDA_OK(cudaFuncSetAttribute(kmatw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+    kmatw_tc2_kernel<<<grid, T2_THREADS, T2_SMEM, st>>>(P);
+    JRK_LAUNCHED();
+    return JRK_OK;
+}
+
+}  // namespace jrk
