@@ -17,7 +17,7 @@ SOURCES = ["capi.cu", "gram_direct.cu", "gram_tf32.cu", "gram_tf32_pm0.cu", "gra
            "kmatw_tc.cu", "kmatw_tc2.cu", "kgrad.cu"]
 NVCC = os.environ.get("JRK_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("JRK_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _deps_mtime():

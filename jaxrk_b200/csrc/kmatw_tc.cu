@@ -791,7 +791,9 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
                                                                       allow_fast, a_scale, yn_all, nmax, 1.f / fabsf(mult));
         JRK_LAUNCHED();
         if (allow_fast == 2) {
+            if (getenv("JRK_TC_DEBUG_SYNC")) { cudaError_t e = cudaStreamSynchronize(st); fprintf(stderr, "[tc] v1 pre-pass done: %s\n", cudaGetErrorString(e)); }
             if (int rc2 = kmatw_tc2_pack(Y, W, M, d, m, ldy, ldw, col_pref, ep.c, yn_all, nmax, img, st)) return rc2;
+            if (getenv("JRK_TC_DEBUG_SYNC")) { cudaError_t e = cudaStreamSynchronize(st); fprintf(stderr, "[tc] v2 pack done: %s\n", cudaGetErrorString(e)); }
         }
     }
     TcParams P;
@@ -810,6 +812,7 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     int rc;
     if (allow_fast == 2) {
         if (int rc2 = kmatw_tc2_apply(X, N, d, ldx, xn, img, M, nmax, ep.c, nconst, row_pref, P.out, P.ldo, P.m, st)) return rc2;
+        if (getenv("JRK_TC_DEBUG_SYNC")) { cudaError_t e = cudaStreamSynchronize(st); fprintf(stderr, "[tc] v2 kernel done: %s\n", cudaGetErrorString(e)); }
     }
     if (pm == PM_SQEXP) rc = tc_launch<PM_SQEXP>(P, ep, st);
     else if (pm == PM_LAPLACE) rc = tc_launch<PM_LAPLACE>(P, ep, st);

@@ -49,20 +49,43 @@ namespace {
 constexpr int T2_BM = 128, T2_NT = 64, T2_MT = 16;
 constexpr int T2_NS = 6;                      // S / e stages in TMEM (64 columns each)
 constexpr int T2_NOB = 3;                     // O windows in TMEM
-constexpr int T2_WIN = 4;                     // tiles per O window = epilogue warps per lane quarter
-constexpr int T2_LAG = 2;                     // a warp folds window w - T2_LAG after its tile of window w
-constexpr int T2_SOP = 8;                     // operand (tile image) stages in shared memory
+constexpr int T2_WIN = 4;                     // tiles per O window
+constexpr int T2_LAGT = 2;                    // a window is folded once a tile T2_LAGT beyond its last one has been converted
+constexpr int T2_SOP = 12;                    // operand (tile image) stages in shared memory
 constexpr int T2_STAGE = 12288;               // stage stride: the 12 KB image of 16 < d <= 32
-constexpr int T2_EW = 16;
-constexpr int T2_THREADS = (3 + T2_EW) * 32;
+constexpr int T2_EPQ_MAX = 4;
 constexpr int T2_COL_X = 0, T2_COL_XLO = 16, T2_COL_O = 32, T2_COL_S = 128;
-constexpr int T2_OFF_BAR = T2_SOP * T2_STAGE;
-constexpr int T2_NBAR = 2 * T2_SOP + 3 * T2_NS + 2 * T2_NOB + 1;
+constexpr int T2_OFF_RED = T2_SOP * T2_STAGE;                            // per-warp partial results of a unit (2 buffers)
+constexpr int T2_RED_WARP = T2_MT * 32 * 4;                              // [16 columns][32 lanes] floats
+constexpr int T2_OFF_BAR = T2_OFF_RED + 2 * 4 * T2_EPQ_MAX * T2_RED_WARP;
+constexpr int T2_NBAR = 2 * T2_SOP + 3 * T2_NS + 2 * T2_NOB + 1 + 4 + 1;
 constexpr int T2_SMEM = T2_OFF_BAR + T2_NBAR * 8 + 16 + 1024;
 static_assert(T2_COL_S + T2_NS * 64 <= 512 && T2_COL_O + T2_NOB * 32 <= T2_COL_S, "TMEM budget");
 static_assert(T2_SMEM <= 227 * 1024, "shared memory budget");
-static_assert(T2_LAG < T2_NOB, "a window must be folded before its buffer is needed again");
 
+#ifdef JRK_TC2_WATCHDOG
+// debugging build (JRK_EXTRA_NVCC_FLAGS=-DJRK_TC2_WATCHDOG): the production wait, plus -- on the slow path only -- a
+// report of where a wait has been stuck for more than ~1 s
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p;}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    if (ok) return;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p;}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 2000000000ll) {
+            if ((threadIdx.x & 31) == 0)
+                printf("STUCK block %d warp %d barrier index %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+                       (int)((bar & 0xfff) >> 3), parity);
+            __nanosleep(100000000);
+            __trap();
+        }
+    }
+}
+#else
 __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -76,6 +99,7 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity), "r"(20000u)
         : "memory");
 }
+#endif
 __device__ __forceinline__ void bar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -87,14 +111,22 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                  "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
-    uint32_t r[4];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(taddr)
+// tcgen05.ld of 16 columns WITHOUT the wait: the registers are valid only after ld16_wait(r) on the same array, which
+// names them as read-write operands so that the compiler cannot touch them between the two statements
+__device__ __forceinline__ void ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void ld16_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
                  : "memory");
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 // {hi half <- a, lo half <- b}
 __device__ __forceinline__ uint32_t cvt_f16x2(float a, float b) {
@@ -114,6 +146,20 @@ __device__ __forceinline__ void split_w_pair(float x0, float x1, uint32_t& hi, u
     hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
     lo = cvt_f16x2((x1 - __half2float(h1)) * 2048.f, (x0 - __half2float(h0)) * 2048.f);
 }
+// 16 exponents -> 8 columns of e_hi pairs + 8 columns of e_lo' pairs:  e = ex2(s), e_hi = leading 11 bits (exact in
+// fp16), e_lo' = (e - e_hi) 2^11 >= 0
+__device__ __forceinline__ void exp_split16(const uint32_t (&sv)[16], uint32_t (&eo)[16]) {
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) {
+        const float e0 = ex2_approx(__uint_as_float(sv[c])), e1 = ex2_approx(__uint_as_float(sv[c + 1]));
+        const float h0 = __uint_as_float(__float_as_uint(e0) & 0xFFFFE000u);
+        const float h1 = __uint_as_float(__float_as_uint(e1) & 0xFFFFE000u);
+        float l0, l1;
+        unpack2(mul2(sub2(pack2(e0, e1), pack2(h0, h1)), pack2(2048.f, 2048.f)), l0, l1);
+        eo[c >> 1] = cvt_f16x2(h1, h0);
+        eo[8 + (c >> 1)] = cvt_f16x2(l1, l0);
+    }
+}
 
 struct Tc2Params {
     const float* X; int64_t ldx; int d;
@@ -126,15 +172,18 @@ struct Tc2Params {
     const unsigned* nmax;            // [3] bit patterns: max |c||x|^2, max |c||y|^2, max |W col_pref|
     float x_scale;                   // 2^-r
     float nconst;
+    long long* trace;                // TRACE builds only (tools/tc2_trace.py): per-warp clock64 stamps of CTA 0
 };
+constexpr int T2_TRACE_TILES = 512;  // stamps per warp: [warp][tile][4]
 
-// byte offset (in 16-byte units) of the W' operand of k-step q inside a tile image; the lo operand sits 2048 B further
-__device__ __forceinline__ uint32_t w_off16(int packed, int q) {
-    return packed ? (uint32_t)((q >> 1) * 256 + 4 + 2 * (q & 1)) : (uint32_t)(512 + 2 * q);
-}
-
-__global__ void __launch_bounds__(T2_THREADS, 1) kmatw_tc2_kernel(Tc2Params P) {
+// EPQ: epilogue warps per TMEM lane quarter (= per SM sub-partition);  WIDE: 16 < d <= 32 (two k-steps in GEMM1, 12 KB
+// images) -- compile-time, because the two MMA-issuing warps are serial latency chains (one elected thread each): every
+// instruction on their per-tile path counts (the first version spent ~430 clk per tile issuing 3 MMAs, and was what
+// bounded the kernel: tools/tc2_trace.py)
+template <int EPQ, bool WIDE, bool TRACE = false>
+__global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Params P) {
     if (!tc2_fast_regime(P.nmax)) return;     // the generic kernel (kmatw_tc.cu) serves the problem
+    constexpr int EW = 4 * EPQ;
     extern __shared__ unsigned char t2_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(t2_smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_OFF_BAR);
@@ -144,19 +193,32 @@ __global__ void __launch_bounds__(T2_THREADS, 1) kmatw_tc2_kernel(Tc2Params P) {
     uint64_t* e_ready = s_full + T2_NS;          // [NS]   the four owner warps wrote e
     uint64_t* s_empty = e_ready + T2_NS;         // [NS]   GEMM2 of the stage complete
     uint64_t* o_full = s_empty + T2_NS;          // [NOB]  window complete
-    uint64_t* o_empty = o_full + T2_NOB;         // [NOB]  all 16 warps folded the window
-    uint64_t* x_ready = o_empty + T2_NOB;        // [1]
+    uint64_t* o_empty = o_full + T2_NOB;         // [NOB]  the four owner warps folded the window
+    uint64_t* x_ready = o_empty + T2_NOB;        // [1]    the epilogue warps parked the unit's X block
+    uint64_t* g1_tok = x_ready + 1;              // [4]    issuing warp j finished the GEMM1 phase of a group
+    uint64_t* x_free = g1_tok + 4;               // [1]    every GEMM1 of the unit has completed (X may be replaced)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T2_OFF_BAR + T2_NBAR * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < T2_SOP; ++s) { mbar_init(&op_full[s], 1); mbar_init(&op_empty[s], 1); }
         for (int s = 0; s < T2_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&e_ready[s], 4); mbar_init(&s_empty[s], 1); }
-        for (int s = 0; s < T2_NOB; ++s) { mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], T2_EW); }
-        mbar_init(x_ready, T2_EW);
+        for (int s = 0; s < T2_NOB; ++s) { mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4); }
+        mbar_init(x_ready, EW);
+        for (int s = 0; s < 4; ++s) mbar_init(&g1_tok[s], 1);
+        mbar_init(x_free, 4);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc_512(smem_u32(tmem_slot));
+    // roles: warps 0 .. EW-1 epilogue; then FOUR MMA-issuing warps, one per SM sub-partition, and the TMA producer.
+    // Issuing warp j takes the groups of four tiles (= O windows) with global index = j (mod 4): GEMM1 of its four tiles,
+    // then GEMM2 of the same four once their e is ready.  A single GEMM2 warp cost the epilogue warps of ITS
+    // sub-partition ~60 % of their speed (and GEMM1's ~35 %: tools/tc2_trace.py, profiles/microbench/
+    // issue_interference.cu -- tcgen05.mma issue delays the tcgen05.ld / st of its neighbours), and a tile is only done when
+    // all four lane quarters are; spread over four warps every sub-partition carries the same 2.75 MMAs per tile.
+    // Different groups accumulate into different O windows and different S stages, so no two issuing threads ever touch
+    // the same accumulator; the hand-over of stages between them goes through the s_empty / e_ready mbarriers.
+    constexpr int W_SVC = EW, W_TMA = EW + 4;
+    if (warp == W_SVC) tmem_alloc_512(smem_u32(tmem_slot));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -164,7 +226,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) kmatw_tc2_kernel(Tc2Params P) {
     if (tmem_base != 0) __trap();
 
     const int T = P.n_tiles;
-    if (warp == 0) {
+    if (warp == W_TMA) {
         // ===================== TMA producer: one image per tile =====================
         uint32_t tc = 0;
         const uint32_t bytes = (uint32_t)P.img_bytes;
@@ -179,92 +241,121 @@ __global__ void __launch_bounds__(T2_THREADS, 1) kmatw_tc2_kernel(Tc2Params P) {
                 __syncwarp();
             }
         }
-    } else if (warp == 1) {
-        // ===================== GEMM1 issuer:  S[stage] = x~ . y''  (fp16 hi / lo, one accumulator) =====================
-        constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(T2_NT >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
-        const uint64_t dbase = make_b_desc(smem_u32(smem));
-        const uint32_t b_opfull = smem_u32(op_full), b_sempty = smem_u32(s_empty), b_sfull = smem_u32(s_full), b_xready = smem_u32(x_ready);
-        const int ksh = (P.d + 15) >> 4;
-        const uint64_t y_lo = (uint64_t)(P.packed ? 2 : 4);          // 32 or 64 bytes further inside the rows
-        uint32_t s = 0, s_ph = 0, a = 0, a_ph = 0, uc = 0;
-        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, ++uc) {
-            bar_wait(b_xready, uc & 1);
-            for (int t = 0; t < T; ++t) {
-                bar_wait(b_opfull + s * 8, s_ph);
-                bar_wait(b_sempty + a * 8, a_ph ^ 1);
-                tc_fence_after();
-                const uint64_t dyh = dbase + (uint64_t)((s * T2_STAGE) >> 4), dyl = dyh + y_lo;
-                const uint32_t cs = T2_COL_S + a * 64;
-                if (elect_one()) {
-                    // the small cross terms first, the hi.hi terms last: the accumulator truncates, so only the last
-                    // additions carry a rounding error that matters
-                    for (int ks = 0; ks < ksh; ++ks) {
-                        const uint64_t off = (uint64_t)(ks * 2);
-                        mma_f16_ts(cs, T2_COL_X + ks * 8, dyl + off, idesc1, ks);          // hi_x . lo_y
-                        mma_f16_ts(cs, T2_COL_XLO + ks * 8, dyh + off, idesc1, 1u);        // lo_x . hi_y
-                    }
-                    for (int ks = 0; ks < ksh; ++ks) mma_f16_ts(cs, T2_COL_X + ks * 8, dyh + (uint64_t)(ks * 2), idesc1, 1u);
-                    commit_addr(b_sfull + a * 8);
-                }
-                __syncwarp();
-                if (++s == T2_SOP) { s = 0; s_ph ^= 1; }
-                if (++a == T2_NS) { a = 0; a_ph ^= 1; }
-            }
-        }
-    } else if (warp == 2) {
-        // ===================== GEMM2 issuer:  O[window] += e . W'  (16-bit hi / lo operands) =====================
+    } else if (warp >= W_SVC) {
+        // ===================== MMA issuers =====================
+        const uint32_t j = (uint32_t)(warp - W_SVC);
+        constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(T2_NT >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);       // N = 64
         constexpr uint32_t id16 = (1u << 4) | ((uint32_t)(T2_MT >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);         // N = 16
         constexpr uint32_t id32 = (1u << 4) | ((uint32_t)((2 * T2_MT) >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);   // N = 32
+        constexpr uint64_t YLO = WIDE ? 4 : 2;                       // Y lo: 64 or 32 bytes further inside the rows
         const uint64_t dbase = make_b_desc(smem_u32(smem));
-        const uint32_t b_opfull = smem_u32(op_full), b_opempty = smem_u32(op_empty), b_sempty = smem_u32(s_empty),
-                       b_eready = smem_u32(e_ready), b_ofull = smem_u32(o_full), b_oempty = smem_u32(o_empty);
-        const int packed = P.packed;
-        uint32_t s = 0, s_ph = 0, a = 0, a_ph = 0, ob = 0, ob_ph = 0;
-        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
-            for (int t = 0; t < T; ++t) {
-                const bool win_first = (t & (T2_WIN - 1)) == 0, win_last = ((t & (T2_WIN - 1)) == T2_WIN - 1) || (t == T - 1);
-                if (win_first) bar_wait(b_oempty + ob * 8, ob_ph ^ 1);
-                bar_wait(b_opfull + s * 8, s_ph);
-                bar_wait(b_eready + a * 8, a_ph);
-                tc_fence_after();
-                const uint64_t dw = dbase + (uint64_t)((s * T2_STAGE) >> 4);
-                const uint32_t eh = T2_COL_S + a * 64, oc = T2_COL_O + ob * 32, ox = oc + T2_MT;
-                if (elect_one()) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint64_t dq = dw + (uint64_t)w_off16(packed, q);
-                        const uint32_t acc0 = (win_first && q == 0) ? 0u : 1u;
+        const uint32_t b_opfull = smem_u32(op_full), b_opempty = smem_u32(op_empty), b_sfull = smem_u32(s_full),
+                       b_eready = smem_u32(e_ready), b_sempty = smem_u32(s_empty), b_ofull = smem_u32(o_full),
+                       b_oempty = smem_u32(o_empty), b_xready = smem_u32(x_ready), b_tok = smem_u32(g1_tok),
+                       b_xfree = smem_u32(x_free);
+        const int ngrp = (T + T2_WIN - 1) / T2_WIN;
+        uint32_t gt = 0, gw = 0, uc = 0;           // tiles / windows / units before the current unit
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, ++uc) {
+            bool xseen = false;
+            const int n_first = (int)((j - gw) & 3u);
+            if (n_first >= ngrp && lane == 0) bar_arrive(b_xfree);     // no group of this unit is ours
+            for (int n = n_first; n < ngrp; n += 4) {
+                if (!xseen) { bar_wait(b_xready, uc & 1); xseen = true; }
+                // A parity wait is only meaningful when the waiter is at most ONE phase behind the barrier, and this warp
+                // skips three groups out of four: so the GEMM1 phases of consecutive groups are chained (group w starts
+                // after group w - 1 has issued its GEMM1s).  By induction every barrier waited on below has then completed
+                // the phase before the awaited one (GEMM1 of tile g - 6 / g - 12 has been issued, which waited for it).
+                const uint32_t wg = gw + (uint32_t)n;                   // global group = window index
+                if (wg > 0) bar_wait(b_tok + ((j - 1u) & 3u) * 8, ((wg - 1u) >> 2) & 1u);
+                const int t0 = n * T2_WIN, t1 = (t0 + T2_WIN < T) ? t0 + T2_WIN : T;
+                // ---- GEMM1:  S[stage] = x~ . y''  (fp16 hi / lo, one accumulator) ----
+                for (int t = t0; t < t1; ++t) {
+                    const uint32_t g = gt + (uint32_t)t, s = g % T2_SOP, a = g % T2_NS;
+                    const long long tr0 = TRACE ? clock64() : 0;
+                    bar_wait(b_opfull + s * 8, (g / T2_SOP) & 1);
+                    const long long tr1 = TRACE ? clock64() : 0;
+                    bar_wait(b_sempty + a * 8, ((g / T2_NS) & 1) ^ 1);
+                    tc_fence_after();
+                    const long long tr2 = TRACE ? clock64() : 0;
+                    const uint64_t dy = dbase + (uint64_t)((s * T2_STAGE) >> 4);
+                    const uint32_t cs = T2_COL_S + a * 64;
+                    if (elect_one()) {
+                        // the small cross terms first, the hi.hi terms last: the accumulator truncates, so only the last
+                        // additions carry a rounding error that matters
+                        mma_f16_ts(cs, T2_COL_X, dy + YLO, idesc1, 0u);                        // hi_x . lo_y
+                        mma_f16_ts(cs, T2_COL_XLO, dy, idesc1, 1u);                            // lo_x . hi_y
+                        if (WIDE) {
+                            mma_f16_ts(cs, T2_COL_X + 8, dy + YLO + 2, idesc1, 1u);
+                            mma_f16_ts(cs, T2_COL_XLO + 8, dy + 2, idesc1, 1u);
+                        }
+                        mma_f16_ts(cs, T2_COL_X, dy, idesc1, 1u);                              // hi_x . hi_y
+                        if (WIDE) mma_f16_ts(cs, T2_COL_X + 8, dy + 2, idesc1, 1u);
+                        commit_addr(b_sfull + a * 8);
+                    }
+                    __syncwarp();
+                    if (TRACE && blockIdx.x == 0 && uc == 0 && t < T2_TRACE_TILES && lane == 0) {
+                        long long* tr = P.trace + ((int64_t)17 * T2_TRACE_TILES + t) * 4;
+                        tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = clock64();
+                    }
+                }
+                if (lane == 0) bar_arrive(b_tok + j * 8);
+                if (n + 4 >= ngrp && elect_one()) commit_addr(b_xfree);      // our last GEMM1s of the unit: arrives when they are done
+                __syncwarp();
+                // ---- GEMM2:  O[window] += e . W'  (fp16 hi / lo' operands) ----
+                const uint32_t w = wg, ob = w % T2_NOB;
+                const uint32_t oc = T2_COL_O + ob * 32, ox = oc + T2_MT;
+                const long long tq0 = TRACE ? clock64() : 0;
+                bar_wait(b_oempty + ob * 8, ((w / T2_NOB) & 1) ^ 1);
+                for (int t = t0; t < t1; ++t) {
+                    const uint32_t g = gt + (uint32_t)t, s = g % T2_SOP, a = g % T2_NS;
+                    const long long tr1 = TRACE ? clock64() : 0;
+                    bar_wait(b_eready + a * 8, (g / T2_NS) & 1);      // (this thread has already seen op_full of the tile)
+                    tc_fence_after();
+                    const long long tr2 = TRACE ? clock64() : 0;
+                    const uint64_t dw = dbase + (uint64_t)((s * T2_STAGE) >> 4);
+                    const uint32_t eh = T2_COL_S + a * 64;
+                    if (elect_one()) {
                         // an MMA of N <= 32 costs the same whatever N is: e_hi meets [W'_hi ; W'_lo'] (stacked rows) in ONE
                         // MMA whose 32 result columns are {main | cross}
-                        mma_f16_ts(oc, eh + 16 * q, dq, id32, acc0);                 // e_hi  . [W'_hi ; W'_lo'] -> {main | cross}
-                        mma_f16_ts(ox, eh + 16 * q + 8, dq, id16, 1u);               // e_lo' . W'_hi            -> cross
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            // offset (16-byte units) of the W' operand of k-step q in the image; W'_lo' sits 16 rows = 2048 B further
+                            const uint64_t dq = dw + (uint64_t)(WIDE ? (512 + 2 * q) : ((q >> 1) * 256 + 4 + 2 * (q & 1)));
+                            if (q == 0) mma_f16_ts(oc, eh, dq, id32, t == t0 ? 0u : 1u);    // e_hi . [W'_hi ; W'_lo'] -> {main | cross}
+                            else mma_f16_ts(oc, eh + 16 * q, dq, id32, 1u);
+                            mma_f16_ts(ox, eh + 16 * q + 8, dq, id16, 1u);                  // e_lo' . W'_hi -> cross
+                        }
+                        commit_addr(b_sempty + a * 8);      // S / e stage reusable
+                        commit_addr(b_opempty + s * 8);     // operand stage reusable
+                        if (t == t1 - 1) commit_addr(b_ofull + ob * 8);
                     }
-                    commit_addr(b_sempty + a * 8);      // S / e stage reusable
-                    commit_addr(b_opempty + s * 8);     // operand stage reusable
-                    if (win_last) commit_addr(b_ofull + ob * 8);
+                    __syncwarp();
+                    if (TRACE && blockIdx.x == 0 && uc == 0 && t < T2_TRACE_TILES && lane == 0) {
+                        long long* tr = P.trace + ((int64_t)18 * T2_TRACE_TILES + t) * 4;
+                        tr[0] = (t == t0) ? tq0 : tr1; tr[1] = tr1; tr[2] = tr2; tr[3] = clock64();
+                    }
                 }
-                __syncwarp();
-                if (win_last) { if (++ob == T2_NOB) { ob = 0; ob_ph ^= 1; } }
-                if (++s == T2_SOP) { s = 0; s_ph ^= 1; }
-                if (++a == T2_NS) { a = 0; a_ph ^= 1; }
             }
+            gt += (uint32_t)T;
+            gw += (uint32_t)ngrp;
         }
     } else {
         // ===================== epilogue warps (and X loader) =====================
-        // warp k of a lane quarter owns the quarter (32 rows x 64 columns) of the tiles t = k (mod 4)
-        const int e = warp - 3;
+        // warp k of a lane quarter owns the quarter (32 rows x 64 columns) of the tiles t = k (mod EPQ), and folds the
+        // O windows w = k (mod EPQ) (all 16 + 16 columns of its 32 rows) into FP32 registers
         const int quad = warp & 3;                 // TMEM lane quarter this warp may touch
-        const int k = e >> 2;                      // which tiles; also: which 4 output columns this warp folds
+        const int k = warp >> 2;
         uint32_t lane_base;                        // opaque registers: keep address arithmetic out of the loop
         asm volatile("mov.u32 %0, %1;" : "=r"(lane_base) : "r"(tmem_base + ((uint32_t)(quad * 32) << 16)));
         uint32_t sbase;
         asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));
         const uint32_t b_sfull = sbase + T2_OFF_BAR + 2 * T2_SOP * 8, b_eready = b_sfull + T2_NS * 8,
-                       b_ofull = b_sfull + 3 * T2_NS * 8, b_oempty = b_ofull + T2_NOB * 8, b_xready = b_oempty + T2_NOB * 8;
-        const float lo_w = 1.f / 2048.f;
+                       b_ofull = b_sfull + 3 * T2_NS * 8, b_oempty = b_ofull + T2_NOB * 8, b_xready = b_oempty + T2_NOB * 8,
+                       b_xfree = b_xready + 5 * 8;
         const int nwin = (T + T2_WIN - 1) / T2_WIN;
         // 2^ew: the power of two that normalises W' (the pack pre-pass divides by it)
         const float wpow = pow2i(tc2_w_exp(__uint_as_float(__ldg(P.nmax + 2))));
+        float* red = reinterpret_cast<float*>(smem + T2_OFF_RED);
 
         auto park_x = [&](int u) {
             // x~ = x 2^-r as fp16 hi / lo (unscaled lo): 16 values -> 8 packed columns; warps 0 and 1 of the quarter
@@ -289,74 +380,99 @@ __global__ void __launch_bounds__(T2_THREADS, 1) kmatw_tc2_kernel(Tc2Params P) {
             if (lane == 0) bar_arrive(b_xready);
         };
 
-        uint32_t gt = 0, gw = 0;                   // tiles / windows of the units this CTA has finished
+        uint32_t gt = 0, gw = 0, uc = 0;           // tiles / windows / units this CTA has finished
         int u = blockIdx.x;
         if (u < P.n_units) park_x(u);
-        for (; u < P.n_units; u += gridDim.x) {
-            float oacc[4] = {0.f, 0.f, 0.f, 0.f};
-            int folded = 0;
-            auto fold = [&]() {                    // window `folded` of this unit: this warp's 4 + 4 columns -> registers
-                const uint32_t w = gw + (uint32_t)folded, ob = w % T2_NOB;
+        for (; u < P.n_units; u += gridDim.x, ++uc) {
+            float oacc[T2_MT];
+#pragma unroll
+            for (int c = 0; c < T2_MT; ++c) oacc[c] = 0.f;
+            int next_w = k;                        // next window of this unit that this warp folds
+            auto fold = [&]() {
+                const uint32_t w = gw + (uint32_t)next_w, ob = w % T2_NOB;
                 bar_wait(b_ofull + ob * 8, (w / T2_NOB) & 1);
                 tc_fence_after();
-                float o[4], ox[4];
-                tmem_ld4(lane_base + T2_COL_O + ob * 32 + k * 4, o);
-                tmem_ld4(lane_base + T2_COL_O + ob * 32 + T2_MT + k * 4, ox);
-                tmem_ld_wait();
+                uint32_t o[16], ox[16];
+                ld16_async(lane_base + T2_COL_O + ob * 32, o);
+                ld16_async(lane_base + T2_COL_O + ob * 32 + T2_MT, ox);
+                ld16_wait(o);
+                ld16_wait(ox);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(b_oempty + ob * 8);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) oacc[c] += fmaf(ox[c], lo_w, o[c]);
-                ++folded;
+                for (int c = 0; c < T2_MT; ++c) oacc[c] += fmaf(__uint_as_float(ox[c]), 1.f / 2048.f, __uint_as_float(o[c]));
+                next_w += EPQ;
             };
-            for (int t = k; t < T; t += T2_WIN) {
+            for (int t = k; t < T; t += EPQ) {
                 const uint32_t g = gt + (uint32_t)t, a = g % T2_NS;
+                const long long tr0 = TRACE ? clock64() : 0;
                 bar_wait(b_sfull + a * 8, (g / T2_NS) & 1);
                 tc_fence_after();
+                const long long tr1 = TRACE ? clock64() : 0;
                 const uint32_t sc = lane_base + T2_COL_S + a * 64;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    // 16 S columns -> 8 columns of e_hi pairs + 8 columns of e_lo pairs, in place
-                    float sv[16];
-                    tmem_ld16(sc + 16 * q, sv);
-                    tmem_ld_wait();
-                    uint32_t eo[16];
-#pragma unroll
-                    for (int c = 0; c < 16; c += 2) {
-                        const float e0 = ex2_approx(sv[c]), e1 = ex2_approx(sv[c + 1]);
-                        const float h0 = __uint_as_float(__float_as_uint(e0) & 0xFFFFE000u);   // 11 significant bits:
-                        const float h1 = __uint_as_float(__float_as_uint(e1) & 0xFFFFE000u);   // exact in fp16
-                        float l0, l1;
-                        unpack2(mul2(sub2(pack2(e0, e1), pack2(h0, h1)), pack2(2048.f, 2048.f)), l0, l1);   // lo' >= 0
-                        eo[c >> 1] = cvt_f16x2(h1, h0);
-                        eo[8 + (c >> 1)] = cvt_f16x2(l1, l0);
-                    }
-                    tmem_st16(sc + 16 * q, eo);
-                }
+                // four chunks of 16 S columns -> 8 + 8 columns of e pairs, in place; the next chunk's load is in flight
+                // while the current one goes through the MUFU
+                uint32_t s0[16], s1[16], eo[16];
+                ld16_async(sc, s0);
+                ld16_wait(s0);
+                ld16_async(sc + 16, s1);
+                exp_split16(s0, eo);
+                tmem_st16(sc, eo);
+                ld16_wait(s1);
+                ld16_async(sc + 32, s0);
+                exp_split16(s1, eo);
+                tmem_st16(sc + 16, eo);
+                ld16_wait(s0);
+                ld16_async(sc + 48, s1);
+                exp_split16(s0, eo);
+                tmem_st16(sc + 32, eo);
+                ld16_wait(s1);
+                exp_split16(s1, eo);
+                tmem_st16(sc + 48, eo);
+                const long long tr2 = TRACE ? clock64() : 0;
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(b_eready + a * 8);
-                if (t >= T2_WIN * T2_LAG) fold();
+                if (TRACE && blockIdx.x == 0 && uc == 0 && t < T2_TRACE_TILES && lane == 0) {
+                    long long* tr = P.trace + ((int64_t)warp * T2_TRACE_TILES + t) * 4;
+                    tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = clock64();
+                }
+                if (next_w < nwin && T2_WIN * next_w + (T2_WIN - 1) + T2_LAGT <= t) fold();
             }
-            // every GEMM1 of this unit has completed once the last tile's s_full is seen: park the next block of X now,
-            // so that the next unit's GEMM1s overlap the tail of this one
+            // once every GEMM1 of this unit has completed (x_free: one commit per issuing warp) the next block of X can be
+            // parked, so that the next unit's GEMM1s overlap the tail of this one
             const int un = u + gridDim.x;
             if (un < P.n_units) {
-                const uint32_t g = gt + (uint32_t)(T - 1);
-                bar_wait(b_sfull + (g % T2_NS) * 8, (g / T2_NS) & 1);
+                bar_wait(b_xfree, uc & 1);
                 tc_fence_after();
                 park_x(un);
             }
-            while (folded < nwin) fold();
-            const int64_t i = (int64_t)u * T2_BM + quad * 32 + lane;
-            if (i < P.N) {
-                const float f = P.nconst * wpow * ex2_approx(__ldg(P.xn + i)) * (P.row_pref ? __ldg(P.row_pref + i) : 1.f);
-                float* dst = P.out + i * P.ldo + k * 4;
+            while (next_w < nwin) fold();
+            // the EPQ partial results of a lane quarter meet in shared memory (two buffers, alternating by unit)
+            float* mine = red + ((uc & 1) * EW + quad * EPQ + k) * (T2_MT * 32);
+            if (EPQ > 1) {
+                if (k != 0) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (k * 4 + c < P.m) dst[c] = f * oacc[c];
+                    for (int c = 0; c < T2_MT; ++c) mine[c * 32 + lane] = oacc[c];
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(32 * EPQ) : "memory");
+            }
+            if (k == 0) {
+#pragma unroll
+                for (int kk = 1; kk < EPQ; ++kk) {
+#pragma unroll
+                    for (int c = 0; c < T2_MT; ++c) oacc[c] += mine[kk * (T2_MT * 32) + c * 32 + lane];
+                }
+                const int64_t i = (int64_t)u * T2_BM + quad * 32 + lane;
+                if (i < P.N) {
+                    const float f = P.nconst * wpow * ex2_approx(__ldg(P.xn + i)) * (P.row_pref ? __ldg(P.row_pref + i) : 1.f);
+                    float* dst = P.out + i * P.ldo;
+#pragma unroll
+                    for (int c = 0; c < T2_MT; ++c)
+                        if (c < P.m) dst[c] = f * oacc[c];
+                }
             }
             gt += (uint32_t)T;
             gw += (uint32_t)nwin;
@@ -366,7 +482,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) kmatw_tc2_kernel(Tc2Params P) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 1) tmem_dealloc_512(tmem_base);
+    if (warp == W_SVC) tmem_dealloc_512(tmem_base);
 }
 
 // ---- pre-pass: per-tile images, one thread per 16-byte piece (8 fp16 / bf16 values) ----
@@ -453,6 +569,11 @@ __global__ void tc2_wmax_kernel(const float* __restrict__ W, int64_t M, int m, i
 
 }  // namespace
 
+// debugging aid of tools/tc2_trace.py (not part of the C ABI in include/jrk.h): a device buffer of
+// 19 x T2_TRACE_TILES x 4 int64 that receives per-tile clock64 stamps of every warp of CTA 0
+static long long* g_tc2_trace = nullptr;
+extern "C" void jrk_debug_tc2_trace(void* device_buffer) { g_tc2_trace = (long long*)device_buffer; }
+
 int tc2_image_bytes(int d) { return d <= 16 ? 8192 : 12288; }
 
 // W maximum (nmax[2]) + tile images of the factored regime.  nmax[0..1] (norm maxima) and yn_all must already be
@@ -484,9 +605,29 @@ int kmatw_tc2_apply(const float* X, int64_t N, int d, int64_t ldx, const float* 
     P.nmax = nmax;
     P.x_scale = tc2_scales(c).x_scale;
     P.nconst = nconst;
+    P.trace = g_tc2_trace;
     const int grid = P.n_units < tf_sm_count() ? P.n_units : tf_sm_count();
-    JRK_CUDA_OK(cudaFuncSetAttribute(kmatw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
-    kmatw_tc2_kernel<<<grid, T2_THREADS, T2_SMEM, st>>>(P);
+    // epilogue warps per SM sub-partition: 4; JRK_TC2_EPQ = 3 for A/B runs
+    int epq = 4;
+    if (const char* e = getenv("JRK_TC2_EPQ")) epq = atoi(e);
+#define T2_LAUNCH(EPQ_, WIDE_, TRACE_)                                                                               \
+    do {                                                                                                             \
+        JRK_CUDA_OK(cudaFuncSetAttribute(kmatw_tc2_kernel<EPQ_, WIDE_, TRACE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         T2_SMEM));                                                                  \
+        kmatw_tc2_kernel<EPQ_, WIDE_, TRACE_><<<grid, (5 + 4 * EPQ_) * 32, T2_SMEM, st>>>(P);                         \
+    } while (0)
+    const bool wide = d > 16;
+    if (g_tc2_trace) {
+        if (epq == 4) T2_LAUNCH(4, false, true);
+        else T2_LAUNCH(3, false, true);
+    } else if (epq == 3) {
+        if (wide) T2_LAUNCH(3, true, false);
+        else T2_LAUNCH(3, false, false);
+    } else {
+        if (wide) T2_LAUNCH(4, true, false);
+        else T2_LAUNCH(4, false, false);
+    }
+#undef T2_LAUNCH
     JRK_LAUNCHED();
     return JRK_OK;
 }

@@ -17,7 +17,10 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "dram__bytes_read.su
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_xu.sum", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed_pipe_xu.sum",
+        "lts__t_bytes.sum", "lts__t_sectors_op_read.sum", "l1tex__m_xbar2l1tex_read_bytes.sum",
+        "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
