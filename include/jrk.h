@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define JRK_ABI_VERSION 2
+#define JRK_ABI_VERSION 3
 
 /* error codes */
 #define JRK_OK 0
@@ -70,7 +70,21 @@ extern "C" {
 #define JRK_KIND_PERIODIC 1
 #define JRK_KIND_THRESHSPIKE 2
 
+/* process-wide switches (jrk_set_option / jrk_get_option).  The environment variable of the same name as the
+ * option (JRK_KMATW_TC, JRK_TC_FAST, JRK_TC_V2, JRK_TC2_EPQ, JRK_GRAM_H16) only provides the INITIAL value, read once
+ * per process; nothing in the compute entry points reads the environment. */
+#define JRK_OPT_KMATW_TC 0  /* 1 (default): jrk_kmatw_f32 uses the tensor-core kernels where eligible; 0: FP32-pipe kernel */
+#define JRK_OPT_TC_FAST 1   /* 1 (default): factored p = 2 regime of the tensor-core K@W; 0: generic epilogue always   */
+#define JRK_OPT_TC_V2 2     /* 1 (default): second-generation kernel (kmatw_tc2.cu) in the factored regime             */
+#define JRK_OPT_TC2_EPQ 3   /* epilogue warps per SM sub-partition of the second-generation kernel: 4 (default) or 3   */
+#define JRK_OPT_GRAM_H16 4  /* 1 (default): fp16 hi / lo operands for the tensor Gram at 16 < d <= 64; 0: tf32        */
+#define JRK_OPT_COUNT_ 5
+
 int jrk_abi_version(void);
+
+/* Returns 0, or JRK_ERR_INVALID_ARG for an unknown option / value. */
+int jrk_set_option(int option, int value);
+int jrk_get_option(int option);
 
 /* Copies the calling thread's last error message (NUL-terminated, truncated to n). */
 int jrk_last_error(char *buf, size_t n);
@@ -160,9 +174,9 @@ int jrk_kmatw_kind_f32(const float *X, const float *Y, const float *W, float *ou
 int jrk_dist_diag_f32(const float *X, const float *Y, float *out, int64_t N, int d,
                       int64_t ldx, int64_t ldy, float scale, const float *dim_scale, float power, void *stream);
 
-/* 1 when jrk_kmatw_f32 would run both contractions of this problem on the tensor cores (kmatw_tc.cu: d <= 32,
- * m <= 16, no per-dimension scale, row_reduce NONE / SUM / MEAN, large N and M, JRK_KMATW_TC != "0"), else 0
- * (FP32-pipe kernel).
+/* 1 when jrk_kmatw_f32 would run both contractions of this problem on the tensor cores (kmatw_tc.cu / kmatw_tc2.cu:
+ * d <= 32, any m (column blocks of 16), no per-dimension scale, row_reduce NONE / SUM / MEAN, N >= 8192, M >= 4096,
+ * JRK_OPT_KMATW_TC != 0), else 0 (FP32-pipe kernel).
  * Introspection only (bench.py picks the roofline by it); results agree within the documented tolerance. */
 int jrk_kmatw_uses_tensor_cores(int64_t N, int64_t M, int d, int m, int has_dim_scale, int row_reduce);
 
@@ -224,6 +238,39 @@ int jrk_kmatw_f32_host(const float *X, const float *Y, const float *W, float *ou
                        float scale, const float *dim_scale, float power, float nconst,
                        const float *row_pref, const float *col_pref,
                        int row_reduce, int64_t group, int device);
+
+/* ------------------------------------------------------------------------------
+ * Plans: the Y / W side of jrk_kmatw_f32 kept on the device across applies.
+ * The reference evaluates FiniteVec.inner / FiniteVec.__call__ / FiniteOp.__matmul__ (jaxrk/rkhs/vector.py:62-75,
+ * 203-204, jaxrk/rkhs/operator.py:33-56) against the same inspection points and linear map for every new batch of
+ * points; a plan is that fixed side: device copies of Y, W, col_pref, dim_scale and -- where the tensor-core kernels
+ * apply -- the packed tile images, so an apply moves and touches X only.
+ *   create      Y (M x d, ldy), W (M x m, ldw), col_pref (len M, nullable), dim_scale (len d, nullable) are HOST pointers
+ *               when src_is_host != 0 (`stream` is then ignored), else DEVICE pointers on `device`, read on `stream`.
+ *               Returns after the plan is complete (it synchronises); nothing of the caller's is retained.
+ *   apply       DEVICE pointers X (N x d, ldx), out (rows x m, ldo), row_pref (len N, nullable); enqueues on `stream`,
+ *               never synchronises; scratch as in jrk_kmatw_f32 (jrk_kmatw_plan_workspace_bytes).
+ *   apply_host  HOST pointers, dense (ld = d / m); copies inside, returns when `out` is complete.
+ * Results are those of jrk_kmatw_f32 on the same inputs.  A plan is not thread-safe (one apply at a time).
+ * ------------------------------------------------------------------------------ */
+typedef struct jrk_kmatw_plan jrk_kmatw_plan;
+
+int jrk_kmatw_plan_create(jrk_kmatw_plan **plan, const float *Y, const float *W,
+                          int64_t M, int d, int m, int64_t ldy, int64_t ldw,
+                          float scale, const float *dim_scale, float power, float nconst,
+                          const float *col_pref, int src_is_host, int device, void *stream);
+
+size_t jrk_kmatw_plan_workspace_bytes(const jrk_kmatw_plan *plan, int64_t N, int row_reduce, int64_t group);
+
+int jrk_kmatw_plan_apply(const jrk_kmatw_plan *plan, const float *X, float *out,
+                         int64_t N, int64_t ldx, int64_t ldo,
+                         const float *row_pref, int row_reduce, int64_t group,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+int jrk_kmatw_plan_apply_host(jrk_kmatw_plan *plan, const float *X, float *out, int64_t N,
+                              const float *row_pref, int row_reduce, int64_t group);
+
+int jrk_kmatw_plan_destroy(jrk_kmatw_plan *plan);
 
 /* Number of kernel launches issued by this library in the calling process (all
  * threads), for bench.py's `gpu_launches` claim. */

@@ -22,6 +22,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libjaxrk_b200.so")
 PATH_AUTO, PATH_DIRECT, PATH_TF32X3 = 0, 1, 2
 KIND_GENGAUSS, KIND_PERIODIC, KIND_THRESHSPIKE = 0, 1, 2
 REDUCE_NONE, REDUCE_SUM, REDUCE_MEAN, REDUCE_BALANCED, REDUCE_BALANCED_MEAN = 0, 1, 2, 3, 4
+OPT_KMATW_TC, OPT_TC_FAST, OPT_TC_V2, OPT_TC2_EPQ, OPT_GRAM_H16 = 0, 1, 2, 3, 4
+ABI_VERSION = 3
 
 # every symbol include/jrk.h declares: name -> (restype, argtypes)
 _F = ctypes.POINTER(c_float)
@@ -30,6 +32,15 @@ SIGNATURES = {
     "jrk_last_error": (c_int, [ctypes.c_char_p, c_size_t]),
     "jrk_device_count": (c_int, []),
     "jrk_launch_count": (c_int64, []),
+    "jrk_set_option": (c_int, [c_int, c_int]),
+    "jrk_get_option": (c_int, [c_int]),
+    "jrk_kmatw_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_int64,
+                                      c_float, c_void_p, c_float, c_float, c_void_p, c_int, c_int, c_void_p]),
+    "jrk_kmatw_plan_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int, c_int64]),
+    "jrk_kmatw_plan_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64,
+                                     c_void_p, c_size_t, c_void_p]),
+    "jrk_kmatw_plan_apply_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64]),
+    "jrk_kmatw_plan_destroy": (c_int, [c_void_p]),
     "jrk_gram_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "jrk_gram_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64,
                              c_float, c_void_p, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p]),
@@ -87,7 +98,7 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.jrk_abi_version() != 2:
+        if L.jrk_abi_version() != ABI_VERSION:
             raise ImportError("libjaxrk_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -106,6 +117,32 @@ def _check(rc: int):
 
 def launch_count() -> int:
     return int(lib().jrk_launch_count())
+
+
+def set_option(option: int, value: int) -> int:
+    """jrk_set_option; returns the previous value (so that a caller can restore it)."""
+    prev = int(lib().jrk_get_option(option))
+    _check(lib().jrk_set_option(option, int(value)))
+    return prev
+
+
+def get_option(option: int) -> int:
+    return int(lib().jrk_get_option(option))
+
+
+class option:
+    """`with nat.option(nat.OPT_KMATW_TC, 0): ...` -- a process-wide switch for the duration of a block (tests, A/B runs)."""
+
+    def __init__(self, opt: int, value: int):
+        self.opt, self.value = opt, value
+
+    def __enter__(self):
+        self.prev = set_option(self.opt, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(self.opt, self.prev)
+        return False
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -391,3 +428,79 @@ def kmatw_host(X, Y, W, out, scale: float, power: float, nconst: float, dim_scal
                                     _host_ptr(dim_scale), power, nconst, _host_ptr(row_pref), _host_ptr(col_pref),
                                     row_reduce, group, device))
     return out
+
+
+def _rows_out(N: int, row_reduce: int, group: int) -> int:
+    if row_reduce in (REDUCE_SUM, REDUCE_MEAN):
+        return 1
+    if row_reduce in (REDUCE_BALANCED, REDUCE_BALANCED_MEAN):
+        if group < 1 or N % group:
+            raise ValueError("group must divide N")
+        return N // group
+    return N
+
+
+class KmatwPlan:
+    """jrk_kmatw_plan_*: the Y / W side of row_reduce(diag(row_pref) K(X, Y) diag(col_pref) W) kept on the device
+    (copies of Y, W and -- for the tensor-core kernels -- the packed tile images).  `apply` takes CUDA tensors and
+    enqueues on torch's current stream; `apply_host` takes host arrays and includes the copies."""
+
+    def __init__(self, Y, W, scale: float, power: float, nconst: float, dim_scale=None, col_pref=None, device: int = 0):
+        host = not (isinstance(Y, torch.Tensor) and Y.is_cuda)
+        if host:
+            import numpy as np
+            Y = np.ascontiguousarray(Y, dtype=np.float32) if not isinstance(Y, torch.Tensor) else Y.contiguous().float()
+            W = np.ascontiguousarray(W, dtype=np.float32) if not isinstance(W, torch.Tensor) else W.contiguous().float()
+            yp, wp = _host_ptr(Y), _host_ptr(W)
+            ldy, ldw = int(Y.shape[1]), int(W.shape[1])
+            dsp = _host_ptr(None if dim_scale is None else np.ascontiguousarray(dim_scale, dtype=np.float32).reshape(-1))
+            cpp = _host_ptr(None if col_pref is None else np.ascontiguousarray(col_pref, dtype=np.float32).reshape(-1))
+            stream, self.device = None, int(device)
+        else:
+            Y, W = _dev2d(Y, "Y"), _dev2d(W, "W")
+            yp, wp, ldy, ldw = _ptr(Y), _ptr(W), _ld(Y), _ld(W)
+            ds = _vec(dim_scale, Y.shape[1], "dim_scale", Y.device)
+            cp = _vec(col_pref, Y.shape[0], "col_pref", Y.device)
+            dsp, cpp = _ptr(ds), _ptr(cp)
+            stream, self.device = _stream(Y.device), int(Y.device.index or 0)
+        M, d = int(Y.shape[0]), int(Y.shape[1])
+        if int(W.shape[0]) != M:
+            raise ValueError(f"W must have {M} rows")
+        self.M, self.d, self.m = M, d, int(W.shape[1])
+        h = c_void_p()
+        _check(lib().jrk_kmatw_plan_create(ctypes.byref(h), yp, wp, M, d, self.m, ldy, ldw, scale, dsp, power, nconst, cpp,
+                                           1 if host else 0, self.device, stream))
+        self._h = h
+
+    def apply(self, X, row_pref=None, row_reduce: int = REDUCE_NONE, group: int = 0, out: Optional[torch.Tensor] = None):
+        X = _dev2d(X, "X")
+        N = int(X.shape[0])
+        if X.shape[1] != self.d:
+            raise ValueError(f"X must have {self.d} columns")
+        rp = _vec(row_pref, N, "row_pref", X.device)
+        rows = _rows_out(N, row_reduce, group)
+        if out is None:
+            out = torch.empty((rows, self.m), dtype=torch.float32, device=X.device)
+        with torch.cuda.device(X.device):
+            wsb = lib().jrk_kmatw_plan_workspace_bytes(self._h, N, row_reduce, group)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=X.device) if wsb else None
+            _check(lib().jrk_kmatw_plan_apply(self._h, _ptr(X), _ptr(out), N, _ld(X), self.m, _ptr(rp), row_reduce, group,
+                                              _ptr(ws), wsb, _stream(X.device)))
+        return out
+
+    def apply_host(self, X, out, row_pref=None, row_reduce: int = REDUCE_NONE, group: int = 0):
+        N = int(X.shape[0])
+        assert tuple(out.shape) == (_rows_out(N, row_reduce, group), self.m)
+        _check(lib().jrk_kmatw_plan_apply_host(self._h, _host_ptr(X), _host_ptr(out), N, _host_ptr(row_pref), row_reduce, group))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().jrk_kmatw_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass

@@ -2,6 +2,7 @@
 // selection, host-buffer (end-to-end) variants.  No torch / XLA types here.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -9,7 +10,6 @@
 namespace jrk {
 
 thread_local char g_last_error[512] = {0};
-thread_local ExtraKind g_extra_kind;
 int kgrad(int mode, const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, int64_t N,
           int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float scale,
           float power, float nconst, void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -21,7 +21,7 @@ std::atomic<int64_t> g_launches{0};
 // kernels (one translation unit each)
 int gram_direct(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
                 int64_t ldk, float scale, const float* dim_scale, float power, float nconst, int out_kind,
-                cudaStream_t st);
+                const ExtraKind& ex, cudaStream_t st);
 int gram_tf32x3(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
                 int64_t ldk, float scale, const float* dim_scale, float power, float nconst, void* workspace,
                 size_t workspace_bytes, cudaStream_t st);
@@ -29,20 +29,58 @@ size_t gram_tf32x3_workspace_bytes(int64_t N, int64_t M, int d);
 int kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,
           int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale, const float* dim_scale, float power,
           float nconst, const float* row_pref, const float* col_pref, int row_reduce, int64_t group,
-          void* workspace, size_t workspace_bytes, cudaStream_t st);
+          const ExtraKind& ex, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce, int64_t group);
-bool kmatw_uses_tc(int64_t N, int64_t M, int d, int m, bool has_dim_scale, int row_reduce);
+bool kmatw_uses_tc(int64_t N, int64_t M, int d, int m, bool has_dim_scale, int row_reduce, const ExtraKind& ex);
 int gram_groupsum(const float* X, const float* Y, float* out, int64_t N, int64_t M, int d, int64_t ldx,
                   int64_t ldy, int64_t ldo, float scale, const float* dim_scale, float power, float nconst,
                   const float* row_pref, const float* col_pref, int64_t gx, int64_t gy, int average,
                   void* workspace, size_t workspace_bytes, cudaStream_t st);
 
-static int check_kernel_params(const char* fn, int d, float scale, float power, float nconst) {
+// ---- process-wide options (jrk_set_option) ----
+static std::atomic<int> g_options[JRK_OPT_COUNT_];
+static std::atomic<int> g_options_init{0};
+static const int kOptionDefault[JRK_OPT_COUNT_] = {1, 1, 1, 4, 1};
+static const char* const kOptionEnv[JRK_OPT_COUNT_] = {"JRK_KMATW_TC", "JRK_TC_FAST", "JRK_TC_V2", "JRK_TC2_EPQ", "JRK_GRAM_H16"};
+static void options_init() {
+    // the environment variable of the same name gives the INITIAL value, once per process
+    int expected = 0;
+    if (!g_options_init.compare_exchange_strong(expected, 1)) {
+        while (g_options_init.load() != 2) {}
+        return;
+    }
+    for (int i = 0; i < JRK_OPT_COUNT_; ++i) {
+        const char* e = getenv(kOptionEnv[i]);
+        g_options[i].store(e && *e ? atoi(e) : kOptionDefault[i]);
+    }
+    g_options_init.store(2);
+}
+int jrk_option(int opt) {
+    if (g_options_init.load(std::memory_order_acquire) != 2) options_init();
+    return (opt >= 0 && opt < JRK_OPT_COUNT_) ? g_options[opt].load(std::memory_order_relaxed) : 0;
+}
+
+// Stream-ordered scratch comes from the device's default memory pool, which by default gives everything back to the
+// driver at the next synchronisation: every call would then pay for fresh allocations (hundreds of MB at configs[2];
+// this was the erratic 390 .. 790 ms of round 1's end-to-end K@W).  Keep the pool's memory instead.
+void keep_pool_memory(int device) {
+    static std::atomic<unsigned long long> done{0};
+    if (device < 0 || device >= 64 || (done.load() >> device) & 1ull) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    done.fetch_or(1ull << device);
+}
+
+static int check_kernel_params(const char* fn, int d, float scale, float power, float nconst, bool any_power = false) {
     if (d < 1) return fail(JRK_ERR_INVALID_ARG, "%s: d must be >= 1 (got %d)", fn, d);
     if (!(scale > 0.f) || !std::isfinite(scale))
         return fail(JRK_ERR_INVALID_ARG, "%s: scale must be positive and finite (got %g)", fn, (double)scale);
     // GenGaussKernel.make asserts 0 < shape <= 2 (jaxrk/kern/rbf.py:71); ThreshSpikeKernel takes any positive shape
-    if (!(power > 0.f) || (power > 2.f && g_extra_kind.kind == 0))
+    if (!(power > 0.f) || (power > 2.f && !any_power))
         return fail(JRK_ERR_INVALID_ARG, "%s: power must be in (0, 2] (got %g)", fn, (double)power);
     if (!std::isfinite(nconst)) return fail(JRK_ERR_INVALID_ARG, "%s: nconst must be finite", fn);
     return JRK_OK;
@@ -97,27 +135,45 @@ int jrk_device_count(void) {
 
 int64_t jrk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int jrk_set_option(int option, int value) {
+    if (option < 0 || option >= JRK_OPT_COUNT_) return fail(JRK_ERR_INVALID_ARG, "jrk_set_option: unknown option %d", option);
+    if (option == JRK_OPT_TC2_EPQ && value != 3 && value != 4)
+        return fail(JRK_ERR_INVALID_ARG, "jrk_set_option: JRK_OPT_TC2_EPQ must be 3 or 4");
+    jrk_option(option);   // make sure the defaults are in place
+    g_options[option].store(value);
+    return JRK_OK;
+}
+
+int jrk_get_option(int option) { return jrk_option(option); }
+
 size_t jrk_gram_workspace_bytes(int64_t N, int64_t M, int d, int path) {
     if (resolve_gram_path(path, d, N, M) == JRK_PATH_TF32X3) return gram_tf32x3_workspace_bytes(N, M, d);
     return 0;
 }
 
-int jrk_gram_f32(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
-                 int64_t ldk, float scale, const float* dim_scale, float power, float nconst, int path,
-                 void* workspace, size_t workspace_bytes, void* stream) {
+static int gram_any(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
+                    int64_t ldk, float scale, const float* dim_scale, float power, float nconst, int path,
+                    const ExtraKind& ex, void* workspace, size_t workspace_bytes, void* stream) {
     if (N < 0 || M < 0) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: negative size");
     if (!Y) { Y = X; M = N; ldy = ldx; }
     if (N > 0 && M > 0 && (!X || !K)) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: X and K must not be NULL");
-    if (int rc = check_kernel_params("jrk_gram_f32", d, scale, power, nconst)) return rc;
+    if (int rc = check_kernel_params("jrk_gram_f32", d, scale, power, nconst, ex.kind != 0)) return rc;
     if (ldx < d || ldy < d || ldk < M) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: leading dimension too small");
     if (path < JRK_PATH_AUTO || path > JRK_PATH_TF32X3) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_f32: bad path %d", path);
     if (N == 0 || M == 0) return JRK_OK;
     if (int rc = have_device("jrk_gram_f32")) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (resolve_gram_path(path, d, N, M) == JRK_PATH_TF32X3)
+    if (ex.kind == 0 && resolve_gram_path(path, d, N, M) == JRK_PATH_TF32X3)
         return gram_tf32x3(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, workspace,
                            workspace_bytes, st);
-    return gram_direct(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, 0, st);
+    return gram_direct(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, 0, ex, st);
+}
+
+int jrk_gram_f32(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
+                 int64_t ldk, float scale, const float* dim_scale, float power, float nconst, int path,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+    return gram_any(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, path, ExtraKind(), workspace,
+                    workspace_bytes, stream);
 }
 
 int jrk_dist_f32(const float* X, const float* Y, float* D, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
@@ -129,7 +185,7 @@ int jrk_dist_f32(const float* X, const float* Y, float* D, int64_t N, int64_t M,
     if (ldx < d || ldy < d || ldd < M) return fail(JRK_ERR_INVALID_ARG, "jrk_dist_f32: leading dimension too small");
     if (N == 0 || M == 0) return JRK_OK;
     if (int rc = have_device("jrk_dist_f32")) return rc;
-    return gram_direct(X, Y, D, N, M, d, ldx, ldy, ldd, scale, dim_scale, power, 1.f, 1, (cudaStream_t)stream);
+    return gram_direct(X, Y, D, N, M, d, ldx, ldy, ldd, scale, dim_scale, power, 1.f, 1, ExtraKind(), (cudaStream_t)stream);
 }
 
 int jrk_dist_diag_f32(const float* X, const float* Y, float* out, int64_t N, int d, int64_t ldx, int64_t ldy,
@@ -142,6 +198,11 @@ int jrk_dist_diag_f32(const float* X, const float* Y, float* out, int64_t N, int
     if (int rc = have_device("jrk_dist_diag_f32")) return rc;
     return dist_diag(X, Y, out, N, d, ldx, ldy, scale, dim_scale, power, (cudaStream_t)stream);
 }
+
+static int kmatw_any(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,
+                     int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale, const float* dim_scale, float power,
+                     float nconst, const float* row_pref, const float* col_pref, int row_reduce, int64_t group,
+                     const ExtraKind& ex, void* workspace, size_t workspace_bytes, void* stream);
 
 // kparams -> (scale, power, nconst) of the shared launchers + the sibling-kernel selector
 static int parse_kind(const char* fn, int kind, const float* kp, int n, float& scale, float& power, float& nconst,
@@ -182,9 +243,8 @@ int jrk_gram_kind_f32(const float* X, const float* Y, float* K, int64_t N, int64
         return jrk_gram_f32(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, path, workspace,
                             workspace_bytes, stream);
     if (path == JRK_PATH_TF32X3) return fail(JRK_ERR_UNSUPPORTED, "jrk_gram_kind_f32: sibling kernels use the direct path");
-    ExtraKindScope scope(ex.kind, ex.a0, ex.a1, ex.a2);
-    return jrk_gram_f32(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, JRK_PATH_DIRECT, workspace,
-                        workspace_bytes, stream);
+    return gram_any(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, JRK_PATH_DIRECT, ex, workspace,
+                    workspace_bytes, stream);
 }
 
 int jrk_kmatw_kind_f32(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,
@@ -194,9 +254,8 @@ int jrk_kmatw_kind_f32(const float* X, const float* Y, const float* W, float* ou
     float scale, power, nconst;
     ExtraKind ex;
     if (int rc = parse_kind("jrk_kmatw_kind_f32", kind, kparams, n_kparams, scale, power, nconst, ex)) return rc;
-    ExtraKindScope scope(ex.kind, ex.a0, ex.a1, ex.a2);
-    return jrk_kmatw_f32(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, dim_scale, power, nconst, row_pref,
-                         col_pref, row_reduce, group, workspace, workspace_bytes, stream);
+    return kmatw_any(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, dim_scale, power, nconst, row_pref, col_pref,
+                     row_reduce, group, ex, workspace, workspace_bytes, stream);
 }
 
 size_t jrk_grad_workspace_bytes(int64_t N, int64_t M, int d) { return kgrad_workspace_bytes(N, M, d); }
@@ -233,15 +292,15 @@ size_t jrk_kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_red
 }
 
 int jrk_kmatw_uses_tensor_cores(int64_t N, int64_t M, int d, int m, int has_dim_scale, int row_reduce) {
-    return kmatw_uses_tc(N, M, d, m, has_dim_scale != 0, row_reduce) ? 1 : 0;
+    return kmatw_uses_tc(N, M, d, m, has_dim_scale != 0, row_reduce, ExtraKind()) ? 1 : 0;
 }
 
 static int check_kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d,
                        int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale, float power,
-                       float nconst, int row_reduce, int64_t group) {
+                       float nconst, int row_reduce, int64_t group, bool any_power = false) {
     if (!X || !Y || !W || !out) return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_f32: NULL pointer");
     if (N < 1 || M < 1 || m < 1) return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_f32: N, M, m must be >= 1");
-    if (int rc = check_kernel_params("jrk_kmatw_f32", d, scale, power, nconst)) return rc;
+    if (int rc = check_kernel_params("jrk_kmatw_f32", d, scale, power, nconst, any_power)) return rc;
     if (ldx < d || ldy < d || ldw < m || ldo < m) return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_f32: leading dimension too small");
     if (row_reduce < JRK_REDUCE_NONE || row_reduce > JRK_REDUCE_BALANCED_MEAN)
         return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_f32: bad row_reduce %d", row_reduce);
@@ -257,11 +316,24 @@ int jrk_kmatw_f32(const float* X, const float* Y, const float* W, float* out, in
                   int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale, const float* dim_scale,
                   float power, float nconst, const float* row_pref, const float* col_pref, int row_reduce,
                   int64_t group, void* workspace, size_t workspace_bytes, void* stream) {
-    if (int rc = check_kmatw(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, power, nconst, row_reduce, group)) return rc;
+    return kmatw_any(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, dim_scale, power, nconst, row_pref, col_pref,
+                     row_reduce, group, ExtraKind(), workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+static int kmatw_any(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,
+                     int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale, const float* dim_scale, float power,
+                     float nconst, const float* row_pref, const float* col_pref, int row_reduce, int64_t group,
+                     const ExtraKind& ex, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_kmatw(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, power, nconst, row_reduce, group, ex.kind != 0))
+        return rc;
     if (int rc = have_device("jrk_kmatw_f32")) return rc;
     return kmatw(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, dim_scale, power, nconst, row_pref, col_pref,
-                 row_reduce, group, workspace, workspace_bytes, (cudaStream_t)stream);
+                 row_reduce, group, ex, workspace, workspace_bytes, (cudaStream_t)stream);
 }
+
+extern "C" {
 
 int jrk_gram_groupsum_f32(const float* X, const float* Y, float* out, int64_t N, int64_t M, int d, int64_t ldx,
                           int64_t ldy, int64_t ldo, float scale, const float* dim_scale, float power, float nconst,
@@ -291,6 +363,16 @@ struct DevBuf {
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
     template <typename T> T* as() { return (T*)p; }
 };
+struct DeviceGuard {     // the host-buffer entry points run on `device` and leave the caller's current device alone
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(device) == cudaSuccess;
+        cudaGetLastError();
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 struct StreamGuard {
     cudaStream_t s = nullptr;
     ~StreamGuard() { if (s) cudaStreamDestroy(s); }
@@ -312,7 +394,9 @@ int jrk_gram_f32_host(const float* X, const float* Y, float* K, int64_t N, int64
     if (int rc = check_kernel_params("jrk_gram_f32_host", d, scale, power, nconst)) return rc;
     if (N == 0 || M == 0) return JRK_OK;
     if (int rc = have_device("jrk_gram_f32_host")) return rc;
-    JRK_CUDA_OK(cudaSetDevice(device));
+    DeviceGuard dev_guard(device);
+    if (!dev_guard.ok) return fail(JRK_ERR_CUDA, "jrk_gram_f32_host: cudaSetDevice(%d) failed", device);
+    keep_pool_memory(device);
 
     StreamGuard sc, sd;  // compute / download
     JRK_CUDA_OK(cudaStreamCreateWithFlags(&sc.s, cudaStreamNonBlocking));
@@ -367,7 +451,9 @@ int jrk_kmatw_f32_host(const float* X, const float* Y, const float* W, float* ou
                        const float* col_pref, int row_reduce, int64_t group, int device) {
     if (int rc = check_kmatw(X, Y, W, out, N, M, d, m, d, d, m, m, scale, power, nconst, row_reduce, group)) return rc;
     if (int rc = have_device("jrk_kmatw_f32_host")) return rc;
-    JRK_CUDA_OK(cudaSetDevice(device));
+    DeviceGuard dev_guard(device);
+    if (!dev_guard.ok) return fail(JRK_ERR_CUDA, "jrk_kmatw_f32_host: cudaSetDevice(%d) failed", device);
+    keep_pool_memory(device);
     StreamGuard sc;
     JRK_CUDA_OK(cudaStreamCreateWithFlags(&sc.s, cudaStreamNonBlocking));
     int64_t out_rows = N;

@@ -116,17 +116,16 @@ struct EpiParams {
     float a2;      // THRESHSPIKE: non_spike
 };
 
-// The sibling-kernel entry points (capi.cu) reuse the GenGauss launchers: they set this thread-local selector
-// (RAII: ExtraKindScope) around the call, make_epi / pick_pmode pick it up, and the tensor-core paths refuse it.
+// The sibling-kernel entry points (capi.cu) reuse the GenGauss launchers: the selector travels as an explicit argument
+// (default: GenGauss), make_epi / pick_pmode pick it up, and the tensor-core paths refuse it.
 struct ExtraKind {
     int kind = 0;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 };
-extern thread_local ExtraKind g_extra_kind;
-struct ExtraKindScope {
-    ExtraKindScope(int kind, float a0, float a1, float a2) { g_extra_kind.kind = kind; g_extra_kind.a0 = a0; g_extra_kind.a1 = a1; g_extra_kind.a2 = a2; }
-    ~ExtraKindScope() { g_extra_kind = ExtraKind(); }
-};
+
+// Process-wide switches of the library (include/jrk.h: jrk_set_option / JRK_OPT_*), read once per call from an atomic;
+// the environment variable of the same name only provides the initial value at first use.
+int jrk_option(int opt);
 
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -159,17 +158,17 @@ __device__ __forceinline__ float kexp_unnorm(float sq, const EpiParams& e) {
     }
 }
 
-inline int pick_pmode(float power) {
-    if (g_extra_kind.kind != 0) return PM_EXTRA;
+inline int pick_pmode(float power, const ExtraKind& ex = ExtraKind()) {
+    if (ex.kind != 0) return PM_EXTRA;
     if (power == 2.0f) return PM_SQEXP;
     if (power == 1.0f) return PM_LAPLACE;
     return PM_GENERAL;
 }
 
-inline EpiParams make_epi(float scale, float power, float nconst) {
+inline EpiParams make_epi(float scale, float power, float nconst, const ExtraKind& ex = ExtraKind()) {
     EpiParams e;
     double s = (double)scale;
-    int pm = pick_pmode(power);
+    int pm = pick_pmode(power, ex);
     if (pm == PM_EXTRA) pm = (power == 2.0f) ? PM_SQEXP : (power == 1.0f) ? PM_LAPLACE : PM_GENERAL;   // e.c unused
     if (pm == PM_SQEXP) e.c = (float)(-s * s * 1.4426950408889634);
     else if (pm == PM_LAPLACE) e.c = (float)(-s * 1.4426950408889634);
@@ -178,10 +177,10 @@ inline EpiParams make_epi(float scale, float power, float nconst) {
     e.nconst = nconst;
     e.s = scale;
     e.p = power;
-    e.kind = g_extra_kind.kind;
-    e.a0 = g_extra_kind.a0;
-    e.a1 = g_extra_kind.a1;
-    e.a2 = g_extra_kind.a2;
+    e.kind = ex.kind;
+    e.a0 = ex.a0;
+    e.a1 = ex.a1;
+    e.a2 = ex.a2;
     return e;
 }
 

@@ -132,9 +132,9 @@ int dist_diag(const float* X, const float* Y, float* out, int64_t N, int d, int6
 // slabs so that gridDim.y stays within limits for N up to 2^31.
 int gram_direct(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
                 int64_t ldk, float scale, const float* dim_scale, float power, float nconst, int out_kind,
-                cudaStream_t st) {
-    EpiParams ep = make_epi(scale, power, nconst);
-    const int pm = pick_pmode(power);
+                const ExtraKind& ex, cudaStream_t st) {
+    EpiParams ep = make_epi(scale, power, nconst, ex);
+    const int pm = pick_pmode(power, ex);
     const int64_t slab = (int64_t)65535 * GD_BM;
     for (int64_t r = 0; r < N; r += slab) {
         int64_t n = (N - r < slab) ? N - r : slab;

@@ -7,7 +7,7 @@ namespace jrk {
 
 int gram_direct(const float* X, const float* Y, float* K, int64_t N, int64_t M, int d, int64_t ldx, int64_t ldy,
                 int64_t ldk, float scale, const float* dim_scale, float power, float nconst, int out_kind,
-                cudaStream_t st);
+                const ExtraKind& ex, cudaStream_t st);
 
 namespace tf32 {
 
@@ -128,11 +128,10 @@ __global__ void tf_norm_kernel(const float* __restrict__ A, int64_t rows, int64_
 
 // d <= 16: tf32 operands padded to 32 columns; above: fp16 hi / lo operands padded to 64 / 128 (measured, 65536^2:
 // d = 16 tf32 3.05 vs fp16 3.09 ms, d = 32 tf32 3.22 vs fp16 3.13 ms, d = 64 tf32 3.86 vs fp16 3.40 ms).  Zero k-steps
-// are skipped in both forms.  JRK_GRAM_H16=0 selects tf32 operands for d <= 64 (A/B comparison).
+// are skipped in both forms.  JRK_OPT_GRAM_H16 = 0 selects tf32 operands for d <= 64 (A/B comparison).
 inline bool tf_use_h16(int d) {
     if (d <= 16) return false;
-    const char* e = getenv("JRK_GRAM_H16");
-    return !(e && e[0] == '0' && d <= 64);
+    return !(jrk_option(JRK_OPT_GRAM_H16) == 0 && d <= 64);
 }
 inline int tf_dp(int d) { return tf_use_h16(d) ? (d <= 64 ? 64 : 128) : (d <= 32 ? 32 : 64); }
 inline bool tf_usable_in_place(const float* A, int64_t lda, int d, int DP, const float* dim_scale) {
@@ -158,7 +157,7 @@ int gram_tf32x3(const float* X, const float* Y, float* K, int64_t N, int64_t M, 
     // d > 128 does not fit the TMEM-resident A operand of this kernel: served by direct differencing
     // (so is an output pitch beyond the kernel's 32-bit row offsets)
     if (d > 128 || ldk >= (1LL << 24))
-        return gram_direct(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, 0, st);
+        return gram_direct(X, Y, K, N, M, d, ldx, ldy, ldk, scale, dim_scale, power, nconst, 0, ExtraKind(), st);
     const int DP = tf_dp(d);
     const bool x_ok = tf_usable_in_place(X, ldx, d, DP, dim_scale);
     const bool y_ok = tf_usable_in_place(Y, ldy, d, DP, dim_scale);

@@ -23,6 +23,7 @@
 #include "common.cuh"
 
 namespace jrk {
+namespace tf32 { int tf_sm_count(); }
 
 namespace {
 
@@ -193,16 +194,7 @@ int kg_launch(dim3 grid, cudaStream_t st, const float* X, int64_t ldx, const flo
     return JRK_OK;
 }
 
-int kg_sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+int kg_sm_count() { return tf32::tf_sm_count(); }   // per-device cache (gram_tf32.cu)
 
 struct KgPlan {
     int nsplit;
@@ -233,7 +225,6 @@ int kgrad(int mode, const float* X, const float* Y, const float* W, const float*
           int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float scale,
           float power, float nconst, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (d > 64) return fail(JRK_ERR_UNSUPPORTED, "kgrad: d = %d > 64 is not supported by the fused backward kernel", d);
-    if (g_extra_kind.kind != 0) return fail(JRK_ERR_UNSUPPORTED, "kgrad: GenGauss kernels only");
     const EpiParams ep = make_epi(scale, power, nconst);
     const int pm = pick_pmode(power);
     const KgPlan p = kg_plan(N, M);

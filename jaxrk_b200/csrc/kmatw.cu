@@ -130,10 +130,11 @@ size_t kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce,
 static int kmatw_block(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d,
                        int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale,
                        const float* dim_scale, float power, float nconst, const float* row_pref,
-                       const float* col_pref, int row_reduce, int64_t group, Scratch& scr, cudaStream_t st) {
+                       const float* col_pref, int row_reduce, int64_t group, const ExtraKind& ex, Scratch& scr,
+                       cudaStream_t st) {
     const KwPlan p = kw_plan(N, M, d, m);
-    const EpiParams ep = make_epi(scale, power, nconst);
-    const int pm = pick_pmode(power);
+    const EpiParams ep = make_epi(scale, power, nconst, ex);
+    const int pm = pick_pmode(power, ex);
 
     // ---- operands: dense, padded, pre-scaled copies where the caller's layout differs -----
     const float* Yp = Y;
@@ -203,11 +204,11 @@ static int kmatw_block(const float* X, const float* Y, const float* W, float* ou
     return JRK_OK;
 }
 
-// The dispatch rule, in one place (also behind jrk_kmatw_uses_tensor_cores): JRK_KMATW_TC=0 forces the FP32-pipe kernel.
-bool kmatw_uses_tc(int64_t N, int64_t M, int d, int m, bool has_dim_scale, int row_reduce) {
-    const char* e = getenv("JRK_KMATW_TC");
-    if (e && e[0] == '0') return false;
-    if (g_extra_kind.kind != 0) return false;   // sibling kernels: FP32-pipe kernel only
+// The dispatch rule, in one place (also behind jrk_kmatw_uses_tensor_cores): JRK_OPT_KMATW_TC = 0 forces the FP32-pipe
+// kernel.  Wide W (16 < m <= TC_WIDE_M_MAX) runs on the tensor cores too, in column blocks of 16.
+bool kmatw_uses_tc(int64_t N, int64_t M, int d, int m, bool has_dim_scale, int row_reduce, const ExtraKind& ex) {
+    if (jrk_option(JRK_OPT_KMATW_TC) == 0) return false;
+    if (ex.kind != 0) return false;   // sibling kernels: FP32-pipe kernel only
     static const float dummy = 1.f;
     return kmatw_tc_eligible(N, M, d, m, has_dim_scale ? &dummy : nullptr, row_reduce, 1.f);
 }
@@ -215,10 +216,10 @@ bool kmatw_uses_tc(int64_t N, int64_t M, int d, int m, bool has_dim_scale, int r
 int kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,
           int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale, const float* dim_scale, float power,
           float nconst, const float* row_pref, const float* col_pref, int row_reduce, int64_t group,
-          void* workspace, size_t workspace_bytes, cudaStream_t st) {
+          const ExtraKind& ex, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (d > 128) return fail(JRK_ERR_UNSUPPORTED, "kmatw: d = %d > 128 not supported by the fused kernel", d);
     // both contractions on the tensor cores when the problem is large, narrow and plain (kmatw_tc.cu)
-    if (kmatw_uses_tc(N, M, d, m, dim_scale != nullptr, row_reduce))
+    if (kmatw_uses_tc(N, M, d, m, dim_scale != nullptr, row_reduce, ex))
         return kmatw_tc(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, power, nconst, row_pref, col_pref,
                         row_reduce, workspace, workspace_bytes, st);
     Scratch scr(workspace, workspace_bytes, st);
@@ -227,7 +228,7 @@ int kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N,
         const int mb = (m - c0 < 32) ? m - c0 : 32;
         scr.used = 0;
         int rc = kmatw_block(X, Y, W + c0, out + c0, N, M, d, mb, ldx, ldy, ldw, ldo, scale, dim_scale, power,
-                             nconst, row_pref, col_pref, row_reduce, group, scr, st);
+                             nconst, row_pref, col_pref, row_reduce, group, ex, scr, st);
         if (rc) return rc;
     }
     return JRK_OK;

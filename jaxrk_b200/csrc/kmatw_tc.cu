@@ -740,80 +740,112 @@ bool kmatw_tc_eligible(int64_t N, int64_t M, int d, int m, const float* dim_scal
     (void)nconst;
     // Sum / Mean over rows: the N x m result goes to scratch and is reduced in a fixed order (tc_rowsum_kernel)
     if (dim_scale || !(row_reduce == JRK_REDUCE_NONE || row_reduce == JRK_REDUCE_SUM || row_reduce == JRK_REDUCE_MEAN)) return false;
-    if (d < 1 || d > TC_DP || m < 1 || m > TC_MT) return false;
+    // wide W runs in column blocks of 16: one MUFU-bound pass per block, still ~2.5x the FP32-pipe kernel's 32 columns
+    if (d < 1 || d > TC_DP || m < 1) return false;
     // enough row blocks to fill the machine and enough columns to amortise the pre-pass
     return N >= (int64_t)TC_BM * 64 && M >= 4096 && M <= ((int64_t)1 << 30) && N <= ((int64_t)1 << 36);
 }
 
 constexpr int64_t TC_RS_CHUNK = 1024;    // rows per partial sum of the Sum / Mean reduction
 
-size_t kmatw_tc_workspace_bytes(int64_t N, int64_t M) {
+// ---- the Y / W side (what a plan keeps: jrk_kmatw_plan_*) and the X side (what an apply needs) ----
+size_t kmatw_tc_prep_bytes(int64_t M, int d) {
     const int64_t n_tiles = (M + TC_NT - 1) / TC_NT;
-    const size_t reduce_bytes = align256((size_t)N * TC_MT * 4) + align256((size_t)((N + TC_RS_CHUNK - 1) / TC_RS_CHUNK) * TC_MT * 4);
-    return reduce_bytes + align256((size_t)n_tiles * tc_image(TC_DP).bytes) + align256((size_t)N * 4) + align256((size_t)M * 4) + 1024;
+    return align256((size_t)n_tiles * tc_image(d).bytes) + align256((size_t)M * 4) + 256;
+}
+size_t kmatw_tc_apply_bytes(int64_t N) {
+    return align256((size_t)N * TC_MT * 4) + align256((size_t)((N + TC_RS_CHUNK - 1) / TC_RS_CHUNK) * TC_MT * 4) +
+           align256((size_t)N * 4) + 256;
+}
+size_t kmatw_tc_workspace_bytes(int64_t N, int64_t M) { return kmatw_tc_prep_bytes(M, TC_DP) + kmatw_tc_apply_bytes(N) + 1024; }
+
+struct TcPrep {            // device pointers into the prep buffer
+    unsigned char* img;    // tile images: second generation (factored regime) or first generation, decided on the device
+    float* yn_all;         // mult |y_j|^2
+    unsigned* ymax;        // [2] bit patterns: max |mult| |y|^2, max |W col_pref|
+};
+static TcPrep tc_prep_layout(void* buf, int64_t M, int d) {
+    const int64_t n_tiles = (M + TC_NT - 1) / TC_NT;
+    char* b = (char*)buf;
+    TcPrep p;
+    p.img = (unsigned char*)b;
+    b += align256((size_t)n_tiles * tc_image(d).bytes);
+    p.yn_all = (float*)b;
+    b += align256((size_t)M * 4);
+    p.ymax = (unsigned*)b;
+    return p;
 }
 
-int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
-             int64_t ldy, int64_t ldw, int64_t ldo, float scale, float power, float nconst, const float* row_pref,
-             const float* col_pref, int row_reduce, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    Scratch scr(workspace, workspace_bytes, st);
-    JRK_CUDA_OK(scr.reserve(kmatw_tc_workspace_bytes(N, M)));
+static int tc_allow_fast(int pm) {
+    int allow_fast = (pm == PM_SQEXP) && jrk_option(JRK_OPT_TC_FAST) != 0;
+    if (allow_fast && jrk_option(JRK_OPT_TC_V2) != 0) allow_fast = 2;
+    return allow_fast;
+}
+
+// Y-side pre-pass: row norms of Y, their maximum, max |W col_pref| and the tile images.
+//   which & 1: first-generation image (generic epilogue; and the factored regime when JRK_OPT_TC_V2 = 0) into pr.img
+//   which & 2: second-generation image (factored regime) into pr.img
+// Each pack kernel decides on the device, from nmax4, whether the image is its to write; with both bits set exactly one
+// of them writes.  nmax_x == nullptr (plan creation): the x maximum counts as zero, i.e. the second-generation image is
+// written whenever Y ALONE is inside the regime.
+static int tc_prepare(const float* Y, const float* W, int64_t M, int d, int m, int64_t ldy, int64_t ldw, const float* col_pref,
+                      const EpiParams& ep, int pm, const TcPrep& pr, const unsigned* nmax_x, unsigned* nmax4, int which,
+                      cudaStream_t st) {
     const int64_t n_tiles = (M + TC_NT - 1) / TC_NT;
     const TcImage L = tc_image(d);
-    unsigned char* img = scr.take<unsigned char>((size_t)n_tiles * L.bytes);
-    float* xn = scr.take<float>((size_t)N);
-    float* yn_all = scr.take<float>((size_t)M);
-    unsigned* nmax = scr.take<unsigned>(4);       // max |c||x|^2, max |c||y|^2, max |W col_pref| (kmatw_tc2.cu)
+    const float mult = (pm == PM_SQEXP) ? ep.c : 1.f;
+    const float a_scale = (pm == PM_SQEXP) ? -2.f * ep.c : -2.f;
+    const int allow_fast = tc_allow_fast(pm);
+    // nmax4 = {max |c||x|^2 (copied or zero), max |c||y|^2, max |W col_pref|, -}
+    JRK_CUDA_OK(cudaMemsetAsync(nmax4, 0, 4 * sizeof(unsigned), st));
+    if (nmax_x) JRK_CUDA_OK(cudaMemcpyAsync(nmax4, nmax_x, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    tc_rownorm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(Y, M, M, d, ldy, mult, pr.yn_all, nmax4 + 1);
+    JRK_LAUNCHED();
+    if (which & 1) {
+        const int64_t tot = n_tiles * (TC_NT * L.ypieces + 256);
+        tc_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, col_pref, (int)n_tiles, mult, L, pr.img,
+                                                                      allow_fast, a_scale, pr.yn_all, nmax4, 1.f / fabsf(mult));
+        JRK_LAUNCHED();
+    }
+    if ((which & 2) && allow_fast == 2) {
+        if (int rc = kmatw_tc2_pack(Y, W, M, d, m, ldy, ldw, col_pref, ep.c, pr.yn_all, nmax4, pr.img, st)) return rc;
+    } else {
+        // max |W col_pref| is part of the prepared state either way
+        if (int rc = kmatw_tc2_wmax(W, M, m, ldw, col_pref, nmax4, st)) return rc;
+    }
+    JRK_CUDA_OK(cudaMemcpyAsync(pr.ymax, nmax4 + 1, 2 * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    return JRK_OK;
+}
+
+// X-side: both generations of the main kernel (each returns at once outside its regime), then the optional Sum / Mean
+// over rows.  nmax4 = {max |c||x|^2, max |c||y|^2, max |W col_pref|}; img2 / img1: second- / first-generation images.
+static int tc_apply(const float* X, const float* Y, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx, int64_t ldy,
+                    int64_t ldo, const EpiParams& ep, int pm, float nconst, const float* row_pref, int row_reduce,
+                    const unsigned char* img2, const unsigned char* img1, const float* xn, const unsigned* nmax4, float* Tbuf,
+                    float* rpart, cudaStream_t st) {
+    const int64_t n_tiles = (M + TC_NT - 1) / TC_NT;
+    const TcImage L = tc_image(d);
+    const float mult = (pm == PM_SQEXP) ? ep.c : 1.f;
     const bool reduce_rows = row_reduce == JRK_REDUCE_SUM || row_reduce == JRK_REDUCE_MEAN;
     const int64_t nchunks = (N + TC_RS_CHUNK - 1) / TC_RS_CHUNK;
-    float* Tbuf = reduce_rows ? scr.take<float>((size_t)N * TC_MT) : nullptr;
-    float* rpart = reduce_rows ? scr.take<float>((size_t)nchunks * TC_MT) : nullptr;
-
-    EpiParams ep = make_epi(scale, power, nconst);
-    const int pm = pick_pmode(power);
-    if (pm == PM_EXTRA) return fail(JRK_ERR_UNSUPPORTED, "kmatw_tc: sibling kernels use the FP32-pipe kernel");
-    const float mult = (pm == PM_SQEXP) ? ep.c : 1.f;
-    JRK_CUDA_OK(cudaMemsetAsync(nmax, 0, 2 * sizeof(unsigned), st));
-    const float a_scale = (pm == PM_SQEXP) ? -2.f * ep.c : -2.f;
-    const char* fast_env = getenv("JRK_TC_FAST");
-    const char* v2_env = getenv("JRK_TC_V2");
-    int allow_fast = (pm == PM_SQEXP) && !(fast_env && fast_env[0] == '0');
-    if (allow_fast && !(v2_env && v2_env[0] == '0')) allow_fast = 2;
-    {
-        // scaled row norms and their maxima first: the pack kernel and the main kernel both decide from the maxima
-        // (on the device, no host synchronisation) whether the factored p = 2 path applies
-        tc_rownorm_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(X, N, N, d, ldx, mult, xn, nmax);
-        JRK_LAUNCHED();
-        tc_rownorm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(Y, M, M, d, ldy, mult, yn_all, nmax + 1);
-        JRK_LAUNCHED();
-        const int64_t tot = n_tiles * (TC_NT * L.ypieces + 256);
-        tc_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, col_pref, (int)n_tiles, mult, L, img,
-                                                                      allow_fast, a_scale, yn_all, nmax, 1.f / fabsf(mult));
-        JRK_LAUNCHED();
-        if (allow_fast == 2) {
-            if (getenv("JRK_TC_DEBUG_SYNC")) { cudaError_t e = cudaStreamSynchronize(st); fprintf(stderr, "[tc] v1 pre-pass done: %s\n", cudaGetErrorString(e)); }
-            if (int rc2 = kmatw_tc2_pack(Y, W, M, d, m, ldy, ldw, col_pref, ep.c, yn_all, nmax, img, st)) return rc2;
-            if (getenv("JRK_TC_DEBUG_SYNC")) { cudaError_t e = cudaStreamSynchronize(st); fprintf(stderr, "[tc] v2 pack done: %s\n", cudaGetErrorString(e)); }
-        }
-    }
+    const int allow_fast = tc_allow_fast(pm);
     TcParams P;
-    P.X = X; P.ldx = ldx; P.d = d; P.Y = Y; P.ldy = ldy; P.xn = xn; P.img = img; P.L = L; P.row_pref = row_pref;
+    P.X = X; P.ldx = ldx; P.d = d; P.Y = Y; P.ldy = ldy; P.xn = xn; P.img = img1; P.L = L; P.row_pref = row_pref;
     P.out = reduce_rows ? Tbuf : out; P.ldo = reduce_rows ? TC_MT : ldo; P.m = reduce_rows ? TC_MT : m; P.N = N; P.M = M;
     P.n_tiles = (int)n_tiles;
     P.n_units = (int)((N + TC_BM - 1) / TC_BM);
     P.ksteps = (d + 7) / 8;
-    P.a = a_scale;
+    P.a = (pm == PM_SQEXP) ? -2.f * ep.c : -2.f;
     P.allow_fast = allow_fast;
     P.inv_abs_mult = 1.f / fabsf(mult);
     // p = 2: the near-zero test only matters when the norms are large against the length scale; the kernel decides
     // from the device-side maxima of the pre-pass (no host synchronisation)
     P.check = 0;
-    P.nmax = nmax;
-    int rc;
+    P.nmax = nmax4;
     if (allow_fast == 2) {
-        if (int rc2 = kmatw_tc2_apply(X, N, d, ldx, xn, img, M, nmax, ep.c, nconst, row_pref, P.out, P.ldo, P.m, st)) return rc2;
-        if (getenv("JRK_TC_DEBUG_SYNC")) { cudaError_t e = cudaStreamSynchronize(st); fprintf(stderr, "[tc] v2 kernel done: %s\n", cudaGetErrorString(e)); }
+        if (int rc = kmatw_tc2_apply(X, N, d, ldx, xn, img2, M, nmax4, ep.c, nconst, row_pref, P.out, P.ldo, P.m, st)) return rc;
     }
+    int rc;
     if (pm == PM_SQEXP) rc = tc_launch<PM_SQEXP>(P, ep, st);
     else if (pm == PM_LAPLACE) rc = tc_launch<PM_LAPLACE>(P, ep, st);
     else rc = tc_launch<PM_GENERAL>(P, ep, st);
@@ -822,6 +854,107 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
     JRK_LAUNCHED();
     tc_rowsum_final_kernel<<<1, 32, 0, st>>>(rpart, nchunks, row_reduce == JRK_REDUCE_MEAN ? 1.f / (float)N : 1.f, out, m);
     JRK_LAUNCHED();
+    return JRK_OK;
+}
+
+int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
+             int64_t ldy, int64_t ldw, int64_t ldo, float scale, float power, float nconst, const float* row_pref,
+             const float* col_pref, int row_reduce, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    Scratch scr(workspace, workspace_bytes, st);
+    JRK_CUDA_OK(scr.reserve(kmatw_tc_workspace_bytes(N, M)));
+    const TcPrep pr = tc_prep_layout(scr.take<char>(kmatw_tc_prep_bytes(M, d)), M, d);
+    float* xn = scr.take<float>((size_t)N);
+    unsigned* nmax_x = scr.take<unsigned>(4);
+    unsigned* nmax4 = scr.take<unsigned>(4);
+    const bool reduce_rows = row_reduce == JRK_REDUCE_SUM || row_reduce == JRK_REDUCE_MEAN;
+    float* Tbuf = reduce_rows ? scr.take<float>((size_t)N * TC_MT) : nullptr;
+    float* rpart = reduce_rows ? scr.take<float>((size_t)((N + TC_RS_CHUNK - 1) / TC_RS_CHUNK) * TC_MT) : nullptr;
+
+    const EpiParams ep = make_epi(scale, power, nconst);
+    const int pm = pick_pmode(power);
+    const float mult = (pm == PM_SQEXP) ? ep.c : 1.f;
+    JRK_CUDA_OK(cudaMemsetAsync(nmax_x, 0, 4 * sizeof(unsigned), st));
+    tc_rownorm_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(X, N, N, d, ldx, mult, xn, nmax_x);
+    JRK_LAUNCHED();
+    for (int c0 = 0; c0 < m; c0 += TC_MT) {     // wide W: column blocks of 16 (e is recomputed per block)
+        const int mb = (m - c0 < TC_MT) ? m - c0 : TC_MT;
+        if (int rc = tc_prepare(Y, W + c0, M, d, mb, ldy, ldw, col_pref, ep, pm, pr, nmax_x, nmax4, 3, st)) return rc;
+        if (int rc = tc_apply(X, Y, out + c0, N, M, d, mb, ldx, ldy, ldo, ep, pm, nconst, row_pref, row_reduce, pr.img, pr.img, xn,
+                              nmax4, Tbuf, rpart, st))
+            return rc;
+    }
+    return JRK_OK;
+}
+
+// ---- plan support (kmatw_plan.cu): the Y / W side is prepared once, every apply only brings X ----
+// The plan keeps, per 16-column block of W, the second-generation tile images (packed with the x maximum taken as zero:
+// valid whenever the pair (X, Y) is inside the factored regime), the scaled norms of Y and the two maxima.  An apply
+// whose X pushes the pair out of that regime -- or a kernel outside it (p != 2, large norms) -- packs first-generation
+// images into its own scratch, on the device's own decision: nothing is read back, nothing synchronises.
+size_t kmatw_tc_plan_prep_bytes(int64_t M, int d, int m) { return (size_t)((m + TC_MT - 1) / TC_MT) * kmatw_tc_prep_bytes(M, d); }
+size_t kmatw_tc_plan_apply_bytes(int64_t N, int64_t M, int d) { return kmatw_tc_apply_bytes(N) + kmatw_tc_prep_bytes(M, d) + 2048; }
+
+int kmatw_tc_plan_prepare(const float* Y, const float* W, int64_t M, int d, int m, int64_t ldy, int64_t ldw,
+                          const float* col_pref, float scale, float power, float nconst, void* prep, unsigned* nmax4_scratch,
+                          cudaStream_t st) {
+    const EpiParams ep = make_epi(scale, power, nconst);
+    const int pm = pick_pmode(power);
+    const size_t per = kmatw_tc_prep_bytes(M, d);
+    int b = 0;
+    for (int c0 = 0; c0 < m; c0 += TC_MT, ++b) {
+        const int mb = (m - c0 < TC_MT) ? m - c0 : TC_MT;
+        const TcPrep pr = tc_prep_layout((char*)prep + (size_t)b * per, M, d);
+        if (int rc = tc_prepare(Y, W + c0, M, d, mb, ldy, ldw, col_pref, ep, pm, pr, nullptr, nmax4_scratch, 2, st)) return rc;
+    }
+    return JRK_OK;
+}
+
+// nmax4 = {x maximum, y maximum, W maximum} of one column block
+__global__ void tc_plan_nmax_kernel(const unsigned* nmax_x, const unsigned* ymax, unsigned* nmax4) {
+    nmax4[0] = nmax_x[0]; nmax4[1] = ymax[0]; nmax4[2] = ymax[1]; nmax4[3] = 0u;
+}
+
+int kmatw_tc_plan_apply(const float* X, const float* Y, const float* W, const float* col_pref, const void* prep, float* out,
+                        int64_t N, int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale,
+                        float power, float nconst, const float* row_pref, int row_reduce, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st) {
+    Scratch scr(workspace, workspace_bytes, st);
+    JRK_CUDA_OK(scr.reserve(kmatw_tc_plan_apply_bytes(N, M, d)));
+    const TcPrep own = tc_prep_layout(scr.take<char>(kmatw_tc_prep_bytes(M, d)), M, d);   // first-generation image, if needed
+    float* xn = scr.take<float>((size_t)N);
+    unsigned* nmax_x = scr.take<unsigned>(4);
+    unsigned* nmax4 = scr.take<unsigned>(4);
+    const bool reduce_rows = row_reduce == JRK_REDUCE_SUM || row_reduce == JRK_REDUCE_MEAN;
+    float* Tbuf = reduce_rows ? scr.take<float>((size_t)N * TC_MT) : nullptr;
+    float* rpart = reduce_rows ? scr.take<float>((size_t)((N + TC_RS_CHUNK - 1) / TC_RS_CHUNK) * TC_MT) : nullptr;
+    const EpiParams ep = make_epi(scale, power, nconst);
+    const int pm = pick_pmode(power);
+    const float mult = (pm == PM_SQEXP) ? ep.c : 1.f;
+    const float a_scale = (pm == PM_SQEXP) ? -2.f * ep.c : -2.f;
+    const int allow_fast = tc_allow_fast(pm);
+    const int64_t n_tiles = (M + TC_NT - 1) / TC_NT;
+    const TcImage L = tc_image(d);
+    JRK_CUDA_OK(cudaMemsetAsync(nmax_x, 0, 4 * sizeof(unsigned), st));
+    tc_rownorm_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(X, N, N, d, ldx, mult, xn, nmax_x);
+    JRK_LAUNCHED();
+    const size_t per = kmatw_tc_prep_bytes(M, d);
+    int b = 0;
+    for (int c0 = 0; c0 < m; c0 += TC_MT, ++b) {
+        const int mb = (m - c0 < TC_MT) ? m - c0 : TC_MT;
+        const TcPrep pr = tc_prep_layout((char*)prep + (size_t)b * per, M, d);
+        tc_plan_nmax_kernel<<<1, 1, 0, st>>>(nmax_x, pr.ymax, nmax4);
+        JRK_LAUNCHED();
+        // first-generation image into the apply's scratch: the pack kernel returns at once when the second-generation
+        // kernel serves the regime (allow_fast == 2)
+        const int64_t tot = n_tiles * (TC_NT * L.ypieces + 256);
+        tc_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W + c0, mb, ldw, col_pref, (int)n_tiles, mult, L,
+                                                                      own.img, allow_fast, a_scale, pr.yn_all, nmax4,
+                                                                      1.f / fabsf(mult));
+        JRK_LAUNCHED();
+        if (int rc = tc_apply(X, Y, out + c0, N, M, d, mb, ldx, ldy, ldo, ep, pm, nconst, row_pref, row_reduce, pr.img, own.img, xn,
+                              nmax4, Tbuf, rpart, st))
+            return rc;
+    }
     return JRK_OK;
 }
 

@@ -578,14 +578,19 @@ int tc2_image_bytes(int d) { return d <= 16 ? 8192 : 12288; }
 
 // W maximum (nmax[2]) + tile images of the factored regime.  nmax[0..1] (norm maxima) and yn_all must already be
 // enqueued on `st`.  Both kernels return at once outside the factored regime.
+int kmatw_tc2_wmax(const float* W, int64_t M, int m, int64_t ldw, const float* col_pref, unsigned* nmax, cudaStream_t st) {
+    JRK_CUDA_OK(cudaMemsetAsync(nmax + 2, 0, sizeof(unsigned), st));
+    tc2_wmax_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(W, M, m, ldw, col_pref, nmax + 2);
+    JRK_LAUNCHED();
+    return JRK_OK;
+}
+
 int kmatw_tc2_pack(const float* Y, const float* W, int64_t M, int d, int m, int64_t ldy, int64_t ldw,
                    const float* col_pref, float c, const float* yn_all, unsigned* nmax, unsigned char* img,
                    cudaStream_t st) {
     const int64_t n_tiles = (M + T2_NT - 1) / T2_NT;
     const int img_bytes = tc2_image_bytes(d);
-    JRK_CUDA_OK(cudaMemsetAsync(nmax + 2, 0, sizeof(unsigned), st));
-    tc2_wmax_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(W, M, m, ldw, col_pref, nmax + 2);
-    JRK_LAUNCHED();
+    if (int rc = kmatw_tc2_wmax(W, M, m, ldw, col_pref, nmax, st)) return rc;
     const Tc2Scales sc = tc2_scales(c);
     const int64_t tot = n_tiles * (img_bytes >> 4);
     tc2_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, col_pref, (int)n_tiles, img, img_bytes,
@@ -608,8 +613,7 @@ int kmatw_tc2_apply(const float* X, int64_t N, int d, int64_t ldx, const float* 
     P.trace = g_tc2_trace;
     const int grid = P.n_units < tf_sm_count() ? P.n_units : tf_sm_count();
     // epilogue warps per SM sub-partition: 4; JRK_TC2_EPQ = 3 for A/B runs
-    int epq = 4;
-    if (const char* e = getenv("JRK_TC2_EPQ")) epq = atoi(e);
+    const int epq = jrk_option(JRK_OPT_TC2_EPQ);
 #define T2_LAUNCH(EPQ_, WIDE_, TRACE_)                                                                               \
     do {                                                                                                             \
         JRK_CUDA_OK(cudaFuncSetAttribute(kmatw_tc2_kernel<EPQ_, WIDE_, TRACE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

@@ -43,6 +43,9 @@ inline Tc2Scales tc2_scales(float c) {
 
 int tc2_image_bytes(int d);
 
+// nmax[2] = max |W col_pref|
+int kmatw_tc2_wmax(const float* W, int64_t M, int m, int64_t ldw, const float* col_pref, unsigned* nmax, cudaStream_t st);
+
 // W maximum (nmax[2]) and the tile images of the factored regime.  nmax[0..1] (norm maxima, tc_rownorm_kernel) and
 // yn_all (c |y_j|^2) must already be enqueued on `st`.  The kernels return at once outside the factored regime.
 int kmatw_tc2_pack(const float* Y, const float* W, int64_t M, int d, int m, int64_t ldy, int64_t ldw,

@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(raw, n), f"{n} declared in include/jrk.h but not exported"
         assert n in nat.SIGNATURES, f"{n} has no ctypes signature in jaxrk_b200/_native.py"
     assert sorted(nat.SIGNATURES) == names
-    assert nat.lib().jrk_abi_version() == 2
+    assert nat.lib().jrk_abi_version() == nat.ABI_VERSION == 3
 
 
 def test_sm100a_code_is_embedded():
@@ -113,3 +113,42 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     with pytest.raises(ImportError) as e:
         nat.lib()
     assert "no CPU or eager fallback" in str(e.value)
+
+
+def test_options_are_explicit_process_state_not_environment_reads():
+    """jrk_set_option / jrk_get_option (ABI 3): defaults, validation, and no getenv on the compute paths (the
+    environment only seeds the initial value, in capi.cu)."""
+    L = nat.lib()
+    assert nat.get_option(nat.OPT_KMATW_TC) in (0, 1)
+    prev = nat.set_option(nat.OPT_TC2_EPQ, 3)
+    assert nat.get_option(nat.OPT_TC2_EPQ) == 3
+    nat.set_option(nat.OPT_TC2_EPQ, prev)
+    assert L.jrk_set_option(99, 1) == 1 and "unknown option" in nat.last_error()
+    assert L.jrk_set_option(nat.OPT_TC2_EPQ, 7) == 1
+    with nat.option(nat.OPT_GRAM_H16, 0):
+        assert nat.get_option(nat.OPT_GRAM_H16) == 0
+    assert nat.get_option(nat.OPT_GRAM_H16) == 1
+    csrc = os.path.join(ROOT, "jaxrk_b200", "csrc")
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cuh")) and f != "capi.cu":
+            assert "getenv" not in open(os.path.join(csrc, f)).read(), f"{f} reads the environment"
+    assert "thread_local ExtraKind" not in open(os.path.join(csrc, "capi.cu")).read()
+
+
+def test_plan_argument_validation_and_lifetime_without_a_device():
+    L = nat.lib()
+    h = ctypes.c_void_p()
+    p = ctypes.c_void_p(256)
+    assert L.jrk_kmatw_plan_create(None, p, p, 8, 2, 1, 2, 1, 1.0, None, 2.0, 1.0, None, 1, 0, None) == 1
+    assert L.jrk_kmatw_plan_create(ctypes.byref(h), None, p, 8, 2, 1, 2, 1, 1.0, None, 2.0, 1.0, None, 1, 0, None) == 1
+    assert L.jrk_kmatw_plan_create(ctypes.byref(h), p, p, 8, 2, 1, 1, 1, 1.0, None, 2.0, 1.0, None, 1, 0, None) == 1      # ldy < d
+    assert L.jrk_kmatw_plan_create(ctypes.byref(h), p, p, 8, 2, 1, 2, 1, 1.0, None, 2.5, 1.0, None, 1, 0, None) == 1      # power
+    assert h.value is None
+    assert L.jrk_kmatw_plan_destroy(None) == 0
+    assert L.jrk_kmatw_plan_apply(None, p, p, 4, 2, 1, None, 0, 0, None, 0, None) == 1
+    assert L.jrk_kmatw_plan_workspace_bytes(None, 4, 0, 0) == 0
+    if not torch.cuda.is_available():
+        Y = np.zeros((8, 2), np.float32)
+        with pytest.raises(nat.JrkError) as e:
+            nat.KmatwPlan(Y, np.zeros((8, 1), np.float32), 1.0, 2.0, 1.0)
+        assert e.value.code == 2 and "no CPU fallback" in str(e.value)

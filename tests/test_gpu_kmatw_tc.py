@@ -14,10 +14,13 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture
-def force(monkeypatch):
+def force():
+    prev = nat.get_option(nat.OPT_KMATW_TC)
+
     def _set(on):
-        monkeypatch.setenv("JRK_KMATW_TC", "1" if on else "0")
-    return _set
+        nat.set_option(nat.OPT_KMATW_TC, 1 if on else 0)
+    yield _set
+    nat.set_option(nat.OPT_KMATW_TC, prev)
 
 
 def _sample_truth(X, Y, W, s, p, rows, rp=None, cp=None):
@@ -39,7 +42,8 @@ def test_tc_path_matches_oracle_and_fp32_kernel(kname, d, m, force):
     force(True)
     n0 = nat.launch_count()
     T = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst)
-    assert nat.launch_count() - n0 == 4, "pack + 2 norms + tensor-core kernel"
+    # X norms | Y norms, first-generation pack, max|W|, [sqexp: second-generation pack] | main kernel(s)
+    assert nat.launch_count() - n0 == (7 if kname == "sqexp" else 5), "pre-pass + tensor-core kernel(s)"
     force(False)
     F = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst)
     rows = np.r_[0:64, N - 64:N]
@@ -97,10 +101,10 @@ def test_tc_path_through_the_api_cfg5_apply_shape(force):
 
 
 @pytest.mark.parametrize("ls_factor,expect", [(1.0, "fast"), (0.75, "fast"), (0.6, "fast-edge"), (0.4, "generic")])
-def test_tc_factored_sqexp_path_regimes(ls_factor, expect, force, monkeypatch):
+def test_tc_factored_sqexp_path_regimes(ls_factor, expect, force):
     """p = 2: below |c| (max|x|^2 + max|y|^2) = 12 the kernel factors K_ij = 2^(c|x|^2) 2^(-2c x.y) 2^(c|y|^2)
     (kmatw_tc.cu: TC_FAST_BOUND = 12); above it the generic epilogue runs.  Both must agree with the oracle and with the
-    generic epilogue forced by JRK_TC_FAST=0."""
+    generic epilogue forced by JRK_OPT_TC_FAST = 0 and the first-generation kernel (JRK_OPT_TC_V2 = 0)."""
     N, M, d, m = 8192 + 5, 8192 + 64 + 3, 16, 16
     X, Y, W = gauss(0, N, d), gauss(1, M, d), np.abs(gauss(2, M, m))      # all-positive sums: the hard case
     s, scale, p, nconst = kparams("sqexp", np.sqrt(d) * ls_factor)
@@ -112,13 +116,15 @@ def test_tc_factored_sqexp_path_regimes(ls_factor, expect, force, monkeypatch):
         assert bound_val <= 12.0 and (expect == "fast" or bound_val > 10.0)
     force(True)
     T = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst)
-    monkeypatch.setenv("JRK_TC_FAST", "0")
-    G = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst)
-    monkeypatch.delenv("JRK_TC_FAST")
+    with nat.option(nat.OPT_TC_FAST, 0):
+        G = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst)
+    with nat.option(nat.OPT_TC_V2, 0):
+        V1 = nat.kmatw(cu(X), cu(Y), cu(W), scale, p, nconst)
     rows = np.r_[0:96, N - 96:N]
     truth, bound = _sample_truth(X, Y, W, s, p, rows)
     assert_kmatw_close(T.cpu().numpy()[rows], truth, bound, f"tc sqexp {expect}")
     assert_kmatw_close(G.cpu().numpy()[rows], truth, bound, f"tc sqexp {expect}, generic epilogue")
+    assert_kmatw_close(V1.cpu().numpy()[rows], truth, bound, f"tc sqexp {expect}, first-generation kernel")
     b = torch.from_numpy(bound.max(0)).to(T.device).float()
     assert ((T - G).abs() <= 2e-6 + 2e-5 * b).all()
 

@@ -15,8 +15,8 @@ def run(N, M, d, m, p, positive=False, timing=False):
     X = torch.randn(N, d, generator=g, device=dev); Y = torch.randn(M, d, generator=g, device=dev)
     W = torch.rand(M, m, generator=g, device=dev) if positive else torch.randn(M, m, generator=g, device=dev)
     s, nc = float(0.70710695 / np.sqrt(d)) if p == 2.0 else float(1 / np.sqrt(d)), 0.25
-    os.environ["JRK_KMATW_TC"] = "1"; A = nat.kmatw(X, Y, W, s, p, nc); torch.cuda.synchronize()
-    os.environ["JRK_KMATW_TC"] = "0"; B = nat.kmatw(X, Y, W, s, p, nc); torch.cuda.synchronize()
+    nat.set_option(nat.OPT_KMATW_TC, 1); A = nat.kmatw(X, Y, W, s, p, nc); torch.cuda.synchronize()
+    nat.set_option(nat.OPT_KMATW_TC, 0); B = nat.kmatw(X, Y, W, s, p, nc); torch.cuda.synchronize()
     rows = torch.arange(0, N, max(1, N // 64), device=dev)[:64]
     Kt = nc * torch.exp(-(s * torch.cdist(X[rows].double(), Y.double())) ** p)
     T = Kt @ W.double(); bound = Kt @ W.double().abs()
@@ -24,8 +24,8 @@ def run(N, M, d, m, p, positive=False, timing=False):
     eb = ((B[rows].double() - T).abs() / (1e-6 + 1e-5 * bound)).max().item()
     msg = f"N={N} M={M} d={d} m={m} p={p} pos={positive}: tc err/lim {ea:.3f}  fp32 err/lim {eb:.3f}"
     if timing:
-        os.environ["JRK_KMATW_TC"] = "1"; ta = t(lambda: nat.kmatw(X, Y, W, s, p, nc))
-        os.environ["JRK_KMATW_TC"] = "0"; tb = t(lambda: nat.kmatw(X, Y, W, s, p, nc))
+        nat.set_option(nat.OPT_KMATW_TC, 1); ta = t(lambda: nat.kmatw(X, Y, W, s, p, nc))
+        nat.set_option(nat.OPT_KMATW_TC, 0); tb = t(lambda: nat.kmatw(X, Y, W, s, p, nc))
         msg += f" | tc {ta:.2f} ms ({N*M/ta/1e6:.0f} Gpairs/s)  fp32 {tb:.2f} ms ({N*M/tb/1e6:.0f} Gpairs/s)"
     print(msg, flush=True)
 import sys as _s
@@ -46,9 +46,9 @@ if len(_s.argv) > 1 and _s.argv[1] == "edge":
         bnd = c * float((X * X).sum(1).max() + (Y * Y).sum(1).max())
         for positive in (True, False):
             W = torch.rand(M, m, generator=g, device=dev) if positive else torch.randn(M, m, generator=g, device=dev)
-            os.environ["JRK_KMATW_TC"] = "1"
+            nat.set_option(nat.OPT_KMATW_TC, 1)
             for fast in ("1", "0"):
-                os.environ["JRK_TC_FAST"] = fast
+                nat.set_option(nat.OPT_TC_FAST, int(fast))
                 A = nat.kmatw(X, Y, W, s, 2.0, nc); torch.cuda.synchronize()
                 rows = torch.arange(0, N, N // 64, device=dev)[:64]
                 Kt = nc * torch.exp(-(s * torch.cdist(X[rows].double(), Y.double())) ** 2)
@@ -58,7 +58,7 @@ if len(_s.argv) > 1 and _s.argv[1] == "edge":
     _s.exit(0)
 if len(_s.argv) > 1 and _s.argv[1] == "fast":
     for f in ("1", "0"):
-        os.environ["JRK_TC_FAST"] = f; print("JRK_TC_FAST", f)
+        nat.set_option(nat.OPT_TC_FAST, int(f)); print("JRK_TC_FAST", f)
         run(16384, 65536, 16, 16, 2.0, positive=True)
         run(131072, 1 << 20, 16, 16, 2.0, positive=True, timing=True)
         run(131072, 1 << 20, 8, 16, 2.0, timing=True)

@@ -27,7 +27,7 @@ for p in (2.0, 1.0, 1.5):
         nat.gram(X, None, 0.1, p, 0.2, path=nat.PATH_TF32X3)
     for (N, M, d, m, s_) in ((8192 + 5, 4096 + 70, 16, 16, 0.15), (8192, 4096 + 3, 7, 3, 0.2), (8192 + 130, 4096, 30, 16, 1.5)):
         X, Y, W = r(N, d), r(M, d), r(M, m)
-        os.environ["JRK_KMATW_TC"] = "1"
+        nat.set_option(nat.OPT_KMATW_TC, 1)
         nat.kmatw(X, Y, W, s_, p, 0.2)                                     # factored (small s_) / generic
         nat.kmatw(X, Y, W, s_, p, 0.2, row_reduce=nat.REDUCE_SUM)
     # fused backward kernels and the sibling epilogues

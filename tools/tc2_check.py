@@ -11,6 +11,19 @@ from jaxrk_b200 import _native as nat  # noqa: E402
 
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(0)
+VARIANTS = (("v2", {}), ("v2/epq3", {nat.OPT_TC2_EPQ: 3}), ("v1", {nat.OPT_TC_V2: 0}))
+
+
+class Options:
+    def __init__(self, opts):
+        self.opts = opts
+
+    def __enter__(self):
+        self.prev = {k: nat.set_option(k, v) for k, v in self.opts.items()}
+
+    def __exit__(self, *exc):
+        for k, v in self.prev.items():
+            nat.set_option(k, v)
 
 
 def timeit(fn, reps=3):
@@ -50,17 +63,14 @@ def acc(N, M, d, m, ls_factor=1.0, positive=False, prefs=False, wscale=1.0):
     rows = torch.unique(torch.cat([torch.arange(0, N, max(1, N // 192), device=dev), torch.arange(N - 64, N, device=dev),
                                    torch.arange(0, 64, device=dev)]))
     res = {}
-    for name, env in (("v2", {"JRK_KMATW_TC": "1", "JRK_TC_V2": "1"}), ("v2/epq2", {"JRK_TC2_EPQ": "2"}), ("v2/epq4", {"JRK_TC2_EPQ": "4"}),
-                      ("v1", {"JRK_KMATW_TC": "1", "JRK_TC_V2": "0"}), ("fp32", {"JRK_KMATW_TC": "0"})):
-        os.environ.update(env)
-        A = nat.kmatw(X, Y, W, s, 2.0, nc, row_pref=rp, col_pref=cp)
-        torch.cuda.synchronize()
+    for name, opts in VARIANTS + (("fp32", {nat.OPT_KMATW_TC: 0}),):
+        with Options(opts):
+            A = nat.kmatw(X, Y, W, s, 2.0, nc, row_pref=rp, col_pref=cp)
+            torch.cuda.synchronize()
         res[name] = err_vs_truth(A, X, Y, W, s, nc, rows, rp, cp)
-        if name == "v2/epq4":
-            os.environ.pop("JRK_TC2_EPQ")
     print(f"N={N} M={M} d={d} m={m} ls*{ls_factor} bound={bnd:.2f} pos={positive} prefs={prefs} wscale={wscale:g}: err/lim "
           + "  ".join(f"{k} {v:.3f}" for k, v in res.items()), flush=True)
-    return max(res["v2"], res["v2/epq2"], res["v2/epq4"])
+    return max(res["v2"], res["v2/epq3"])
 
 
 def time_one(N, M, d, m, reps=3):
@@ -69,17 +79,16 @@ def time_one(N, M, d, m, reps=3):
     W = torch.rand(M, m, generator=g, device=dev)
     s, nc = float(0.70710695 / np.sqrt(d)), 0.25
     out = {}
-    for name, env in (("v2/epq2", {"JRK_KMATW_TC": "1", "JRK_TC_V2": "1", "JRK_TC2_EPQ": "2"}),
-                      ("v2/epq3", {"JRK_KMATW_TC": "1", "JRK_TC_V2": "1", "JRK_TC2_EPQ": "3"}),
-                      ("v2/epq4", {"JRK_KMATW_TC": "1", "JRK_TC_V2": "1", "JRK_TC2_EPQ": "4"}),
-                      ("v1", {"JRK_KMATW_TC": "1", "JRK_TC_V2": "0"})):
-        os.environ.update(env)
-        ms = timeit(lambda: nat.kmatw(X, Y, W, s, 2.0, nc), reps)
-        out[name] = ms
-    os.environ.pop("JRK_TC2_EPQ")
+    for name, opts in VARIANTS:
+        with Options(opts):
+            out[name] = timeit(lambda: nat.kmatw(X, Y, W, s, 2.0, nc), reps)
+    plan = nat.KmatwPlan(Y, W, s, 2.0, nc)
+    out["v2/plan"] = timeit(lambda: plan.apply(X), reps)
+    P = plan.apply(X)
+    plan.close()
     rows = torch.arange(0, N, N // 64, device=dev)[:64]
-    os.environ.update({"JRK_KMATW_TC": "1", "JRK_TC_V2": "1"})
     A = nat.kmatw(X, Y, W, s, 2.0, nc)
+    assert torch.equal(A, P), "a plan apply must give the one-shot result bit for bit"
     e = err_vs_truth(A, X, Y, W, s, nc, rows)
     print(f"N={N} M={M} d={d} m={m}: " + "  ".join(f"{k} {v:.2f} ms ({N * M / v / 1e9:.3f}e12 pairs/s, {N * M / v / 1e6 / 4637:.3f} of MUFU)"
                                                     for k, v in out.items()) + f"  v2 err/lim {e:.3f}", flush=True)

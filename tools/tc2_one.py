@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from jaxrk_b200 import _native as nat
 N, M, d, m = (int(v) for v in sys.argv[1:5])
 if len(sys.argv) > 5:
-    os.environ["JRK_TC2_EPQ"] = sys.argv[5]
+    nat.set_option(nat.OPT_TC2_EPQ, int(sys.argv[5]))
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(int(os.environ.get('SEED', '0')))
 X = torch.randn(N, d, generator=g, device=dev); Y = torch.randn(M, d, generator=g, device=dev); W = torch.randn(M, m, generator=g, device=dev)

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from jaxrk_b200 import _native as nat  # noqa: E402
 
 epq = sys.argv[1] if len(sys.argv) > 1 else "4"
-os.environ["JRK_TC2_EPQ"] = epq
+nat.set_option(nat.OPT_TC2_EPQ, int(epq))
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(0)
 N, M, d, m = 148 * 128 * 2, 512 * 64, 16, 16
