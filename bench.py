@@ -1,24 +1,28 @@
 #!/usr/bin/env python
 """Headline benchmark of the JaxRK hot path on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload gram|kmatw] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload kmatw|gram] [--impl b200|reference]
 
 One "step" is one pass of the hot path over one batch of synthetic N(0, I) inputs.
 
-  workload gram  (default; BASELINE.json configs[1]): materialised GenGaussKernel Gram, N = M = 65536,
-                 d = 64, fp32.  HBM-write-bound.  N GPUs: X is row-sharded, every rank owns 65536 rows
-                 (weak scaling, no data-path collective; the Gram stays row-sharded).
-  workload kmatw (configs[2]): fused, never-materialised K(X, Y) @ W, N = M = 2^20, d = 16, m = 16.
-                 FP32-pipe-bound.  N GPUs: the 2^20 rows of X are sharded (strong scaling), Y / W replicated.
-                 Reported under "also" of the default line, or as the main line with --workload kmatw.
+  workload kmatw (default; BASELINE.json configs[2], the configuration north_star's target is quoted on): fused,
+                 never-materialised K(X, Y) @ W, N = M = 2^20, d = 16, m = 16, fp32.  Both contractions on tcgen05,
+                 bound by the MUFU pipe (one ex2 per pair).  N GPUs: the 2^20 rows of X are split over the ranks
+                 (STRONG scaling), Y / W replicated, no data-path collective (the result stays row-sharded).
+  workload gram  (configs[1]): materialised GenGaussKernel Gram, N = M = 65536 per rank, d = 64, HBM-write-bound
+                 (weak scaling).  Reported under "also" of the default line, or as the main line with --workload gram.
+  also           kmatw_cfg3_mean: the same K@W with `Mean` over rows (out 1 x 16): local sums + ONE all_reduce (NCCL)
+                 inside the CUDA-event window, its latency reported separately;  gram_1m_d16_streamed: north_star's
+                 "Gram at N = M = 1M, d = 16", streamed in row blocks.
 
-`value`  kernel evaluations / s, whole job, inputs resident in HBM, CUDA events on the launch stream, an L2
-         flush between timed iterations, max over ranks.
-`e2e`    the same metric through the host-buffer C-ABI call (jrk_*_f32_host): pinned host inputs are copied
-         to the device and the result is copied back inside the timed region.
-`--impl reference` times the restated reference op sequence on the host (oracle/torch_ref.py: torch-CPU eager
-         float32, one library call per reference op, all host cores; the reference itself is pure Python over
-         jax/XLA, which is absent from the image) on a bounded row sample of the same workload.
+`value`  kernel evaluations / s, whole job, inputs resident in HBM, CUDA events on the launch stream, an L2 flush
+         between timed iterations, max over ranks.
+`e2e`    the same metric through the host-buffer C-ABI call (jrk_*_f32_host): ALL inputs are copied from pinned host
+         memory to the device and the result is copied back inside the timed region; `e2e.plan` is the same with the
+         Y / W side kept on the device by a plan (jrk_kmatw_plan_apply_host: X in, result out).
+`--impl reference` times the restated reference op sequence on the host (oracle/torch_ref.py: torch-CPU eager float32,
+         one library call per reference op, all host cores; the reference itself is pure Python over jax/XLA, which is
+         absent from the image) on a bounded row sample of the same workload, with the same `config`.
 """
 import argparse
 import json
@@ -33,9 +37,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # name: N (rows per rank for gram / total rows for kmatw), M, d, m
-    "gram": dict(N=65536, M=65536, d=64, m=0, config="configs[1]: GenGaussKernel Gram N=M=65536 d=64 fp32 materialised"),
-    "kmatw": dict(N=1 << 20, M=1 << 20, d=16, m=16, config="configs[2]: fused K(X,Y)@W N=M=2^20 d=16 m=16, never materialised"),
+    # name: N (total rows for kmatw / rows per rank for gram), M, d, m
+    "kmatw": dict(N=1 << 20, M=1 << 20, d=16, m=16, scaling="strong",
+                  config="configs[2]: fused K(X,Y)@W N=M=2^20 d=16 m=16, never materialised"),
+    "gram": dict(N=65536, M=65536, d=64, m=0, scaling="weak",
+                 config="configs[1]: GenGaussKernel Gram N=M=65536 d=64 fp32 materialised"),
 }
 # north_star's "Gram at N = M = 1M, d = 16": 4.4 TB cannot be materialised, so it is STREAMED: every
 # GPU writes its rows block by block (16384 x 2^20 = 68.7 GB) into one reused buffer; evals/s = N M / time.
@@ -50,6 +56,19 @@ def kernel_params(d):
     k = GenGaussKernel.make_gauss(float(np.sqrt(d)))
     scale, dim_scale, power, nconst = k.kernel_args()
     return scale, power, nconst
+
+
+def workload_config(name, world):
+    """The `config` of the JSON line: ONE function for both arms, so that the driver sees the same workload."""
+    w = WORKLOADS[name]
+    n_local = w["N"] // world if w["scaling"] == "strong" else w["N"]
+    cfg = {"workload": w["config"], "kernel": "GenGaussKernel.make_gauss(sqrt(d)) (p = 2)", "rows_per_gpu": n_local,
+           "global_rows": n_local * world, "M": w["M"], "d": w["d"],
+           "sharding": "X row-blocks per rank, Y" + ("/W" if w["m"] else "") + " replicated, no data-path collective",
+           "l2": "256 MiB L2 flush between timed iterations"}
+    if w["m"]:
+        cfg["m"] = w["m"]
+    return cfg
 
 
 def peaks():
@@ -182,52 +201,24 @@ def run_reference(args):
     val = tot_ev / tot_t
     sample = f"{rows} rows x {w['M']} columns of the workload per step (d={w['d']}" + (f", m={w['m']}" if w["m"] else "") + ")"
     line = {"metric": "kernel_evals_per_s", "value": val, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic N(0, I)", "impl": "reference",
-            "config": {"workload": w["config"], "kernel": "GenGaussKernel.make_gauss(sqrt(d)) (p = 2)"},
+            "config": workload_config(name, max(1, args.gpus)),
             "cpu_baseline": {"value": val, "unit": "evals/s", "cores": thr, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "restated reference op sequence, torch-CPU eager float32 (oracle/torch_ref.py), all host threads; "
-                    "the reference itself needs jax/jaxlib, absent from the image"}
+            "note": "PORT, not jaxlib: the restated reference op sequence in torch-CPU eager float32 (oracle/torch_ref.py), all "
+                    "host threads, a bounded row sample of the same workload per step (a rate, so independent of the sample "
+                    "size); the reference itself needs jax/jaxlib, absent from the image"}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def run_workload(name, args, torch, nat, dist_ctx, with_cpu):
-    rank, world, dev = dist_ctx
-    w = WORKLOADS[name]
-    M, d, m = w["M"], w["d"], w["m"]
-    if name == "gram":
-        n_local, n_total, scaling = w["N"], w["N"] * world, "weak"
-    else:
-        n_local, n_total, scaling = w["N"] // world, w["N"], "strong"
-    scale, power, nconst = kernel_params(d)
-
-    def randn(seed, *shape):
-        g = torch.Generator(device=dev).manual_seed(seed)
-        return torch.randn(*shape, generator=g, device=dev, dtype=torch.float32)
-
-    X = randn(100 + rank, n_local, d)      # this rank's row block
-    Y = randn(1, M, d)                     # replicated
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    if name == "gram":
-        out = torch.empty((n_local, M), dtype=torch.float32, device=dev)
-        ws_bytes = nat.lib().jrk_gram_workspace_bytes(n_local, M, d, nat.PATH_AUTO)
-        step = lambda: nat.gram(X, Y, scale, power, nconst, out=out)  # noqa: E731
-        alg_bytes = 4.0 * n_local * M + 4.0 * d * (n_local + M)
-    else:
-        W = randn(2, M, m)
-        out = torch.empty((n_local, m), dtype=torch.float32, device=dev)
-        step = lambda: nat.kmatw(X, Y, W, scale, power, nconst, out=out)  # noqa: E731
-        alg_ops = float(n_local) * M * (2 * d + m + 2)  # FP32-pipe lane-ops (DESIGN.md "Rooflines")
-
-    steps = args.steps if name == "gram" else max(1, min(args.steps, 5))
-    warm = args.warmup if name == "gram" else max(1, min(args.warmup, 3))
-    for _ in range(warm):
-        step()
+def _timed_steps(torch, dev, world, steps, flush, step, nat):
+    """K timed iterations (CUDA events on the launch stream, L2 flush between them, barrier on both sides); returns
+    (seconds of this rank summed over the steps, launches, clocks)."""
     torch.cuda.synchronize(dev)
     if world > 1:
         torch.distributed.barrier()
@@ -248,11 +239,47 @@ def run_workload(name, args, torch, nat, dist_ctx, with_cpu):
     if world > 1:
         torch.distributed.barrier()
     clocks = sampler.stop()
-    t_local = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
-    t = torch.tensor([t_local], dtype=torch.float64, device=dev)
+    return sum(a.elapsed_time(b) for a, b in evs) * 1e-3, launches, clocks
+
+
+def _max_over_ranks(torch, dev, world, seconds):
+    t = torch.tensor([seconds], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    t_step = float(t.item()) / steps
+    return float(t.item())
+
+
+def run_workload(name, args, torch, nat, dist_ctx, with_cpu):
+    rank, world, dev = dist_ctx
+    w = WORKLOADS[name]
+    M, d, m = w["M"], w["d"], w["m"]
+    scaling = w["scaling"]
+    n_local = w["N"] // world if scaling == "strong" else w["N"]
+    n_total = n_local * world
+    scale, power, nconst = kernel_params(d)
+
+    def randn(seed, *shape):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        return torch.randn(*shape, generator=g, device=dev, dtype=torch.float32)
+
+    X = randn(100 + rank, n_local, d)      # this rank's row block
+    Y = randn(1, M, d)                     # replicated
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    if name == "gram":
+        out = torch.empty((n_local, M), dtype=torch.float32, device=dev)
+        step = lambda: nat.gram(X, Y, scale, power, nconst, out=out)  # noqa: E731
+        alg_bytes = 4.0 * n_local * M + 4.0 * d * (n_local + M)
+    else:
+        W = randn(2, M, m)
+        out = torch.empty((n_local, m), dtype=torch.float32, device=dev)
+        step = lambda: nat.kmatw(X, Y, W, scale, power, nconst, out=out)  # noqa: E731
+        alg_ops = float(n_local) * M * (2 * d + m + 2)  # FP32-pipe lane-ops (DESIGN.md "Rooflines")
+
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    for _ in range(warm):
+        step()
+    t_local, launches, clocks = _timed_steps(torch, dev, world, steps, flush, step, nat)
+    t_step = _max_over_ranks(torch, dev, world, t_local) / steps
     value = float(n_total) * M / t_step
 
     hbm, hbm_src, _ = peaks()
@@ -262,14 +289,18 @@ def run_workload(name, args, torch, nat, dist_ctx, with_cpu):
                 "traffic": traffic_for(name), "peak_source": hbm_src, "kernel_ms": t_local / steps * 1e3,
                 "algorithmic_bytes_per_launch": alg_bytes}
     elif nat.lib().jrk_kmatw_uses_tensor_cores(n_local, M, d, m, 0, 0):
-        # both contractions on tcgen05 (kmatw_tc.cu): what remains per pair is one MUFU ex2 and ~9 issue slots, so
-        # the bound is the MUFU pipe; the FP32-pipe kernel's figure of merit is kept alongside for comparison
+        # both contractions on tcgen05 (kmatw_tc2.cu): what remains per pair is one MUFU ex2, so the bound is the MUFU
+        # pipe; the FP32-pipe kernel's figure of merit is kept alongside for comparison
         pk, src = mufu_peak()
         achieved = float(n_local) * M / (t_local / steps)
         fpk, _ = fp32_pipe_peak()
         roof = {"bound": "mufu", "achieved": achieved / 1e12, "peak": pk / 1e12, "unit": "T ex2/s",
-                "frac": achieved / pk, "traffic": traffic_for("kmatw_tc"), "peak_source": src,
-                "kernel_ms": t_local / steps * 1e3, "mufu_per_eval": 1, "path": "tcgen05 3xTF32 (kmatw_tc.cu)",
+                "frac": achieved / pk, "traffic": traffic_for("kmatw_tc2"), "peak_source": src,
+                "kernel_ms": t_local / steps * 1e3, "mufu_per_eval": 1,
+                "path": "tcgen05, fp16 hi/lo operands for both GEMMs (kmatw_tc2.cu)",
+                "note": "the step also contains ~1 ms of pre-pass kernels (row norms, tile images); `traffic` = DRAM bytes "
+                        "of the main kernel per launch from ncu (algorithmic: 4 (N + M) (d + m) bytes)",
+                "algorithmic_bytes_per_launch": 4.0 * (n_local + M) * (d + m),
                 "fp32_pipe_equiv_frac": alg_ops / (t_local / steps) / fpk,
                 "tflops_equiv": float(n_local) * M * (3 * d + 2 * m + 4) / (t_local / steps) / 1e12}
     else:
@@ -280,10 +311,11 @@ def run_workload(name, args, torch, nat, dist_ctx, with_cpu):
                 "kernel_ms": t_local / steps * 1e3, "lane_ops_per_eval": 2 * d + m + 2, "path": "FP32 pipe (kmatw.cu)",
                 "mufu_per_eval": 1, "tflops_equiv": float(n_local) * M * (3 * d + 2 * m + 4) / (t_local / steps) / 1e12}
 
-    # ---- end to end through the host-buffer C-ABI entry point ---------------------------------
+    # ---- end to end through the host-buffer C-ABI entry points ---------------------------------
     Xh = X.cpu().pin_memory()
     Yh = Y.cpu().pin_memory()
     e2e_steps = max(1, min(steps, 3))
+    plan_e2e = None
     if name == "gram":
         # the whole N_local x M result crosses PCIe every step, through a pinned host buffer of one 16384-row slab
         # (4.3 GB per rank instead of 17.2 GB: eight ranks share one host)
@@ -303,37 +335,107 @@ def run_workload(name, args, torch, nat, dist_ctx, with_cpu):
         host_step = lambda: nat.kmatw_host(Xh, Yh, Wh, outh, scale, power, nconst, device=dev.index)  # noqa: E731
     del out
     torch.cuda.empty_cache()
-    host_step()  # warm-up (page tables, allocator)
-    if world > 1:
-        torch.distributed.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        host_step()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
-    e2e_val = float(n_total) * M * e2e_steps / float(te.item())
-    # spot-check the e2e result against the resident one (same kernels)
-    chk = float(outh[:4].abs().sum())
+
+    def time_host(fn):
+        fn()  # warm-up (page tables, allocator)
+        if world > 1:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        return _max_over_ranks(torch, dev, world, time.perf_counter() - t0) / e2e_steps
+
+    te = time_host(host_step)
+    e2e_val = float(n_total) * M / te
+    chk = float(outh[:4].abs().sum())      # spot-check the e2e result (same kernels as the resident run)
     assert np.isfinite(chk) and chk > 0
+    if name == "kmatw":
+        # the operator's fixed side (Y, W) kept on the device by a plan: a step moves X in and the result out
+        plan = nat.KmatwPlan(Yh, Wh, scale, power, nconst, device=dev.index)
+        ref4 = outh[:4].clone()
+        tp = time_host(lambda: plan.apply_host(Xh, outh))
+        assert bool(torch.equal(ref4, outh[:4])), "plan and one-shot results must agree bit for bit"
+        plan.close()
+        plan_e2e = {"value": float(n_total) * M / tp, "unit": "evals/s", "ms_per_step": tp * 1e3,
+                    "h2d_bytes_per_step": int(4 * d * n_local), "d2h_bytes_per_step": int(d2h),
+                    "what": "jrk_kmatw_plan_apply_host: Y / W and their tile images stay on the device"}
 
     res = {"value": value, "ms_per_step": t_step * 1e3, "steps": steps, "warmup": warm, "scaling": scaling,
            "roofline": roof, "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "steps": e2e_steps, "ms_per_step": float(te.item()) / e2e_steps * 1e3},
-           "config": {"workload": w["config"], "kernel": "GenGaussKernel.make_gauss(sqrt(d)) (p = 2)",
-                      "rows_per_gpu": n_local, "global_rows": n_total, "M": M, "d": d,
-                      "l2": "256 MiB L2 flush between timed iterations",
-                      "sharding": "X row-blocks per rank, Y" + ("/W" if m else "") + " replicated, no data-path collective"}}
-    if m:
-        res["config"]["m"] = m
+                   "steps": e2e_steps, "ms_per_step": te * 1e3,
+                   "what": "jrk_%s_f32_host: every input copied from pinned host memory, result copied back" % name},
+           "config": workload_config(name, world)}
+    if plan_e2e:
+        res["e2e"]["plan"] = plan_e2e
+    if name == "gram" and world > 1:
+        res["e2e"]["note"] = "a materialised Gram moves 17.2 GB per rank device->host: all ranks share one host's PCIe/memory"
     if with_cpu and rank == 0 and world == 1:
         rows = cpu_rows_for(name)
         ev, dt, thr = cpu_reference_sample(name, rows)
         res["cpu_baseline"] = {"value": ev, "unit": "evals/s", "cores": thr, "kind": "port",
                                "sample": f"{rows} rows x {M} columns of the same workload, {dt:.1f} s, oracle/torch_ref.py "
-                                         "(reference op sequence, torch-CPU eager)"}
+                                         "(PORT of the reference op sequence, torch-CPU eager; jaxlib is absent)"}
     return res
+
+
+def run_kmatw_mean(args, torch, nat, dist_ctx):
+    """cfg3 variant of SURVEY.md §8(d): K@W with `Mean` over rows (jaxrk/reduce/base.py:142-150), out 1 x 16.  Every rank
+    reduces its row block inside the kernel path (local sums), then ONE all_reduce(SUM) of 16 floats over NCCL and the
+    division by the global N -- exactly what jaxrk_b200.sharded.sharded_inner_local does; the collective sits inside the
+    CUDA-event window and is also timed on its own."""
+    rank, world, dev = dist_ctx
+    w = WORKLOADS["kmatw"]
+    M, d, m = w["M"], w["d"], w["m"]
+    n_local, n_total = w["N"] // world, w["N"]
+    scale, power, nconst = kernel_params(d)
+
+    def randn(seed, *shape):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        return torch.randn(*shape, generator=g, device=dev, dtype=torch.float32)
+
+    X, Y, W = randn(100 + rank, n_local, d), randn(1, M, d), randn(2, M, m)
+    part = torch.empty((1, m), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ar_events = []
+
+    def step():
+        nat.kmatw(X, Y, W, scale, power, nconst, row_reduce=nat.REDUCE_SUM, out=part)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        if world > 1:
+            torch.distributed.all_reduce(part, op=torch.distributed.ReduceOp.SUM)
+        part.div_(float(n_total))
+        a1.record()
+        ar_events.append((a0, a1))
+
+    steps = max(1, min(args.steps, 5))
+    for _ in range(3):
+        step()
+    ar_events.clear()
+    t_local, launches, clocks = _timed_steps(torch, dev, world, steps, flush, step, nat)
+    t_step = _max_over_ranks(torch, dev, world, t_local) / steps
+    ar_ms = float(np.median([a.elapsed_time(b) for a, b in ar_events]))
+    # cross-check against the public API (same kernels, same collective)
+    from jaxrk_b200 import sharded
+    from jaxrk_b200.kern import GenGaussKernel
+    from jaxrk_b200.reduce import LinearReduce, Mean
+    from jaxrk_b200.rkhs import FiniteVec
+    k = GenGaussKernel.make_gauss(float(np.sqrt(d)))
+    api = sharded.sharded_inner_local(k, X, [Mean()], n_total, rank * n_local, FiniteVec(k, Y, [LinearReduce(W.T.contiguous())]))
+    err = float((api - part).abs().max() / (part.abs().max() + 1e-30))
+    assert err < 1e-5, err
+    pk, src = mufu_peak()
+    achieved = float(n_local) * M / (t_local / steps)
+    return {"value": float(n_total) * M / t_step, "ms_per_step": t_step * 1e3, "steps": steps, "scaling": "strong",
+            "collective": {"op": "all_reduce(SUM) of 1 x 16 float32 + division by the global N", "backend": "nccl" if world > 1 else "none (1 rank)",
+                           "median_ms_inside_the_step": ar_ms, "ranks": world},
+            "api_check_rel_err": err,
+            "roofline": {"bound": "mufu", "achieved": achieved / 1e12, "peak": pk / 1e12, "unit": "T ex2/s", "frac": achieved / pk,
+                         "traffic": None, "peak_source": src},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "config": {"workload": "configs[2] variant: K(X,Y)@W with Mean over rows, out 1 x 16 (sharded_inner_local)",
+                       "rows_per_gpu": n_local, "global_rows": n_total, "M": M, "d": d, "m": m}}
 
 
 def run_gram1m(args, torch, nat, dist_ctx):
@@ -365,13 +467,11 @@ def run_gram1m(args, torch, nat, dist_ctx):
     torch.cuda.synchronize(dev)
     launches = nat.launch_count() - l0
     clocks = sampler.stop()
-    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
-    t_local = float(t.item())
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    t_local = e0.elapsed_time(e1) * 1e-3
+    t_all = _max_over_ranks(torch, dev, world, t_local)
     hbm, hbm_src, _ = peaks()
     achieved = 4.0 * n_local * M / t_local / 1e9
-    return {"value": float(N) * M / float(t.item()), "ms_per_step": float(t.item()) * 1e3, "steps": 1, "scaling": "strong",
+    return {"value": float(N) * M / t_all, "ms_per_step": t_all * 1e3, "steps": 1, "scaling": "strong",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": None, "peak_source": hbm_src + " (sustained for seconds: the power cap applies)",
                          "algorithmic_bytes_per_step": 4.0 * n_local * M},
@@ -397,16 +497,17 @@ def run_b200(args):
     ctx = (rank, world, dev)
     main = run_workload(args.workload, args, torch, nat, ctx, with_cpu=True)
     also = {}
-    if args.workload == "gram" and not args.no_also:
-        try:
-            also["kmatw_cfg3"] = run_workload("kmatw", args, torch, nat, ctx, with_cpu=(world == 1))
-        except Exception as e:  # noqa: BLE001  (the headline line must still print)
-            also["kmatw_cfg3"] = {"error": repr(e)}
-        try:
-            torch.cuda.empty_cache()
-            also["gram_1m_d16_streamed"] = run_gram1m(args, torch, nat, ctx)
-        except Exception as e:  # noqa: BLE001
-            also["gram_1m_d16_streamed"] = {"error": repr(e)}
+    if not args.no_also:
+        extra = [("kmatw_cfg3_mean", lambda: run_kmatw_mean(args, torch, nat, ctx)),
+                 ("gram_cfg2" if args.workload == "kmatw" else "kmatw_cfg3",
+                  lambda: run_workload("gram" if args.workload == "kmatw" else "kmatw", args, torch, nat, ctx, with_cpu=False)),
+                 ("gram_1m_d16_streamed", lambda: run_gram1m(args, torch, nat, ctx))]
+        for key, fn in extra:
+            try:
+                torch.cuda.empty_cache()
+                also[key] = fn()
+            except Exception as e:  # noqa: BLE001  (the headline line must still print)
+                also[key] = {"error": repr(e)}
     if rank == 0:
         line = {"metric": "kernel_evals_per_s", "value": main["value"], "unit": "evals/s", "n_gpus": world,
                 "steps": main["steps"], "warmup": main["warmup"], "ms_per_step": main["ms_per_step"],
@@ -429,9 +530,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="gram")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="kmatw")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--no-also", action="store_true", help="skip the secondary (kmatw) workload")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
