@@ -38,6 +38,61 @@ class LinearReduce(Reduce):
         return un, cts, LinearReduce(m)
 
 
+class KernelMapReduce(LinearReduce):
+    """A LinearReduce whose map is itself an inner product,  linear_map = R_V K(V, X) R_X^T  (len(V) x len(X side)) --
+    exactly what FiniteOp.__matmul__ builds for `op @ vec` (jaxrk/rkhs/operator.py:46-52: `LinearReduce(lin_map.T)` with
+    lin_map = matr @ inner(inp_feat, vec)) -- kept in FACTORED form:
+
+      * `reduce_first_ax(a)` = linear_map @ a is evaluated as ONE fused, skinny K(V, X) @ (R_X^T a): this is the
+        re-association of FiniteVec.get_mean_var (jaxrk/rkhs/vector.py:126-134) for the result of an operator apply --
+        `L @ Y_ref` never materialises the len(V) x len(X) map (SURVEY.md section 8f-1);
+      * `linear_map` (the attribute users and `inner` read) materialises the map on first access, through the same
+        fused path (K evaluated once; wide maps go through the row-slab route of rkhs/_lowering.py), and keeps it.
+
+    `normalize` reproduces FiniteOp's `lin_map / lin_map.sum(1, keepdims=True)` (operator.py:49-50)."""
+
+    def __init__(self, vec, inp, normalize: bool = False):
+        self._vec, self._inp, self._normalize = vec, inp, normalize
+        self._map = None
+        self._col_scale = None
+
+    def _scale(self):
+        if self._normalize and self._col_scale is None:
+            from ..rkhs.vector import inner
+            self._col_scale = 1.0 / inner(self._vec.sum(), self._inp)        # 1 x len(inp): column sums of the map
+        return self._col_scale
+
+    @property
+    def linear_map(self):
+        if self._map is None:
+            from ..rkhs.vector import inner
+            m = inner(self._vec, self._inp)
+            if self._normalize:
+                m = m * self._scale()
+            self._map = m
+        return self._map
+
+    @property
+    def is_materialised(self) -> bool:
+        return self._map is not None
+
+    def reduce_first_ax(self, inp):
+        assert len(inp.shape) == 2
+        assert len(self._inp) == inp.shape[0]
+        if self._map is not None:
+            return self._map.to(inp.device) @ inp
+        from ..rkhs.vector import inner
+        a = asarray(inp)
+        if self._normalize:
+            a = self._scale().reshape(-1, 1).to(a.device) * a
+        return inner(self._vec, self._inp.extend_reduce([LinearReduce(a.T.contiguous())]))
+
+    def new_len(self, original_len: int):
+        assert len(self._inp) == original_len, \
+            self.__class__.__name__ + " expects a gram with %d columns" % len(self._inp)
+        return len(self._vec)
+
+
 class SparseReduce(Reduce):
     """Sum / average rows of the input selected by index arrays (lincomb.py:27-87).  Index
     structured, so it is applied to a materialised Gram (not folded into the fused kernels)."""

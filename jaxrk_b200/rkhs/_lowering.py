@@ -82,7 +82,7 @@ def fold_chain(chain: Optional[List[Reduce]], n: int, dev) -> Folded:
         elif type(r) is BalancedRed:
             assert n % r.points_per_split == 0
             f.kind, f.group, f.average = BALANCED, r.points_per_split, r.average
-        elif type(r) is LinearReduce:
+        elif isinstance(r, LinearReduce):      # incl. KernelMapReduce (materialises its map here)
             assert r.linear_map.shape[1] == n
             f.kind, f.A = LINEAR, r.linear_map.to(dev)
         elif type(r) is SparseReduce and r.num_rows() * n <= SPARSE_DENSE_LIMIT:
@@ -113,9 +113,56 @@ def _row_reduce_of(f: Folded):
     return nat.REDUCE_NONE, 0
 
 
+WIDE_M = 64                       # columns of W from which "Gram slab + library GEMM" beats the FP32-pipe kernel's column blocks
+WIDE_SLAB_BYTES = 2 << 30         # FP32 bytes of one materialised row slab of K
+
+
+def _kmatw_wide(X, Y, W, spec, row_pref, col_pref) -> torch.Tensor:
+    """diag(row_pref) K(X, Y) diag(col_pref) W for WIDE W outside the tensor-core window (d > 32, per-dimension scales,
+    sibling kernels, small problems) -- FiniteOp.__matmul__ with many output features (jaxrk/rkhs/operator.py:46-52).
+    K is evaluated ONCE, slab by slab, by the fused Gram kernel (HBM-bound); the dense contraction is the library's FP32
+    GEMM (cuBLAS SGEMM, TF32 off: the same arithmetic class as the reference's XLA dot), as the solve's products are.
+    [Measured and rejected: the contraction on the tensor cores as three fp16 hi / lo' GEMMs with FP32 output
+    (torch.mm(..., out_dtype=float32)): the tensor core's accumulator truncates, an all-positive contraction of 4096
+    terms comes out 5e-5 low -- five times the tolerance -- and chunks short enough to fix that (256) move more bytes
+    than the GEMM has flops for.  Inside the tensor-core window the fused kernel (column blocks of 16, each block folded
+    into FP32 registers every 256 terms) is both exact enough and faster than SGEMM: 109 vs ~65 TFLOP/s equivalent.]"""
+    N, M, m = X.shape[0], Y.shape[0], W.shape[1]
+    Ws = W if col_pref is None else col_pref[:, None] * W
+    out = torch.empty((N, m), dtype=torch.float32, device=X.device)
+    slab = max(128, min(N, (WIDE_SLAB_BYTES // (4 * M)) // 128 * 128))
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for r0 in range(0, N, slab):
+            r1 = min(N, r0 + slab)
+            K = nat.gram_spec(X[r0:r1], Y, spec)                      # the only kernel evaluations of the slab
+            if row_pref is not None:
+                K.mul_(row_pref[r0:r1, None])
+            torch.mm(K, Ws, out=out[r0:r1])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    return out
+
+
 def _kmatw_side(X, Y, fx: Folded, fy: Folded, spec) -> torch.Tensor:
     """fold_x(K(X, Y)) applied with W = fold_y^T; fy is LINEAR / SUM / MEAN."""
     W = _w_of(fy, X.device)
+    tc = (spec.kind == nat.KIND_GENGAUSS and spec.dim_scale is None
+          and nat.lib().jrk_kmatw_uses_tensor_cores(X.shape[0], Y.shape[0], X.shape[1], W.shape[1], 0, 0))
+    if W.shape[1] >= WIDE_M and not tc:
+        # wide maps (operator application) outside the tensor-core window: Gram slabs + library GEMM, the row fold on
+        # the N x m result
+        T = _kmatw_wide(X, Y, W, spec, fx.pref, fy.pref)
+        if fx.kind == LINEAR:
+            return fx.A @ T
+        if fx.kind == SUM:
+            return T.sum(0, keepdim=True)
+        if fx.kind == MEAN:
+            return T.mean(0, keepdim=True)
+        if fx.kind == BALANCED:
+            return BalancedRed(fx.group, fx.average)(T, 0)
+        return T
     if fx.kind == LINEAR:
         T = nat.kmatw_spec(X, Y, W, spec, row_pref=fx.pref, col_pref=fy.pref)
         return fx.A @ T  # (mx x N) @ (N x my): small dense GEMM, stays in the library path

@@ -13,7 +13,7 @@ import torch
 
 from .._array import asarray
 from ..reduce.base import Sum
-from ..reduce.lincomb import LinearReduce
+from ..reduce.lincomb import KernelMapReduce, LinearReduce
 from .base import LinOp
 from .vector import FiniteVec, inner
 
@@ -50,14 +50,12 @@ class FiniteOp(LinOp):
         return FiniteOp(other.inp_feat, self.outp_feat, core if self.matr is None else self.matr @ core)
 
     def _apply_to(self, vec) -> FiniteVec:
-        # coefficients over the output features: matr . <inp_feat, vec>  (len(outp_feat) x len(vec)); the inner
-        # product is the hot part (fused Gram / K@W), the small dense products stay on the library path
-        coeff = inner(self.inp_feat, vec)
-        if self.matr is not None:
-            coeff = self.matr @ coeff
-        if self._normalize:
-            coeff = coeff / coeff.sum(1, keepdim=True)
-        chain = [LinearReduce(coeff.T)]
+        # coefficients over the output features: (matr . <inp_feat, vec>)^T = <vec, matr-reduced inp_feat>, i.e. ONE fused
+        # K(V, X) @ matr^T with the test points as rows (never an N x T Gram followed by a dense product as in
+        # operator.py:46).  The map stays in factored form (KernelMapReduce): get_mean_var, point evaluations and further
+        # applies contract it with a skinny right-hand side; reading `.linear_map` materialises it.
+        inp = self.inp_feat if self.matr is None else self.inp_feat.extend_reduce([LinearReduce(self.matr)])
+        chain = [KernelMapReduce(vec, inp, normalize=self._normalize)]
         if len(vec) == 1:
             chain.append(Sum())
         return self.outp_feat.extend_reduce(chain)
