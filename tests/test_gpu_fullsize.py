@@ -52,6 +52,37 @@ def test_cfg2_gram_65536_d64_sampled_entries_and_row_checksums():
     del K
 
 
+def _c_oracle():
+    from oracle import c_oracle
+    import ctypes
+    return c_oracle.COracle(ctypes.CDLL(c_oracle.build()))
+
+
+def _schedule_rows(N, n_extra=108, seed=0):
+    """Rows that touch every CTA of the persistent schedule: unit u (128 rows) runs on CTA u % 148; one row per residue
+    (different wave, lane quarter and lane each), the first and last rows, the last unit, plus random ones: 256+ rows."""
+    rng = np.random.RandomState(seed)
+    n_units = (N + 127) // 128
+    rows = []
+    for r in range(min(148, n_units)):
+        waves = (n_units - 1 - r) // 148 + 1
+        u = r + 148 * rng.randint(0, waves)
+        rows.append(min(N - 1, u * 128 + rng.randint(0, 128)))
+    rows += [0, 1, 127, 128, N - 129, N - 128, N - 2, N - 1]
+    rows += list(rng.randint(0, N, n_extra))
+    return np.unique(np.array(rows))
+
+
+def _check_rows(T, X, Y, W, rows, scale, power, nconst, what):
+    orc_c = _c_oracle()
+    Xr = X[torch.from_numpy(rows).to(dev)].cpu().numpy()
+    truth, bnd = orc_c.kmatw_truth64(Xr, Y.cpu().numpy(), W.cpu().numpy(), float(scale), float(power), float(nconst), with_abs=True)
+    got = T[torch.from_numpy(rows).to(dev)].cpu().numpy().astype(np.float64)
+    err = np.abs(got - truth) / (ATOL + RTOL * bnd)
+    assert err.max() <= 1.0, f"{what}: worst error {err.max():.3f} of the tolerance at row {rows[err.max(1).argmax()]}"
+    return float(err.max())
+
+
 def test_cfg3_kmatw_2pow20_linearity_row_blocks_and_sampled_rows():
     N = M = 1 << 20
     d, m = 16, 16
@@ -72,14 +103,45 @@ def test_cfg3_kmatw_2pow20_linearity_row_blocks_and_sampled_rows():
     cs = T1.sum(0, keepdim=True, dtype=torch.float64)
     bound = T1.abs().sum(0, keepdim=True, dtype=torch.float64)
     assert ((S.double() - cs).abs() <= 1e-6 + 1e-5 * bound).all()
-    # 6 sampled rows against the float64 oracle (6 x 2^20 kernel values on the host)
-    rows = np.array([0, 1, 77777, N // 2, N - 2, N - 1])
-    Xr = X[torch.from_numpy(rows).to(dev)].cpu().numpy()
-    Yh, Wh = Y.cpu().numpy(), W1.cpu().numpy()
-    truth = orc.kmatw_truth64(Xr, Yh, Wh, s, power, nconst=nconst)
-    bnd = orc.kmatw_absbound64(Xr, Yh, Wh, s, power, nconst=nconst)
-    got = T1[torch.from_numpy(rows).to(dev)].cpu().numpy().astype(np.float64)
-    assert (np.abs(got - truth) <= ATOL + RTOL * bnd).all()
+    # 256+ sampled rows -- every CTA of the 148-CTA schedule, every wave position, the last unit -- against the float64
+    # C oracle (OpenMP): 2.7e8 kernel values on the host
+    rows = _schedule_rows(N)
+    assert len(rows) >= 256
+    _check_rows(T1, X, Y, W1, rows, scale, power, nconst, "cfg3")
+    # a plan gives the same numbers
+    plan = nat.KmatwPlan(Y, W1, scale, power, nconst)
+    assert torch.equal(plan.apply(X), T1)
+    plan.close()
+
+
+def test_cfg3_size_all_positive_weights_and_laplace():
+    """The hard case for the truncating tensor-core accumulation (all-positive W, 2^20 terms per output) and the generic
+    epilogue (make_laplace) at the full cfg3 size, on sampled rows."""
+    N = M = 1 << 20
+    d, m = 16, 16
+    X, Y = randn(100, N, d), randn(1, M, d)
+    W = torch.rand(M, m, generator=torch.Generator(device=dev).manual_seed(7), device=dev)
+    rows = _schedule_rows(N, n_extra=20, seed=1)
+    k, scale, power, nconst, s = kernel_for(d)
+    T = nat.kmatw(X, Y, W, scale, power, nconst)
+    worst = _check_rows(T, X, Y, W, rows, scale, power, nconst, "cfg3, all-positive W")
+    assert worst < 0.8
+    kl = GenGaussKernel.make_laplace(float(np.sqrt(d)))
+    sc, _, pw, nc = kl.kernel_args()
+    Wn = randn(2, M, m)
+    Tl = nat.kmatw(X, Y, Wn, sc, pw, nc)
+    _check_rows(Tl, X, Y, Wn, rows[::4], sc, pw, nc, "cfg3 size, make_laplace")
+
+
+@pytest.mark.parametrize("d,m", [(16, 24), (16, 32), (48, 16), (128, 8)])
+def test_kmatw_outside_the_narrow_window_at_n65536(d, m):
+    """16 < m <= 32 (tensor cores, column blocks of 16) and 32 < d <= 128 (FP32-pipe kernel) at N = M = 65536."""
+    N = M = 65536
+    X, Y, W = randn(100, N, d), randn(1, M, d), randn(2, M, m)
+    k, scale, power, nconst, s = kernel_for(d)
+    assert nat.lib().jrk_kmatw_uses_tensor_cores(N, M, d, m, 0, 0) == (1 if d <= 32 else 0)
+    T = nat.kmatw(X, Y, W, scale, power, nconst)
+    _check_rows(T, X, Y, W, _schedule_rows(N, n_extra=0, seed=2)[::2], scale, power, nconst, f"d={d} m={m}")
 
 
 def test_cfg4_batched_inner_products_4m_points_symmetric_and_sampled_groups():
@@ -105,10 +167,36 @@ def test_cfg5_operator_apply_sampled_rows():
     assert torch.equal(Gm, Gm.T) and bool((torch.diagonal(Gm) == Gm[0, 0]).all())
     out = inner(FiniteVec(k, Xt), FiniteVec(k, X, [LinearReduce(A)]))     # operator applied to 2^20 test points
     assert tuple(out.shape) == (T, m)
-    rows = np.array([0, 12345, T - 1])
-    Xr = Xt[torch.from_numpy(rows).to(dev)].cpu().numpy()
-    Xh, Wh = X.cpu().numpy(), A.t().contiguous().cpu().numpy()
-    truth = orc.kmatw_truth64(Xr, Xh, Wh, s, power, nconst=nconst)
-    bnd = orc.kmatw_absbound64(Xr, Xh, Wh, s, power, nconst=nconst)
-    got = out[torch.from_numpy(rows).to(dev)].cpu().numpy().astype(np.float64)
-    assert (np.abs(got - truth) <= ATOL + RTOL * bnd).all()
+    _check_rows(out, Xt, X, A.t().contiguous(), _schedule_rows(T, n_extra=0, seed=3)[::2], scale, power, nconst, "cfg5 apply")
+
+
+def test_cfg5_cdo_through_the_operator_objects_full_size():
+    """BASELINE configs[4] through the operator objects (jaxrk/rkhs/operator.py:128-185): Cdo(inp, outp, ref, regul) with
+    N = 32768 points (two Gram builds feeding the library's regularised inverses), applied to 2^20 test points.  The
+    coefficient map (2^20 x 256 over the reference grid) is ONE fused K(X_test, X) @ A^T; 74+ sampled rows against the
+    float64 oracle with the operator's own folded float32 map A."""
+    from jaxrk_b200.reduce import KernelMapReduce
+    from jaxrk_b200.rkhs import _lowering as low
+    from jaxrk_b200.rkhs.operator import Cdo
+    N, T, d, R = 32768, 1 << 20, 16, 256
+    X, Xt = randn(2, N, d), randn(3, T, d)
+    Yv = (torch.sin(X[:, :1]) + 0.1 * randn(5, N, 1))
+    Rf = torch.linspace(-2, 2, R, device=dev)[:, None]
+    kx, scale, power, nconst, s = kernel_for(d)
+    ky = GenGaussKernel.make_gauss(0.3)
+    inp, outp, ref = FiniteVec(kx, X), FiniteVec(ky, Yv), FiniteVec(ky, Rf)
+    cdo = Cdo(inp, outp, ref, regul=1.0)
+    _ = cdo.inp_feat.reduce[-1].linear_map                   # the operator's own N x N map (Cmo's solve), built once
+    n0 = nat.launch_count()
+    res = cdo @ Xt
+    assert isinstance(res.reduce[-1], KernelMapReduce) and len(res) == T
+    coeff = res.reduce[-1].linear_map                        # T x R
+    launches = nat.launch_count() - n0
+    assert tuple(coeff.shape) == (T, R) and bool(torch.isfinite(coeff).all())
+    assert launches <= 16 * 8, "K(X_test, X) must be evaluated once per 16-column block, not per output feature"
+    inp_side = cdo.inp_feat.extend_reduce([LinearReduce(cdo.matr)])
+    A = low.fold_chain(inp_side.reduce, N, dev).A            # R x N, float32: the map the fused kernel contracted with
+    _check_rows(coeff, Xt, X, A.t().contiguous(), _schedule_rows(T, n_extra=0, seed=4)[::2], scale, power, nconst, "Cdo @ X_test")
+    # the estimated conditional density is evaluated on the reference grid without materialising anything else
+    dens = res(Rf)
+    assert tuple(dens.shape) == (T, R) and bool(torch.isfinite(dens).all())
