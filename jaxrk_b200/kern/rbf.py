@@ -85,9 +85,15 @@ class GenGaussKernel(DensityKernel):
         Y = None if Y is None else as2d(Y, X.device)
         args = self.kernel_args()
         if diag or args is None:
+            if self.wants_grad(X, Y):
+                from ..rkhs._lowering import grad_unsupported
+                raise grad_unsupported("GenGaussKernel(diag=True / per-dimension nconst)")
             nc = torch.from_numpy(self.nconst).to(X.device)
             return nc * torch.exp(-self.dist(X, Y, diag))  # rbf.py:104-105 literally (O(N d) / quirk Q2)
         scale, dim_scale, power, nconst = args
+        if self.wants_grad(X, Y) and (dim_scale is not None or X.shape[1] > 64):
+            from ..rkhs._lowering import grad_unsupported
+            raise grad_unsupported(f"GenGaussKernel Gram with d = {X.shape[1]}" + (" and per-dimension scales" if dim_scale is not None else ""))
         if self.wants_grad(X, Y) and dim_scale is None:
             from .. import autograd as ag
             if self.scale_tensor is not None:
@@ -110,9 +116,13 @@ class PeriodicKernel(Kernel):
     products with reduce chains go through jrk_kmatw_kind_f32."""
 
     def __init__(self, period, length_scale: float):
-        period, length_scale = float(period), float(length_scale)
-        assert period > 0 and length_scale > 0
-        self.dist = ScaledPairwiseDistance(scaler=SimpleScaler(1. / period), power=1.)
+        # `period` may be an Array (rbf.py:109): one entry per dimension goes through SimpleScaler as a per-dimension
+        # scale (the C ABI's dim_scale), a single entry is the global scale
+        per = np.asarray(period.detach().cpu().numpy() if isinstance(period, torch.Tensor) else period, dtype=np.float64)
+        length_scale = float(length_scale)
+        assert (per > 0).all() and length_scale > 0
+        s = 1. / float(per.reshape(-1)[0]) if per.size == 1 else (1. / per).astype(f32)
+        self.dist = ScaledPairwiseDistance(scaler=SimpleScaler(s), power=1.)
         self.ls = length_scale
 
     def kernel_spec(self):

@@ -37,6 +37,8 @@ from ..reduce.lincomb import LinearReduce, SparseReduce
 
 NONE, SUM, MEAN, BALANCED, LINEAR = "none", "sum", "mean", "balanced", "linear"
 SPARSE_DENSE_LIMIT = 1 << 26      # elements of the dense form of a SparseReduce that may be built (256 MB)
+SPARSE_FOLD_ROWS = 64             # ... and only for few output rows: every 16 (tensor cores) / 32 (FP32 pipe) of them cost
+                                  # one more pass over K, beyond ~64 rows one materialised Gram + gather is cheaper
 
 
 @dataclass
@@ -85,7 +87,7 @@ def fold_chain(chain: Optional[List[Reduce]], n: int, dev) -> Folded:
         elif isinstance(r, LinearReduce):      # incl. KernelMapReduce (materialises its map here)
             assert r.linear_map.shape[1] == n
             f.kind, f.A = LINEAR, r.linear_map.to(dev)
-        elif type(r) is SparseReduce and r.num_rows() * n <= SPARSE_DENSE_LIMIT:
+        elif type(r) is SparseReduce and r.num_rows() <= SPARSE_FOLD_ROWS and r.num_rows() * n <= SPARSE_DENSE_LIMIT:
             # a sparse averaging map small enough to hold densely: folded like a LinearReduce (fused K@W, the Gram is
             # not materialised); larger ones fall through to the generic route below
             f.kind, f.A = LINEAR, r.to_linear_map(n, dev)
@@ -150,9 +152,10 @@ def _kmatw_side(X, Y, fx: Folded, fy: Folded, spec) -> torch.Tensor:
     W = _w_of(fy, X.device)
     tc = (spec.kind == nat.KIND_GENGAUSS and spec.dim_scale is None
           and nat.lib().jrk_kmatw_uses_tensor_cores(X.shape[0], Y.shape[0], X.shape[1], W.shape[1], 0, 0))
-    if W.shape[1] >= WIDE_M and not tc:
-        # wide maps (operator application) outside the tensor-core window: Gram slabs + library GEMM, the row fold on
-        # the N x m result
+    if (W.shape[1] >= WIDE_M and not tc) or X.shape[1] > 128:
+        # wide maps (operator application) outside the tensor-core window, and d > 128 (beyond the fused K@W kernels:
+        # jrk_kmatw_f32 stops at d = 128, the Gram kernel does not): Gram slabs + library GEMM, the row fold on the
+        # N x m result
         T = _kmatw_wide(X, Y, W, spec, fx.pref, fy.pref)
         if fx.kind == LINEAR:
             return fx.A @ T
@@ -190,10 +193,30 @@ def kernel_spec_of(k):
 
 def _chain_tensors(chain):
     for r in chain or []:
+        if getattr(r, "is_materialised", True) is False:     # a factored KernelMapReduce: do not build its map here
+            continue
         for name in ("prefactors", "linear_map"):
             t = getattr(r, name, None)
             if isinstance(t, torch.Tensor):
                 yield t
+
+
+class GradUnsupported(NotImplementedError):
+    """Gradients were requested where no fused backward kernel exists.  Raised instead of returning a tensor without a
+    graph (which would silently drop the gradient) -- and instead of an eager torch re-implementation of the kernel."""
+
+
+def needs_grad(k, *tensors) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    st = getattr(k, "scale_tensor", None)
+    return any(isinstance(t, torch.Tensor) and t.requires_grad for t in (st, *tensors))
+
+
+def grad_unsupported(what: str):
+    return GradUnsupported(
+        f"{what}: gradients are only available for GenGauss kernels with a GLOBAL scale and d <= 64 (the fused backward "
+        "kernels jrk_kmatw_grad_f32 / jrk_gram_grad_f32); detach the inputs or call under torch.no_grad() to get the value")
 
 
 def _reduced_gram_autograd(k, spec, X, fx: Folded, Y, fy: Folded, self_gram: bool) -> torch.Tensor:
@@ -284,8 +307,10 @@ def reduced_gram(k, X, chain_x, Y, chain_y, self_gram: bool = False) -> torch.Te
     fy = fold_chain(chain_y, Y.shape[0], dev)
     skinny = (LINEAR, SUM, MEAN)
 
-    if (gg and dim_scale is None and X.shape[1] <= 64 and hasattr(k, "wants_grad")
-            and k.wants_grad(X, Y, *_chain_tensors(chain_x), *_chain_tensors(chain_y))):
+    if needs_grad(k, X, Y, *_chain_tensors(chain_x), *_chain_tensors(chain_y)):
+        if not (gg and dim_scale is None and X.shape[1] <= 64 and hasattr(k, "wants_grad")):
+            raise grad_unsupported(f"inner product over {type(k).__name__} with d = {X.shape[1]}"
+                                   + (" and per-dimension scales" if gg and dim_scale is not None else ""))
         out = _reduced_gram_autograd(k, spec, X, fx, Y, fy, self_gram)
         out = Reduce.apply(out, fx.post, 0)
         return Reduce.apply(out, fy.post, 1)

@@ -46,7 +46,10 @@ class FiniteVec(Vec):
             Y = self
         self_gram = Y is self or Y.insp_pts is self.insp_pts
         if Y is self:  # Cov_solve asks for inner(inp_feat) twice (operator.py:138 and :46): keep it
-            key = tuple(id(r) for r in self.reduce)
+            # the key covers in-place updates of the points / chain tensors (an optimiser step bumps `_version`) and
+            # the autograd mode (a result computed under no_grad must not be handed to a recording caller)
+            key = (tuple(id(r) for r in self.reduce), self.insp_pts._version,
+                   tuple(t._version for t in _lowering._chain_tensors(self.reduce)), torch.is_grad_enabled())
             if self._inner_cache is None or self._inner_cache[0] != key:
                 res = _lowering.reduced_gram(self.k, self.insp_pts, self.reduce, self.insp_pts, self.reduce, True)
                 if res.requires_grad:   # part of an autograd graph: not cached (a graph is backpropagated once)
@@ -156,8 +159,14 @@ class _ProductSqExp:
     def __init__(self, nconst: float):
         self._nconst = float(nconst)
 
+    scale_tensor = None
+
     def kernel_args(self):
         return 1.0, None, 2.0, self._nconst
+
+    def wants_grad(self, *tensors) -> bool:
+        """As GenGaussKernel.wants_grad: the concatenated, pre-scaled inputs carry the graph of both factors."""
+        return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
 
 
 def _is_product(op) -> bool:

@@ -165,3 +165,39 @@ def test_no_grad_path_is_unchanged():
     K2 = k(Xg)
     assert not K1.requires_grad and K2.requires_grad
     assert torch.equal(K0, K1) and torch.allclose(K0, K2, rtol=1e-6, atol=1e-8)
+
+
+def test_gradients_are_never_dropped_silently():
+    """where no fused backward kernel exists (d > 64, per-dimension scales, sibling kernels, diag=True) a
+    request for gradients raises instead of returning a tensor without a graph."""
+    from jaxrk_b200.kern import GenGaussKernel, PeriodicKernel
+    from jaxrk_b200.reduce import LinearReduce, Prefactors
+    from jaxrk_b200.rkhs import FiniteVec, inner
+    from jaxrk_b200.rkhs._lowering import GradUnsupported
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(0)
+    X80 = torch.randn(64, 80, generator=g, device=dev, requires_grad=True)
+    Y80 = torch.randn(50, 80, generator=g, device=dev)
+    k = GenGaussKernel.make_gauss(9.0)
+    with pytest.raises(GradUnsupported):
+        k(X80, Y80)
+    with pytest.raises(GradUnsupported):
+        inner(FiniteVec(k, X80), FiniteVec(k, Y80, [LinearReduce(torch.randn(3, 50, device=dev))]))
+    with torch.no_grad():                                      # the value itself is available
+        assert tuple(k(X80, Y80).shape) == (64, 50)
+    assert tuple(k(X80.detach(), Y80).shape) == (64, 50)
+    X4 = torch.randn(64, 4, generator=g, device=dev, requires_grad=True)
+    Y4 = torch.randn(50, 4, generator=g, device=dev)
+    per = PeriodicKernel(2.0, 1.0)
+    with pytest.raises(GradUnsupported):
+        inner(FiniteVec(per, X4), FiniteVec(per, Y4, [Prefactors(torch.rand(50, device=dev))]).sum())
+    with pytest.raises(GradUnsupported):
+        k(X4, X4, diag=True)
+    # a chain parameter that requires grad counts as well
+    A = torch.randn(3, 50, device=dev, requires_grad=True)
+    with pytest.raises(GradUnsupported):
+        inner(FiniteVec(k, X80.detach()), FiniteVec(k, Y80, [LinearReduce(A)]))
+    # ... and inside the window the gradient reaches it
+    out = inner(FiniteVec(k, X4.detach()), FiniteVec(k, Y4, [LinearReduce(A)]))
+    out.sum().backward()
+    assert A.grad is not None and bool(torch.isfinite(A.grad).all())

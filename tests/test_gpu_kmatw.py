@@ -201,3 +201,25 @@ def test_kmatw_long_accumulation_all_positive_weights():
     d2 = torch.cdist(X[:4096].double(), Y.double()) ** 2
     tm = (nconst * torch.exp(-(scale * scale) * d2)).sum(1).mean()
     assert abs(mean.item() - tm.item()) / tm.item() < 1e-5
+
+
+def test_inner_products_beyond_d128_take_the_gram_slab_route():
+    """jrk_kmatw_f32 stops at d = 128; FiniteVec.inner must still work there (Gram by the direct kernel, the
+    contraction by the library), as the reference does for any d."""
+    from jaxrk_b200.kern import GenGaussKernel
+    from jaxrk_b200.reduce import BalancedRed, LinearReduce, Mean, Prefactors
+    from jaxrk_b200.rkhs import FiniteVec, inner
+    rng = np.random.RandomState(0)
+    N, M, d, m = 600, 900, 150, 5
+    X, Y, A = rng.randn(N, d).astype(f32), rng.randn(M, d).astype(f32), rng.randn(m, M).astype(f32)
+    pp = rng.rand(N).astype(f32)
+    k = GenGaussKernel.make_gauss(float(np.sqrt(d)))
+    s = orc.simple_scaler_s(orc.gauss_length_scale(float(np.sqrt(d))))
+    G = orc.gengauss_gram_truth64(X, Y, s, 2.0)
+    got = inner(FiniteVec(k, X, [Prefactors(pp), BalancedRed(4)]), FiniteVec(k, Y, [LinearReduce(A)]))
+    want = ((pp[:, None] * G) @ A.T.astype(np.float64)).reshape(N // 4, 4, m).sum(1)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-5, atol=1e-6)
+    got2 = inner(FiniteVec(k, X, [Mean()]), FiniteVec(k, Y, [Mean()]))
+    np.testing.assert_allclose(got2.cpu().numpy(), G.mean(keepdims=True).reshape(1, 1), rtol=2e-5)
+    with pytest.raises(nat.JrkError):                          # the C entry point itself says so loudly
+        nat.kmatw(cu(X), cu(Y), cu(A.T.copy()), 0.1, 2.0, 1.0)
