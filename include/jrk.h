@@ -71,14 +71,15 @@ extern "C" {
 #define JRK_KIND_THRESHSPIKE 2
 
 /* process-wide switches (jrk_set_option / jrk_get_option).  The environment variable of the same name as the
- * option (JRK_KMATW_TC, JRK_TC_FAST, JRK_TC_V2, JRK_TC2_EPQ, JRK_GRAM_H16) only provides the INITIAL value, read once
+ * option (JRK_KMATW_TC, JRK_TC_FAST, JRK_TC_V2, JRK_TC2_EPQ, JRK_GRAM_H16, JRK_TC2_TOKEN) only provides the INITIAL value, read once
  * per process; nothing in the compute entry points reads the environment. */
 #define JRK_OPT_KMATW_TC 0  /* 1 (default): jrk_kmatw_f32 uses the tensor-core kernels where eligible; 0: FP32-pipe kernel */
 #define JRK_OPT_TC_FAST 1   /* 1 (default): factored p = 2 regime of the tensor-core K@W; 0: generic epilogue always   */
 #define JRK_OPT_TC_V2 2     /* 1 (default): second-generation kernel (kmatw_tc2.cu) in the factored regime             */
 #define JRK_OPT_TC2_EPQ 3   /* epilogue warps per SM sub-partition of the second-generation kernel: 4 (default) or 3   */
 #define JRK_OPT_GRAM_H16 4  /* 1 (default): fp16 hi / lo operands for the tensor Gram at 16 < d <= 64; 0: tf32        */
-#define JRK_OPT_COUNT_ 5
+#define JRK_OPT_TC2_TOKEN 5 /* stagger token of the second-generation kernel's epilogue warps: 0 off, 1..3 chunks        */
+#define JRK_OPT_COUNT_ 6
 
 int jrk_abi_version(void);
 

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libjaxrk_b200.so")
 PATH_AUTO, PATH_DIRECT, PATH_TF32X3 = 0, 1, 2
 KIND_GENGAUSS, KIND_PERIODIC, KIND_THRESHSPIKE = 0, 1, 2
 REDUCE_NONE, REDUCE_SUM, REDUCE_MEAN, REDUCE_BALANCED, REDUCE_BALANCED_MEAN = 0, 1, 2, 3, 4
-OPT_KMATW_TC, OPT_TC_FAST, OPT_TC_V2, OPT_TC2_EPQ, OPT_GRAM_H16 = 0, 1, 2, 3, 4
+OPT_KMATW_TC, OPT_TC_FAST, OPT_TC_V2, OPT_TC2_EPQ, OPT_GRAM_H16, OPT_TC2_TOKEN = 0, 1, 2, 3, 4, 5
 ABI_VERSION = 3
 
 # every symbol include/jrk.h declares: name -> (restype, argtypes)

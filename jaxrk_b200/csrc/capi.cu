@@ -40,8 +40,8 @@ int gram_groupsum(const float* X, const float* Y, float* out, int64_t N, int64_t
 // ---- process-wide options (jrk_set_option) ----
 static std::atomic<int> g_options[JRK_OPT_COUNT_];
 static std::atomic<int> g_options_init{0};
-static const int kOptionDefault[JRK_OPT_COUNT_] = {1, 1, 1, 4, 1};
-static const char* const kOptionEnv[JRK_OPT_COUNT_] = {"JRK_KMATW_TC", "JRK_TC_FAST", "JRK_TC_V2", "JRK_TC2_EPQ", "JRK_GRAM_H16"};
+static const int kOptionDefault[JRK_OPT_COUNT_] = {1, 1, 1, 4, 1, 0};
+static const char* const kOptionEnv[JRK_OPT_COUNT_] = {"JRK_KMATW_TC", "JRK_TC_FAST", "JRK_TC_V2", "JRK_TC2_EPQ", "JRK_GRAM_H16", "JRK_TC2_TOKEN"};
 static void options_init() {
     // the environment variable of the same name gives the INITIAL value, once per process
     int expected = 0;
@@ -139,6 +139,8 @@ int jrk_set_option(int option, int value) {
     if (option < 0 || option >= JRK_OPT_COUNT_) return fail(JRK_ERR_INVALID_ARG, "jrk_set_option: unknown option %d", option);
     if (option == JRK_OPT_TC2_EPQ && value != 3 && value != 4)
         return fail(JRK_ERR_INVALID_ARG, "jrk_set_option: JRK_OPT_TC2_EPQ must be 3 or 4");
+    if (option == JRK_OPT_TC2_TOKEN && (value < 0 || value > 3))
+        return fail(JRK_ERR_INVALID_ARG, "jrk_set_option: JRK_OPT_TC2_TOKEN must be 0 .. 3");
     jrk_option(option);   // make sure the defaults are in place
     g_options[option].store(value);
     return JRK_OK;

@@ -58,7 +58,7 @@ constexpr int T2_COL_X = 0, T2_COL_XLO = 16, T2_COL_O = 32, T2_COL_S = 128;
 constexpr int T2_OFF_RED = T2_SOP * T2_STAGE;                            // per-warp partial results of a unit (2 buffers)
 constexpr int T2_RED_WARP = T2_MT * 32 * 4;                              // [16 columns][32 lanes] floats
 constexpr int T2_OFF_BAR = T2_OFF_RED + 2 * 4 * T2_EPQ_MAX * T2_RED_WARP;
-constexpr int T2_NBAR = 2 * T2_SOP + 3 * T2_NS + 2 * T2_NOB + 1 + 4 + 1;
+constexpr int T2_NBAR = 2 * T2_SOP + 3 * T2_NS + 2 * T2_NOB + 1 + 4 + 1 + 4 * T2_EPQ_MAX;
 constexpr int T2_SMEM = T2_OFF_BAR + T2_NBAR * 8 + 16 + 1024;
 static_assert(T2_COL_S + T2_NS * 64 <= 512 && T2_COL_O + T2_NOB * 32 <= T2_COL_S, "TMEM budget");
 static_assert(T2_SMEM <= 227 * 1024, "shared memory budget");
@@ -80,7 +80,8 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
             if ((threadIdx.x & 31) == 0)
                 printf("STUCK block %d warp %d barrier index %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
                        (int)((bar & 0xfff) >> 3), parity);
-            __nanosleep(100000000);
+            const long long t1 = clock64();
+            while (clock64() - t1 < 6000000000ll) __nanosleep(1000000);     // let every stuck warp report first
             __trap();
         }
     }
@@ -172,6 +173,8 @@ struct Tc2Params {
     const unsigned* nmax;            // [3] bit patterns: max |c||x|^2, max |c||y|^2, max |W col_pref|
     float x_scale;                   // 2^-r
     float nconst;
+    int token_rel;                   // stagger token: chunks (1 .. 3) a warp must be into its tile before the next tile of
+                                     // the lane quarter may start; 0 = off
     long long* trace;                // TRACE builds only (tools/tc2_trace.py): per-warp clock64 stamps of CTA 0
 };
 constexpr int T2_TRACE_TILES = 512;  // stamps per warp: [warp][tile][4]
@@ -197,6 +200,7 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
     uint64_t* x_ready = o_empty + T2_NOB;        // [1]    the epilogue warps parked the unit's X block
     uint64_t* g1_tok = x_ready + 1;              // [4]    issuing warp j finished the GEMM1 phase of a group
     uint64_t* x_free = g1_tok + 4;               // [1]    every GEMM1 of the unit has completed (X may be replaced)
+    uint64_t* half_done = x_free + 1;            // [4][EPQ_MAX]  epilogue warp (quarter, k) is P.token_rel chunks into its tile
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T2_OFF_BAR + T2_NBAR * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -207,6 +211,7 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
         mbar_init(x_ready, EW);
         for (int s = 0; s < 4; ++s) mbar_init(&g1_tok[s], 1);
         mbar_init(x_free, 4);
+        for (int s = 0; s < 4 * T2_EPQ_MAX; ++s) mbar_init(&half_done[s], 1);
         fence_mbar_init();
     }
     // roles: warps 0 .. EW-1 epilogue; then FOUR MMA-issuing warps, one per SM sub-partition, and the TMA producer.
@@ -351,7 +356,13 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
         asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));
         const uint32_t b_sfull = sbase + T2_OFF_BAR + 2 * T2_SOP * 8, b_eready = b_sfull + T2_NS * 8,
                        b_ofull = b_sfull + 3 * T2_NS * 8, b_oempty = b_ofull + T2_NOB * 8, b_xready = b_oempty + T2_NOB * 8,
-                       b_xfree = b_xready + 5 * 8;
+                       b_xfree = b_xready + 5 * 8, b_half = b_xfree + 8 + (uint32_t)(quad * T2_EPQ_MAX) * 8;
+        // Stagger token (P.token_rel = 1 .. 3, 0 = off): the four warps of a sub-partition share ONE MUFU pipe; left alone
+        // they fall into lockstep (all convert, then all store / fold / wait together, and the pipe idles: tools/
+        // tc2_trace.py).  With the token a warp starts tile t only after the owner of tile t - 1 (same lane quarter) is
+        // token_rel chunks into it, so the MUFU phases interleave and one warp's bookkeeping hides behind another's ex2.
+        const int token_rel = P.token_rel;
+
         const int nwin = (T + T2_WIN - 1) / T2_WIN;
         // 2^ew: the power of two that normalises W' (the pack pre-pass divides by it)
         const float wpow = pow2i(tc2_w_exp(__uint_as_float(__ldg(P.nmax + 2))));
@@ -407,6 +418,17 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
             for (int t = k; t < T; t += EPQ) {
                 const uint32_t g = gt + (uint32_t)t, a = g % T2_NS;
                 const long long tr0 = TRACE ? clock64() : 0;
+                if (token_rel && (t > 0 || uc > 0)) {
+                    // EVERY tile but the very first waits for its predecessor, across unit boundaries too: a parity wait
+                    // is only right when the barrier is 0 or 1 phases from the awaited one, and an unbroken chain is
+                    // what guarantees that (a warp that skips a wait can run ahead, its successors pass "early" on the
+                    // wrong parity, and the chain dead-locks two tiles later)
+                    const int tp = t > 0 ? t - 1 : T - 1;                            // the previous tile ...
+                    const uint32_t kq = (uint32_t)(tp % EPQ);                        // ... its owner ...
+                    const uint32_t tpu_q = (uint32_t)((T - (int)kq + EPQ - 1) / EPQ);
+                    const uint32_t idx = (t > 0 ? uc : uc - 1) * tpu_q + (uint32_t)(tp / EPQ);   // ... and which of its arrivals
+                    bar_wait(b_half + kq * 8, idx & 1);
+                }
                 bar_wait(b_sfull + a * 8, (g / T2_NS) & 1);
                 tc_fence_after();
                 const long long tr1 = TRACE ? clock64() : 0;
@@ -419,14 +441,17 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
                 ld16_async(sc + 16, s1);
                 exp_split16(s0, eo);
                 tmem_st16(sc, eo);
+                if (token_rel == 1 && lane == 0) bar_arrive(b_half + k * 8);
                 ld16_wait(s1);
                 ld16_async(sc + 32, s0);
                 exp_split16(s1, eo);
                 tmem_st16(sc + 16, eo);
+                if (token_rel == 2 && lane == 0) bar_arrive(b_half + k * 8);
                 ld16_wait(s0);
                 ld16_async(sc + 48, s1);
                 exp_split16(s0, eo);
                 tmem_st16(sc + 32, eo);
+                if (token_rel == 3 && lane == 0) bar_arrive(b_half + k * 8);
                 ld16_wait(s1);
                 exp_split16(s1, eo);
                 tmem_st16(sc + 48, eo);
@@ -610,6 +635,7 @@ int kmatw_tc2_apply(const float* X, int64_t N, int d, int64_t ldx, const float* 
     P.nmax = nmax;
     P.x_scale = tc2_scales(c).x_scale;
     P.nconst = nconst;
+    P.token_rel = jrk_option(JRK_OPT_TC2_TOKEN);
     P.trace = g_tc2_trace;
     const int grid = P.n_units < tf_sm_count() ? P.n_units : tf_sm_count();
     // epilogue warps per SM sub-partition: 4; JRK_TC2_EPQ = 3 for A/B runs

@@ -11,7 +11,8 @@ from jaxrk_b200 import _native as nat  # noqa: E402
 
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(0)
-VARIANTS = (("v2", {}), ("v2/epq3", {nat.OPT_TC2_EPQ: 3}), ("v1", {nat.OPT_TC_V2: 0}))
+VARIANTS = (("v2", {}), ("v2/tok1", {nat.OPT_TC2_TOKEN: 1}), ("v2/tok2", {nat.OPT_TC2_TOKEN: 2}), ("v2/tok3", {nat.OPT_TC2_TOKEN: 3}),
+            ("v2/epq3", {nat.OPT_TC2_EPQ: 3}), ("v2/epq3tok2", {nat.OPT_TC2_EPQ: 3, nat.OPT_TC2_TOKEN: 2}), ("v1", {nat.OPT_TC_V2: 0}))
 
 
 class Options:
@@ -70,7 +71,7 @@ def acc(N, M, d, m, ls_factor=1.0, positive=False, prefs=False, wscale=1.0):
         res[name] = err_vs_truth(A, X, Y, W, s, nc, rows, rp, cp)
     print(f"N={N} M={M} d={d} m={m} ls*{ls_factor} bound={bnd:.2f} pos={positive} prefs={prefs} wscale={wscale:g}: err/lim "
           + "  ".join(f"{k} {v:.3f}" for k, v in res.items()), flush=True)
-    return max(res["v2"], res["v2/epq3"])
+    return max(res["v2"], res["v2/epq3"], res["v2/tok2"])
 
 
 def time_one(N, M, d, m, reps=3):

@@ -6,6 +6,8 @@ from jaxrk_b200 import _native as nat
 N, M, d, m = (int(v) for v in sys.argv[1:5])
 if len(sys.argv) > 5:
     nat.set_option(nat.OPT_TC2_EPQ, int(sys.argv[5]))
+if len(sys.argv) > 6:
+    nat.set_option(nat.OPT_TC2_TOKEN, int(sys.argv[6]))
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(int(os.environ.get('SEED', '0')))
 X = torch.randn(N, d, generator=g, device=dev); Y = torch.randn(M, d, generator=g, device=dev); W = torch.randn(M, m, generator=g, device=dev)

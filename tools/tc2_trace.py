@@ -12,6 +12,8 @@ from jaxrk_b200 import _native as nat  # noqa: E402
 
 epq = sys.argv[1] if len(sys.argv) > 1 else "4"
 nat.set_option(nat.OPT_TC2_EPQ, int(epq))
+tok = sys.argv[2] if len(sys.argv) > 2 else "0"
+nat.set_option(nat.OPT_TC2_TOKEN, int(tok))
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(0)
 N, M, d, m = 148 * 128 * 2, 512 * 64, 16, 16
@@ -31,5 +33,5 @@ torch.cuda.synchronize()
 L.jrk_debug_tc2_trace(None)
 out = buf.cpu().numpy().reshape(19, 512, 4)
 os.makedirs("gpurun_out", exist_ok=True)
-np.save(f"gpurun_out/tc2_trace_epq{epq}.npy", out)
+np.save(f"gpurun_out/tc2_trace_epq{epq}" + (f"_tok{tok}" if tok != "0" else "") + ".npy", out)
 print("saved", out.shape, int((out != 0).sum()))

@@ -2,7 +2,8 @@
 import sys
 import numpy as np
 epq = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-tr = np.load(f'gpurun_out/tc2_trace_epq{epq}.npy')
+suffix = ('_tok' + sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] != '0' else ''
+tr = np.load(f'gpurun_out/tc2_trace_epq{epq}{suffix}.npy')
 t0 = tr[tr > 0].min()
 tr = np.where(tr > 0, tr - t0, 0)
 g1, g2 = tr[17], tr[18]
