@@ -65,33 +65,53 @@ __device__ __forceinline__ void exp_split16(const uint32_t (&sv)[16], uint32_t (
     }
 }
 
-template <int V>
-__global__ void __launch_bounds__(16 * 32, 1) epi_kernel(long long* cyc, uint32_t* sink) {
+// variants of the conversion for the pipe question: which pipe do the f32 -> f16x2 conversions run on?
+//   PK = 0: cvt.rn.f16x2.f32 (F2FP.F16.F32.PACK_AB)   PK = 1: PRMT (bf16-style truncation: wrong numbers, ALU pipe)
+//   PK = 2: no packing at all (xor)                   PK = 3: MUFU only (no split arithmetic either)
+template <int PK>
+__device__ __forceinline__ void exp_split16_v(const uint32_t (&sv)[16], uint32_t (&eo)[16]) {
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) {
+        const float e0 = ex2_approx(__uint_as_float(sv[c])), e1 = ex2_approx(__uint_as_float(sv[c + 1]));
+        if (PK == 3) { eo[c >> 1] = __float_as_uint(e0); eo[8 + (c >> 1)] = __float_as_uint(e1); continue; }
+        const float h0 = __uint_as_float(__float_as_uint(e0) & 0xFFFFE000u);
+        const float h1 = __uint_as_float(__float_as_uint(e1) & 0xFFFFE000u);
+        float l0, l1;
+        unpack2(mul2(sub2(pack2(e0, e1), pack2(h0, h1)), pack2(2048.f, 2048.f)), l0, l1);
+        if (PK == 0) { eo[c >> 1] = cvt_f16x2(h1, h0); eo[8 + (c >> 1)] = cvt_f16x2(l1, l0); }
+        else if (PK == 1) { eo[c >> 1] = __byte_perm(__float_as_uint(h0), __float_as_uint(h1), 0x7632); eo[8 + (c >> 1)] = __byte_perm(__float_as_uint(l0), __float_as_uint(l1), 0x7632); }
+        else { eo[c >> 1] = __float_as_uint(h0) ^ __float_as_uint(h1); eo[8 + (c >> 1)] = __float_as_uint(l0) ^ __float_as_uint(l1); }
+    }
+}
+
+template <int V, int WPS = 4>
+__global__ void __launch_bounds__(WPS * 4 * 32, 1) epi_kernel(long long* cyc, uint32_t* sink) {
     __shared__ uint32_t slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tmem_alloc_512(smem_u32(&slot));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tb = slot + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 128;   // 2 x 64 columns per warp
+    const uint32_t tb = slot + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * (WPS == 4 ? 128 : 64);   // 2 x 64 (or 1 x 64) columns per warp
     uint32_t acc = 0;
     {   // initialise the warp's TMEM block
         uint32_t z[16];
         for (int c = 0; c < 16; ++c) z[c] = 0x3a800000u + lane + c;
-        for (int q = 0; q < 8; ++q) tmem_st16(tb + 16 * q, z);
+        for (int q = 0; q < (WPS == 4 ? 8 : 4); ++q) tmem_st16(tb + 16 * q, z);
         tmem_st_wait();
     }
     __syncthreads();
     const long long t0 = clock64();
     for (int t = 0; t < TILES; ++t) {
-        const uint32_t sc = tb + (t & 1) * 64;
+        const uint32_t sc = tb + (WPS == 4 ? (t & 1) * 64 : 0);
         uint32_t s0[16], s1[16], eo[16];
-        if (V == 0) {
+        if (V == 0 || V >= 8) {
 #pragma unroll
             for (int c = 0; c < 16; ++c) s0[c] = 0x3a800000u + lane + c + t;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                exp_split16(s0, eo);
+                if (V == 0) exp_split16(s0, eo);
+                else exp_split16_v<V - 8>(s0, eo);
 #pragma unroll
                 for (int c = 0; c < 16; ++c) { acc ^= eo[c]; s0[c] = (eo[c] & 0x007fffffu) | 0x3a800000u; }
             }
@@ -189,24 +209,25 @@ __global__ void __launch_bounds__(16 * 32, 1) epi_kernel(long long* cyc, uint32_
     if (warp == 0) tmem_dealloc_512(slot);
 }
 
-template <int V>
+template <int V, int WPS = 4>
 void run(long long* cyc, uint32_t* sink, const char* what) {
-    epi_kernel<V><<<1, 16 * 32>>>(cyc, sink);
+    epi_kernel<V, WPS><<<1, WPS * 4 * 32>>>(cyc, sink);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("variant %d: %s\n", V, cudaGetErrorString(e)); return; }
-    long long h[16];
-    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    long long h[32];
+    cudaMemcpy(h, cyc, WPS * 4 * 8, cudaMemcpyDeviceToHost);
     double mx = 0;
-    for (int w = 0; w < 16; ++w) mx = h[w] > mx ? (double)h[w] : mx;
+    for (int w = 0; w < WPS * 4; ++w) mx = h[w] > mx ? (double)h[w] : mx;
     // a sub-partition's 4 warps convert 4 x TILES quarter-tiles: TILES "rounds" of 4 x 64 MUFU x 8 clk = 2048 clk
-    printf("{\"variant\": %d, \"what\": \"%s\", \"clk_per_tile\": %.1f, \"mufu_frac\": %.3f}\n", V, what, mx / TILES / 4.0, 512.0 * 4.0 * TILES / mx);
+    printf("{\"variant\": %d, \"warps_per_subpartition\": %d, \"what\": \"%s\", \"clk_per_tile\": %.1f, \"mufu_frac\": %.3f}\n", V, WPS, what,
+           mx / TILES / WPS, 512.0 * WPS * TILES / mx);
 }
 
 int main() {
     long long* cyc;
     uint32_t* sink;
-    cudaMalloc(&cyc, 16 * 8);
-    cudaMalloc(&sink, 16 * 32 * 4);
+    cudaMalloc(&cyc, 32 * 8);
+    cudaMalloc(&sink, 32 * 32 * 4);
     run<0>(cyc, sink, "registers only");
     run<1>(cyc, sink, "ld16 + wait, st16 per chunk");
     run<2>(cyc, sink, "ld16 pipelined, st16");
@@ -215,5 +236,17 @@ int main() {
     run<5>(cyc, sink, "ld32 x 2, st16");
     run<6>(cyc, sink, "ld64, st16");
     run<7>(cyc, sink, "ld16 pipelined, st8 + st8");
+    run<8>(cyc, sink, "registers only, F2FP packing (= variant 0)");
+    run<9>(cyc, sink, "registers only, PRMT packing instead of F2FP");
+    run<10>(cyc, sink, "registers only, no packing");
+    run<11>(cyc, sink, "registers only, MUFU alone");
+    run<0, 6>(cyc, sink, "registers only");
+    run<2, 6>(cyc, sink, "ld16 pipelined, st16");
+    run<0, 8>(cyc, sink, "registers only");
+    run<2, 8>(cyc, sink, "ld16 pipelined, st16");
+    run<0, 2>(cyc, sink, "registers only");
+    run<2, 2>(cyc, sink, "ld16 pipelined, st16");
+    run<0, 3>(cyc, sink, "registers only");
+    run<2, 3>(cyc, sink, "ld16 pipelined, st16");
     return 0;
 }

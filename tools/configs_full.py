@@ -66,4 +66,20 @@ if what in ("cfg5", "all"):
     inner(FiniteVec(k, Xt[:16384]), FiniteVec(k, X, [LinearReduce(W)]))     # warm-up
     out, t_apply = timed(lambda: inner(FiniteVec(k, Xt), FiniteVec(k, X, [LinearReduce(W)])))
     print(json.dumps({"config": "cfg5-apply", "T": T, "N": N, "m": m, "out": list(out.shape), "seconds": t_apply,
-                      "evals_per_s": T * N / t_apply, "fp32_pipe_frac": T * N / t_apply * (2 * d + m + 2) / 3.69e13}), flush=True)
+                      "evals_per_s": T * N / t_apply, "mufu_frac": T * N / t_apply / 4.637e12}), flush=True)
+    # the same through the operator objects: Cdo(inp, outp, ref, regul) @ X_test with a 256-point reference grid
+    from jaxrk_b200.rkhs.operator import Cdo  # noqa: E402
+    R = 256
+    Yv = torch.sin(X[:, :1]) + 0.1 * randn(5, N, 1)
+    ky = GenGaussKernel.make_gauss(0.3)
+    cdo, t_build = timed(lambda: Cdo(FiniteVec(k, X), FiniteVec(ky, Yv), FiniteVec(ky, torch.linspace(-2, 2, R, device=dev)[:, None]), regul=1.0))
+    _, t_map = timed(lambda: cdo.inp_feat.reduce[-1].linear_map)        # Cmo's N x N coefficient map: K(X, X) @ matr^T, m = N
+    res = cdo @ Xt
+    n0 = nat.launch_count()
+    coeff, t_cdo = timed(lambda: res.reduce[-1].linear_map)
+    print(json.dumps({"config": "cfg5-Cdo through the operator objects", "N": N, "T": T, "R": R, "build_seconds (2 Grams + library inverses)": t_build,
+                      "Cmo map K(X,X)@matr^T (m = N = 32768) seconds": t_map, "Cmo map TFLOP/s equivalent": 2.0 * N * N * N / t_map / 1e12,
+                      "apply_seconds (K(X_test, X) @ A^T, m = 256)": t_cdo, "apply_evals_per_s": T * N / t_cdo,
+                      "apply_TFLOP/s equivalent": 2.0 * T * N * R / t_cdo / 1e12, "launches": nat.launch_count() - n0}), flush=True)
+    mv, t_mv = timed(lambda: res.get_mean_var())
+    print(json.dumps({"config": "cfg5-get_mean_var on the applied operator (skinny, map not materialised twice)", "seconds": t_mv}), flush=True)
