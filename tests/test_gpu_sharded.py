@@ -40,16 +40,24 @@ print("rank", rank, "ok")
 '''
 
 
+def _worlds():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    return sorted({2, min(n, 8)} - {0, 1}) if n >= 2 else [2]
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_nccl_world_size_2(tmp_path):
+@pytest.mark.parametrize("world", _worlds())
+def test_nccl_world(tmp_path, world):
+    """world = 2 and, on a bigger box, every GPU of the node (gpurun --gpus 8): sharded_inner's all_reduce / all_gather and
+    sharded_gram over NCCL against the single-GPU result."""
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     root = os.path.dirname(HERE)
-    procs = [subprocess.Popen([sys.executable, str(script), str(r), "2", str(port)], cwd=root, stdout=subprocess.PIPE,
-                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world), str(port)], cwd=root, stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(world)]
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o[-3000:]
