@@ -25,7 +25,19 @@
 namespace jrk {
 namespace tf32 { int tf_sm_count(); }
 
+// kgrad_tc.cu
+bool kgrad_tc_eligible(int64_t N, int64_t M, int d, int m, int pm);
+size_t kgrad_tc_workspace_bytes(int64_t N, int64_t M);
+int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, int64_t N, int64_t M,
+             int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float c, float fac, float fac_s,
+             void* scratch, const unsigned** nmax_out, cudaStream_t st);
+
 namespace {
+
+// the regime test of kmatw_tc2.cuh (TC_FAST_BOUND = 12) on the two norm maxima of the pre-pass
+__device__ __forceinline__ bool kg_fast_regime(const unsigned* nmax) {
+    return (__uint_as_float(__ldg(nmax)) + __uint_as_float(__ldg(nmax + 1))) <= 12.0f;
+}
 
 constexpr int KG_ROWS = 128, KG_TJ = 32;
 
@@ -33,7 +45,10 @@ template <int D, int MT, int MODE, int PM>
 __global__ void __launch_bounds__(KG_ROWS, 2)
 kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ Y, int64_t ldy, int d,
              const float* __restrict__ W, int64_t ldw, const float* __restrict__ G, int64_t ldg, int m,
-             int64_t N, int64_t M, int64_t cols_per_split, EpiParams ep, float* __restrict__ part, int stride) {
+             int64_t N, int64_t M, int64_t cols_per_split, EpiParams ep, float* __restrict__ part, int stride,
+             const unsigned* __restrict__ skip_if_fast) {
+    // the tensor-core kernel (kgrad_tc.cu) was launched next to this one: inside its regime the result is its to write
+    if (skip_if_fast && kg_fast_regime(skip_if_fast)) return;
     // part layout: [split][row][stride], stride = d + 2: {dL/dx contribution (d), S0 (unused by finalize), S2}
     __shared__ __align__(16) float sY[KG_TJ][D];
     __shared__ __align__(16) float sA[(MODE == 0) ? KG_TJ * MT : KG_ROWS * (KG_TJ + 1)];
@@ -174,7 +189,9 @@ kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__
 
 // gX[i, k] = fac * sum_split part[split][i][k];  gs_rows[i] = -(fac / s) * sum_split part[split][i][d + 1]
 __global__ void kgrad_finalize_kernel(const float* __restrict__ part, int nsplit, int64_t N, int d, int stride, float fac,
-                                      float fac_s, float* __restrict__ gX, int64_t ldgx, float* __restrict__ gs_rows) {
+                                      float fac_s, float* __restrict__ gX, int64_t ldgx, float* __restrict__ gs_rows,
+                                      const unsigned* __restrict__ skip_if_fast) {
+    if (skip_if_fast && kg_fast_regime(skip_if_fast)) return;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t i = idx / (d + 1);
     const int k = (int)(idx % (d + 1));
@@ -188,8 +205,8 @@ __global__ void kgrad_finalize_kernel(const float* __restrict__ part, int nsplit
 template <int D, int MT, int MODE, int PM>
 int kg_launch(dim3 grid, cudaStream_t st, const float* X, int64_t ldx, const float* Y, int64_t ldy, int d, const float* W,
               int64_t ldw, const float* G, int64_t ldg, int m, int64_t N, int64_t M, int64_t cps, const EpiParams& ep,
-              float* part, int stride) {
-    kgrad_kernel<D, MT, MODE, PM><<<grid, KG_ROWS, 0, st>>>(X, ldx, Y, ldy, d, W, ldw, G, ldg, m, N, M, cps, ep, part, stride);
+              float* part, int stride, const unsigned* skip) {
+    kgrad_kernel<D, MT, MODE, PM><<<grid, KG_ROWS, 0, st>>>(X, ldx, Y, ldy, d, W, ldw, G, ldg, m, N, M, cps, ep, part, stride, skip);
     JRK_LAUNCHED();
     return JRK_OK;
 }
@@ -217,7 +234,9 @@ KgPlan kg_plan(int64_t N, int64_t M) {
 
 size_t kgrad_workspace_bytes(int64_t N, int64_t M, int d) {
     const KgPlan p = kg_plan(N, M);
-    return align256((size_t)p.nsplit * (size_t)N * (size_t)(d + 2) * 4) + 512;
+    size_t b = align256((size_t)p.nsplit * (size_t)N * (size_t)(d + 2) * 4) + 512;
+    if (kgrad_tc_eligible(N, M, d, 1, PM_SQEXP)) b += kgrad_tc_workspace_bytes(N, M);
+    return b;
 }
 
 // mode 0: K@W cotangent (W: M x m, G: N x m);  mode 1: Gram cotangent (G = Gbar: N x M, W unused, m = 0)
@@ -235,6 +254,14 @@ int kgrad(int mode, const float* X, const float* Y, const float* W, const float*
     const double s = (double)scale;
     const float fac = (float)((double)nconst * (pm == PM_SQEXP ? 2.0 * s * s : pm == PM_LAPLACE ? s : (double)power));
     const float fac_s = (float)(-(double)fac / s);
+    // K@W cotangent, p = 2, d <= 16, m <= 16, large: both inner products on the tensor cores (kgrad_tc.cu).  Whether the
+    // problem lies inside its regime is known on the device only, so the FP32 kernels below are enqueued as well and
+    // return at once when it does.
+    const unsigned* skip = nullptr;
+    if (mode == 0 && kgrad_tc_eligible(N, M, d, m, pm)) {
+        void* tcs = scr.take<char>(kgrad_tc_workspace_bytes(N, M));
+        if (int rc = kgrad_tc(X, Y, W, G, gX, gs_rows, N, M, d, m, ldx, ldy, ldw, ldg, ldgx, ep.c, fac, fac_s, tcs, &skip, st)) return rc;
+    }
     const int64_t nblk = (N + KG_ROWS - 1) / KG_ROWS;
     if (nblk > 2147483647LL) return fail(JRK_ERR_UNSUPPORTED, "kgrad: too many rows");
     dim3 grid((unsigned)nblk, (unsigned)p.nsplit);
@@ -245,7 +272,7 @@ int kgrad(int mode, const float* X, const float* Y, const float* W, const float*
     const int MT = m <= 4 ? 4 : m <= 16 ? 16 : 32;
     int rc;
 #define KG_GO(D_, MT_, MODE_, PM_) \
-    rc = kg_launch<D_, MT_, MODE_, PM_>(grid, st, X, ldx, Y, ldy, d, W, ldw, G, ldg, m, N, M, p.cols_per_split, ep, part, stride)
+    rc = kg_launch<D_, MT_, MODE_, PM_>(grid, st, X, ldx, Y, ldy, d, W, ldw, G, ldg, m, N, M, p.cols_per_split, ep, part, stride, skip)
 #define KG_MT(D_, PM_)                                   \
     do {                                                 \
         if (mode == 1) KG_GO(D_, 4, 1, PM_);             \
@@ -268,7 +295,7 @@ int kgrad(int mode, const float* X, const float* Y, const float* W, const float*
 #undef KG_GO
     if (rc) return rc;
     const int64_t tot = N * (d + 1);
-    kgrad_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(part, p.nsplit, N, d, stride, fac, fac_s, gX, ldgx, gs_rows);
+    kgrad_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(part, p.nsplit, N, d, stride, fac, fac_s, gX, ldgx, gs_rows, skip);
     JRK_LAUNCHED();
     return JRK_OK;
 }

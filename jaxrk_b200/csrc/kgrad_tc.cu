@@ -1,0 +1,457 @@
+// Kernel (g'): the K@W vector-Jacobian product with both inner products on the tensor cores -- the factored p = 2
+// regime of kmatw_tc2.cu (|c| (max|x|^2 + max|y|^2) <= 12, decided on the device), d <= 16, m <= 16.
+//
+// Replaces the same reference behaviour as kgrad.cu MODE 0: what jax.grad derives from FiniteVec.inner
+// (jaxrk/rkhs/vector.py:62-75) with a LinearReduce on the Y side (jaxrk/reduce/lincomb.py:137-140) for GenGaussKernel
+// with power = 2 (jaxrk/kern/rbf.py:84-105) -- gradients with respect to the points and the scale, K never materialised.
+//
+//   t_ij = a_ij K_ij / nconst,   a_ij = G_i . W_j,   K_ij / nconst = 2^(c|x_i|^2) 2^(S_ij) 2^(c|y_j|^2),  S = -2c x.y
+//   gX_i      = fac  (sum_j t_ij y_j - x_i sum_j t_ij)
+//   gs_rows_i = fac_s (|x_i|^2 sum_j t_ij - 2 x_i . sum_j t_ij y_j + sum_j t_ij |y_j|^2)
+//
+// kgrad.cu spends 3d + m + 8 FP32 lane-operations per pair (differences, the m-term dot product a_ij, the d + 2
+// accumulations).  Here the two inner products run on tcgen05 into TMEM,
+//   GEMM1   S = x~ . y''          kind::f16, fp16 hi / lo operands, exactly as kmatw_tc2.cu
+//   GEMM1b  g = G . W'^T          kind::tf32, 3 x TF32 (hi / lo: no range restriction on G or W),  W' = W 2^(c|y|^2)
+// and an epilogue thread (one TMEM lane = one row i) is left with  tt = ex2(S) g  and the d + 2 accumulations
+// sum_j tt (y_j, 1, |y_j|^2) in FP32 registers: 18 FMA lane-operations per pair instead of 72.  y_j, 1 and |y_j|^2 come
+// from the same tile image as FP32, read as shared-memory broadcasts.  Accumulation is hierarchical (per tile of 32
+// columns, then per unit), so the rounding error does not grow with M.
+//
+// Roofline: FP32 pipe, d + 2 = 18 lane-operations per pair -> 3.69e13 / 18 = 2.05e12 pairs/s; next to it 5 LDS (4 x
+// 128-bit + 1 x 64-bit broadcast) and one MUFU per pair.
+//
+// Layout per CTA (persistent, one per SM): 16 epilogue warps (4 per TMEM lane quarter; tile t belongs to warp t mod 4 of
+// each quarter), one MMA-issuing warp, one TMA warp.  TMEM: x~ hi [0, 8) lo [8, 16) | G hi [16, 32) lo [32, 48) | six
+// stages [128 + 64 a, +64) = {S [32) | g [32)}.  Tile image (32 rows of Y, 8448 bytes, one cp.async.bulk):
+//   rows 0..31   (128 B, SWIZZLE_128B): [y'' hi 32 B | y'' lo 32 B | y FP32 64 B]
+//   rows 32..63  (128 B, SWIZZLE_128B): [W' tf32 hi 64 B | W' tf32 lo 64 B]
+//   then 32 x {1.0f, |y_j|^2}
+#include <cmath>
+#include <cstdlib>
+
+#include "gram_tf32_kernel.cuh"
+#include "kmatw_tc2.cuh"
+#include "tc2_prims.cuh"
+
+namespace jrk {
+
+using namespace tf32;
+using namespace tcp;
+
+namespace {
+
+constexpr int GT_BM = 128, GT_NT = 32, GT_D = 16, GT_MT = 16;
+constexpr int GT_NS = 6;                       // {S | g} stages in TMEM (64 columns each)
+constexpr int GT_SOP = 10;                     // tile-image stages in shared memory
+constexpr int GT_IMG = 8448;                   // bytes of one tile image
+constexpr int GT_STAGE = 9216;                 // stage stride (1024-byte aligned)
+constexpr int GT_EPQ = 4, GT_EW = 4 * GT_EPQ;
+constexpr int GT_COL_X = 0, GT_COL_XLO = 8, GT_COL_G = 16, GT_COL_GLO = 32, GT_COL_S = 128;
+constexpr int GT_NACC = GT_D + 2;              // sum tt y_k (16), sum tt, sum tt |y|^2
+constexpr int GT_OFF_RED = GT_SOP * GT_STAGE;
+constexpr int GT_RED_WARP = GT_NACC * 32 * 4;  // [18][32 lanes] floats
+constexpr int GT_OFF_BAR = GT_OFF_RED + 2 * GT_EW * GT_RED_WARP;
+constexpr int GT_NBAR = 2 * GT_SOP + 2 * GT_NS + 2;
+constexpr int GT_SMEM = GT_OFF_BAR + GT_NBAR * 8 + 16 + 1024;
+constexpr int GT_THREADS = (GT_EW + 2) * 32;
+static_assert(GT_COL_S + GT_NS * 64 <= 512, "TMEM budget");
+static_assert(GT_SMEM <= 227 * 1024, "shared memory budget");
+
+struct GtParams {
+    const float* X; int64_t ldx; int d;
+    const float* G; int64_t ldg; int m;
+    const float* xn;                  // c |x_i|^2
+    const unsigned char* img;
+    float* gX; int64_t ldgx;
+    float* gs_rows;                   // nullable
+    int64_t N;
+    int n_tiles, n_units;
+    const unsigned* nmax;             // [2] bit patterns: max |c||x|^2, max |c||y|^2
+    float x_scale, inv_c;             // 2^-r of GEMM1;  1 / c (|x_i|^2 = xn_i / c)
+    float fac, fac_s;
+};
+
+__device__ __forceinline__ void lds_2x64(uint32_t addr, f32x2& a, f32x2& b) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ f32x2 lds_64(uint32_t addr) {
+    f32x2 a;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(a) : "r"(addr));
+    return a;
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
+    if (!tc2_fast_regime(P.nmax)) return;      // kgrad.cu serves the problem
+    extern __shared__ unsigned char gt_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gt_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GT_OFF_BAR);
+    uint64_t* op_full = bars;                  // [SOP]  tile image landed
+    uint64_t* op_empty = op_full + GT_SOP;     // [SOP]  the four owner warps are done with the image
+    uint64_t* s_full = op_empty + GT_SOP;      // [NS]   GEMM1 + GEMM1b of the stage complete
+    uint64_t* s_empty = s_full + GT_NS;        // [NS]   the four owner warps read the stage
+    uint64_t* x_ready = s_empty + GT_NS;       // [1]    x~ and G of the unit are parked
+    uint64_t* x_free = x_ready + 1;            // [1]    every MMA of the unit has completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + GT_OFF_BAR + GT_NBAR * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GT_SOP; ++s) { mbar_init(&op_full[s], 1); mbar_init(&op_empty[s], 4); }
+        for (int s = 0; s < GT_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
+        mbar_init(x_ready, GT_EW);
+        mbar_init(x_free, 1);
+        fence_mbar_init();
+    }
+    constexpr int W_MMA = GT_EW, W_TMA = GT_EW + 1;
+    if (warp == W_MMA) tmem_alloc_512(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tmem_base != 0) __trap();
+
+    const int T = P.n_tiles;
+    if (warp == W_TMA) {
+        // ===================== TMA producer: one image per tile =====================
+        uint32_t tc = 0;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+            for (int t = 0; t < T; ++t, ++tc) {
+                const int s = tc % GT_SOP;
+                mbar_wait_hint(&op_empty[s], ((tc / GT_SOP) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&op_full[s], GT_IMG);
+                    bulk_g2s(smem + s * GT_STAGE, P.img + (int64_t)t * GT_IMG, GT_IMG, &op_full[s]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ===================== MMA issuer: 3 (fp16) + 6 (tf32) MMAs of N = 32 per tile =====================
+        constexpr uint32_t id_h = (1u << 4) | ((uint32_t)(GT_NT >> 3) << 17) | ((uint32_t)(GT_BM >> 4) << 24);
+        constexpr uint32_t id_t = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GT_NT >> 3) << 17) | ((uint32_t)(GT_BM >> 4) << 24);
+        const uint64_t dbase = make_b_desc(smem_u32(smem));
+        const uint32_t b_opfull = smem_u32(op_full), b_sfull = smem_u32(s_full), b_sempty = smem_u32(s_empty),
+                       b_xready = smem_u32(x_ready), b_xfree = smem_u32(x_free);
+        uint32_t gt = 0, uc = 0;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, ++uc) {
+            bar_wait(b_xready, uc & 1);
+            tc_fence_after();
+            for (int t = 0; t < T; ++t) {
+                const uint32_t g = gt + (uint32_t)t, s = g % GT_SOP, a = g % GT_NS;
+                bar_wait(b_opfull + s * 8, (g / GT_SOP) & 1);
+                bar_wait(b_sempty + a * 8, ((g / GT_NS) & 1) ^ 1);
+                tc_fence_after();
+                const uint64_t dy = dbase + (uint64_t)((s * GT_STAGE) >> 4);
+                const uint64_t dw = dy + (uint64_t)(4096 >> 4);
+                const uint32_t cs = GT_COL_S + a * 64, cg = cs + 32;
+                if (elect_one()) {
+                    // the small cross terms first, the hi.hi terms last (the accumulator truncates)
+                    mma_f16_ts(cs, GT_COL_X, dy + 2, id_h, 0u);                    // hi_x . lo_y
+                    mma_f16_ts(cs, GT_COL_XLO, dy, id_h, 1u);                      // lo_x . hi_y
+                    mma_f16_ts(cs, GT_COL_X, dy, id_h, 1u);                        // hi_x . hi_y
+                    mma_tf32_ts(cg, GT_COL_G, dw + 4, id_t, 0u);                   // hi_g . lo_w  (k-steps 0, 1)
+                    mma_tf32_ts(cg, GT_COL_G + 8, dw + 6, id_t, 1u);
+                    mma_tf32_ts(cg, GT_COL_GLO, dw, id_t, 1u);                     // lo_g . hi_w
+                    mma_tf32_ts(cg, GT_COL_GLO + 8, dw + 2, id_t, 1u);
+                    mma_tf32_ts(cg, GT_COL_G, dw, id_t, 1u);                       // hi_g . hi_w
+                    mma_tf32_ts(cg, GT_COL_G + 8, dw + 2, id_t, 1u);
+                    commit_addr(b_sfull + a * 8);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) commit_addr(b_xfree);
+            __syncwarp();
+            gt += (uint32_t)T;
+        }
+    } else {
+        // ===================== epilogue warps (and X / G loaders) =====================
+        const int quad = warp & 3, k = warp >> 2;
+        uint32_t lane_base;
+        asm volatile("mov.u32 %0, %1;" : "=r"(lane_base) : "r"(tmem_base + ((uint32_t)(quad * 32) << 16)));
+        uint32_t sbase;
+        asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));
+        const uint32_t b_opfull = sbase + GT_OFF_BAR, b_opempty = b_opfull + GT_SOP * 8, b_sfull = b_opempty + GT_SOP * 8,
+                       b_sempty = b_sfull + GT_NS * 8, b_xready = b_sempty + GT_NS * 8, b_xfree = b_xready + 8;
+        float* red = reinterpret_cast<float*>(smem + GT_OFF_RED);
+
+        auto park = [&](int u) {
+            // warp 0 of the quarter: x~ = x 2^-r as fp16 hi / lo pairs;  warps 1 / 2: G as tf32 hi / lo
+            const int64_t i = (int64_t)u * GT_BM + quad * 32 + lane;
+            const bool iok = i < P.N;
+            if (k == 0) {
+                const float* xrow = P.X + (iok ? i : 0) * P.ldx;
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float v0 = (iok && 2 * q < P.d) ? __ldg(xrow + 2 * q) : 0.f;
+                    const float v1 = (iok && 2 * q + 1 < P.d) ? __ldg(xrow + 2 * q + 1) : 0.f;
+                    split_h16u_pair(v0 * P.x_scale, v1 * P.x_scale, hi[q], lo[q]);
+                }
+                tmem_st8(lane_base + GT_COL_X, hi);
+                tmem_st8(lane_base + GT_COL_XLO, lo);
+                tmem_st_wait();
+            } else if (k <= 2) {
+                const float* grow = P.G + (iok ? i : 0) * P.ldg;
+                uint32_t v[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float g = (iok && c < P.m) ? __ldg(grow + c) : 0.f;
+                    const uint32_t hi = __float_as_uint(g) & 0xFFFFE000u;
+                    v[c] = (k == 1) ? hi : __float_as_uint(g - __uint_as_float(hi));
+                }
+                tmem_st16(lane_base + (k == 1 ? GT_COL_G : GT_COL_GLO), v);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(b_xready);
+        };
+
+        uint32_t gt = 0, uc = 0;
+        int u = blockIdx.x;
+        if (u < P.n_units) park(u);
+        for (; u < P.n_units; u += gridDim.x, ++uc) {
+            f32x2 acc[GT_NACC / 2];             // (y0, y1) .. (y14, y15), (1, |y|^2)
+#pragma unroll
+            for (int q = 0; q < GT_NACC / 2; ++q) acc[q] = 0ull;
+            for (int t = k; t < T; t += GT_EPQ) {
+                const uint32_t g = gt + (uint32_t)t, a = g % GT_NS, s = g % GT_SOP;
+                bar_wait(b_sfull + a * 8, (g / GT_NS) & 1);
+                bar_wait(b_opfull + s * 8, (g / GT_SOP) & 1);     // (complete long ago: makes the TMA writes visible to this thread)
+                tc_fence_after();
+                const uint32_t sc = lane_base + GT_COL_S + a * 64;
+                const uint32_t st = sbase + s * GT_STAGE;
+                // four chunks of 8 columns; the next chunk's S and g are in flight while the current one is consumed
+                uint32_t s0[8], g0[8], s1[8], g1[8];
+                ld8_async(sc, s0);
+                ld8_async(sc + 32, g0);
+                f32x2 tacc[GT_NACC / 2];
+#pragma unroll
+                for (int q = 0; q < GT_NACC / 2; ++q) tacc[q] = 0ull;
+                auto chunk = [&](const uint32_t (&sv)[8], const uint32_t (&gv)[8], int j0) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int j = j0 + c;
+                        const float tv = ex2_approx(__uint_as_float(sv[c])) * __uint_as_float(gv[c]);
+                        const f32x2 tt = pack2(tv, tv);
+                        const uint32_t row = st + j * 128;
+                        f32x2 y0, y1, y2, y3, y4, y5, y6, y7;
+                        lds_2x64(row + ((4 ^ (j & 7)) << 4), y0, y1);
+                        lds_2x64(row + ((5 ^ (j & 7)) << 4), y2, y3);
+                        lds_2x64(row + ((6 ^ (j & 7)) << 4), y4, y5);
+                        lds_2x64(row + ((7 ^ (j & 7)) << 4), y6, y7);
+                        const f32x2 on = lds_64(st + 8192 + j * 8);
+                        tacc[0] = fma2(tt, y0, tacc[0]);
+                        tacc[1] = fma2(tt, y1, tacc[1]);
+                        tacc[2] = fma2(tt, y2, tacc[2]);
+                        tacc[3] = fma2(tt, y3, tacc[3]);
+                        tacc[4] = fma2(tt, y4, tacc[4]);
+                        tacc[5] = fma2(tt, y5, tacc[5]);
+                        tacc[6] = fma2(tt, y6, tacc[6]);
+                        tacc[7] = fma2(tt, y7, tacc[7]);
+                        tacc[8] = fma2(tt, on, tacc[8]);
+                    }
+                };
+                ld8_wait(s0);
+                ld8_wait(g0);
+                ld8_async(sc + 8, s1);
+                ld8_async(sc + 40, g1);
+                chunk(s0, g0, 0);
+                ld8_wait(s1);
+                ld8_wait(g1);
+                ld8_async(sc + 16, s0);
+                ld8_async(sc + 48, g0);
+                chunk(s1, g1, 8);
+                ld8_wait(s0);
+                ld8_wait(g0);
+                ld8_async(sc + 24, s1);
+                ld8_async(sc + 56, g1);
+                chunk(s0, g0, 16);
+                ld8_wait(s1);
+                ld8_wait(g1);
+                tc_fence_before();
+                chunk(s1, g1, 24);
+                __syncwarp();
+                if (lane == 0) {
+                    bar_arrive(b_sempty + a * 8);
+                    bar_arrive(b_opempty + s * 8);
+                }
+#pragma unroll
+                for (int q = 0; q < GT_NACC / 2; ++q) acc[q] = add2(acc[q], tacc[q]);
+            }
+            // once every MMA of this unit has completed the next block of x~ / G can be parked
+            const int un = u + gridDim.x;
+            if (un < P.n_units) {
+                bar_wait(b_xfree, uc & 1);
+                tc_fence_after();
+                park(un);
+            }
+            // the four partial results of a lane quarter meet in shared memory (two buffers, alternating by unit)
+            float* mine = red + ((uc & 1) * GT_EW + quad * GT_EPQ + k) * (GT_NACC * 32);
+            float av[GT_NACC];
+#pragma unroll
+            for (int q = 0; q < GT_NACC / 2; ++q) unpack2(acc[q], av[2 * q], av[2 * q + 1]);
+            if (k != 0) {
+#pragma unroll
+                for (int c = 0; c < GT_NACC; ++c) mine[c * 32 + lane] = av[c];
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(32 * GT_EPQ) : "memory");
+            if (k == 0) {
+#pragma unroll
+                for (int kk = 1; kk < GT_EPQ; ++kk) {
+#pragma unroll
+                    for (int c = 0; c < GT_NACC; ++c) av[c] += mine[kk * (GT_NACC * 32) + c * 32 + lane];
+                }
+                const int64_t i = (int64_t)u * GT_BM + quad * 32 + lane;
+                if (i < P.N) {
+                    const float xn = __ldg(P.xn + i);
+                    const float rowf = ex2_approx(xn);                  // 2^(c|x_i|^2)
+                    const float s0v = av[GT_D], s2v = av[GT_D + 1];
+                    const float* xrow = P.X + i * P.ldx;
+                    float* dst = P.gX + i * P.ldgx;
+                    float xs1 = 0.f;
+                    const float f = P.fac * rowf;
+#pragma unroll
+                    for (int c = 0; c < GT_D; ++c) {
+                        if (c < P.d) {
+                            const float xv = __ldg(xrow + c);
+                            xs1 = fmaf(xv, av[c], xs1);
+                            dst[c] = f * (av[c] - xv * s0v);
+                        }
+                    }
+                    if (P.gs_rows) P.gs_rows[i] = P.fac_s * rowf * (xn * P.inv_c * s0v - 2.f * xs1 + s2v);
+                }
+            }
+            gt += (uint32_t)T;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == W_MMA) tmem_dealloc_512(tmem_base);
+}
+
+// out[r] = c |row r|^2;  *gmax = max |c| |row|^2 (atomicMax on the bit pattern)
+__global__ void gt_rownorm_kernel(const float* __restrict__ A, int64_t rows, int d, int64_t lda, float c,
+                                  float* __restrict__ out, unsigned* __restrict__ gmax) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float q = 0.f;
+    if (r < rows) {
+        for (int k = 0; k < d; ++k) {
+            const float v = __ldg(A + r * lda + k);
+            q = fmaf(v, v, q);
+        }
+        out[r] = c * q;
+    }
+    float mx = fabsf(c) * q;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx == mx) atomicMax(gmax, __float_as_uint(mx));
+}
+
+// tile images: one thread per 16-byte piece (528 per tile)
+__global__ void gt_pack_kernel(const float* __restrict__ Y, int64_t M, int d, int64_t ldy, const float* __restrict__ W,
+                               int m, int64_t ldw, int n_tiles, unsigned char* __restrict__ img, float y_scale,
+                               float inv_c, const float* __restrict__ yn, const unsigned* __restrict__ nmax) {
+    if (!tc2_fast_regime(nmax)) return;
+    constexpr int CPT = GT_IMG / 16;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_tiles * CPT) return;
+    const int64_t t = idx / CPT;
+    const int p = (int)(idx % CPT);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (p < 512) {
+        const int rr = p >> 3, r = rr & 31, cl = (p & 7) ^ (r & 7);        // logical 16-byte chunk of the row
+        const int64_t j = t * GT_NT + r;
+        const bool jok = j < M;
+        if (rr < 32) {
+            if (cl < 4) {
+                // y'' = y y_scale as fp16 hi (chunks 0, 1) / lo (chunks 2, 3), 8 features per chunk
+                const int k0 = 8 * (cl & 1);
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float v0 = (jok && k0 + 2 * q < d) ? __ldg(Y + j * ldy + k0 + 2 * q) * y_scale : 0.f;
+                    const float v1 = (jok && k0 + 2 * q + 1 < d) ? __ldg(Y + j * ldy + k0 + 2 * q + 1) * y_scale : 0.f;
+                    uint32_t hi, lo;
+                    split_h16u_pair(v0, v1, hi, lo);
+                    w[q] = cl < 2 ? hi : lo;
+                }
+                o = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+                // y as FP32, 4 features per chunk
+                const int k0 = 4 * (cl - 4);
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = (jok && k0 + q < d) ? __ldg(Y + j * ldy + k0 + q) : 0.f;
+                o = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+            }
+        } else {
+            // W' = W 2^(c|y|^2) as tf32 hi (chunks 0..3) / lo (chunks 4..7), 4 columns per chunk
+            const int c0 = 4 * (cl & 3);
+            const float colf = jok ? ex2_approx(__ldg(yn + j)) : 0.f;
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float v = (jok && c0 + q < m) ? __ldg(W + j * ldw + c0 + q) * colf : 0.f;
+                const uint32_t hi = __float_as_uint(v) & 0xFFFFE000u;
+                w[q] = cl < 4 ? hi : __float_as_uint(v - __uint_as_float(hi));
+            }
+            o = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    } else {
+        // {1, |y_j|^2} for two consecutive rows
+        const int r = 2 * (p - 512);
+        const int64_t j = t * GT_NT + r;
+        const float n0 = (j < M) ? __ldg(yn + j) * inv_c : 0.f, n1 = (j + 1 < M) ? __ldg(yn + j + 1) * inv_c : 0.f;
+        o = make_uint4(__float_as_uint(1.f), __float_as_uint(n0), __float_as_uint(1.f), __float_as_uint(n1));
+    }
+    *reinterpret_cast<uint4*>(img + t * GT_IMG + (int64_t)p * 16) = o;
+}
+
+}  // namespace
+
+bool kgrad_tc_eligible(int64_t N, int64_t M, int d, int m, int pm) {
+    return pm == PM_SQEXP && d <= GT_D && m <= GT_MT && N >= 4096 && M >= 4096 && jrk_option(JRK_OPT_KMATW_TC) != 0 &&
+           jrk_option(JRK_OPT_TC_FAST) != 0;
+}
+
+size_t kgrad_tc_workspace_bytes(int64_t N, int64_t M) {
+    const int64_t n_tiles = (M + GT_NT - 1) / GT_NT;
+    return align256((size_t)N * 4) + align256((size_t)M * 4) + 256 + align256((size_t)n_tiles * GT_IMG) + 1024;
+}
+
+// Enqueues the pre-pass and the tensor-core kernel; *nmax_out receives the device pointer of the two norm maxima, from
+// which the caller's FP32 kernels decide (on the device) whether the result is theirs to write.
+int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, int64_t N, int64_t M,
+             int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float c, float fac, float fac_s,
+             void* scratch, const unsigned** nmax_out, cudaStream_t st) {
+    char* p = (char*)scratch;
+    float* xn = (float*)p; p += align256((size_t)N * 4);
+    float* yn = (float*)p; p += align256((size_t)M * 4);
+    unsigned* nmax = (unsigned*)p; p += 256;
+    unsigned char* img = (unsigned char*)p;
+    const int n_tiles = (int)((M + GT_NT - 1) / GT_NT);
+    JRK_CUDA_OK(cudaMemsetAsync(nmax, 0, 16, st));
+    gt_rownorm_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(X, N, d, ldx, c, xn, nmax);
+    JRK_LAUNCHED();
+    gt_rownorm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, c, yn, nmax + 1);
+    JRK_LAUNCHED();
+    const Tc2Scales sc = tc2_scales(c);
+    const int64_t tot = (int64_t)n_tiles * (GT_IMG / 16);
+    gt_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, n_tiles, img, sc.y_scale, 1.f / c, yn, nmax);
+    JRK_LAUNCHED();
+    GtParams P;
+    P.X = X; P.ldx = ldx; P.d = d; P.G = G; P.ldg = ldg; P.m = m; P.xn = xn; P.img = img; P.gX = gX; P.ldgx = ldgx;
+    P.gs_rows = gs_rows; P.N = N; P.n_tiles = n_tiles; P.n_units = (int)((N + GT_BM - 1) / GT_BM); P.nmax = nmax;
+    P.x_scale = sc.x_scale; P.inv_c = 1.f / c; P.fac = fac; P.fac_s = fac_s;
+    const int grid = P.n_units < tf_sm_count() ? P.n_units : tf_sm_count();
+    JRK_CUDA_OK(cudaFuncSetAttribute(kgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
+    kgrad_tc_kernel<<<grid, GT_THREADS, GT_SMEM, st>>>(P);
+    JRK_LAUNCHED();
+    *nmax_out = nmax;
+    return JRK_OK;
+}
+
+}  // namespace jrk
