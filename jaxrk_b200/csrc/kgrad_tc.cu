@@ -18,12 +18,15 @@
 // from the same tile image as FP32, read as shared-memory broadcasts.  Accumulation is hierarchical (per tile of 32
 // columns, then per unit), so the rounding error does not grow with M.
 //
-// Roofline: FP32 pipe, d + 2 = 18 lane-operations per pair -> 3.69e13 / 18 = 2.05e12 pairs/s; next to it 5 LDS (4 x
-// 128-bit + 1 x 64-bit broadcast) and one MUFU per pair.
+// Roofline: FP32 pipe, d + 2 = 18 lane-operations per pair -> 3.69e13 / 18 = 2.05e12 pairs/s (measured: 1.16e12, FMA pipe
+// 66 % busy; kgrad.cu: 2.3 - 3.2e11).  An epilogue thread owns one row of EACH of the unit's two row blocks, so every
+// y_j it reads from shared memory (4 x 128-bit + 1 x 64-bit broadcast loads) serves two pairs: with one row block the
+// kernel was bound by the shared-memory load pipe (8.8e11; ncu: mio_throttle the top stall).
 //
-// Layout per CTA (persistent, one per SM): 16 epilogue warps (4 per TMEM lane quarter; tile t belongs to warp t mod 4 of
-// each quarter), one MMA-issuing warp, one TMA warp.  TMEM: x~ hi [0, 8) lo [8, 16) | G hi [16, 32) lo [32, 48) | six
-// stages [128 + 64 a, +64) = {S [32) | g [32)}.  Tile image (32 rows of Y, 8448 bytes, one cp.async.bulk):
+// Layout per CTA (persistent, one per SM): 12 epilogue warps (3 per TMEM lane quarter; tile t belongs to warp t mod 3 of
+// each quarter), one MMA-issuing warp (18 MMAs of N = 32 per tile), one TMA warp.  TMEM: per row block h = 0, 1 at
+// column 48 h: x~ hi [0, 8) lo [8, 16) | G hi [16, 32) lo [32, 48);  three stages [128 + 128 a, +128) =
+// 2 x {S [32) | g [32)}.  Tile image (32 rows of Y, 8448 bytes, one cp.async.bulk):
 //   rows 0..31   (128 B, SWIZZLE_128B): [y'' hi 32 B | y'' lo 32 B | y FP32 64 B]
 //   rows 32..63  (128 B, SWIZZLE_128B): [W' tf32 hi 64 B | W' tf32 lo 64 B]
 //   then 32 x {1.0f, |y_j|^2}
@@ -42,21 +45,25 @@ using namespace tcp;
 namespace {
 
 constexpr int GT_BM = 128, GT_NT = 32, GT_D = 16, GT_MT = 16;
-constexpr int GT_NS = 6;                       // {S | g} stages in TMEM (64 columns each)
-constexpr int GT_SOP = 10;                     // tile-image stages in shared memory
+constexpr int GT_R = 2;                        // row blocks (of 128) per unit: an epilogue thread owns one row of each,
+                                               // so every y_j it reads from shared memory serves GT_R pairs
+constexpr int GT_ROWS = GT_R * GT_BM;
+constexpr int GT_NS = 3;                       // stages in TMEM: GT_R x {S [32) | g [32)} = 128 columns each
+constexpr int GT_SOP = 8;                      // tile-image stages in shared memory
 constexpr int GT_IMG = 8448;                   // bytes of one tile image
 constexpr int GT_STAGE = 9216;                 // stage stride (1024-byte aligned)
-constexpr int GT_EPQ = 4, GT_EW = 4 * GT_EPQ;
-constexpr int GT_COL_X = 0, GT_COL_XLO = 8, GT_COL_G = 16, GT_COL_GLO = 32, GT_COL_S = 128;
+constexpr int GT_EPQ = 3, GT_EW = 4 * GT_EPQ;  // epilogue warps per TMEM lane quarter: one per stage (2 measured no faster)
+constexpr int GT_COL_X = 0, GT_COL_XLO = 8, GT_COL_G = 16, GT_COL_GLO = 32, GT_COL_BLK = 48, GT_COL_S = 128;
 constexpr int GT_NACC = GT_D + 2;              // sum tt y_k (16), sum tt, sum tt |y|^2
 constexpr int GT_OFF_RED = GT_SOP * GT_STAGE;
-constexpr int GT_RED_WARP = GT_NACC * 32 * 4;  // [18][32 lanes] floats
+constexpr int GT_RED_WARP = GT_R * GT_NACC * 32 * 4;   // [R][18][32 lanes] floats
 constexpr int GT_OFF_BAR = GT_OFF_RED + 2 * GT_EW * GT_RED_WARP;
 constexpr int GT_NBAR = 2 * GT_SOP + 2 * GT_NS + 2;
 constexpr int GT_SMEM = GT_OFF_BAR + GT_NBAR * 8 + 16 + 1024;
 constexpr int GT_THREADS = (GT_EW + 2) * 32;
-static_assert(GT_COL_S + GT_NS * 64 <= 512, "TMEM budget");
+static_assert(GT_COL_S + GT_NS * 64 * GT_R <= 512 && GT_R * GT_COL_BLK <= GT_COL_S, "TMEM budget");
 static_assert(GT_SMEM <= 227 * 1024, "shared memory budget");
+static_assert(GT_EPQ >= 3, "warps 0 / 1 / 2 of a lane quarter park x~ / G hi / G lo");
 
 struct GtParams {
     const float* X; int64_t ldx; int d;
@@ -88,7 +95,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GT_OFF_BAR);
     uint64_t* op_full = bars;                  // [SOP]  tile image landed
     uint64_t* op_empty = op_full + GT_SOP;     // [SOP]  the four owner warps are done with the image
-    uint64_t* s_full = op_empty + GT_SOP;      // [NS]   GEMM1 + GEMM1b of the stage complete
+    uint64_t* s_full = op_empty + GT_SOP;      // [NS]   the MMAs of the stage are complete
     uint64_t* s_empty = s_full + GT_NS;        // [NS]   the four owner warps read the stage
     uint64_t* x_ready = s_empty + GT_NS;       // [1]    x~ and G of the unit are parked
     uint64_t* x_free = x_ready + 1;            // [1]    every MMA of the unit has completed
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
             }
         }
     } else if (warp == W_MMA) {
-        // ===================== MMA issuer: 3 (fp16) + 6 (tf32) MMAs of N = 32 per tile =====================
+        // ===================== MMA issuer: per row block 3 (fp16) + 6 (tf32) MMAs of N = 32 per tile =====================
         constexpr uint32_t id_h = (1u << 4) | ((uint32_t)(GT_NT >> 3) << 17) | ((uint32_t)(GT_BM >> 4) << 24);
         constexpr uint32_t id_t = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GT_NT >> 3) << 17) | ((uint32_t)(GT_BM >> 4) << 24);
         const uint64_t dbase = make_b_desc(smem_u32(smem));
@@ -143,18 +150,21 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                 tc_fence_after();
                 const uint64_t dy = dbase + (uint64_t)((s * GT_STAGE) >> 4);
                 const uint64_t dw = dy + (uint64_t)(4096 >> 4);
-                const uint32_t cs = GT_COL_S + a * 64, cg = cs + 32;
                 if (elect_one()) {
-                    // the small cross terms first, the hi.hi terms last (the accumulator truncates)
-                    mma_f16_ts(cs, GT_COL_X, dy + 2, id_h, 0u);                    // hi_x . lo_y
-                    mma_f16_ts(cs, GT_COL_XLO, dy, id_h, 1u);                      // lo_x . hi_y
-                    mma_f16_ts(cs, GT_COL_X, dy, id_h, 1u);                        // hi_x . hi_y
-                    mma_tf32_ts(cg, GT_COL_G, dw + 4, id_t, 0u);                   // hi_g . lo_w  (k-steps 0, 1)
-                    mma_tf32_ts(cg, GT_COL_G + 8, dw + 6, id_t, 1u);
-                    mma_tf32_ts(cg, GT_COL_GLO, dw, id_t, 1u);                     // lo_g . hi_w
-                    mma_tf32_ts(cg, GT_COL_GLO + 8, dw + 2, id_t, 1u);
-                    mma_tf32_ts(cg, GT_COL_G, dw, id_t, 1u);                       // hi_g . hi_w
-                    mma_tf32_ts(cg, GT_COL_G + 8, dw + 2, id_t, 1u);
+#pragma unroll
+                    for (int h = 0; h < GT_R; ++h) {
+                        const uint32_t cs = GT_COL_S + a * (64 * GT_R) + h * 64, cg = cs + 32, cx = h * GT_COL_BLK;
+                        // the small cross terms first, the hi.hi terms last (the accumulator truncates)
+                        mma_f16_ts(cs, cx + GT_COL_X, dy + 2, id_h, 0u);               // hi_x . lo_y
+                        mma_f16_ts(cs, cx + GT_COL_XLO, dy, id_h, 1u);                 // lo_x . hi_y
+                        mma_f16_ts(cs, cx + GT_COL_X, dy, id_h, 1u);                   // hi_x . hi_y
+                        mma_tf32_ts(cg, cx + GT_COL_G, dw + 4, id_t, 0u);              // hi_g . lo_w  (k-steps 0, 1)
+                        mma_tf32_ts(cg, cx + GT_COL_G + 8, dw + 6, id_t, 1u);
+                        mma_tf32_ts(cg, cx + GT_COL_GLO, dw, id_t, 1u);                // lo_g . hi_w
+                        mma_tf32_ts(cg, cx + GT_COL_GLO + 8, dw + 2, id_t, 1u);
+                        mma_tf32_ts(cg, cx + GT_COL_G, dw, id_t, 1u);                  // hi_g . hi_w
+                        mma_tf32_ts(cg, cx + GT_COL_G + 8, dw + 2, id_t, 1u);
+                    }
                     commit_addr(b_sfull + a * 8);
                 }
                 __syncwarp();
@@ -165,6 +175,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
         }
     } else {
         // ===================== epilogue warps (and X / G loaders) =====================
+        // warp k of a lane quarter owns the quarter of the tiles t = k (mod EPQ): 32 lanes x 32 columns of every row block
         const int quad = warp & 3, k = warp >> 2;
         uint32_t lane_base;
         asm volatile("mov.u32 %0, %1;" : "=r"(lane_base) : "r"(tmem_base + ((uint32_t)(quad * 32) << 16)));
@@ -176,32 +187,35 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
 
         auto park = [&](int u) {
             // warp 0 of the quarter: x~ = x 2^-r as fp16 hi / lo pairs;  warps 1 / 2: G as tf32 hi / lo
-            const int64_t i = (int64_t)u * GT_BM + quad * 32 + lane;
-            const bool iok = i < P.N;
-            if (k == 0) {
-                const float* xrow = P.X + (iok ? i : 0) * P.ldx;
-                uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float v0 = (iok && 2 * q < P.d) ? __ldg(xrow + 2 * q) : 0.f;
-                    const float v1 = (iok && 2 * q + 1 < P.d) ? __ldg(xrow + 2 * q + 1) : 0.f;
-                    split_h16u_pair(v0 * P.x_scale, v1 * P.x_scale, hi[q], lo[q]);
-                }
-                tmem_st8(lane_base + GT_COL_X, hi);
-                tmem_st8(lane_base + GT_COL_XLO, lo);
-                tmem_st_wait();
-            } else if (k <= 2) {
-                const float* grow = P.G + (iok ? i : 0) * P.ldg;
-                uint32_t v[16];
+            for (int h = 0; h < GT_R; ++h) {
+                const int64_t i = (int64_t)u * GT_ROWS + h * GT_BM + quad * 32 + lane;
+                const bool iok = i < P.N;
+                const uint32_t cx = lane_base + h * GT_COL_BLK;
+                if (k == 0) {
+                    const float* xrow = P.X + (iok ? i : 0) * P.ldx;
+                    uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float g = (iok && c < P.m) ? __ldg(grow + c) : 0.f;
-                    const uint32_t hi = __float_as_uint(g) & 0xFFFFE000u;
-                    v[c] = (k == 1) ? hi : __float_as_uint(g - __uint_as_float(hi));
+                    for (int q = 0; q < 8; ++q) {
+                        const float v0 = (iok && 2 * q < P.d) ? __ldg(xrow + 2 * q) : 0.f;
+                        const float v1 = (iok && 2 * q + 1 < P.d) ? __ldg(xrow + 2 * q + 1) : 0.f;
+                        split_h16u_pair(v0 * P.x_scale, v1 * P.x_scale, hi[q], lo[q]);
+                    }
+                    tmem_st8(cx + GT_COL_X, hi);
+                    tmem_st8(cx + GT_COL_XLO, lo);
+                } else {
+                    const float* grow = P.G + (iok ? i : 0) * P.ldg;
+                    uint32_t v[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float g = (iok && c < P.m) ? __ldg(grow + c) : 0.f;
+                        const uint32_t hi = __float_as_uint(g) & 0xFFFFE000u;
+                        v[c] = (k == 1) ? hi : __float_as_uint(g - __uint_as_float(hi));
+                    }
+                    tmem_st16(cx + (k == 1 ? GT_COL_G : GT_COL_GLO), v);
                 }
-                tmem_st16(lane_base + (k == 1 ? GT_COL_G : GT_COL_GLO), v);
-                tmem_st_wait();
             }
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) bar_arrive(b_xready);
@@ -211,29 +225,57 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
         int u = blockIdx.x;
         if (u < P.n_units) park(u);
         for (; u < P.n_units; u += gridDim.x, ++uc) {
-            f32x2 acc[GT_NACC / 2];             // (y0, y1) .. (y14, y15), (1, |y|^2)
+            f32x2 acc[GT_R][GT_NACC / 2];       // per row block: (y0, y1) .. (y14, y15), (1, |y|^2)
 #pragma unroll
-            for (int q = 0; q < GT_NACC / 2; ++q) acc[q] = 0ull;
+            for (int h = 0; h < GT_R; ++h)
+#pragma unroll
+                for (int q = 0; q < GT_NACC / 2; ++q) acc[h][q] = 0ull;
             for (int t = k; t < T; t += GT_EPQ) {
                 const uint32_t g = gt + (uint32_t)t, a = g % GT_NS, s = g % GT_SOP;
                 bar_wait(b_sfull + a * 8, (g / GT_NS) & 1);
                 bar_wait(b_opfull + s * 8, (g / GT_SOP) & 1);     // (complete long ago: makes the TMA writes visible to this thread)
                 tc_fence_after();
-                const uint32_t sc = lane_base + GT_COL_S + a * 64;
+                const uint32_t sc = lane_base + GT_COL_S + a * (64 * GT_R);
                 const uint32_t st = sbase + s * GT_STAGE;
-                // four chunks of 8 columns; the next chunk's S and g are in flight while the current one is consumed
-                uint32_t s0[8], g0[8], s1[8], g1[8];
-                ld8_async(sc, s0);
-                ld8_async(sc + 32, g0);
-                f32x2 tacc[GT_NACC / 2];
+                // tile-local sums first (hierarchical accumulation: the rounding error does not grow with M)
+                f32x2 tacc[GT_R][GT_NACC / 2];
 #pragma unroll
-                for (int q = 0; q < GT_NACC / 2; ++q) tacc[q] = 0ull;
-                auto chunk = [&](const uint32_t (&sv)[8], const uint32_t (&gv)[8], int j0) {
+                for (int h = 0; h < GT_R; ++h)
+#pragma unroll
+                    for (int q = 0; q < GT_NACC / 2; ++q) tacc[h][q] = 0ull;
+                uint32_t sv[GT_R][8], gv[GT_R][8];
+#pragma unroll
+                for (int h = 0; h < GT_R; ++h) {
+                    ld8_async(sc + h * 64, sv[h]);
+                    ld8_async(sc + h * 64 + 32, gv[h]);
+                }
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    float tv[GT_R][8];
+#pragma unroll
+                    for (int h = 0; h < GT_R; ++h) {
+                        ld8_wait(sv[h]);
+                        ld8_wait(gv[h]);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) tv[h][c] = ex2_approx(__uint_as_float(sv[h][c])) * __uint_as_float(gv[h][c]);
+                    }
+                    if (ch < 3) {
+                        // the next chunk's S and g are in flight while this one goes through the FMA pipe
+#pragma unroll
+                        for (int h = 0; h < GT_R; ++h) {
+                            ld8_async(sc + h * 64 + 8 * (ch + 1), sv[h]);
+                            ld8_async(sc + h * 64 + 32 + 8 * (ch + 1), gv[h]);
+                        }
+                    } else {
+                        // every S / g value of the tile is in registers: the stage goes back to the MMA warp now, a quarter
+                        // of the tile's FMA work before this warp needs it again (NS = EPQ: it is the warp's next stage)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) bar_arrive(b_sempty + a * 8);
+                    }
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const int j = j0 + c;
-                        const float tv = ex2_approx(__uint_as_float(sv[c])) * __uint_as_float(gv[c]);
-                        const f32x2 tt = pack2(tv, tv);
+                        const int j = 8 * ch + c;
                         const uint32_t row = st + j * 128;
                         f32x2 y0, y1, y2, y3, y4, y5, y6, y7;
                         lds_2x64(row + ((4 ^ (j & 7)) << 4), y0, y1);
@@ -241,43 +283,27 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                         lds_2x64(row + ((6 ^ (j & 7)) << 4), y4, y5);
                         lds_2x64(row + ((7 ^ (j & 7)) << 4), y6, y7);
                         const f32x2 on = lds_64(st + 8192 + j * 8);
-                        tacc[0] = fma2(tt, y0, tacc[0]);
-                        tacc[1] = fma2(tt, y1, tacc[1]);
-                        tacc[2] = fma2(tt, y2, tacc[2]);
-                        tacc[3] = fma2(tt, y3, tacc[3]);
-                        tacc[4] = fma2(tt, y4, tacc[4]);
-                        tacc[5] = fma2(tt, y5, tacc[5]);
-                        tacc[6] = fma2(tt, y6, tacc[6]);
-                        tacc[7] = fma2(tt, y7, tacc[7]);
-                        tacc[8] = fma2(tt, on, tacc[8]);
-                    }
-                };
-                ld8_wait(s0);
-                ld8_wait(g0);
-                ld8_async(sc + 8, s1);
-                ld8_async(sc + 40, g1);
-                chunk(s0, g0, 0);
-                ld8_wait(s1);
-                ld8_wait(g1);
-                ld8_async(sc + 16, s0);
-                ld8_async(sc + 48, g0);
-                chunk(s1, g1, 8);
-                ld8_wait(s0);
-                ld8_wait(g0);
-                ld8_async(sc + 24, s1);
-                ld8_async(sc + 56, g1);
-                chunk(s0, g0, 16);
-                ld8_wait(s1);
-                ld8_wait(g1);
-                tc_fence_before();
-                chunk(s1, g1, 24);
-                __syncwarp();
-                if (lane == 0) {
-                    bar_arrive(b_sempty + a * 8);
-                    bar_arrive(b_opempty + s * 8);
-                }
 #pragma unroll
-                for (int q = 0; q < GT_NACC / 2; ++q) acc[q] = add2(acc[q], tacc[q]);
+                        for (int h = 0; h < GT_R; ++h) {
+                            const f32x2 tt = pack2(tv[h][c], tv[h][c]);
+                            tacc[h][0] = fma2(tt, y0, tacc[h][0]);
+                            tacc[h][1] = fma2(tt, y1, tacc[h][1]);
+                            tacc[h][2] = fma2(tt, y2, tacc[h][2]);
+                            tacc[h][3] = fma2(tt, y3, tacc[h][3]);
+                            tacc[h][4] = fma2(tt, y4, tacc[h][4]);
+                            tacc[h][5] = fma2(tt, y5, tacc[h][5]);
+                            tacc[h][6] = fma2(tt, y6, tacc[h][6]);
+                            tacc[h][7] = fma2(tt, y7, tacc[h][7]);
+                            tacc[h][8] = fma2(tt, on, tacc[h][8]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) bar_arrive(b_opempty + s * 8);
+#pragma unroll
+                for (int h = 0; h < GT_R; ++h)
+#pragma unroll
+                    for (int q = 0; q < GT_NACC / 2; ++q) acc[h][q] = add2(acc[h][q], tacc[h][q]);
             }
             // once every MMA of this unit has completed the next block of x~ / G can be parked
             const int un = u + gridDim.x;
@@ -286,40 +312,48 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                 tc_fence_after();
                 park(un);
             }
-            // the four partial results of a lane quarter meet in shared memory (two buffers, alternating by unit)
-            float* mine = red + ((uc & 1) * GT_EW + quad * GT_EPQ + k) * (GT_NACC * 32);
-            float av[GT_NACC];
+            // the EPQ partial results of a lane quarter meet in shared memory (two buffers, alternating by unit)
+            float* mine = red + ((uc & 1) * GT_EW + quad * GT_EPQ + k) * (GT_R * GT_NACC * 32);
+            float av[GT_R][GT_NACC];
 #pragma unroll
-            for (int q = 0; q < GT_NACC / 2; ++q) unpack2(acc[q], av[2 * q], av[2 * q + 1]);
+            for (int h = 0; h < GT_R; ++h)
+#pragma unroll
+                for (int q = 0; q < GT_NACC / 2; ++q) unpack2(acc[h][q], av[h][2 * q], av[h][2 * q + 1]);
             if (k != 0) {
 #pragma unroll
-                for (int c = 0; c < GT_NACC; ++c) mine[c * 32 + lane] = av[c];
+                for (int h = 0; h < GT_R; ++h)
+#pragma unroll
+                    for (int c = 0; c < GT_NACC; ++c) mine[(h * GT_NACC + c) * 32 + lane] = av[h][c];
             }
             asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(32 * GT_EPQ) : "memory");
             if (k == 0) {
 #pragma unroll
-                for (int kk = 1; kk < GT_EPQ; ++kk) {
+                for (int h = 0; h < GT_R; ++h) {
 #pragma unroll
-                    for (int c = 0; c < GT_NACC; ++c) av[c] += mine[kk * (GT_NACC * 32) + c * 32 + lane];
-                }
-                const int64_t i = (int64_t)u * GT_BM + quad * 32 + lane;
-                if (i < P.N) {
-                    const float xn = __ldg(P.xn + i);
-                    const float rowf = ex2_approx(xn);                  // 2^(c|x_i|^2)
-                    const float s0v = av[GT_D], s2v = av[GT_D + 1];
-                    const float* xrow = P.X + i * P.ldx;
-                    float* dst = P.gX + i * P.ldgx;
-                    float xs1 = 0.f;
-                    const float f = P.fac * rowf;
+                    for (int kk = 1; kk < GT_EPQ; ++kk) {
 #pragma unroll
-                    for (int c = 0; c < GT_D; ++c) {
-                        if (c < P.d) {
-                            const float xv = __ldg(xrow + c);
-                            xs1 = fmaf(xv, av[c], xs1);
-                            dst[c] = f * (av[c] - xv * s0v);
-                        }
+                        for (int c = 0; c < GT_NACC; ++c)
+                            av[h][c] += mine[kk * (GT_R * GT_NACC * 32) + (h * GT_NACC + c) * 32 + lane];
                     }
-                    if (P.gs_rows) P.gs_rows[i] = P.fac_s * rowf * (xn * P.inv_c * s0v - 2.f * xs1 + s2v);
+                    const int64_t i = (int64_t)u * GT_ROWS + h * GT_BM + quad * 32 + lane;
+                    if (i < P.N) {
+                        const float xn = __ldg(P.xn + i);
+                        const float rowf = ex2_approx(xn);                  // 2^(c|x_i|^2)
+                        const float s0v = av[h][GT_D], s2v = av[h][GT_D + 1];
+                        const float* xrow = P.X + i * P.ldx;
+                        float* dst = P.gX + i * P.ldgx;
+                        float xs1 = 0.f;
+                        const float f = P.fac * rowf;
+#pragma unroll
+                        for (int c = 0; c < GT_D; ++c) {
+                            if (c < P.d) {
+                                const float xv = __ldg(xrow + c);
+                                xs1 = fmaf(xv, av[h][c], xs1);
+                                dst[c] = f * (av[h][c] - xv * s0v);
+                            }
+                        }
+                        if (P.gs_rows) P.gs_rows[i] = P.fac_s * rowf * (xn * P.inv_c * s0v - 2.f * xs1 + s2v);
+                    }
                 }
             }
             gt += (uint32_t)T;
@@ -444,7 +478,7 @@ int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, flo
     JRK_LAUNCHED();
     GtParams P;
     P.X = X; P.ldx = ldx; P.d = d; P.G = G; P.ldg = ldg; P.m = m; P.xn = xn; P.img = img; P.gX = gX; P.ldgx = ldgx;
-    P.gs_rows = gs_rows; P.N = N; P.n_tiles = n_tiles; P.n_units = (int)((N + GT_BM - 1) / GT_BM); P.nmax = nmax;
+    P.gs_rows = gs_rows; P.N = N; P.n_tiles = n_tiles; P.n_units = (int)((N + GT_ROWS - 1) / GT_ROWS); P.nmax = nmax;
     P.x_scale = sc.x_scale; P.inv_c = 1.f / c; P.fac = fac; P.fac_s = fac_s;
     const int grid = P.n_units < tf_sm_count() ? P.n_units : tf_sm_count();
     JRK_CUDA_OK(cudaFuncSetAttribute(kgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));

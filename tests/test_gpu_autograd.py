@@ -201,3 +201,85 @@ def test_gradients_are_never_dropped_silently():
     out = inner(FiniteVec(k, X4.detach()), FiniteVec(k, Y4, [LinearReduce(A)]))
     out.sum().backward()
     assert A.grad is not None and bool(torch.isfinite(A.grad).all())
+
+
+# ---- the tensor-core backward (csrc/kgrad_tc.cu): p = 2, d <= 16, m <= 16, N, M >= 4096, factored regime ----
+def _tc_grad_case(N, M, d, m, ls, seed, positive):
+    rng = np.random.RandomState(seed)
+    X, Y = rng.randn(N, d).astype(f32), rng.randn(M, d).astype(f32)
+    W, G = rng.randn(M, m).astype(f32), rng.randn(N, m).astype(f32)
+    if positive:
+        W, G = np.abs(W), np.abs(G)
+    s = orc.simple_scaler_s(orc.gauss_length_scale(ls))
+    return X, Y, W, G, s, float(s[0, 0]), float(orc.gengauss_nconst_ref32(s, 2.0).reshape(-1)[0])
+
+
+@pytest.mark.parametrize("N,M,d,m,ls,positive", [(8192, 8192, 16, 16, 4.0, False), (4173, 4109, 7, 5, 2.5, False),
+                                                 (8192, 4096, 16, 1, 4.0, True), (4224, 6000, 3, 16, 1.7, False),
+                                                 (4096 + 255, 4096 + 31, 16, 16, 3.0, True)])
+def test_kmatw_grad_tensor_core_path(N, M, d, m, ls, positive):
+    """dX, dY and dscale of the tensor-core kernel on sampled rows (first / last, so that both row blocks of a unit and the
+    ragged last unit / tile are covered) against the float64 oracle, with the FP32-pipe kernel's own tolerance."""
+    X, Y, W, G, s, scale, nconst = _tc_grad_case(N, M, d, m, ls, N % 7, positive)
+    n0 = nat.launch_count()
+    gx, gs = nat.kmatw_grad(cu(X), cu(Y), cu(W), cu(G), scale, 2.0, nconst)
+    assert nat.launch_count() - n0 == 6      # 2 row-norm kernels, images, tensor-core kernel, (skipped) FP32 kernel + finalize
+    gy, _ = nat.kmatw_grad(cu(Y), cu(X), cu(G), cu(W), scale, 2.0, nconst, want_scale=False)
+    rows = np.r_[0:40, 120:136, 250:262, N - 40:N]
+    A = G[rows].astype(np.float64) @ W.astype(np.float64).T
+    Aabs = np.abs(G[rows]).astype(np.float64) @ np.abs(W).astype(np.float64).T
+    gX, _, gsum, _ = orc.gengauss_vjp_truth64(X[rows], Y, A, s, 2.0, nconst=nconst)
+    _, _, _, (mx, _, ms) = orc.gengauss_vjp_truth64(X[rows], Y, Aabs, s, 2.0, nconst=nconst)
+    _check(gx.cpu().numpy()[rows], gX, mx, "tensor-core dL/dX")
+    _check(float(gs.double()[torch.from_numpy(rows).to(gs.device)].sum()), gsum, ms, "tensor-core dL/dscale")
+    cols = np.r_[0:40, M - 40:M]
+    A2 = G.astype(np.float64) @ W[cols].astype(np.float64).T
+    A2abs = np.abs(G).astype(np.float64) @ np.abs(W[cols]).astype(np.float64).T
+    _, gY, _, _ = orc.gengauss_vjp_truth64(X, Y[cols], A2, s, 2.0, nconst=nconst)
+    _, _, _, (_, my, _) = orc.gengauss_vjp_truth64(X, Y[cols], A2abs, s, 2.0, nconst=nconst)
+    _check(gy.cpu().numpy()[cols], gY, my, "tensor-core dL/dY")
+    # every row against the FP32-pipe kernel (same tolerance doubled: two approximations of the same number)
+    with nat.option(nat.OPT_KMATW_TC, 0):
+        gx0, gs0 = nat.kmatw_grad(cu(X), cu(Y), cu(W), cu(G), scale, 2.0, nconst)
+    lim = 2 * (AT + RT * torch.from_numpy(mx.max(axis=0)).float().to(gx.device).max())
+    assert float((gx - gx0).abs().max()) <= float(lim) * 50      # loose global bound: sampled rows carry the real check
+    assert torch.isfinite(gx).all() and torch.isfinite(gs).all()
+
+
+def test_kmatw_grad_outside_the_factored_regime_is_the_fp32_kernel():
+    """Short length scale: |c| (max|x|^2 + max|y|^2) > 12, decided on the device; the tensor-core kernel returns at once and
+    the FP32-pipe kernel writes the result -- bit-identical to the run with the tensor path switched off."""
+    X, Y, W, G, s, scale, nconst = _tc_grad_case(8192, 4096, 16, 16, 0.5, 4, False)
+    gx, gs = nat.kmatw_grad(cu(X), cu(Y), cu(W), cu(G), scale, 2.0, nconst)
+    with nat.option(nat.OPT_KMATW_TC, 0):
+        gx0, gs0 = nat.kmatw_grad(cu(X), cu(Y), cu(W), cu(G), scale, 2.0, nconst)
+    assert torch.equal(gx, gx0) and torch.equal(gs, gs0)
+
+
+def test_inner_backward_through_the_api_on_the_tensor_core_path():
+    """loss = sum(inner(FiniteVec(X), FiniteVec(Y, LinearReduce(W^T))) * C) at a size where forward AND backward run on the
+    tensor cores, against float64 autograd of the reference's op sequence on sampled rows."""
+    from jaxrk_b200.kern import GenGaussKernel
+    from jaxrk_b200.reduce import LinearReduce
+    from jaxrk_b200.rkhs import FiniteVec, inner
+    N, M, d, m = 8192, 4096, 16, 8
+    rng = np.random.RandomState(11)
+    X, Y = rng.randn(N, d).astype(f32), rng.randn(M, d).astype(f32)
+    W, C = rng.randn(m, M).astype(f32), rng.randn(N, m).astype(f32)
+    Xt = cu(X).requires_grad_(True)
+    Yt = cu(Y).requires_grad_(True)
+    Wt = cu(W).requires_grad_(True)
+    k = GenGaussKernel.make_gauss(4.0)
+    out = inner(FiniteVec(k, Xt), FiniteVec(k, Yt, [LinearReduce(Wt)]))
+    (out * cu(C)).sum().backward()
+    s = orc.simple_scaler_s(orc.gauss_length_scale(4.0))
+    nconst = float(orc.gengauss_nconst_ref32(s, 2.0).reshape(-1)[0])
+    rows = np.r_[0:32, N - 32:N]
+    A = C[rows].astype(np.float64) @ W.astype(np.float64)
+    Aabs = np.abs(C[rows]).astype(np.float64) @ np.abs(W).astype(np.float64)
+    gX, _, _, _ = orc.gengauss_vjp_truth64(X[rows], Y, A, s, 2.0, nconst=nconst)
+    _, _, _, (mx, _, _) = orc.gengauss_vjp_truth64(X[rows], Y, Aabs, s, 2.0, nconst=nconst)
+    _check(Xt.grad.cpu().numpy()[rows], gX, mx, "API dL/dX")
+    K = orc.gengauss_gram_truth64(X, Y[:64], s, 2.0)                   # dW[c, j] = sum_i C[i, c] K_ij
+    _check(Wt.grad.cpu().numpy()[:, :64], C.astype(np.float64).T @ K, np.abs(C).astype(np.float64).T @ np.abs(K), "API dL/dW")
+    assert Yt.grad is not None and torch.isfinite(Yt.grad).all()

@@ -92,4 +92,5 @@ if __name__ == "__main__":
         check(8192, 8192, 16, 16, 0.5, seed=4)            # outside the factored regime: the FP32 kernel must serve it
     if what in ("time", "all"):
         timeit(131072, 131072, 16, 16)
+        timeit(151552, 131072, 16, 16)
         timeit(37888, 1048576, 16, 16)

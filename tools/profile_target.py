@@ -42,6 +42,14 @@ def kmatw_tc():
     torch.cuda.synchronize()
 
 
+def kgrad_tc():
+    N, M, d, m = 148 * 256, 131072, 16, 16
+    X, Y, W, G = randn(0, N, d), randn(1, M, d), randn(2, M, m), randn(3, N, m)
+    for _ in range(2):
+        nat.kmatw_grad(X, Y, W, G, 0.1767767, 2.0, 0.25)
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gram64", "all"):
@@ -54,4 +62,6 @@ if __name__ == "__main__":
         kmatw()
     if what == "kmatw_tc":
         kmatw_tc()
+    if what == "kgrad_tc":
+        kgrad_tc()
     print("done", nat.launch_count())

@@ -82,14 +82,16 @@ def bench_groupsum():
 
 def bench_grad():
     """Fused backward kernels: pairs/s and the FP32-pipe fraction (3d + m + 8 lane-ops per pair, kgrad.cu)."""
-    for (N, M, d, m) in [(131072, 131072, 16, 16), (131072, 131072, 8, 1), (65536, 131072, 32, 16), (32768, 131072, 64, 16)]:
+    for (N, M, d, m) in [(131072, 131072, 16, 16), (151552, 1048576, 16, 16), (131072, 131072, 8, 1), (65536, 131072, 32, 16), (32768, 131072, 64, 16)]:
         X, Y, W, G = randn(0, N, d), randn(1, M, d), randn(2, M, m), randn(3, N, m)
         for power in (2.0, 1.0, 1.5):
             s, p, nc = kp(power, d)
             best, med = timeit(lambda: nat.kmatw_grad(X, Y, W, G, s, p, nc), reps=3, warm=1)
             ev = N * M / best
+            tc = power == 2.0 and d <= 16 and m <= 16            # kgrad_tc.cu: d + 2 FP32 lane-ops per pair
             print(json.dumps({"op": "kmatw_grad", "N": N, "M": M, "d": d, "m": m, "power": power, "ms": best * 1e3,
-                              "pairs_per_s": ev, "fma_frac": ev * (3 * d + m + 8) / FMA}), flush=True)
+                              "pairs_per_s": ev, "kernel": "kgrad_tc (tcgen05 + FP32 accumulation)" if tc else "kgrad (FP32 pipe)",
+                              "fma_frac": ev * ((d + 2) if tc else (3 * d + m + 8)) / FMA}), flush=True)
     for (N, M, d) in [(32768, 32768, 16), (32768, 32768, 64)]:
         X, Y, Gb = randn(0, N, d), randn(1, M, d), randn(4, N, M)
         s, p, nc = kp(2.0, d)
