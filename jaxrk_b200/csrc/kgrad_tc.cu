@@ -55,6 +55,8 @@ constexpr int GT_STAGE = 9216;                 // stage stride (1024-byte aligne
 constexpr int GT_EPQ = 3, GT_EW = 4 * GT_EPQ;  // epilogue warps per TMEM lane quarter: one per stage (2 measured no faster)
 constexpr int GT_COL_X = 0, GT_COL_XLO = 8, GT_COL_G = 16, GT_COL_GLO = 32, GT_COL_BLK = 48, GT_COL_S = 128;
 constexpr int GT_NACC = GT_D + 2;              // sum tt y_k (16), sum tt, sum tt |y|^2
+constexpr int GT_FLUSH = 16;                   // own tiles between two flushes of the register sums into shared memory
+                                               // (hierarchical accumulation: the rounding error does not grow with M)
 constexpr int GT_OFF_RED = GT_SOP * GT_STAGE;
 constexpr int GT_RED_WARP = GT_R * GT_NACC * 32 * 4;   // [R][18][32 lanes] floats
 constexpr int GT_OFF_BAR = GT_OFF_RED + 2 * GT_EW * GT_RED_WARP;
@@ -230,6 +232,24 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
             for (int h = 0; h < GT_R; ++h)
 #pragma unroll
                 for (int q = 0; q < GT_NACC / 2; ++q) acc[h][q] = 0ull;
+            // this warp's slot of the unit's reduce buffer (two buffers, alternating by unit): [R][18][32 lanes]
+            float* mine = red + ((uc & 1) * GT_EW + quad * GT_EPQ + k) * (GT_R * GT_NACC * 32);
+            bool first_flush = true;
+            auto flush = [&]() {
+#pragma unroll
+                for (int h = 0; h < GT_R; ++h)
+#pragma unroll
+                    for (int q = 0; q < GT_NACC / 2; ++q) {
+                        float a0, a1;
+                        unpack2(acc[h][q], a0, a1);
+                        float* p0 = mine + (h * GT_NACC + 2 * q) * 32 + lane;
+                        if (first_flush) { p0[0] = a0; p0[32] = a1; }
+                        else { p0[0] += a0; p0[32] += a1; }
+                        acc[h][q] = 0ull;
+                    }
+                first_flush = false;
+            };
+            int since = 0;
             for (int t = k; t < T; t += GT_EPQ) {
                 const uint32_t g = gt + (uint32_t)t, a = g % GT_NS, s = g % GT_SOP;
                 bar_wait(b_sfull + a * 8, (g / GT_NS) & 1);
@@ -237,12 +257,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                 tc_fence_after();
                 const uint32_t sc = lane_base + GT_COL_S + a * (64 * GT_R);
                 const uint32_t st = sbase + s * GT_STAGE;
-                // tile-local sums first (hierarchical accumulation: the rounding error does not grow with M)
-                f32x2 tacc[GT_R][GT_NACC / 2];
-#pragma unroll
-                for (int h = 0; h < GT_R; ++h)
-#pragma unroll
-                    for (int q = 0; q < GT_NACC / 2; ++q) tacc[h][q] = 0ull;
                 uint32_t sv[GT_R][8], gv[GT_R][8];
 #pragma unroll
                 for (int h = 0; h < GT_R; ++h) {
@@ -286,24 +300,21 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
 #pragma unroll
                         for (int h = 0; h < GT_R; ++h) {
                             const f32x2 tt = pack2(tv[h][c], tv[h][c]);
-                            tacc[h][0] = fma2(tt, y0, tacc[h][0]);
-                            tacc[h][1] = fma2(tt, y1, tacc[h][1]);
-                            tacc[h][2] = fma2(tt, y2, tacc[h][2]);
-                            tacc[h][3] = fma2(tt, y3, tacc[h][3]);
-                            tacc[h][4] = fma2(tt, y4, tacc[h][4]);
-                            tacc[h][5] = fma2(tt, y5, tacc[h][5]);
-                            tacc[h][6] = fma2(tt, y6, tacc[h][6]);
-                            tacc[h][7] = fma2(tt, y7, tacc[h][7]);
-                            tacc[h][8] = fma2(tt, on, tacc[h][8]);
+                            acc[h][0] = fma2(tt, y0, acc[h][0]);
+                            acc[h][1] = fma2(tt, y1, acc[h][1]);
+                            acc[h][2] = fma2(tt, y2, acc[h][2]);
+                            acc[h][3] = fma2(tt, y3, acc[h][3]);
+                            acc[h][4] = fma2(tt, y4, acc[h][4]);
+                            acc[h][5] = fma2(tt, y5, acc[h][5]);
+                            acc[h][6] = fma2(tt, y6, acc[h][6]);
+                            acc[h][7] = fma2(tt, y7, acc[h][7]);
+                            acc[h][8] = fma2(tt, on, acc[h][8]);
                         }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) bar_arrive(b_opempty + s * 8);
-#pragma unroll
-                for (int h = 0; h < GT_R; ++h)
-#pragma unroll
-                    for (int q = 0; q < GT_NACC / 2; ++q) acc[h][q] = add2(acc[h][q], tacc[h][q]);
+                if (++since == GT_FLUSH) { flush(); since = 0; }
             }
             // once every MMA of this unit has completed the next block of x~ / G can be parked
             const int un = u + gridDim.x;
@@ -312,34 +323,25 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                 tc_fence_after();
                 park(un);
             }
-            // the EPQ partial results of a lane quarter meet in shared memory (two buffers, alternating by unit)
-            float* mine = red + ((uc & 1) * GT_EW + quad * GT_EPQ + k) * (GT_R * GT_NACC * 32);
-            float av[GT_R][GT_NACC];
-#pragma unroll
-            for (int h = 0; h < GT_R; ++h)
-#pragma unroll
-                for (int q = 0; q < GT_NACC / 2; ++q) unpack2(acc[h][q], av[h][2 * q], av[h][2 * q + 1]);
-            if (k != 0) {
-#pragma unroll
-                for (int h = 0; h < GT_R; ++h)
-#pragma unroll
-                    for (int c = 0; c < GT_NACC; ++c) mine[(h * GT_NACC + c) * 32 + lane] = av[h][c];
-            }
+            // the EPQ partial results of a lane quarter meet in shared memory
+            flush();
             asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(32 * GT_EPQ) : "memory");
             if (k == 0) {
 #pragma unroll
                 for (int h = 0; h < GT_R; ++h) {
+                    float av[GT_NACC];
 #pragma unroll
-                    for (int kk = 1; kk < GT_EPQ; ++kk) {
+                    for (int c = 0; c < GT_NACC; ++c) {
+                        float v = 0.f;
 #pragma unroll
-                        for (int c = 0; c < GT_NACC; ++c)
-                            av[h][c] += mine[kk * (GT_R * GT_NACC * 32) + (h * GT_NACC + c) * 32 + lane];
+                        for (int kk = 0; kk < GT_EPQ; ++kk) v += mine[kk * (GT_R * GT_NACC * 32) + (h * GT_NACC + c) * 32 + lane];
+                        av[c] = v;
                     }
                     const int64_t i = (int64_t)u * GT_ROWS + h * GT_BM + quad * 32 + lane;
                     if (i < P.N) {
                         const float xn = __ldg(P.xn + i);
                         const float rowf = ex2_approx(xn);                  // 2^(c|x_i|^2)
-                        const float s0v = av[h][GT_D], s2v = av[h][GT_D + 1];
+                        const float s0v = av[GT_D], s2v = av[GT_D + 1];
                         const float* xrow = P.X + i * P.ldx;
                         float* dst = P.gX + i * P.ldgx;
                         float xs1 = 0.f;
@@ -348,8 +350,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                         for (int c = 0; c < GT_D; ++c) {
                             if (c < P.d) {
                                 const float xv = __ldg(xrow + c);
-                                xs1 = fmaf(xv, av[h][c], xs1);
-                                dst[c] = f * (av[h][c] - xv * s0v);
+                                xs1 = fmaf(xv, av[c], xs1);
+                                dst[c] = f * (av[c] - xv * s0v);
                             }
                         }
                         if (P.gs_rows) P.gs_rows[i] = P.fac_s * rowf * (xn * P.inv_c * s0v - 2.f * xs1 + s2v);
