@@ -175,6 +175,17 @@ int jrk_kmatw_kind_f32(const float *X, const float *Y, const float *W, float *ou
 int jrk_dist_diag_f32(const float *X, const float *Y, float *out, int64_t N, int d,
                       int64_t ldx, int64_t ldy, float scale, const float *dim_scale, float power, void *stream);
 
+/* ------------------------------------------------------------------------------
+ * One pass over a materialised Gram (in place when out == K):
+ *     out[i, j] = K[i, j] * row_mul[i] * col_mul[j] + row_add[i] + col_add[j] + add_const
+ * -- Prefactors on both axes (jaxrk/reduce/base.py:84-101) and Center on either or both axes
+ * (jaxrk/reduce/base.py:183-192: C G C = G - 1 colmean^T - rowmean 1^T + mean) applied to the N x M array in ONE read +
+ * write instead of one pass per chain element.  All four vectors are nullable.
+ * ------------------------------------------------------------------------------ */
+int jrk_gram_affine_f32(const float *K, float *out, int64_t N, int64_t M, int64_t ldk, int64_t ldo,
+                        const float *row_mul, const float *col_mul, const float *row_add, const float *col_add,
+                        float add_const, void *stream);
+
 /* 1 when jrk_kmatw_f32 would run both contractions of this problem on the tensor cores (kmatw_tc.cu / kmatw_tc2.cu:
  * d <= 32, any m (column blocks of 16), no per-dimension scale, row_reduce NONE / SUM / MEAN, N >= 8192, M >= 4096,
  * JRK_OPT_KMATW_TC != 0), else 0 (FP32-pipe kernel).

@@ -48,6 +48,8 @@ SIGNATURES = {
                              c_float, c_void_p, c_float, c_void_p]),
     "jrk_dist_diag_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_float, c_void_p,
                                   c_float, c_void_p]),
+    "jrk_gram_affine_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_float, c_void_p]),
     "jrk_gram_kind_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64,
                                   c_int, _F, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "jrk_kmatw_kind_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
@@ -284,6 +286,24 @@ def dist_diag(X, Y, scale: float, power: float, dim_scale=None) -> torch.Tensor:
     with torch.cuda.device(X.device):
         _check(lib().jrk_dist_diag_f32(_ptr(X), _ptr(Y), _ptr(out), N, d, _ld(X), _ld(Y), scale, _ptr(ds), power,
                                        _stream(X.device)))
+    return out
+
+
+def gram_affine(K, row_mul=None, col_mul=None, row_add=None, col_add=None, add_const: float = 0.0, out=None) -> torch.Tensor:
+    """jrk_gram_affine_f32: out = K * row_mul[:, None] * col_mul[None, :] + row_add[:, None] + col_add[None, :] + add_const
+    in one pass; in place (out = K) by default."""
+    K = _dev2d(K, "K")
+    N, M = K.shape
+    out = K if out is None else out
+    if out.shape != K.shape or out.dtype != torch.float32 or out.device != K.device or out.stride(1) != 1:
+        raise ValueError("out must be a float32 N x M matrix with unit column stride on K's device")
+    vs = [_vec(v, n, name, K.device) for v, n, name in ((row_mul, N, "row_mul"), (col_mul, M, "col_mul"),
+                                                         (row_add, N, "row_add"), (col_add, M, "col_add"))]
+    if N == 0 or M == 0:
+        return out
+    with torch.cuda.device(K.device):
+        _check(lib().jrk_gram_affine_f32(_ptr(K), _ptr(out), N, M, _ld(K) if N > 1 else M, _ld(out) if N > 1 else M,
+                                         _ptr(vs[0]), _ptr(vs[1]), _ptr(vs[2]), _ptr(vs[3]), float(add_const), _stream(K.device)))
     return out
 
 

@@ -14,7 +14,7 @@ OBJ = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(HERE, "lib", "libjaxrk_b200.so")
 SOURCES = ["capi.cu", "gram_direct.cu", "gram_tf32.cu", "gram_tf32_pm0.cu", "gram_tf32_pm1.cu", "gram_tf32_pm2.cu",
            "gram_groupsum.cu", "kmatw.cu", "kmatw_pm0.cu", "kmatw_pm1.cu", "kmatw_pm2.cu", "kmatw_pm3.cu",
-           "kmatw_tc.cu", "kmatw_tc2.cu", "kmatw_plan.cu", "kgrad.cu", "kgrad_tc.cu"]
+           "kmatw_tc.cu", "kmatw_tc2.cu", "kmatw_plan.cu", "kgrad.cu", "kgrad_tc.cu", "gram_affine.cu"]
 NVCC = os.environ.get("JRK_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("JRK_EXTRA_NVCC_FLAGS", "").split()

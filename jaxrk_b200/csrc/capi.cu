@@ -14,6 +14,8 @@ int kgrad(int mode, const float* X, const float* Y, const float* W, const float*
           int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float scale,
           float power, float nconst, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t kgrad_workspace_bytes(int64_t N, int64_t M, int d);
+int gram_affine(const float* K, float* out, int64_t N, int64_t M, int64_t ldk, int64_t ldo, const float* row_mul,
+                const float* col_mul, const float* row_add, const float* col_add, float add_const, cudaStream_t st);
 int dist_diag(const float* X, const float* Y, float* out, int64_t N, int d, int64_t ldx, int64_t ldy, float scale,
               const float* dim_scale, float power, cudaStream_t st);
 std::atomic<int64_t> g_launches{0};
@@ -199,6 +201,16 @@ int jrk_dist_diag_f32(const float* X, const float* Y, float* out, int64_t N, int
     if (N == 0) return JRK_OK;
     if (int rc = have_device("jrk_dist_diag_f32")) return rc;
     return dist_diag(X, Y, out, N, d, ldx, ldy, scale, dim_scale, power, (cudaStream_t)stream);
+}
+
+int jrk_gram_affine_f32(const float* K, float* out, int64_t N, int64_t M, int64_t ldk, int64_t ldo, const float* row_mul,
+                        const float* col_mul, const float* row_add, const float* col_add, float add_const, void* stream) {
+    if (N < 0 || M < 0) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_affine_f32: bad size");
+    if (N == 0 || M == 0) return JRK_OK;
+    if (!K || !out) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_affine_f32: NULL pointer");
+    if (ldk < M || ldo < M) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_affine_f32: leading dimension too small");
+    if (int rc = have_device("jrk_gram_affine_f32")) return rc;
+    return gram_affine(K, out, N, M, ldk, ldo, row_mul, col_mul, row_add, col_add, add_const, (cudaStream_t)stream);
 }
 
 static int kmatw_any(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,

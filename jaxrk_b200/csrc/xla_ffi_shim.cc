@@ -69,6 +69,16 @@ static ffi::Error DistDiagImpl(cudaStream_t stream, F32Buf x, F32Buf y, F32Buf d
                                       opt(dim_scale), power, stream));
 }
 
+// out = K * row_mul * col_mul + row_add + col_add + add_const   (Prefactors / Center on a materialised Gram in one pass,
+// jaxrk/reduce/base.py:84-101, 183-192); bind with input_output_aliases={0: 0} to run it in place
+static ffi::Error GramAffineImpl(cudaStream_t stream, F32Buf k, F32Buf row_mul, F32Buf col_mul, F32Buf row_add, F32Buf col_add,
+                                 float add_const, F32Res out) {
+    if (!is_mat(k)) return ffi::Error::InvalidArgument("K must be N x M");
+    const int64_t N = k.dimensions()[0], M = k.dimensions()[1];
+    return to_error(jrk_gram_affine_f32(k.typed_data(), out->typed_data(), N, M, M, M, opt(row_mul), opt(col_mul), opt(row_add),
+                                        opt(col_add), add_const, stream));
+}
+
 // out = row_reduce(diag(row_pref) K(X, Y) diag(col_pref) W)   (jaxrk/rkhs/vector.py:62-75)
 static ffi::Error KmatwImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, F32Buf x, F32Buf y, F32Buf w, F32Buf dim_scale,
                             F32Buf row_pref, F32Buf col_pref, float scale, float power, float nconst, int32_t row_reduce,
@@ -177,6 +187,12 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(jrk_dist_f32_ffi, DistImpl,
 XLA_FFI_DEFINE_HANDLER_SYMBOL(jrk_dist_diag_f32_ffi, DistDiagImpl,
                               JRK_STREAM.Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>()
                                   .Attr<float>("scale").Attr<float>("power")
+                                  .Ret<F32Buf>(),
+                              {ffi::Traits::kCmdBufferCompatible});
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(jrk_gram_affine_f32_ffi, GramAffineImpl,
+                              JRK_STREAM.Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>()
+                                  .Attr<float>("add_const")
                                   .Ret<F32Buf>(),
                               {ffi::Traits::kCmdBufferCompatible});
 

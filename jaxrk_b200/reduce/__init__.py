@@ -1,2 +1,2 @@
 from .base import Reduce, NoReduce, Prefactors, TileView, Sum, Mean, BalancedRed, Center
-from .lincomb import LinearReduce, SparseReduce, KernelMapReduce
+from .lincomb import LinearReduce, SparseReduce, BlockReduce, KernelMapReduce

@@ -93,6 +93,56 @@ class KernelMapReduce(LinearReduce):
         return len(self._vec)
 
 
+class BlockReduce(Reduce):
+    """Sum / average consecutive blocks of rows: block b is rows block_boundaries[b] .. block_boundaries[b + 1] - 1
+    (jaxrk/reduce/lincomb.py:89-129).  The reference's reduce_first_ax concatenates the per-block 1-D sums into ONE 1-D
+    array and its new_len returns the last boundary (lincomb.py:114-119): unusable inside a chain, and no reference test
+    exercises it (tests/test_reduce.py:31 is commented out).  Implemented here with the evident intent -- one output row
+    per block -- so that `sum_from_block` composes like `LinearReduce.sum_from_unique`.  Few blocks are folded into the
+    fused K@W kernel as a dense map (rkhs/_lowering.py); many blocks reduce a materialised Gram by prefix sums."""
+
+    def __init__(self, block_boundaries, average: bool = True):
+        b = np.asarray(block_boundaries.detach().cpu().numpy() if isinstance(block_boundaries, torch.Tensor) else block_boundaries)
+        b = b.astype(np.int64).reshape(-1)
+        assert b.size >= 2 and (np.diff(b) > 0).all() and b[0] >= 0
+        self.block_boundaries = b
+        self.average = bool(average)
+
+    def num_rows(self) -> int:
+        return int(self.block_boundaries.size - 1)
+
+    def reduce_first_ax(self, inp):
+        inp = asarray(inp)
+        assert len(inp.shape) == 2
+        assert self.block_boundaries[-1] <= len(inp), self.__class__.__name__ + " expects a longer gram to operate on"
+        b = torch.as_tensor(self.block_boundaries, device=inp.device)
+        # block sums as differences of an exclusive prefix sum (float64 accumulation: the differences cancel)
+        cs = torch.zeros((inp.shape[0] + 1, inp.shape[1]), dtype=torch.float64, device=inp.device)
+        torch.cumsum(inp.double(), 0, out=cs[1:])
+        out = cs[b[1:]] - cs[b[:-1]]
+        if self.average:
+            out = out / (b[1:] - b[:-1]).double()[:, None]
+        return out.to(inp.dtype)
+
+    def new_len(self, original_len: int):
+        assert self.block_boundaries[-1] <= original_len
+        return self.num_rows()
+
+    def to_linear_map(self, n: int, device=None) -> torch.Tensor:
+        assert self.block_boundaries[-1] <= n
+        A = torch.zeros((self.num_rows(), n), dtype=torch.float32, device=device)
+        for r, (s, e) in enumerate(zip(self.block_boundaries[:-1], self.block_boundaries[1:])):
+            A[r, int(s):int(e)] = (1.0 / float(e - s)) if self.average else 1.0
+        return A
+
+    @classmethod
+    def sum_from_block(cls, input, mean: bool = True) -> "BlockReduce":
+        """lincomb.py:121-128: a block ends wherever consecutive entries of `input` differ."""
+        inp = np.asarray(input.detach().cpu().numpy() if isinstance(input, torch.Tensor) else input).reshape(-1)
+        change = [0] + list(np.argwhere(inp[:-1] != inp[1:]).flatten() + 1) + [len(inp)]
+        return BlockReduce(np.array(change), mean)
+
+
 class SparseReduce(Reduce):
     """Sum / average rows of the input selected by index arrays (lincomb.py:27-87).  Index
     structured, so it is applied to a materialised Gram (not folded into the fused kernels)."""

@@ -32,8 +32,8 @@ from typing import List, Optional
 import torch
 
 from .. import _native as nat
-from ..reduce.base import BalancedRed, Mean, Prefactors, Reduce, Sum
-from ..reduce.lincomb import LinearReduce, SparseReduce
+from ..reduce.base import BalancedRed, Center, Mean, Prefactors, Reduce, Sum
+from ..reduce.lincomb import BlockReduce, LinearReduce, SparseReduce
 
 NONE, SUM, MEAN, BALANCED, LINEAR = "none", "sum", "mean", "balanced", "linear"
 SPARSE_DENSE_LIMIT = 1 << 26      # elements of the dense form of a SparseReduce that may be built (256 MB)
@@ -62,6 +62,26 @@ class Folded:
         return self.n
 
 
+def _center_then(r: Reduce, n: int, dev) -> Optional[torch.Tensor]:
+    """The dense map of  r . Center  when it is small:  r (I - 1 1^T / n) = r - (r 1) 1^T / n, or None."""
+    if type(r) in (Sum, Mean):
+        return torch.zeros((1, n), dtype=torch.float32, device=dev)                 # 1^T (I - 1 1^T / n) = 0
+    if isinstance(r, LinearReduce):
+        A = r.linear_map.to(dev)
+    elif type(r) in (SparseReduce, BlockReduce) and r.num_rows() <= SPARSE_FOLD_ROWS:
+        A = r.to_linear_map(n, dev)
+    elif type(r) is BalancedRed and n // r.points_per_split <= SPARSE_FOLD_ROWS:
+        A = r.reduce_first_ax(torch.eye(n, dtype=torch.float32, device=dev)) if n <= 4096 else None
+        if A is None:
+            g = n // r.points_per_split
+            A = torch.zeros((g, n), dtype=torch.float32, device=dev)
+            A.view(g, g, r.points_per_split)[torch.arange(g), torch.arange(g)] = (1.0 / r.points_per_split) if r.average else 1.0
+    else:
+        return None
+    assert A.shape[1] == n
+    return A - A.sum(1, keepdim=True) / n
+
+
 def fold_chain(chain: Optional[List[Reduce]], n: int, dev) -> Folded:
     f = Folded(n=n)
     chain = list(chain or [])
@@ -87,10 +107,17 @@ def fold_chain(chain: Optional[List[Reduce]], n: int, dev) -> Folded:
         elif isinstance(r, LinearReduce):      # incl. KernelMapReduce (materialises its map here)
             assert r.linear_map.shape[1] == n
             f.kind, f.A = LINEAR, r.linear_map.to(dev)
-        elif type(r) is SparseReduce and r.num_rows() <= SPARSE_FOLD_ROWS and r.num_rows() * n <= SPARSE_DENSE_LIMIT:
-            # a sparse averaging map small enough to hold densely: folded like a LinearReduce (fused K@W, the Gram is
-            # not materialised); larger ones fall through to the generic route below
+        elif type(r) in (SparseReduce, BlockReduce) and r.num_rows() <= SPARSE_FOLD_ROWS and r.num_rows() * n <= SPARSE_DENSE_LIMIT:
+            # a sparse / block averaging map small enough to hold densely: folded like a LinearReduce (fused K@W, the Gram
+            # is not materialised); larger ones fall through to the generic route below
             f.kind, f.A = LINEAR, r.to_linear_map(n, dev)
+        elif type(r) is Center and idx + 1 < len(chain) and (A := _center_then(chain[idx + 1], n, dev)) is not None:
+            # Center followed by a small linear map: (r . Center) is itself a dense map -- the centring is folded into the
+            # fused K@W (jaxrk/reduce/base.py:183-192 composed with the next element); the element after it is consumed
+            f.kind, f.A = LINEAR, A
+            for r2 in chain[idx + 2:]:
+                f.A = r2.reduce_first_ax(f.A)
+            break
         else:  # Center, TileView, SparseReduce, user types: not folded
             f.post = chain[idx:]
             break
@@ -335,6 +362,27 @@ def reduced_gram(k, X, chain_x, Y, chain_y, self_gram: bool = False) -> torch.Te
                                 False, dim_scale=dim_scale, row_pref=fy.pref, col_pref=fx.pref).t()
         if fx.average or fy.average:
             out = out * (1.0 / ((fx.group if fx.average else 1) * (fy.group if fy.average else 1)))
+    elif fx.kind == NONE and fy.kind == NONE:
+        # materialised Gram; Prefactors on both axes and a leading Center on either axis are applied in ONE pass over it
+        # (jrk_gram_affine_f32).  C_N G C_M = G - 1 colmean^T - rowmean 1^T + mean: the means are skinny fused K@W
+        # calls (they never read the Gram).
+        cx = bool(fx.post) and type(fx.post[0]) is Center
+        cy = bool(fy.post) and type(fy.post[0]) is Center
+        row_add = col_add = None
+        const = 0.0
+        N_, M_ = X.shape[0], Y.shape[0]
+        if cx:      # column means of G' = D_p K D_q:  q_j sum_i K_ji p_i / N
+            col_add = -_kmatw_side(Y, X, Folded(n=M_, pref=fy.pref), Folded(n=N_, pref=fx.pref, kind=MEAN), spec).reshape(-1)
+            fx.post = fx.post[1:]
+        if cy:
+            row_add = -_kmatw_side(X, Y, Folded(n=N_, pref=fx.pref), Folded(n=M_, pref=fy.pref, kind=MEAN), spec).reshape(-1)
+            fy.post = fy.post[1:]
+        if cx and cy:
+            const = -float(row_add.double().mean())           # + mean(G')
+        G = nat.gram_spec(X, None if self_gram else Y, spec)
+        if fx.pref is not None or fy.pref is not None or cx or cy:
+            nat.gram_affine(G, row_mul=fx.pref, col_mul=fy.pref, row_add=row_add, col_add=col_add, add_const=const)
+        out = G
     else:
         G = nat.gram_spec(X, None if self_gram else Y, spec)
         if fx.pref is not None:

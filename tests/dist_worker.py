@@ -25,6 +25,7 @@ def main(rank, world, port, out_dir):
 
     arr._device = torch.device("cpu")
     nat.gram, nat.dist, nat.kmatw, nat.gram_groupsum = stand.fake_gram, stand.fake_dist, stand.fake_kmatw, stand.fake_groupsum
+    nat.gram_affine = stand.fake_gram_affine
 
     rng = np.random.RandomState(7)
     P, Q = rng.randn(24, 4).astype(np.float32), rng.randn(36, 4).astype(np.float32)

@@ -19,6 +19,7 @@ COMPUTE = {
     "jrk_gram_f32": ["dim_scale"],
     "jrk_dist_f32": ["dim_scale"],
     "jrk_dist_diag_f32": ["dim_scale"],
+    "jrk_gram_affine_f32": ["row_mul", "col_mul", "row_add", "col_add"],
     "jrk_kmatw_f32": ["dim_scale", "row_pref", "col_pref"],
     "jrk_gram_kind_f32": ["dim_scale"],
     "jrk_kmatw_kind_f32": ["dim_scale", "row_pref", "col_pref"],

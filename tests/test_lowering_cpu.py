@@ -15,7 +15,7 @@ import torch
 import jaxrk_b200._array as arr
 from jaxrk_b200 import _native as nat
 from jaxrk_b200.kern import GenGaussKernel
-from jaxrk_b200.reduce import BalancedRed, Center, LinearReduce, Mean, Prefactors, Reduce, Sum, TileView
+from jaxrk_b200.reduce import BalancedRed, BlockReduce, Center, LinearReduce, Mean, Prefactors, Reduce, Sum, TileView
 from jaxrk_b200.rkhs import Cdo, Cmo, Cov_inv, CovOp, FiniteOp, FiniteVec, inner
 from jaxrk_b200.rkhs import _lowering as low
 from oracle import jaxrk_oracle as orc
@@ -83,6 +83,22 @@ def fake_dist_diag(X, Y, scale, power, dim_scale=None):
     return torch.from_numpy(orc.scaled_dist_diag_truth64(_np(X).astype(f32), _np(Y).astype(f32), s, power).astype(f32))
 
 
+def fake_gram_affine(K, row_mul=None, col_mul=None, row_add=None, col_add=None, add_const=0.0, out=None):
+    CALLS.append("gram_affine")
+    G = _np(K)
+    if row_mul is not None:
+        G = G * _np(row_mul)[:, None]
+    if col_mul is not None:
+        G = G * _np(col_mul)[None, :]
+    if row_add is not None:
+        G = G + _np(row_add)[:, None]
+    if col_add is not None:
+        G = G + _np(col_add)[None, :]
+    res = torch.from_numpy((G + add_const).astype(f32))
+    (K if out is None else out).copy_(res)
+    return K if out is None else out
+
+
 @pytest.fixture(autouse=True)
 def cpu_standins(monkeypatch):
     monkeypatch.setattr(arr, "_device", torch.device("cpu"))
@@ -91,6 +107,7 @@ def cpu_standins(monkeypatch):
     monkeypatch.setattr(nat, "kmatw", fake_kmatw)
     monkeypatch.setattr(nat, "gram_groupsum", fake_groupsum)
     monkeypatch.setattr(nat, "dist_diag", fake_dist_diag)
+    monkeypatch.setattr(nat, "gram_affine", fake_gram_affine)
     CALLS.clear()
     yield
 
@@ -183,7 +200,8 @@ def test_lowering_picks_the_fused_kernels(golden):
     assert calls(cx["pref_bal3"], cy["sum"]) == ["kmatw"]   # BalancedRed folded as row reduce
     assert calls(cx["sum"], cy["bal6avg"]) == ["kmatw"]     # transposed, balanced on the other side
     assert calls(cx["bal2_center"], cy["mean"]) == ["kmatw"]  # Center acts on the reduced result
-    assert calls(cx["center"], cy["none"]) == ["gram"]      # not foldable: materialise + Reduce.apply
+    # Center on a materialised Gram: the column means as one skinny fused call, then Gram + ONE affine pass
+    assert calls(cx["center"], cy["none"]) == ["kmatw", "gram", "gram_affine"]
     X = np.random.RandomState(0).randn(256, 3).astype(f32)
     CALLS.clear()
     v = FiniteVec(kg, X, [BalancedRed(128, True)])
@@ -412,3 +430,43 @@ def test_sparse_reduce_is_folded_into_the_fused_product_when_small():
         np.testing.assert_allclose(got2.numpy(), SparseReduce(idcs, True).reduce_first_ax(k(X, Y)).numpy(), rtol=2e-5, atol=1e-6)
     finally:
         lowmod.SPARSE_DENSE_LIMIT = old
+
+
+def test_center_and_block_reduce_lowering():
+    """Center (jaxrk/reduce/base.py:183-192) and BlockReduce (jaxrk/reduce/lincomb.py:89-129, intended semantics) through
+    the lowering: Center followed by a small linear map folds into the fused K@W; Center as the last element of a chain
+    on a materialised Gram becomes ONE affine pass whose means are skinny fused calls -- both against the array-level
+    semantics applied to the float64 Gram."""
+    rng = np.random.RandomState(5)
+    N, M, d = 24, 18, 3
+    X, Y = rng.randn(N, d).astype(f32), rng.randn(M, d).astype(f32)
+    pp, qq = np.abs(rng.randn(N)).astype(f32) + 0.1, rng.randn(M).astype(f32)
+    A = rng.randn(5, M).astype(f32)
+    k = GenGaussKernel.make_gauss(1.3)
+    K = torch.from_numpy(np.asarray(_truth_gram(X, Y, *k.kernel_args()[:1], k.kernel_args()[2], k.kernel_args()[3], None)).astype(f32))
+    blk = BlockReduce([0, 5, 6, 18], average=True)
+    cases = {
+        "center | none": ([Center()], []),
+        "pref, center | pref": ([Prefactors(pp), Center()], [Prefactors(qq)]),
+        "center | center": ([Center()], [Center()]),
+        "pref, center | pref, center, sum": ([Prefactors(pp), Center()], [Prefactors(qq), Center(), Sum()]),
+        "center, bal | center, lin": ([Center(), BalancedRed(4, True)], [Center(), LinearReduce(A)]),
+        "none | block": ([], [blk]),
+        "center | block, center": ([Center()], [blk, Center()]),
+        "bal | center, block": ([BalancedRed(3)], [Center(), blk]),
+    }
+    for name, (cx, cy) in cases.items():
+        CALLS.clear()
+        got = inner(FiniteVec(k, X, cx), FiniteVec(k, Y, cy))
+        want = Reduce.apply(Reduce.apply(K, cx, 0), cy, 1)
+        assert got.shape == want.shape, name
+        assert torch.allclose(got, want, rtol=2e-5, atol=2e-6), (name, float((got - want).abs().max()))
+        if name in ("center | none", "pref, center | pref", "center | center"):
+            assert CALLS.count("gram") == 1 and CALLS.count("gram_affine") == 1, (name, CALLS)
+        if name in ("pref, center | pref, center, sum", "center, bal | center, lin", "none | block", "bal | center, block"):
+            assert "gram" not in CALLS, (name, CALLS)           # fused K@W: the Gram is never materialised
+    b2 = BlockReduce.sum_from_block(np.array([3, 3, 7, 7, 7, 1]), mean=False)
+    assert list(b2.block_boundaries) == [0, 2, 5, 6] and b2.new_len(6) == 3
+    G6 = torch.from_numpy(rng.randn(6, 4).astype(f32))
+    assert torch.allclose(b2(G6, 0), torch.stack([G6[0:2].sum(0), G6[2:5].sum(0), G6[5:6].sum(0)]), atol=1e-6)
+    assert torch.allclose(b2(G6.T.contiguous(), 1), b2(G6, 0).T, atol=1e-6)
