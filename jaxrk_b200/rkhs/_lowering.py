@@ -320,6 +320,43 @@ def _groupsum_tensor(X, Y, fx: Folded, fy: Folded, scale, power, nconst, self_gr
     return out
 
 
+DIAG_GROUP_LOOP = 4096           # BalancedRed self inner products: up to this many groups get one fused call each
+
+
+def reduced_gram_diag(k, X, chain) -> Optional[torch.Tensor]:
+    """diag(R K(X, X) R^T) WITHOUT the full reduced Gram, or None when the chain does not allow it -- what the RKHS
+    distances between two vectors need from each of them (jaxrk/utilities/distances.py:41-42 takes the diagonals of
+    a.inner() and b.inner(), jaxrk/utilities/gram.py:30-35).  BalancedRed (mean embeddings): entry a is the sum over the
+    a-th diagonal BLOCK only, one fused Sum-reduced K@W per group (sum_g g^2 kernel values instead of N^2);
+    LinearReduce: one fused K(X, X) A^T and a row-wise dot product; no reduce: k(x_i, x_i)."""
+    spec = kernel_spec_of(k)
+    if spec is None or needs_grad(k, X, *_chain_tensors(chain)):
+        return None
+    dev = X.device
+    f = fold_chain(chain, X.shape[0], dev)
+    if f.post:
+        return None
+    n = X.shape[0]
+    if f.kind == NONE:
+        d0 = k(X, X, diag=True).reshape(-1)
+        return d0 if f.pref is None else d0 * f.pref * f.pref
+    if f.kind in (SUM, MEAN):
+        return None                                            # a 1 x 1 result: the full route is the same work
+    if f.kind == LINEAR:
+        T = _kmatw_side(X, X, Folded(n=n, pref=f.pref), Folded(n=n, pref=f.pref, kind=LINEAR, A=f.A), spec)   # D_p K D_p A^T
+        return (f.A.t() * T).sum(0)
+    if f.kind == BALANCED and n // f.group <= DIAG_GROUP_LOOP:
+        g = f.group
+        out = torch.empty((n // g,), dtype=torch.float32, device=dev)
+        ones = torch.ones((g, 1), dtype=torch.float32, device=dev)
+        for a in range(n // g):
+            Xg = X[a * g:(a + 1) * g]
+            pg = None if f.pref is None else f.pref[a * g:(a + 1) * g]
+            out[a:a + 1] = nat.kmatw_spec(Xg, Xg, ones, spec, row_pref=pg, col_pref=pg, row_reduce=nat.REDUCE_SUM).reshape(-1)
+        return out / float(g * g) if f.average else out
+    return None
+
+
 def reduced_gram(k, X, chain_x, Y, chain_y, self_gram: bool = False) -> torch.Tensor:
     """R_X K(X, Y) R_Y^T.  `self_gram` says Y is X (enables the symmetric self-Gram kernel)."""
     dev = X.device

@@ -39,6 +39,10 @@ class FiniteVec(Vec):
         if not full and Y is not None:
             raise ValueError("Ambiguous inputs: `full` and `y` are not compatible.")
         if not full:  # diagonal of the self inner product (the reference's branch is dead: vector.py:66-67)
+            if self._inner_cache is None:       # without the full reduced Gram where the chain allows it
+                dg = _lowering.reduced_gram_diag(self.k, self.insp_pts, self.reduce)
+                if dg is not None:
+                    return dg
             return torch.diagonal(self.inner())
         if Y is not None:
             assert self.k == Y.k  # object identity, as in the reference (quirk Q5)

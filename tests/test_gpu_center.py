@@ -97,3 +97,41 @@ def test_block_reduce_folded_and_generic():
     got2 = inner(FiniteVec(k, X), FiniteVec(k, Y, [many]))
     np.testing.assert_allclose(n(got2), G.reshape(N, 150, 20).sum(2), rtol=3e-5, atol=1e-6)
     assert many.new_len(M) == 150 and few.new_len(M) == 3
+
+
+def test_rkhs_cdist_between_mean_embeddings_needs_one_reduced_gram():
+    """dist(a, b) for two vectors of mean embeddings (jaxrk/utilities/distances.py:28-42): the cross reduced Gram, the two
+    diagonals WITHOUT their reduced Grams (block sums), one combining pass -- against float64, and against the
+    three-Gram form of the reference."""
+    from jaxrk_b200.utilities import dist, rkhs_gram_cdist
+    rng = np.random.RandomState(3)
+    ga_, gb_, na, nb, d = 256, 128, 12, 20, 6
+    X, Y = rng.randn(na * ga_, d).astype(f32), (rng.randn(nb * gb_, d) + 0.3).astype(f32)
+    p = (np.abs(rng.randn(na * ga_)) + 0.2).astype(f32)
+    k = GenGaussKernel.make_gauss(2.5)
+    s = orc.simple_scaler_s(orc.gauss_length_scale(2.5))
+    a = FiniteVec(k, X, [Prefactors(p), BalancedRed(ga_, True)])
+    b = FiniteVec(k, Y, [BalancedRed(gb_, True)])
+    n0 = nat.launch_count()
+    D = dist(a, b)
+    launches = nat.launch_count() - n0
+    p64 = p.astype(np.float64)
+    Gab = (orc.gengauss_gram_truth64(X, Y, s, 2.0) * p64[:, None]).reshape(na, ga_, nb, gb_).mean((1, 3))
+    Gaa = (orc.gengauss_gram_truth64(X, X, s, 2.0) * p64[:, None] * p64[None, :]).reshape(na, ga_, na, ga_).mean((1, 3))
+    Gbb = orc.gengauss_gram_truth64(Y, Y, s, 2.0).reshape(nb, gb_, nb, gb_).mean((1, 3))
+    want = np.diag(Gaa)[:, None] + np.diag(Gbb)[None, :] - 2 * Gab
+    scale_ = np.diag(Gaa).max() + np.diag(Gbb).max()
+    assert np.abs(n(D) - want).max() <= 3e-5 * scale_
+    three = rkhs_gram_cdist(a.inner(b), a.inner(), b.inner())                         # the reference's form
+    assert float((D - three).abs().max()) <= 3e-5 * scale_
+    assert launches <= 8 + 4 * (na + nb), launches
+    # an element against itself: zero distance on the diagonal up to rounding, and the cached self inner product survives
+    S0 = a.inner().clone()
+    D2 = dist(a, a)
+    assert float(torch.diagonal(D2).abs().max()) <= 3e-5 * scale_ and torch.equal(a.inner(), S0)
+    # LinearReduce elements: diagonal by one fused K(X, X) A^T
+    A = rng.randn(5, na * ga_).astype(f32) / 50
+    c = FiniteVec(k, X, [LinearReduce(A)])
+    dg = c.inner(full=False)
+    full = FiniteVec(k, X, [LinearReduce(A)]).inner()
+    assert torch.allclose(dg, torch.diagonal(full), rtol=3e-5, atol=1e-6)
