@@ -214,20 +214,23 @@ int jrk_gram_groupsum_f32(const float *X, const float *Y, float *out,
  *   jrk_kmatw_grad_f32:  out = K(X, Y) W,  G = dL/dout (N x m):
  *       gX[i, :]   = sum_j (G[i, :] . W[j, :]) dK_ij/dx_i                       (N x d)
  *       gs_rows[i] = sum_j (G[i, :] . W[j, :]) dK_ij/dscale  at fixed nconst    (len N, nullable; dL/dscale = its sum)
+ *       gp_rows[i] = sum_j (G[i, :] . W[j, :]) dK_ij/dpower  at fixed nconst    (len N, nullable; dL/dpower = its sum;
+ *                    dK/dp = -K (s r)^p ln(s r); asking for it runs the general-p epilogue, also for p = 2 and p = 1)
  *   jrk_gram_grad_f32:   K = K(X, Y),  Gbar = dL/dK (N x M): the same with G[i,:].W[j,:] replaced by Gbar[i, j].
  * dL/dY is the same call with the roles exchanged -- (Y, X, G, W) resp. (Y, X, Gbar^T) -- and dL/dW = K(Y, X) G is
- * jrk_kmatw_f32.  GenGauss family only, global scale only (dim_scale unsupported), d <= 64, m <= 32.
+ * jrk_kmatw_f32.  GenGauss family only, global scale only (per-dimension scales are a pre-scaling of the points: their
+ * gradient follows from gX / gY by the chain rule on the caller's side), d <= 64, m <= 32.
  * Pairs at distance zero contribute nothing (p <= 1: the derivative does not exist there, jax.grad gives NaN).
  * ------------------------------------------------------------------------------ */
 int jrk_kmatw_grad_f32(const float *X, const float *Y, const float *W, const float *G,
-                       float *gX, float *gs_rows,
+                       float *gX, float *gs_rows, float *gp_rows,
                        int64_t N, int64_t M, int d, int m,
                        int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx,
                        float scale, float power, float nconst,
                        void *workspace, size_t workspace_bytes, void *stream);
 
 int jrk_gram_grad_f32(const float *X, const float *Y, const float *Gbar,
-                      float *gX, float *gs_rows,
+                      float *gX, float *gs_rows, float *gp_rows,
                       int64_t N, int64_t M, int d,
                       int64_t ldx, int64_t ldy, int64_t ldgb, int64_t ldgx,
                       float scale, float power, float nconst,

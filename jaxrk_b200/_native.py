@@ -56,10 +56,10 @@ SIGNATURES = {
                                    c_int64, c_int64, c_int64, c_int64, c_int, _F, c_int, c_void_p,
                                    c_void_p, c_void_p, c_int, c_int64, c_void_p, c_size_t, c_void_p]),
     "jrk_grad_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
-    "jrk_kmatw_grad_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+    "jrk_kmatw_grad_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                                    c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_float, c_float,
                                    c_void_p, c_size_t, c_void_p]),
-    "jrk_gram_grad_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+    "jrk_gram_grad_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                                   c_int64, c_int64, c_int64, c_int64, c_float, c_float, c_float,
                                   c_void_p, c_size_t, c_void_p]),
     "jrk_kmatw_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int64]),
@@ -307,8 +307,9 @@ def gram_affine(K, row_mul=None, col_mul=None, row_add=None, col_add=None, add_c
     return out
 
 
-def kmatw_grad(X, Y, W, G, scale: float, power: float, nconst: float, want_scale: bool = True):
-    """jrk_kmatw_grad_f32: (gX, gs_rows) for out = K(X, Y) W with cotangent G (N x m); m <= 32, d <= 64."""
+def kmatw_grad(X, Y, W, G, scale: float, power: float, nconst: float, want_scale: bool = True, want_power: bool = False):
+    """jrk_kmatw_grad_f32: (gX, gs_rows) for out = K(X, Y) W with cotangent G (N x m); m <= 32, d <= 64.
+    want_power: a third result gp_rows (per-row dL/dpower at fixed nconst)."""
     X, Y, W, G = _dev2d(X, "X"), _dev2d(Y, "Y"), _dev2d(W, "W"), _dev2d(G, "G")
     N, d = X.shape
     M, m = W.shape
@@ -317,16 +318,17 @@ def kmatw_grad(X, Y, W, G, scale: float, power: float, nconst: float, want_scale
     dev = X.device
     gX = torch.empty((N, d), dtype=torch.float32, device=dev)
     gs = torch.empty((N,), dtype=torch.float32, device=dev) if want_scale else None
+    gp = torch.empty((N,), dtype=torch.float32, device=dev) if want_power else None
     with torch.cuda.device(dev):
         wsb = lib().jrk_grad_workspace_bytes(N, M, d)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        _check(lib().jrk_kmatw_grad_f32(_ptr(X), _ptr(Y), _ptr(W), _ptr(G), _ptr(gX), _ptr(gs), N, M, d, m, _ld(X), _ld(Y),
-                                        _ld(W), _ld(G), d, scale, power, nconst, _ptr(ws), wsb, _stream(dev)))
-    return gX, gs
+        _check(lib().jrk_kmatw_grad_f32(_ptr(X), _ptr(Y), _ptr(W), _ptr(G), _ptr(gX), _ptr(gs), _ptr(gp), N, M, d, m, _ld(X),
+                                        _ld(Y), _ld(W), _ld(G), d, scale, power, nconst, _ptr(ws), wsb, _stream(dev)))
+    return (gX, gs, gp) if want_power else (gX, gs)
 
 
-def gram_grad(X, Y, Gbar, scale: float, power: float, nconst: float, want_scale: bool = True):
-    """jrk_gram_grad_f32: (gX, gs_rows) for K = K(X, Y) with cotangent Gbar (N x M); d <= 64."""
+def gram_grad(X, Y, Gbar, scale: float, power: float, nconst: float, want_scale: bool = True, want_power: bool = False):
+    """jrk_gram_grad_f32: (gX, gs_rows[, gp_rows]) for K = K(X, Y) with cotangent Gbar (N x M); d <= 64."""
     X, Y, Gbar = _dev2d(X, "X"), _dev2d(Y, "Y"), _dev2d(Gbar, "Gbar")
     N, d = X.shape
     M = Y.shape[0]
@@ -335,12 +337,13 @@ def gram_grad(X, Y, Gbar, scale: float, power: float, nconst: float, want_scale:
     dev = X.device
     gX = torch.empty((N, d), dtype=torch.float32, device=dev)
     gs = torch.empty((N,), dtype=torch.float32, device=dev) if want_scale else None
+    gp = torch.empty((N,), dtype=torch.float32, device=dev) if want_power else None
     with torch.cuda.device(dev):
         wsb = lib().jrk_grad_workspace_bytes(N, M, d)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        _check(lib().jrk_gram_grad_f32(_ptr(X), _ptr(Y), _ptr(Gbar), _ptr(gX), _ptr(gs), N, M, d, _ld(X), _ld(Y),
+        _check(lib().jrk_gram_grad_f32(_ptr(X), _ptr(Y), _ptr(Gbar), _ptr(gX), _ptr(gs), _ptr(gp), N, M, d, _ld(X), _ld(Y),
                                        _ld(Gbar), d, scale, power, nconst, _ptr(ws), wsb, _stream(dev)))
-    return gX, gs
+    return (gX, gs, gp) if want_power else (gX, gs)
 
 
 class KernelSpec:

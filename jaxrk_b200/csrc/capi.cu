@@ -10,7 +10,7 @@
 namespace jrk {
 
 thread_local char g_last_error[512] = {0};
-int kgrad(int mode, const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, int64_t N,
+int kgrad(int mode, const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, float* gp_rows, int64_t N,
           int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float scale,
           float power, float nconst, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t kgrad_workspace_bytes(int64_t N, int64_t M, int d);
@@ -275,7 +275,7 @@ int jrk_kmatw_kind_f32(const float* X, const float* Y, const float* W, float* ou
 size_t jrk_grad_workspace_bytes(int64_t N, int64_t M, int d) { return kgrad_workspace_bytes(N, M, d); }
 
 int jrk_kmatw_grad_f32(const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows,
-                       int64_t N, int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg,
+                       float* gp_rows, int64_t N, int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg,
                        int64_t ldgx, float scale, float power, float nconst, void* workspace, size_t workspace_bytes,
                        void* stream) {
     if (!X || !Y || !W || !G || !gX) return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_grad_f32: NULL pointer");
@@ -284,11 +284,11 @@ int jrk_kmatw_grad_f32(const float* X, const float* Y, const float* W, const flo
     if (ldx < d || ldy < d || ldw < m || ldg < m || ldgx < d)
         return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_grad_f32: leading dimension too small");
     if (int rc = have_device("jrk_kmatw_grad_f32")) return rc;
-    return kgrad(0, X, Y, W, G, gX, gs_rows, N, M, d, m, ldx, ldy, ldw, ldg, ldgx, scale, power, nconst, workspace,
+    return kgrad(0, X, Y, W, G, gX, gs_rows, gp_rows, N, M, d, m, ldx, ldy, ldw, ldg, ldgx, scale, power, nconst, workspace,
                  workspace_bytes, (cudaStream_t)stream);
 }
 
-int jrk_gram_grad_f32(const float* X, const float* Y, const float* Gbar, float* gX, float* gs_rows, int64_t N, int64_t M,
+int jrk_gram_grad_f32(const float* X, const float* Y, const float* Gbar, float* gX, float* gs_rows, float* gp_rows, int64_t N, int64_t M,
                       int d, int64_t ldx, int64_t ldy, int64_t ldgb, int64_t ldgx, float scale, float power, float nconst,
                       void* workspace, size_t workspace_bytes, void* stream) {
     if (!X || !Y || !Gbar || !gX) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_grad_f32: NULL pointer");
@@ -297,7 +297,7 @@ int jrk_gram_grad_f32(const float* X, const float* Y, const float* Gbar, float* 
     if (ldx < d || ldy < d || ldgb < M || ldgx < d)
         return fail(JRK_ERR_INVALID_ARG, "jrk_gram_grad_f32: leading dimension too small");
     if (int rc = have_device("jrk_gram_grad_f32")) return rc;
-    return kgrad(1, X, Y, nullptr, Gbar, gX, gs_rows, N, M, d, 0, ldx, ldy, 0, ldgb, ldgx, scale, power, nconst,
+    return kgrad(1, X, Y, nullptr, Gbar, gX, gs_rows, gp_rows, N, M, d, 0, ldx, ldy, 0, ldgb, ldgx, scale, power, nconst,
                  workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

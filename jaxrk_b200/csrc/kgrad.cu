@@ -49,7 +49,7 @@ kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__
              const unsigned* __restrict__ skip_if_fast) {
     // the tensor-core kernel (kgrad_tc.cu) was launched next to this one: inside its regime the result is its to write
     if (skip_if_fast && kg_fast_regime(skip_if_fast)) return;
-    // part layout: [split][row][stride], stride = d + 2: {dL/dx contribution (d), S0 (unused by finalize), S2}
+    // part layout: [split][row][stride], stride = d + 3: {dL/dx contribution (d), S0 (unused by finalize), S2, S3}
     __shared__ __align__(16) float sY[KG_TJ][D];
     __shared__ __align__(16) float sA[(MODE == 0) ? KG_TJ * MT : KG_ROWS * (KG_TJ + 1)];
 
@@ -73,7 +73,7 @@ kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__
             g2[c] = pack2(a0, a1);
         }
     }
-    float s0 = 0.f, s2 = 0.f;
+    float s0 = 0.f, s2 = 0.f, s3 = 0.f;     // s3 (PM_GENERAL only): sum_j t r^2 lg2(s^2 r^2) -> dL/dpower
 
     const int64_t j_begin = (int64_t)blockIdx.y * cols_per_split;
     const int64_t j_end = (j_begin + cols_per_split < M) ? j_begin + cols_per_split : M;
@@ -162,8 +162,11 @@ kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__
                 const float r = sqrt_approx(sq);
                 t = (sq > 0.f) ? a * ex2_approx(r * ep.c) / r : 0.f;
             } else {
-                const float u = ex2_approx(ep.hp * lg2_approx(sq * ep.c));     // (s r)^p
+                const float lg = lg2_approx(sq * ep.c);                        // log2((s r)^2)
+                const float u = ex2_approx(ep.hp * lg);                        // (s r)^p
                 t = (sq > 0.f) ? a * ex2_approx(u * -kLog2e) * u / sq : 0.f;
+                // dK/dp = -K u ln(s r) at fixed nconst:  a (K / nconst) u = t r^2,  ln(s r) = (ln 2 / 2) lg
+                s3 = (sq > 0.f) ? fmaf(t * sq, lg, s3) : s3;
             }
             s0 += t;
             s2 = fmaf(t, sq, s2);
@@ -184,22 +187,27 @@ kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__
         }
         dst[d] = s0;
         dst[d + 1] = s2;
+        dst[d + 2] = s3;
     }
 }
 
-// gX[i, k] = fac * sum_split part[split][i][k];  gs_rows[i] = -(fac / s) * sum_split part[split][i][d + 1]
+// gX[i, k] = fac * sum_split part[split][i][k];  gs_rows[i] = -(fac / s) * sum_split part[split][i][d + 1];
+// gp_rows[i] = fac_p * sum_split part[split][i][d + 2]
 __global__ void kgrad_finalize_kernel(const float* __restrict__ part, int nsplit, int64_t N, int d, int stride, float fac,
-                                      float fac_s, float* __restrict__ gX, int64_t ldgx, float* __restrict__ gs_rows,
+                                      float fac_s, float fac_p, float* __restrict__ gX, int64_t ldgx,
+                                      float* __restrict__ gs_rows, float* __restrict__ gp_rows,
                                       const unsigned* __restrict__ skip_if_fast) {
     if (skip_if_fast && kg_fast_regime(skip_if_fast)) return;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t i = idx / (d + 1);
-    const int k = (int)(idx % (d + 1));
+    const int64_t i = idx / (d + 2);
+    const int k = (int)(idx % (d + 2));
     if (i >= N) return;
+    if ((k == d && !gs_rows) || (k == d + 1 && !gp_rows)) return;
     float acc = 0.f;
-    for (int s = 0; s < nsplit; ++s) acc += part[((int64_t)s * N + i) * stride + (k < d ? k : d + 1)];
+    for (int s = 0; s < nsplit; ++s) acc += part[((int64_t)s * N + i) * stride + (k < d ? k : k + 1)];
     if (k < d) gX[i * ldgx + k] = fac * acc;
-    else if (gs_rows) gs_rows[i] = fac_s * acc;
+    else if (k == d) gs_rows[i] = fac_s * acc;
+    else gp_rows[i] = fac_p * acc;
 }
 
 template <int D, int MT, int MODE, int PM>
@@ -234,26 +242,33 @@ KgPlan kg_plan(int64_t N, int64_t M) {
 
 size_t kgrad_workspace_bytes(int64_t N, int64_t M, int d) {
     const KgPlan p = kg_plan(N, M);
-    size_t b = align256((size_t)p.nsplit * (size_t)N * (size_t)(d + 2) * 4) + 512;
+    size_t b = align256((size_t)p.nsplit * (size_t)N * (size_t)(d + 3) * 4) + 512;
     if (kgrad_tc_eligible(N, M, d, 1, PM_SQEXP)) b += kgrad_tc_workspace_bytes(N, M);
     return b;
 }
 
 // mode 0: K@W cotangent (W: M x m, G: N x m);  mode 1: Gram cotangent (G = Gbar: N x M, W unused, m = 0)
-int kgrad(int mode, const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, int64_t N,
-          int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float scale,
+// gp_rows (nullable): per-row contributions to dL/dpower at fixed nconst; asking for it selects the general-p epilogue
+// (the p = 2 / p = 1 specialisations never form log(s r)).
+int kgrad(int mode, const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, float* gp_rows,
+          int64_t N, int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float scale,
           float power, float nconst, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (d > 64) return fail(JRK_ERR_UNSUPPORTED, "kgrad: d = %d > 64 is not supported by the fused backward kernel", d);
-    const EpiParams ep = make_epi(scale, power, nconst);
-    const int pm = pick_pmode(power);
+    const int pm = gp_rows ? PM_GENERAL : pick_pmode(power);
+    EpiParams ep = make_epi(scale, power, nconst);
+    if (gp_rows && pick_pmode(power) != PM_GENERAL) {       // the general epilogue's constants for p = 2 / p = 1
+        ep.c = scale * scale;
+        ep.hp = 0.5f * power;
+    }
     const KgPlan p = kg_plan(N, M);
     Scratch scr(workspace, workspace_bytes, st);
     JRK_CUDA_OK(scr.reserve(kgrad_workspace_bytes(N, M, d)));
-    const int stride = d + 2;
+    const int stride = d + 3;
     float* part = scr.take<float>((size_t)p.nsplit * N * stride);
     const double s = (double)scale;
     const float fac = (float)((double)nconst * (pm == PM_SQEXP ? 2.0 * s * s : pm == PM_LAPLACE ? s : (double)power));
     const float fac_s = (float)(-(double)fac / s);
+    const float fac_p = (float)(-(double)nconst * 0.5 * 0.6931471805599453);
     // K@W cotangent, p = 2, d <= 16, m <= 16, large: both inner products on the tensor cores (kgrad_tc.cu).  Whether the
     // problem lies inside its regime is known on the device only, so the FP32 kernels below are enqueued as well and
     // return at once when it does.
@@ -294,8 +309,8 @@ int kgrad(int mode, const float* X, const float* Y, const float* W, const float*
 #undef KG_MT
 #undef KG_GO
     if (rc) return rc;
-    const int64_t tot = N * (d + 1);
-    kgrad_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(part, p.nsplit, N, d, stride, fac, fac_s, gX, ldgx, gs_rows, skip);
+    const int64_t tot = N * (d + 2);
+    kgrad_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(part, p.nsplit, N, d, stride, fac, fac_s, fac_p, gX, ldgx, gs_rows, gp_rows, skip);
     JRK_LAUNCHED();
     return JRK_OK;
 }

@@ -139,7 +139,7 @@ static ffi::Error GramGroupsumImpl(cudaStream_t stream, F32Buf x, F32Buf y, F32B
 // (gX, gs_rows) = VJP of out = K(X, Y) W with cotangent G: the backward rule of a jax.custom_vjp around jrk_kmatw_f32_ffi
 // (INTEGRATION.md); dL/dY is the same handler called with (Y, X, G, W), dL/dW = jrk_kmatw_f32_ffi(Y, X, G).
 static ffi::Error KmatwGradImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, F32Buf x, F32Buf y, F32Buf w, F32Buf g,
-                                float scale, float power, float nconst, F32Res gx, F32Res gs_rows) {
+                                float scale, float power, float nconst, F32Res gx, F32Res gs_rows, F32Res gp_rows) {
     if (!is_mat(x) || !is_mat(y) || !is_mat(w) || !is_mat(g) || x.dimensions()[1] != y.dimensions()[1] ||
         w.dimensions()[0] != y.dimensions()[0] || g.dimensions()[0] != x.dimensions()[0] || g.dimensions()[1] != w.dimensions()[1])
         return ffi::Error::InvalidArgument("X: N x d, Y: M x d, W: M x m, G: N x m expected");
@@ -149,13 +149,14 @@ static ffi::Error KmatwGradImpl(cudaStream_t stream, ffi::ScratchAllocator scrat
     const size_t wsb = jrk_grad_workspace_bytes(N, M, d);
     if (!scratch_for(scratch, wsb, &ws)) return ffi::Error::Internal("jrk_kmatw_grad_f32: scratch allocation failed");
     return to_error(jrk_kmatw_grad_f32(x.typed_data(), y.typed_data(), w.typed_data(), g.typed_data(), gx->typed_data(),
-                                       gs_rows->element_count() == 0 ? nullptr : gs_rows->typed_data(), N, M, d, m, d, d, m, m, d,
+                                       gs_rows->element_count() == 0 ? nullptr : gs_rows->typed_data(),
+                                       gp_rows->element_count() == 0 ? nullptr : gp_rows->typed_data(), N, M, d, m, d, d, m, m, d,
                                        scale, power, nconst, ws, wsb, stream));
 }
 
 // (gX, gs_rows) = VJP of K = K(X, Y) with cotangent Gbar (N x M)
 static ffi::Error GramGradImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, F32Buf x, F32Buf y, F32Buf gbar, float scale,
-                               float power, float nconst, F32Res gx, F32Res gs_rows) {
+                               float power, float nconst, F32Res gx, F32Res gs_rows, F32Res gp_rows) {
     if (!is_mat(x) || !is_mat(y) || !is_mat(gbar) || x.dimensions()[1] != y.dimensions()[1] || gbar.dimensions()[0] != x.dimensions()[0] ||
         gbar.dimensions()[1] != y.dimensions()[0])
         return ffi::Error::InvalidArgument("X: N x d, Y: M x d, Gbar: N x M expected");
@@ -165,7 +166,8 @@ static ffi::Error GramGradImpl(cudaStream_t stream, ffi::ScratchAllocator scratc
     const size_t wsb = jrk_grad_workspace_bytes(N, M, d);
     if (!scratch_for(scratch, wsb, &ws)) return ffi::Error::Internal("jrk_gram_grad_f32: scratch allocation failed");
     return to_error(jrk_gram_grad_f32(x.typed_data(), y.typed_data(), gbar.typed_data(), gx->typed_data(),
-                                      gs_rows->element_count() == 0 ? nullptr : gs_rows->typed_data(), N, M, d, d, d, M, d, scale,
+                                      gs_rows->element_count() == 0 ? nullptr : gs_rows->typed_data(),
+                                      gp_rows->element_count() == 0 ? nullptr : gp_rows->typed_data(), N, M, d, d, d, M, d, scale,
                                       power, nconst, ws, wsb, stream));
 }
 
@@ -227,12 +229,12 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(jrk_gram_groupsum_f32_ffi, GramGroupsumImpl,
 XLA_FFI_DEFINE_HANDLER_SYMBOL(jrk_kmatw_grad_f32_ffi, KmatwGradImpl,
                               JRK_STREAM_SCRATCH.Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>()
                                   .Attr<float>("scale").Attr<float>("power").Attr<float>("nconst")
-                                  .Ret<F32Buf>().Ret<F32Buf>(),
+                                  .Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>(),
                               {ffi::Traits::kCmdBufferCompatible});
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(jrk_gram_grad_f32_ffi, GramGradImpl,
                               JRK_STREAM_SCRATCH.Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>()
                                   .Attr<float>("scale").Attr<float>("power").Attr<float>("nconst")
-                                  .Ret<F32Buf>().Ret<F32Buf>(),
+                                  .Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>(),
                               {ffi::Traits::kCmdBufferCompatible});
 #endif  // __has_include("xla/ffi/api/ffi.h")

@@ -23,11 +23,15 @@ def _gammaln32(x):
 
 
 class GenGaussKernel(DensityKernel):
-    def __init__(self, dist: ScaledPairwiseDistance, scale_tensor=None):
+    def __init__(self, dist: ScaledPairwiseDistance, scale_tensor=None, power_tensor=None, dim_scale_tensor=None):
         self.dist = dist
         # differentiable global scale (0-dim tensor, 1 / length_scale) when the kernel was made from a tensor that
         # requires grad: the Gram / inner products are then differentiable in it (jaxrk_b200/autograd.py)
         self.scale_tensor = scale_tensor
+        # likewise the shape parameter (0-dim tensor) and per-dimension scales (len d tensor: a pre-scaling of the points,
+        # jaxrk/kern/util.py:107-116, differentiated through `X * dim_scale` by torch)
+        self.power_tensor = power_tensor
+        self.dim_scale_tensor = dim_scale_tensor
         # rbf.py:34, float32 as under jax without x64
         self.nconst = (f32(dist.power) / (f32(2) * dist._get_scale_param()
                                           * np.exp(_gammaln32(1. / dist.power)))).astype(f32)
@@ -35,18 +39,25 @@ class GenGaussKernel(DensityKernel):
     @classmethod
     def make(cls, length_scale, shape: float) -> "GenGaussKernel":
         """rbf.py:62-73: scale = 1/length_scale, shape in (0, 2]."""
+        scale_t = power_t = dim_t = None
+        if isinstance(shape, torch.Tensor):
+            if shape.requires_grad:
+                power_t = shape.reshape(())
+            shape = float(shape.detach())
         assert shape > 0 and shape <= 2
-        scale_t = None
         if isinstance(length_scale, torch.Tensor):
             if length_scale.requires_grad and length_scale.numel() == 1:
                 scale_t = 1. / length_scale.reshape(())
+            elif length_scale.requires_grad:
+                dim_t = 1. / length_scale.reshape(-1)
             length_scale = length_scale.detach().cpu().numpy()
         if isinstance(length_scale, (float, int)):
             s = 1. / float(length_scale)
         else:
             ls = np.asarray(length_scale)
             s = float(1. / ls) if ls.ndim == 0 else (f32(1.) / ls.astype(f32)).astype(f32)
-        return GenGaussKernel(ScaledPairwiseDistance(scaler=SimpleScaler(s), power=shape), scale_tensor=scale_t)
+        return GenGaussKernel(ScaledPairwiseDistance(scaler=SimpleScaler(s), power=shape), scale_tensor=scale_t,
+                              power_tensor=power_t, dim_scale_tensor=dim_t)
 
     @classmethod
     def make_laplace(cls, length_scale) -> "GenGaussKernel":
@@ -56,7 +67,7 @@ class GenGaussKernel(DensityKernel):
     def make_gauss(cls, length_scale) -> "GenGaussKernel":
         # the reference hard-codes this literal (rbf.py:93); it is not exactly 1/sqrt(2)
         f = 0.70710695
-        if isinstance(length_scale, torch.Tensor) and length_scale.requires_grad and length_scale.numel() == 1:
+        if isinstance(length_scale, torch.Tensor) and length_scale.requires_grad:
             return GenGaussKernel.make(length_scale / f, 2.)
         if isinstance(length_scale, (float, int)):
             return GenGaussKernel.make(float(length_scale) / f, 2.)
@@ -84,6 +95,8 @@ class GenGaussKernel(DensityKernel):
         X = as2d(X)
         Y = None if Y is None else as2d(Y, X.device)
         args = self.kernel_args()
+        if not diag and self.dim_scale_tensor is not None and self.wants_grad(X, Y):
+            return self._call_dim_scale_grad(X, Y)
         if diag or args is None:
             if self.wants_grad(X, Y):
                 from ..rkhs._lowering import grad_unsupported
@@ -96,17 +109,41 @@ class GenGaussKernel(DensityKernel):
             raise grad_unsupported(f"GenGaussKernel Gram with d = {X.shape[1]}" + (" and per-dimension scales" if dim_scale is not None else ""))
         if self.wants_grad(X, Y) and dim_scale is None:
             from .. import autograd as ag
+            pw = self.power_tensor if self.power_tensor is not None else power
             if self.scale_tensor is not None:
-                return ag.gengauss_gram(X, Y, self.scale_tensor, power)          # nconst follows the scale
+                return ag.gengauss_gram(X, Y, self.scale_tensor, pw)             # nconst follows the scale (and the power)
+            if self.power_tensor is not None:
+                return ag.gengauss_gram(X, Y, scale, pw)
             return ag.gengauss_gram(X, Y, scale, power, nconst=nconst)
         return nat.gram(X, Y, scale, power, nconst, dim_scale=dim_scale)
 
+    def grad_inputs(self, X, Y):
+        """(X', Y', scale argument, power argument, nconst argument) for the differentiable entry points of
+        jaxrk_b200/autograd.py: per-dimension scales become a pre-scaling of the points (torch differentiates the
+        multiplication), and the reference's (1, d) normalising constant (quirk Q2: rbf.py:34 over a per-dimension scale)
+        is not reproduced under autograd -- the differentiable per-dimension kernel is exp(-||s * (x - y)||^p) times the
+        constant of a unit global scale."""
+        pw = self.power_tensor if self.power_tensor is not None else float(self.dist.power)
+        if self.dim_scale_tensor is not None:
+            ds = self.dim_scale_tensor.to(X.device)
+            return X * ds, (None if Y is None else Y * ds), 1.0, pw, None
+        if self.scale_tensor is not None:
+            return X, Y, self.scale_tensor, pw, None
+        scale, _, _, nconst = self.kernel_args()
+        return X, Y, scale, pw, (None if self.power_tensor is not None else nconst)
+
+    def _call_dim_scale_grad(self, X, Y):
+        from .. import autograd as ag
+        Xs, Ys, sc, pw, nc = self.grad_inputs(X, Y)
+        return ag.gengauss_gram(Xs, Ys, sc, pw, nconst=nc)
+
     def wants_grad(self, *tensors) -> bool:
-        """True when autograd is recording and one of the tensors -- or this kernel's scale -- requires grad."""
+        """True when autograd is recording and one of the tensors -- or one of this kernel's parameters -- requires grad."""
         if not torch.is_grad_enabled():
             return False
-        if self.scale_tensor is not None and self.scale_tensor.requires_grad:
-            return True
+        for t in (self.scale_tensor, self.power_tensor, self.dim_scale_tensor):
+            if t is not None and t.requires_grad:
+                return True
         return any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
 
 

@@ -236,14 +236,15 @@ class GradUnsupported(NotImplementedError):
 def needs_grad(k, *tensors) -> bool:
     if not torch.is_grad_enabled():
         return False
-    st = getattr(k, "scale_tensor", None)
-    return any(isinstance(t, torch.Tensor) and t.requires_grad for t in (st, *tensors))
+    ks = tuple(getattr(k, name, None) for name in ("scale_tensor", "power_tensor", "dim_scale_tensor"))
+    return any(isinstance(t, torch.Tensor) and t.requires_grad for t in (*ks, *tensors))
 
 
 def grad_unsupported(what: str):
     return GradUnsupported(
-        f"{what}: gradients are only available for GenGauss kernels with a GLOBAL scale and d <= 64 (the fused backward "
-        "kernels jrk_kmatw_grad_f32 / jrk_gram_grad_f32); detach the inputs or call under torch.no_grad() to get the value")
+        f"{what}: gradients are only available for GenGauss kernels with d <= 64 (the fused backward kernels "
+        "jrk_kmatw_grad_f32 / jrk_gram_grad_f32; per-dimension length scales through GenGaussKernel.make(tensor)); detach "
+        "the inputs or call under torch.no_grad() to get the value")
 
 
 def _reduced_gram_autograd(k, spec, X, fx: Folded, Y, fy: Folded, self_gram: bool) -> torch.Tensor:
@@ -252,8 +253,10 @@ def _reduced_gram_autograd(k, spec, X, fx: Folded, Y, fy: Folded, self_gram: boo
     operands, so gradients reach the points, the chain parameters and the kernel's scale."""
     from .. import autograd as ag
     scale, power, nconst = spec.kparams
-    st = getattr(k, "scale_tensor", None)
-    s_arg, nc_arg = (st, None) if st is not None else (scale, nconst)
+    st, pt = getattr(k, "scale_tensor", None), getattr(k, "power_tensor", None)
+    s_arg, nc_arg = (st, None) if st is not None else (scale, None if pt is not None else nconst)
+    if pt is not None:
+        power = pt                                   # a 0-dim tensor: the backward kernels also return dL/dpower
     skinny = (LINEAR, SUM, MEAN)
 
     def side(Xa, fa: Folded, Yb, fb: Folded):      # fold_a(K(Xa, Yb)) applied with W = fold_b^T

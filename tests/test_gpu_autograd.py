@@ -283,3 +283,74 @@ def test_inner_backward_through_the_api_on_the_tensor_core_path():
     K = orc.gengauss_gram_truth64(X, Y[:64], s, 2.0)                   # dW[c, j] = sum_i C[i, c] K_ij
     _check(Wt.grad.cpu().numpy()[:, :64], C.astype(np.float64).T @ K, np.abs(C).astype(np.float64).T @ np.abs(K), "API dL/dW")
     assert Yt.grad is not None and torch.isfinite(Yt.grad).all()
+
+
+# ---- gradients with respect to the shape parameter and per-dimension length scales (SURVEY.md section 8f-2 remainder) ----
+@pytest.mark.parametrize("power", [2.0, 1.0, 1.5, 0.7])
+def test_power_gradient_of_the_fused_backward_kernels(power):
+    """gp_rows of jrk_kmatw_grad_f32 / jrk_gram_grad_f32: sum_j a_ij dK_ij/dpower at fixed nconst, dK/dp = -K u ln(s r),
+    against float64; and asking for it (general-p epilogue) leaves gX / gs_rows within tolerance of the float64 truth."""
+    N, M, d, m = 300, 517, 5, 7
+    X, Y, W, G = gauss(0, N, d), gauss(1, M, d), gauss(2, M, m), gauss(3, N, m)
+    s = orc.simple_scaler_s(2.0)
+    scale = float(s[0, 0])
+    nconst = float(orc.gengauss_nconst_ref32(s, power).reshape(-1)[0])
+    A = G.astype(np.float64) @ W.astype(np.float64).T
+    Aabs = np.abs(G).astype(np.float64) @ np.abs(W).astype(np.float64).T
+    sr = scale * np.sqrt(((X[:, None, :].astype(np.float64) - Y[None, :, :].astype(np.float64)) ** 2).sum(-1))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dk = np.where(sr > 0, -nconst * np.exp(-np.power(sr, power)) * np.power(sr, power) * np.log(sr), 0.0)
+    gx, gs, gp = nat.kmatw_grad(cu(X), cu(Y), cu(W), cu(G), scale, power, nconst, want_power=True)
+    _check(gp.cpu().numpy(), (A * dk).sum(1), (Aabs * np.abs(dk)).sum(1), f"dL/dpower rows p={power}")
+    gX, _, gsum, (mx, _, ms) = orc.gengauss_vjp_truth64(X, Y, A, s, power, nconst=nconst)
+    _, _, _, (mxa, _, msa) = orc.gengauss_vjp_truth64(X, Y, Aabs, s, power, nconst=nconst)
+    _check(gx.cpu().numpy(), gX, mxa, "dL/dX with the general epilogue")
+    _check(float(gs.double().sum()), gsum, msa, "dL/dscale with the general epilogue")
+    Gb = gauss(4, N, M)
+    _, _, gp2 = nat.gram_grad(cu(X), cu(Y), cu(Gb), scale, power, nconst, want_power=True)
+    _check(gp2.cpu().numpy(), (Gb.astype(np.float64) * dk).sum(1), (np.abs(Gb).astype(np.float64) * np.abs(dk)).sum(1), "gram dL/dpower rows")
+
+
+def test_api_gradients_to_shape_and_per_dimension_length_scales():
+    """GenGaussKernel.make(length_scale=tensor, shape=tensor): a loss over the Gram and over a fused inner product
+    differentiated with respect to the shape parameter (the normalising constant follows it through lgamma) and -- for a
+    vector of length scales -- each dimension's scale, against torch float64 autograd of the explicit formula."""
+    from jaxrk_b200.kern import GenGaussKernel
+    from jaxrk_b200.reduce import LinearReduce
+    from jaxrk_b200.rkhs import FiniteVec, inner
+    N, M, d, m = 200, 150, 4, 3
+    Xn, Yn, An, Cn = gauss(0, N, d), gauss(1, M, d), gauss(2, m, M), gauss(3, N, M)
+
+    def nconst64(s, p):
+        return s * p / (2.0 * torch.exp(torch.lgamma(1.0 / p)))
+
+    # (1) scalar length scale + shape
+    ls = torch.tensor(1.7, device="cuda", requires_grad=True)
+    sh = torch.tensor(1.4, device="cuda", requires_grad=True)
+    Xt = cu(Xn).requires_grad_(True)
+    k = GenGaussKernel.make(ls, sh)
+    loss = (k(Xt, cu(Yn)) * cu(Cn)).sum() + inner(FiniteVec(k, Xt), FiniteVec(k, cu(Yn), [LinearReduce(cu(An))])).sum()
+    loss.backward()
+    ls64 = torch.tensor(1.7, dtype=torch.float64, requires_grad=True)
+    sh64 = torch.tensor(1.4, dtype=torch.float64, requires_grad=True)
+    X64 = torch.tensor(Xn, dtype=torch.float64, requires_grad=True)
+    r = torch.cdist(X64, torch.tensor(Yn, dtype=torch.float64))
+    K64 = nconst64(1.0 / ls64, sh64) * torch.exp(-torch.pow(r / ls64, sh64))
+    loss64 = (K64 * torch.tensor(Cn, dtype=torch.float64)).sum() + (K64 @ torch.tensor(An, dtype=torch.float64).T).sum()
+    loss64.backward()
+    assert abs(float(loss) - float(loss64)) <= 1e-4 * abs(float(loss64)) + 1e-5
+    for got, want, name in ((sh.grad, sh64.grad, "shape"), (ls.grad, ls64.grad, "length_scale")):
+        assert abs(float(got) - float(want)) <= 2e-4 * abs(float(want)) + 2e-5, (name, float(got), float(want))
+    np.testing.assert_allclose(Xt.grad.cpu().numpy(), X64.grad.numpy(), rtol=2e-4, atol=2e-5)
+
+    # (2) one length scale per dimension
+    lsv = torch.tensor([1.2, 2.0, 0.8, 1.5], device="cuda", requires_grad=True)
+    kv = GenGaussKernel.make(lsv, 2.0)
+    Kv = kv(cu(Xn), cu(Yn))
+    (Kv * cu(Cn)).sum().backward()
+    lsv64 = torch.tensor([1.2, 2.0, 0.8, 1.5], dtype=torch.float64, requires_grad=True)
+    diff = (torch.tensor(Xn, dtype=torch.float64)[:, None, :] - torch.tensor(Yn, dtype=torch.float64)[None, :, :]) / lsv64
+    Kv64 = nconst64(torch.tensor(1.0, dtype=torch.float64), torch.tensor(2.0, dtype=torch.float64)) * torch.exp(-(diff ** 2).sum(-1))
+    (Kv64 * torch.tensor(Cn, dtype=torch.float64)).sum().backward()
+    np.testing.assert_allclose(Kv.detach().cpu().numpy(), Kv64.detach().numpy(), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(lsv.grad.cpu().numpy(), lsv64.grad.numpy(), rtol=3e-4, atol=3e-5)

@@ -334,7 +334,7 @@ def _fake_vjp(X, Y, A, scale, power, nconst):
     return gX
 
 
-def fake_kmatw_grad(X, Y, W, G, scale, power, nconst, want_scale=True):
+def fake_kmatw_grad(X, Y, W, G, scale, power, nconst, want_scale=True, want_power=False):
     CALLS.append("kmatw_grad")
     A = _np(G) @ _np(W).T
     Xn, Yn = _np(X).astype(f32), _np(Y).astype(f32)
@@ -347,13 +347,20 @@ def fake_kmatw_grad(X, Y, W, G, scale, power, nconst, want_scale=True):
         p = float(f32(power))
         K = nconst * np.exp(-np.power(float(scale) * r, p))
         gs_rows = torch.from_numpy((-(A * K * p * float(scale) ** (p - 1.0) * np.power(r, p)).sum(1)).astype(f32))
+    if want_power:   # dK/dp = -K u ln(s r) at fixed nconst, zero at r = 0
+        sq = ((Xn[:, None, :].astype(np.float64) - Yn[None, :, :].astype(np.float64)) ** 2).sum(-1)
+        sr = float(scale) * np.sqrt(sq)
+        p = float(f32(power))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dk = np.where(sr > 0, -nconst * np.exp(-np.power(sr, p)) * np.power(sr, p) * np.log(sr), 0.0)
+        return torch.from_numpy(gX.astype(f32)), gs_rows, torch.from_numpy((A * dk).sum(1).astype(f32))
     return torch.from_numpy(gX.astype(f32)), gs_rows
 
 
-def fake_gram_grad(X, Y, Gbar, scale, power, nconst, want_scale=True):
+def fake_gram_grad(X, Y, Gbar, scale, power, nconst, want_scale=True, want_power=False):
     CALLS.append("gram_grad")
     ones = torch.eye(Gbar.shape[1], dtype=torch.float32)
-    return fake_kmatw_grad(X, Y, ones, Gbar, scale, power, nconst, want_scale)
+    return fake_kmatw_grad(X, Y, ones, Gbar, scale, power, nconst, want_scale, want_power)
 
 
 def test_autograd_plumbing_on_cpu_with_oracle_backed_kernels(monkeypatch):
