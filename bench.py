@@ -452,6 +452,45 @@ def run_kmatw_mean(args, torch, nat, dist_ctx):
                        "rows_per_gpu": n_local, "global_rows": n_total, "M": M, "d": d, "m": m}}
 
 
+def run_kmatw_backward(args, torch, nat, dist_ctx):
+    """The K@W vector-Jacobian product (dX and dscale rows) at cfg3's M, d, m on a 151552-row block per run (strong: split
+    over the ranks): jrk_kmatw_grad_f32 -> csrc/kgrad_tc.cu (both inner products on tcgen05, d + 2 FP32 accumulations per
+    pair).  Kernel-only; the roofline is the FP32 pipe at d + 2 lane-operations per pair."""
+    rank, world, dev = dist_ctx
+    w = WORKLOADS["kmatw"]
+    M, d, m = w["M"], w["d"], w["m"]
+    n_total = 148 * 256 * 4
+    n_local = n_total // world
+    scale, power, nconst = kernel_params(d)
+
+    def randn(seed, *shape):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        return torch.randn(*shape, generator=g, device=dev, dtype=torch.float32)
+
+    X, Y, W, G = randn(400 + rank, n_local, d), randn(1, M, d), randn(2, M, m), randn(500 + rank, n_local, m)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    keep = {}
+
+    def step():
+        keep["g"] = nat.kmatw_grad(X, Y, W, G, scale, power, nconst)
+
+    steps = max(1, min(args.steps, 3))
+    for _ in range(3):
+        step()
+    t_local, launches, clocks = _timed_steps(torch, dev, world, steps, flush, step, nat)
+    t_step = _max_over_ranks(torch, dev, world, t_local) / steps
+    pk = fp32_pipe_peak()
+    achieved = float(n_local) * M / (t_local / steps) * (d + 2)
+    assert bool(torch.isfinite(keep["g"][0]).all())
+    return {"value": float(n_total) * M / t_step, "unit": "pairs/s", "ms_per_step": t_step * 1e3, "steps": steps, "scaling": "strong",
+            "roofline": {"bound": "fp32", "achieved": achieved / 1e12, "peak": pk[0] / 1e12, "unit": "T lane-ops/s",
+                         "frac": achieved / pk[0], "traffic": None, "peak_source": pk[1], "lane_ops_per_pair": d + 2},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "config": {"workload": "backward of configs[2]: dX and dscale of K(X,Y)@W for a 151552-row block of X",
+                       "rows_per_gpu": n_local, "global_rows": n_total, "M": M, "d": d, "m": m,
+                       "kernel": "kgrad_tc.cu (tcgen05 inner products, FP32 accumulation)"}}
+
+
 def run_gram1m(args, torch, nat, dist_ctx):
     """Streamed Gram N = M = 2^20, d = 16 (kernel-only; there is nowhere to put 4.4 TB, so no e2e leg)."""
     rank, world, dev = dist_ctx
@@ -515,7 +554,8 @@ def run_b200(args):
         extra = [("kmatw_cfg3_mean", lambda: run_kmatw_mean(args, torch, nat, ctx)),
                  ("gram_cfg2" if args.workload == "kmatw" else "kmatw_cfg3",
                   lambda: run_workload("gram" if args.workload == "kmatw" else "kmatw", args, torch, nat, ctx, with_cpu=False)),
-                 ("gram_1m_d16_streamed", lambda: run_gram1m(args, torch, nat, ctx))]
+                 ("gram_1m_d16_streamed", lambda: run_gram1m(args, torch, nat, ctx)),
+                 ("kmatw_cfg3_backward", lambda: run_kmatw_backward(args, torch, nat, ctx))]
         for key, fn in extra:
             try:
                 torch.cuda.empty_cache()

@@ -235,7 +235,13 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
     return d;
 }
 __device__ __forceinline__ void st_global_cs(float* p, float v) {
+#if defined(JRK_ST_PLAIN)        // A/B builds of the store policy (profiles/README.md)
+    asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+#elif defined(JRK_ST_CG)
+    asm volatile("st.global.cg.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+#else
     asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+#endif
 }
 
 // ---------------------------------------------------------------------------------
