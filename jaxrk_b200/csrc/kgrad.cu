@@ -27,6 +27,7 @@ namespace tf32 { int tf_sm_count(); }
 
 // kgrad_tc.cu
 bool kgrad_tc_eligible(int64_t N, int64_t M, int d, int m, int pm);
+bool kgrad_tc_gbar_eligible(int64_t N, int64_t M, int d, int pm, const float* Gbar, int64_t ldgb);
 size_t kgrad_tc_workspace_bytes(int64_t N, int64_t M);
 int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, int64_t N, int64_t M,
              int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float c, float fac, float fac_s,
@@ -273,9 +274,11 @@ int kgrad(int mode, const float* X, const float* Y, const float* W, const float*
     // problem lies inside its regime is known on the device only, so the FP32 kernels below are enqueued as well and
     // return at once when it does.
     const unsigned* skip = nullptr;
-    if (mode == 0 && kgrad_tc_eligible(N, M, d, m, pm)) {
+    if ((mode == 0 && kgrad_tc_eligible(N, M, d, m, pm)) || (mode == 1 && kgrad_tc_gbar_eligible(N, M, d, pm, G, ldg))) {
         void* tcs = scr.take<char>(kgrad_tc_workspace_bytes(N, M));
-        if (int rc = kgrad_tc(X, Y, W, G, gX, gs_rows, N, M, d, m, ldx, ldy, ldw, ldg, ldgx, ep.c, fac, fac_s, tcs, &skip, st)) return rc;
+        if (int rc = kgrad_tc(X, Y, mode == 0 ? W : nullptr, G, gX, gs_rows, N, M, d, m, ldx, ldy, ldw, ldg, ldgx, ep.c, fac,
+                              fac_s, tcs, &skip, st))
+            return rc;
     }
     const int64_t nblk = (N + KG_ROWS - 1) / KG_ROWS;
     if (nblk > 2147483647LL) return fail(JRK_ERR_UNSUPPORTED, "kgrad: too many rows");

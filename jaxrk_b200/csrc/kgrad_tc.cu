@@ -74,7 +74,7 @@ struct GtParams {
     const unsigned char* img;
     float* gX; int64_t ldgx;
     float* gs_rows;                   // nullable
-    int64_t N;
+    int64_t N, M;
     int n_tiles, n_units;
     const unsigned* nmax;             // [2] bit patterns: max |c||x|^2, max |c||y|^2
     float x_scale, inv_c;             // 2^-r of GEMM1;  1 / c (|x_i|^2 = xn_i / c)
@@ -90,6 +90,9 @@ __device__ __forceinline__ f32x2 lds_64(uint32_t addr) {
     return a;
 }
 
+// GBAR = false: K@W cotangent, g = G . W'^T by GEMM1b (P.G: N x m).  GBAR = true: Gram cotangent, g_ij = Gbar[i, j] read
+// from global memory (P.G: N x M, 16-byte aligned rows), the column factor 2^(c|y_j|^2) rides in the image's FP32 fields.
+template <bool GBAR>
 __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
     if (!tc2_fast_regime(P.nmax)) return;      // kgrad.cu serves the problem
     extern __shared__ unsigned char gt_smem_raw[];
@@ -160,12 +163,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                         mma_f16_ts(cs, cx + GT_COL_X, dy + 2, id_h, 0u);               // hi_x . lo_y
                         mma_f16_ts(cs, cx + GT_COL_XLO, dy, id_h, 1u);                 // lo_x . hi_y
                         mma_f16_ts(cs, cx + GT_COL_X, dy, id_h, 1u);                   // hi_x . hi_y
-                        mma_tf32_ts(cg, cx + GT_COL_G, dw + 4, id_t, 0u);              // hi_g . lo_w  (k-steps 0, 1)
-                        mma_tf32_ts(cg, cx + GT_COL_G + 8, dw + 6, id_t, 1u);
-                        mma_tf32_ts(cg, cx + GT_COL_GLO, dw, id_t, 1u);                // lo_g . hi_w
-                        mma_tf32_ts(cg, cx + GT_COL_GLO + 8, dw + 2, id_t, 1u);
-                        mma_tf32_ts(cg, cx + GT_COL_G, dw, id_t, 1u);                  // hi_g . hi_w
-                        mma_tf32_ts(cg, cx + GT_COL_G + 8, dw + 2, id_t, 1u);
+                        if (!GBAR) {
+                            mma_tf32_ts(cg, cx + GT_COL_G, dw + 4, id_t, 0u);          // hi_g . lo_w  (k-steps 0, 1)
+                            mma_tf32_ts(cg, cx + GT_COL_G + 8, dw + 6, id_t, 1u);
+                            mma_tf32_ts(cg, cx + GT_COL_GLO, dw, id_t, 1u);            // lo_g . hi_w
+                            mma_tf32_ts(cg, cx + GT_COL_GLO + 8, dw + 2, id_t, 1u);
+                            mma_tf32_ts(cg, cx + GT_COL_G, dw, id_t, 1u);              // hi_g . hi_w
+                            mma_tf32_ts(cg, cx + GT_COL_G + 8, dw + 2, id_t, 1u);
+                        }
                     }
                     commit_addr(b_sfull + a * 8);
                 }
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                     }
                     tmem_st8(cx + GT_COL_X, hi);
                     tmem_st8(cx + GT_COL_XLO, lo);
-                } else {
+                } else if (!GBAR) {
                     const float* grow = P.G + (iok ? i : 0) * P.ldg;
                     uint32_t v[16];
 #pragma unroll
@@ -250,6 +255,36 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                 first_flush = false;
             };
             int since = 0;
+            // GBAR: this thread's two rows of Gbar; 8 columns per chunk, fetched one chunk ahead (the addresses do not
+            // depend on any barrier, so the pipeline runs across tile boundaries)
+            const float* grow[GT_R];
+            bool gok[GT_R];
+#pragma unroll
+            for (int h = 0; h < GT_R; ++h) {
+                const int64_t i = (int64_t)u * GT_ROWS + h * GT_BM + quad * 32 + lane;
+                gok[h] = i < P.N;
+                grow[h] = P.G + (gok[h] ? i : 0) * P.ldg;
+            }
+            auto load_gbar = [&](int t, int ch, uint32_t (&gv)[GT_R][8]) {
+                const int64_t j0 = (int64_t)t * GT_NT + 8 * ch;
+#pragma unroll
+                for (int h = 0; h < GT_R; ++h) {
+                    if (gok[h] && j0 + 8 <= P.M) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(grow[h] + j0));
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(grow[h] + j0 + 4));
+                        gv[h][0] = __float_as_uint(a.x); gv[h][1] = __float_as_uint(a.y);
+                        gv[h][2] = __float_as_uint(a.z); gv[h][3] = __float_as_uint(a.w);
+                        gv[h][4] = __float_as_uint(b.x); gv[h][5] = __float_as_uint(b.y);
+                        gv[h][6] = __float_as_uint(b.z); gv[h][7] = __float_as_uint(b.w);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            gv[h][c] = (gok[h] && j0 + c < P.M) ? __float_as_uint(__ldg(grow[h] + j0 + c)) : 0u;
+                    }
+                }
+            };
+            uint32_t gnext[GT_R][8];
+            if (GBAR && k < T) load_gbar(k, 0, gnext);
             for (int t = k; t < T; t += GT_EPQ) {
                 const uint32_t g = gt + (uint32_t)t, a = g % GT_NS, s = g % GT_SOP;
                 bar_wait(b_sfull + a * 8, (g / GT_NS) & 1);
@@ -261,7 +296,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
 #pragma unroll
                 for (int h = 0; h < GT_R; ++h) {
                     ld8_async(sc + h * 64, sv[h]);
-                    ld8_async(sc + h * 64 + 32, gv[h]);
+                    if (!GBAR) ld8_async(sc + h * 64 + 32, gv[h]);
                 }
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
@@ -269,16 +304,21 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
 #pragma unroll
                     for (int h = 0; h < GT_R; ++h) {
                         ld8_wait(sv[h]);
-                        ld8_wait(gv[h]);
+                        if (!GBAR) ld8_wait(gv[h]);
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) tv[h][c] = ex2_approx(__uint_as_float(sv[h][c])) * __uint_as_float(gv[h][c]);
+                        for (int c = 0; c < 8; ++c)
+                            tv[h][c] = ex2_approx(__uint_as_float(sv[h][c])) * __uint_as_float(GBAR ? gnext[h][c] : gv[h][c]);
+                    }
+                    if (GBAR) {       // the next chunk of Gbar (of this tile, or the first one of this warp's next tile)
+                        if (ch < 3) load_gbar(t, ch + 1, gnext);
+                        else if (t + GT_EPQ < T) load_gbar(t + GT_EPQ, 0, gnext);
                     }
                     if (ch < 3) {
                         // the next chunk's S and g are in flight while this one goes through the FMA pipe
 #pragma unroll
                         for (int h = 0; h < GT_R; ++h) {
                             ld8_async(sc + h * 64 + 8 * (ch + 1), sv[h]);
-                            ld8_async(sc + h * 64 + 32 + 8 * (ch + 1), gv[h]);
+                            if (!GBAR) ld8_async(sc + h * 64 + 32 + 8 * (ch + 1), gv[h]);
                         }
                     } else {
                         // every S / g value of the tile is in registers: the stage goes back to the MMA warp now, a quarter
@@ -389,7 +429,7 @@ __global__ void gt_rownorm_kernel(const float* __restrict__ A, int64_t rows, int
 // tile images: one thread per 16-byte piece (528 per tile)
 __global__ void gt_pack_kernel(const float* __restrict__ Y, int64_t M, int d, int64_t ldy, const float* __restrict__ W,
                                int m, int64_t ldw, int n_tiles, unsigned char* __restrict__ img, float y_scale,
-                               float inv_c, const float* __restrict__ yn, const unsigned* __restrict__ nmax) {
+                               float inv_c, const float* __restrict__ yn, const unsigned* __restrict__ nmax, int gbar) {
     if (!tc2_fast_regime(nmax)) return;
     constexpr int CPT = GT_IMG / 16;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -418,9 +458,10 @@ __global__ void gt_pack_kernel(const float* __restrict__ Y, int64_t M, int d, in
             } else {
                 // y as FP32, 4 features per chunk
                 const int k0 = 4 * (cl - 4);
+                const float cf = (gbar && jok) ? ex2_approx(__ldg(yn + j)) : 1.f;      // Gram cotangent: 2^(c|y_j|^2) rides here
                 float v[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = (jok && k0 + q < d) ? __ldg(Y + j * ldy + k0 + q) : 0.f;
+                for (int q = 0; q < 4; ++q) v[q] = (jok && k0 + q < d) ? __ldg(Y + j * ldy + k0 + q) * cf : 0.f;
                 o = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
             }
         } else {
@@ -430,7 +471,7 @@ __global__ void gt_pack_kernel(const float* __restrict__ Y, int64_t M, int d, in
             uint32_t w[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float v = (jok && c0 + q < m) ? __ldg(W + j * ldw + c0 + q) * colf : 0.f;
+                const float v = (W && jok && c0 + q < m) ? __ldg(W + j * ldw + c0 + q) * colf : 0.f;
                 const uint32_t hi = __float_as_uint(v) & 0xFFFFE000u;
                 w[q] = cl < 4 ? hi : __float_as_uint(v - __uint_as_float(hi));
             }
@@ -440,8 +481,9 @@ __global__ void gt_pack_kernel(const float* __restrict__ Y, int64_t M, int d, in
         // {1, |y_j|^2} for two consecutive rows
         const int r = 2 * (p - 512);
         const int64_t j = t * GT_NT + r;
-        const float n0 = (j < M) ? __ldg(yn + j) * inv_c : 0.f, n1 = (j + 1 < M) ? __ldg(yn + j + 1) * inv_c : 0.f;
-        o = make_uint4(__float_as_uint(1.f), __float_as_uint(n0), __float_as_uint(1.f), __float_as_uint(n1));
+        const float y0 = (j < M) ? __ldg(yn + j) : 0.f, y1 = (j + 1 < M) ? __ldg(yn + j + 1) : 0.f;
+        const float f0 = gbar ? ex2_approx(y0) : 1.f, f1 = gbar ? ex2_approx(y1) : 1.f;
+        o = make_uint4(__float_as_uint(f0), __float_as_uint(f0 * y0 * inv_c), __float_as_uint(f1), __float_as_uint(f1 * y1 * inv_c));
     }
     *reinterpret_cast<uint4*>(img + t * GT_IMG + (int64_t)p * 16) = o;
 }
@@ -452,6 +494,10 @@ bool kgrad_tc_eligible(int64_t N, int64_t M, int d, int m, int pm) {
     return pm == PM_SQEXP && d <= GT_D && m <= GT_MT && N >= 4096 && M >= 4096 && jrk_option(JRK_OPT_KMATW_TC) != 0 &&
            jrk_option(JRK_OPT_TC_FAST) != 0;
 }
+// Gram cotangent (mode 1): Gbar rows must allow 16-byte loads
+bool kgrad_tc_gbar_eligible(int64_t N, int64_t M, int d, int pm, const float* Gbar, int64_t ldgb) {
+    return kgrad_tc_eligible(N, M, d, 1, pm) && (ldgb % 4 == 0) && ((uintptr_t)Gbar % 16 == 0);
+}
 
 size_t kgrad_tc_workspace_bytes(int64_t N, int64_t M) {
     const int64_t n_tiles = (M + GT_NT - 1) / GT_NT;
@@ -460,9 +506,11 @@ size_t kgrad_tc_workspace_bytes(int64_t N, int64_t M) {
 
 // Enqueues the pre-pass and the tensor-core kernel; *nmax_out receives the device pointer of the two norm maxima, from
 // which the caller's FP32 kernels decide (on the device) whether the result is theirs to write.
+// W == nullptr: Gram cotangent, G = Gbar (N x M).
 int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, int64_t N, int64_t M,
              int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float c, float fac, float fac_s,
              void* scratch, const unsigned** nmax_out, cudaStream_t st) {
+    const bool gbar = W == nullptr;
     char* p = (char*)scratch;
     float* xn = (float*)p; p += align256((size_t)N * 4);
     float* yn = (float*)p; p += align256((size_t)M * 4);
@@ -476,15 +524,20 @@ int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, flo
     JRK_LAUNCHED();
     const Tc2Scales sc = tc2_scales(c);
     const int64_t tot = (int64_t)n_tiles * (GT_IMG / 16);
-    gt_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, n_tiles, img, sc.y_scale, 1.f / c, yn, nmax);
+    gt_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, W, m, ldw, n_tiles, img, sc.y_scale, 1.f / c, yn, nmax, gbar ? 1 : 0);
     JRK_LAUNCHED();
     GtParams P;
     P.X = X; P.ldx = ldx; P.d = d; P.G = G; P.ldg = ldg; P.m = m; P.xn = xn; P.img = img; P.gX = gX; P.ldgx = ldgx;
-    P.gs_rows = gs_rows; P.N = N; P.n_tiles = n_tiles; P.n_units = (int)((N + GT_ROWS - 1) / GT_ROWS); P.nmax = nmax;
+    P.gs_rows = gs_rows; P.N = N; P.M = M; P.n_tiles = n_tiles; P.n_units = (int)((N + GT_ROWS - 1) / GT_ROWS); P.nmax = nmax;
     P.x_scale = sc.x_scale; P.inv_c = 1.f / c; P.fac = fac; P.fac_s = fac_s;
     const int grid = P.n_units < tf_sm_count() ? P.n_units : tf_sm_count();
-    JRK_CUDA_OK(cudaFuncSetAttribute(kgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
-    kgrad_tc_kernel<<<grid, GT_THREADS, GT_SMEM, st>>>(P);
+    if (gbar) {
+        JRK_CUDA_OK(cudaFuncSetAttribute(kgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
+        kgrad_tc_kernel<true><<<grid, GT_THREADS, GT_SMEM, st>>>(P);
+    } else {
+        JRK_CUDA_OK(cudaFuncSetAttribute(kgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
+        kgrad_tc_kernel<false><<<grid, GT_THREADS, GT_SMEM, st>>>(P);
+    }
     JRK_LAUNCHED();
     *nmax_out = nmax;
     return JRK_OK;

@@ -354,3 +354,30 @@ def test_api_gradients_to_shape_and_per_dimension_length_scales():
     (Kv64 * torch.tensor(Cn, dtype=torch.float64)).sum().backward()
     np.testing.assert_allclose(Kv.detach().cpu().numpy(), Kv64.detach().numpy(), rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(lsv.grad.cpu().numpy(), lsv64.grad.numpy(), rtol=3e-4, atol=3e-5)
+
+
+@pytest.mark.parametrize("N,M,d,ls,positive", [(8192, 8192, 16, 4.0, False), (4096 + 300, 4096 + 12, 7, 2.5, True),
+                                               (4224, 6000, 3, 1.7, False)])
+def test_gram_grad_tensor_core_path(N, M, d, ls, positive):
+    """jrk_gram_grad_f32 on the tensor-core kernel (Gram cotangent read from global memory, csrc/kgrad_tc.cu GBAR): sampled
+    rows of dX / dscale and sampled columns of dY against float64."""
+    rng = np.random.RandomState(N % 11)
+    X, Y = rng.randn(N, d).astype(f32), rng.randn(M, d).astype(f32)
+    Gb = rng.randn(N, M).astype(f32)
+    if positive:
+        Gb = np.abs(Gb)
+    s = orc.simple_scaler_s(orc.gauss_length_scale(ls))
+    scale, nconst = float(s[0, 0]), float(orc.gengauss_nconst_ref32(s, 2.0).reshape(-1)[0])
+    n0 = nat.launch_count()
+    gx, gs = nat.gram_grad(cu(X), cu(Y), cu(Gb), scale, 2.0, nconst)
+    assert nat.launch_count() - n0 == 6
+    rows = np.r_[0:32, 128:140, 255:258, N - 32:N]
+    gX, _, gsum, _ = orc.gengauss_vjp_truth64(X[rows], Y, Gb[rows].astype(np.float64), s, 2.0, nconst=nconst)
+    _, _, _, (mx, _, ms) = orc.gengauss_vjp_truth64(X[rows], Y, np.abs(Gb[rows]).astype(np.float64), s, 2.0, nconst=nconst)
+    _check(gx.cpu().numpy()[rows], gX, mx, "tensor-core gram dL/dX")
+    _check(float(gs.double()[torch.from_numpy(rows).to(gs.device)].sum()), gsum, ms, "tensor-core gram dL/dscale")
+    gy, _ = nat.gram_grad(cu(Y), cu(X), cu(np.ascontiguousarray(Gb.T)), scale, 2.0, nconst, want_scale=False)
+    cols = np.r_[0:32, M - 32:M]
+    _, gY, _, _ = orc.gengauss_vjp_truth64(X, Y[cols], Gb[:, cols].astype(np.float64), s, 2.0, nconst=nconst)
+    _, _, _, (_, my, _) = orc.gengauss_vjp_truth64(X, Y[cols], np.abs(Gb[:, cols]).astype(np.float64), s, 2.0, nconst=nconst)
+    _check(gy.cpu().numpy()[cols], gY, my, "tensor-core gram dL/dY")

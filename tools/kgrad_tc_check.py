@@ -58,6 +58,55 @@ def check(N, M, d, m, ls, seed=0, positive=False):
     return out
 
 
+def check_gram(N, M, d, ls, seed=0, positive=False):
+    rng = np.random.RandomState(seed)
+    X, Y = rng.randn(N, d).astype(f32), rng.randn(M, d).astype(f32)
+    Gb = rng.randn(N, M).astype(f32)
+    if positive:
+        Gb = np.abs(Gb)
+    s = orc.simple_scaler_s(orc.gauss_length_scale(ls))
+    scale, p = float(s[0, 0]), 2.0
+    nconst = float(orc.gengauss_nconst_ref32(s, p).reshape(-1)[0])
+    rows = np.r_[0:24, 130:140, N - 24:N]
+    gX, _, gsum, (mx, _, ms) = orc.gengauss_vjp_truth64(X[rows], Y, Gb[rows].astype(np.float64), s, p, nconst=nconst)
+    _, _, _, (mxa, _, msa) = orc.gengauss_vjp_truth64(X[rows], Y, np.abs(Gb[rows]).astype(np.float64), s, p, nconst=nconst)
+    out = {"gram_grad": True, "N": N, "M": M, "d": d, "ls": ls, "positive": positive}
+    for tc in (1, 0):
+        with nat.option(nat.OPT_KMATW_TC, tc):
+            n0 = nat.launch_count()
+            gx, gs = nat.gram_grad(cu(X), cu(Y), cu(Gb), scale, p, nconst)
+            torch.cuda.synchronize()
+            nl = nat.launch_count() - n0
+        ex = np.abs(gx.cpu().numpy()[rows] - gX) / (AT + RT * mxa)
+        es = abs(float(gs.cpu().numpy()[rows].astype(np.float64).sum()) - gsum) / (AT + RT * msa)
+        out["tc" if tc else "fp32"] = {"dX": float(ex.max()), "ds": float(es), "launches": nl}
+    print(out, flush=True)
+
+
+def timeit_gram(N, M, d):
+    g = torch.Generator(device=dev).manual_seed(0)
+    X, Y = torch.randn(N, d, generator=g, device=dev), torch.randn(M, d, generator=g, device=dev)
+    Gb = torch.randn(N, M, generator=g, device=dev)
+    scale = float(0.70710695 / np.sqrt(d))
+    out = {"gram_grad": True, "N": N, "M": M, "d": d}
+    for tc in (1, 0):
+        with nat.option(nat.OPT_KMATW_TC, tc):
+            for _ in range(2):
+                nat.gram_grad(X, Y, Gb, scale, 2.0, 0.25)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                nat.gram_grad(X, Y, Gb, scale, 2.0, 0.25)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            t = min(ts)
+            out["tc" if tc else "fp32"] = {"ms": t, "pairs_per_s": N * M / t * 1e3, "hbm_read_GBps": 4 * N * M / t * 1e-6}
+    print(out, flush=True)
+
+
 def timeit(N, M, d, m):
     g = torch.Generator(device=dev).manual_seed(0)
     X, Y = torch.randn(N, d, generator=g, device=dev), torch.randn(M, d, generator=g, device=dev)
@@ -90,7 +139,12 @@ if __name__ == "__main__":
         check(8192, 4096, 16, 1, 4.0, seed=2, positive=True)
         check(4224, 6000, 3, 16, 1.7, seed=3)
         check(8192, 8192, 16, 16, 0.5, seed=4)            # outside the factored regime: the FP32 kernel must serve it
+        check_gram(8192, 8192, 16, 4.0)
+        check_gram(4096 + 300, 4096 + 13, 7, 2.5, seed=1, positive=True)
+        check_gram(4224, 6000, 3, 1.7, seed=3)
     if what in ("time", "all"):
         timeit(131072, 131072, 16, 16)
         timeit(151552, 131072, 16, 16)
         timeit(37888, 1048576, 16, 16)
+        timeit_gram(32768, 32768, 16)
+        timeit_gram(37888, 131072, 16)
