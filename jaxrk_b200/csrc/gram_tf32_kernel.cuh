@@ -503,6 +503,11 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
                     }
                 }
                 {
+                    // (All 16 epilogue warps were released by the same acc_full barrier, so the four warps that hold the
+                    // four 128-byte quarters of a 512-byte piece of a row store it at about the same time.  That matters:
+                    // HBM takes the bare store pattern at 6.0 TB/s when the quarters arrive together and at 4.9 TB/s when
+                    // they drift apart -- profiles/microbench/gram_epi.cu.  Three accumulator stages, which let the warps
+                    // drift by two tiles, made this kernel 3 % slower.)
                     // row i of this warp's block: base + i * pitch, one 32 x 32 -> 64-bit multiply-add per store
                     const char* kb = reinterpret_cast<const char*>(K + i0 * ldk + j);
                     const uint32_t pitch = (uint32_t)ldk * 4u;   // host guarantees ldk * 4 * NT < 2^32
