@@ -79,6 +79,7 @@ struct GtParams {
     const unsigned* nmax;             // [2] bit patterns: max |c||x|^2, max |c||y|^2
     float x_scale, inv_c;             // 2^-r of GEMM1;  1 / c (|x_i|^2 = xn_i / c)
     float fac, fac_s;
+    int g256;                         // GBAR: rows of Gbar are 32-byte aligned (one 256-bit load per chunk)
 };
 
 __device__ __forceinline__ void lds_2x64(uint32_t addr, f32x2& a, f32x2& b) {
@@ -269,7 +270,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                 const int64_t j0 = (int64_t)t * GT_NT + 8 * ch;
 #pragma unroll
                 for (int h = 0; h < GT_R; ++h) {
-                    if (gok[h] && j0 + 8 <= P.M) {
+                    if (gok[h] && j0 + 8 <= P.M && P.g256) {
+                        // one 32-byte sector per thread and instruction (two 16-byte loads would visit it twice: the
+                        // L1TEX sector rate is what bounds this kernel, ncu: l1tex throughput 98.6 %)
+                        asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(gv[h][0]), "=r"(gv[h][1]), "=r"(gv[h][2]), "=r"(gv[h][3]), "=r"(gv[h][4]),
+                                       "=r"(gv[h][5]), "=r"(gv[h][6]), "=r"(gv[h][7])
+                                     : "l"(grow[h] + j0));
+                    } else if (gok[h] && j0 + 8 <= P.M) {
                         const float4 a = __ldg(reinterpret_cast<const float4*>(grow[h] + j0));
                         const float4 b = __ldg(reinterpret_cast<const float4*>(grow[h] + j0 + 4));
                         gv[h][0] = __float_as_uint(a.x); gv[h][1] = __float_as_uint(a.y);
@@ -530,6 +538,7 @@ int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, flo
     P.X = X; P.ldx = ldx; P.d = d; P.G = G; P.ldg = ldg; P.m = m; P.xn = xn; P.img = img; P.gX = gX; P.ldgx = ldgx;
     P.gs_rows = gs_rows; P.N = N; P.M = M; P.n_tiles = n_tiles; P.n_units = (int)((N + GT_ROWS - 1) / GT_ROWS); P.nmax = nmax;
     P.x_scale = sc.x_scale; P.inv_c = 1.f / c; P.fac = fac; P.fac_s = fac_s;
+    P.g256 = (gbar && ldg % 8 == 0 && (uintptr_t)G % 32 == 0) ? 1 : 0;
     const int grid = P.n_units < tf_sm_count() ? P.n_units : tf_sm_count();
     if (gbar) {
         JRK_CUDA_OK(cudaFuncSetAttribute(kgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));

@@ -50,6 +50,14 @@ def kgrad_tc():
     torch.cuda.synchronize()
 
 
+def gram_grad_tc():
+    N, M, d = 148 * 256, 65536, 16
+    X, Y, Gb = randn(0, N, d), randn(1, M, d), randn(2, N, M)
+    for _ in range(2):
+        nat.gram_grad(X, Y, Gb, 0.1767767, 2.0, 0.25)
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gram64", "all"):
@@ -64,4 +72,6 @@ if __name__ == "__main__":
         kmatw_tc()
     if what == "kgrad_tc":
         kgrad_tc()
+    if what == "gram_grad_tc":
+        gram_grad_tc()
     print("done", nat.launch_count())
