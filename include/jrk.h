@@ -217,6 +217,9 @@ int jrk_gram_groupsum_f32(const float *X, const float *Y, float *out,
  *       gp_rows[i] = sum_j (G[i, :] . W[j, :]) dK_ij/dpower  at fixed nconst    (len N, nullable; dL/dpower = its sum;
  *                    dK/dp = -K (s r)^p ln(s r); asking for it runs the general-p epilogue, also for p = 2 and p = 1)
  *   jrk_gram_grad_f32:   K = K(X, Y),  Gbar = dL/dK (N x M): the same with G[i,:].W[j,:] replaced by Gbar[i, j].
+ *       gbar_transposed != 0: the cotangent is passed as Gbar^T (M x N, ldgb >= N).  The kernels read it fastest in that
+ *       layout (consecutive rows i are consecutive floats), so dL/dY -- the call with the roles exchanged, (Y, X, cotangent
+ *       of shape N x M = its transpose) -- takes dL/dK as it is, and dL/dX wants one transposed copy.
  * dL/dY is the same call with the roles exchanged -- (Y, X, G, W) resp. (Y, X, Gbar^T) -- and dL/dW = K(Y, X) G is
  * jrk_kmatw_f32.  GenGauss family only, global scale only (per-dimension scales are a pre-scaling of the points: their
  * gradient follows from gX / gY by the chain rule on the caller's side), d <= 64, m <= 32.
@@ -232,7 +235,7 @@ int jrk_kmatw_grad_f32(const float *X, const float *Y, const float *W, const flo
 int jrk_gram_grad_f32(const float *X, const float *Y, const float *Gbar,
                       float *gX, float *gs_rows, float *gp_rows,
                       int64_t N, int64_t M, int d,
-                      int64_t ldx, int64_t ldy, int64_t ldgb, int64_t ldgx,
+                      int64_t ldx, int64_t ldy, int64_t ldgb, int64_t ldgx, int gbar_transposed,
                       float scale, float power, float nconst,
                       void *workspace, size_t workspace_bytes, void *stream);
 

@@ -60,7 +60,7 @@ SIGNATURES = {
                                    c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_float, c_float,
                                    c_void_p, c_size_t, c_void_p]),
     "jrk_gram_grad_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
-                                  c_int64, c_int64, c_int64, c_int64, c_float, c_float, c_float,
+                                  c_int64, c_int64, c_int64, c_int64, c_int, c_float, c_float, c_float,
                                   c_void_p, c_size_t, c_void_p]),
     "jrk_kmatw_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int64]),
     "jrk_kmatw_uses_tensor_cores": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
@@ -327,12 +327,14 @@ def kmatw_grad(X, Y, W, G, scale: float, power: float, nconst: float, want_scale
     return (gX, gs, gp) if want_power else (gX, gs)
 
 
-def gram_grad(X, Y, Gbar, scale: float, power: float, nconst: float, want_scale: bool = True, want_power: bool = False):
-    """jrk_gram_grad_f32: (gX, gs_rows[, gp_rows]) for K = K(X, Y) with cotangent Gbar (N x M); d <= 64."""
+def gram_grad(X, Y, Gbar, scale: float, power: float, nconst: float, want_scale: bool = True, want_power: bool = False,
+              transposed: bool = False):
+    """jrk_gram_grad_f32: (gX, gs_rows[, gp_rows]) for K = K(X, Y) with cotangent Gbar (N x M); d <= 64.
+    transposed: `Gbar` holds the cotangent transposed (M x N) -- the layout the kernels read fastest."""
     X, Y, Gbar = _dev2d(X, "X"), _dev2d(Y, "Y"), _dev2d(Gbar, "Gbar")
     N, d = X.shape
     M = Y.shape[0]
-    if Y.shape[1] != d or Gbar.shape != (N, M):
+    if Y.shape[1] != d or Gbar.shape != ((M, N) if transposed else (N, M)):
         raise ValueError("shape mismatch")
     dev = X.device
     gX = torch.empty((N, d), dtype=torch.float32, device=dev)
@@ -342,7 +344,7 @@ def gram_grad(X, Y, Gbar, scale: float, power: float, nconst: float, want_scale:
         wsb = lib().jrk_grad_workspace_bytes(N, M, d)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         _check(lib().jrk_gram_grad_f32(_ptr(X), _ptr(Y), _ptr(Gbar), _ptr(gX), _ptr(gs), _ptr(gp), N, M, d, _ld(X), _ld(Y),
-                                       _ld(Gbar), d, scale, power, nconst, _ptr(ws), wsb, _stream(dev)))
+                                       _ld(Gbar), d, 1 if transposed else 0, scale, power, nconst, _ptr(ws), wsb, _stream(dev)))
     return (gX, gs, gp) if want_power else (gX, gs)
 
 

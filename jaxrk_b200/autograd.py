@@ -62,8 +62,10 @@ class _UnnormGram(torch.autograd.Function):
                                           ctx.needs_input_grad[5])
         Gbar = Gbar.contiguous().float()
         gX = gY = gs = gp = None
+        # the kernels read the cotangent fastest when the points they differentiate run along its contiguous axis: dL/dY
+        # takes Gbar (N x M) as it is, dL/dX one transposed copy
         if need_x or need_s or need_p:
-            res = nat.gram_grad(X, Y, Gbar, s, p, 1.0, want_scale=need_s, want_power=need_p)
+            res = nat.gram_grad(X, Y, Gbar.t().contiguous(), s, p, 1.0, want_scale=need_s, want_power=need_p, transposed=True)
             gX, gs_rows = res[0], res[1]
             if need_s:
                 gs = gs_rows.sum().reshape(scale_t.shape)
@@ -72,7 +74,7 @@ class _UnnormGram(torch.autograd.Function):
             if not need_x:
                 gX = None
         if need_y:
-            gY, _ = nat.gram_grad(Y, X, Gbar.t().contiguous(), s, p, 1.0, want_scale=False)
+            gY, _ = nat.gram_grad(Y, X, Gbar, s, p, 1.0, want_scale=False, transposed=True)
         return gX, gY, gs, None, None, gp
 
 

@@ -12,7 +12,7 @@ namespace jrk {
 thread_local char g_last_error[512] = {0};
 int kgrad(int mode, const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, float* gp_rows, int64_t N,
           int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float scale,
-          float power, float nconst, void* workspace, size_t workspace_bytes, cudaStream_t st);
+          float power, float nconst, int gtrans, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t kgrad_workspace_bytes(int64_t N, int64_t M, int d);
 int gram_affine(const float* K, float* out, int64_t N, int64_t M, int64_t ldk, int64_t ldo, const float* row_mul,
                 const float* col_mul, const float* row_add, const float* col_add, float add_const, cudaStream_t st);
@@ -284,21 +284,21 @@ int jrk_kmatw_grad_f32(const float* X, const float* Y, const float* W, const flo
     if (ldx < d || ldy < d || ldw < m || ldg < m || ldgx < d)
         return fail(JRK_ERR_INVALID_ARG, "jrk_kmatw_grad_f32: leading dimension too small");
     if (int rc = have_device("jrk_kmatw_grad_f32")) return rc;
-    return kgrad(0, X, Y, W, G, gX, gs_rows, gp_rows, N, M, d, m, ldx, ldy, ldw, ldg, ldgx, scale, power, nconst, workspace,
+    return kgrad(0, X, Y, W, G, gX, gs_rows, gp_rows, N, M, d, m, ldx, ldy, ldw, ldg, ldgx, scale, power, nconst, 0, workspace,
                  workspace_bytes, (cudaStream_t)stream);
 }
 
 int jrk_gram_grad_f32(const float* X, const float* Y, const float* Gbar, float* gX, float* gs_rows, float* gp_rows, int64_t N, int64_t M,
-                      int d, int64_t ldx, int64_t ldy, int64_t ldgb, int64_t ldgx, float scale, float power, float nconst,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      int d, int64_t ldx, int64_t ldy, int64_t ldgb, int64_t ldgx, int gbar_transposed, float scale, float power,
+                      float nconst, void* workspace, size_t workspace_bytes, void* stream) {
     if (!X || !Y || !Gbar || !gX) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_grad_f32: NULL pointer");
     if (N < 1 || M < 1) return fail(JRK_ERR_INVALID_ARG, "jrk_gram_grad_f32: N, M must be >= 1");
     if (int rc = check_kernel_params("jrk_gram_grad_f32", d, scale, power, nconst)) return rc;
-    if (ldx < d || ldy < d || ldgb < M || ldgx < d)
+    if (ldx < d || ldy < d || ldgb < (gbar_transposed ? N : M) || ldgx < d)
         return fail(JRK_ERR_INVALID_ARG, "jrk_gram_grad_f32: leading dimension too small");
     if (int rc = have_device("jrk_gram_grad_f32")) return rc;
     return kgrad(1, X, Y, nullptr, Gbar, gX, gs_rows, gp_rows, N, M, d, 0, ldx, ldy, 0, ldgb, ldgx, scale, power, nconst,
-                 workspace, workspace_bytes, (cudaStream_t)stream);
+                 gbar_transposed != 0, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t jrk_kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce, int64_t group) {

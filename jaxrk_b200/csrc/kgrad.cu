@@ -27,11 +27,11 @@ namespace tf32 { int tf_sm_count(); }
 
 // kgrad_tc.cu
 bool kgrad_tc_eligible(int64_t N, int64_t M, int d, int m, int pm);
-bool kgrad_tc_gbar_eligible(int64_t N, int64_t M, int d, int pm, const float* Gbar, int64_t ldgb);
+bool kgrad_tc_gbar_eligible(int64_t N, int64_t M, int d, int pm, const float* Gbar, int64_t ldgb, int transposed);
 size_t kgrad_tc_workspace_bytes(int64_t N, int64_t M);
 int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, int64_t N, int64_t M,
              int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float c, float fac, float fac_s,
-             void* scratch, const unsigned** nmax_out, cudaStream_t st);
+             int gtrans, void* scratch, const unsigned** nmax_out, cudaStream_t st);
 
 namespace {
 
@@ -48,6 +48,7 @@ kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__
              const float* __restrict__ W, int64_t ldw, const float* __restrict__ G, int64_t ldg, int m,
              int64_t N, int64_t M, int64_t cols_per_split, EpiParams ep, float* __restrict__ part, int stride,
              const unsigned* __restrict__ skip_if_fast) {
+    constexpr bool gtrans = MODE == 2;       // MODE 1 / 2: Gram cotangent as Gbar (N x M) / Gbar^T (M x N)
     // the tensor-core kernel (kgrad_tc.cu) was launched next to this one: inside its regime the result is its to write
     if (skip_if_fast && kg_fast_regime(skip_if_fast)) return;
     // part layout: [split][row][stride], stride = d + 3: {dL/dx contribution (d), S0 (unused by finalize), S2, S3}
@@ -80,17 +81,18 @@ kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__
     const int64_t j_end = (j_begin + cols_per_split < M) ? j_begin + cols_per_split : M;
     // MODE 1: this thread's share of the next 128 x 32 block of Gbar, fetched one tile ahead (the global-load latency
     // would otherwise be exposed once per tile: only 8 warps are resident per SM)
-    constexpr int PRE = (MODE == 1) ? KG_TJ : 1;
+    constexpr int PRE = (MODE >= 1) ? KG_TJ : 1;
     float pre[PRE];
     const int64_t r0 = (int64_t)blockIdx.x * KG_ROWS;
     auto fetch_gbar = [&](int64_t j0) {
-        if (MODE == 1) {
+        if (MODE >= 1) {
 #pragma unroll
             for (int q = 0; q < PRE; ++q) {
+                // consecutive threads read consecutive floats: along j for Gbar (N x M), along the rows for Gbar^T (M x N)
                 const int idx = q * KG_ROWS + tid;
-                const int rr = idx / KG_TJ, jj = idx % KG_TJ;
+                const int rr = gtrans ? idx % KG_ROWS : idx / KG_TJ, jj = gtrans ? idx / KG_ROWS : idx % KG_TJ;
                 const int64_t r = r0 + rr, j = j0 + jj;
-                pre[q] = (r < N && j < j_end) ? __ldg(G + r * ldg + j) : 0.f;
+                pre[q] = (r < N && j < j_end) ? __ldg(gtrans ? G + j * ldg + r : G + r * ldg + j) : 0.f;
             }
         }
     };
@@ -114,7 +116,8 @@ kgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__
 #pragma unroll
             for (int q = 0; q < PRE; ++q) {
                 const int idx = q * KG_ROWS + tid;
-                sA[(idx / KG_TJ) * (KG_TJ + 1) + (idx % KG_TJ)] = pre[q];
+                const int rr = gtrans ? idx % KG_ROWS : idx / KG_TJ, jj = gtrans ? idx / KG_ROWS : idx % KG_TJ;
+                sA[rr * (KG_TJ + 1) + jj] = pre[q];
             }
             if (j0 + KG_TJ < j_end) fetch_gbar(j0 + KG_TJ);
         }
@@ -251,9 +254,10 @@ size_t kgrad_workspace_bytes(int64_t N, int64_t M, int d) {
 // mode 0: K@W cotangent (W: M x m, G: N x m);  mode 1: Gram cotangent (G = Gbar: N x M, W unused, m = 0)
 // gp_rows (nullable): per-row contributions to dL/dpower at fixed nconst; asking for it selects the general-p epilogue
 // (the p = 2 / p = 1 specialisations never form log(s r)).
+// gtrans (mode 1 only): the cotangent is given as Gbar^T (M x N, leading dimension ldg >= N).
 int kgrad(int mode, const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, float* gp_rows,
           int64_t N, int64_t M, int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float scale,
-          float power, float nconst, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+          float power, float nconst, int gtrans, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (d > 64) return fail(JRK_ERR_UNSUPPORTED, "kgrad: d = %d > 64 is not supported by the fused backward kernel", d);
     const int pm = gp_rows ? PM_GENERAL : pick_pmode(power);
     EpiParams ep = make_epi(scale, power, nconst);
@@ -274,10 +278,10 @@ int kgrad(int mode, const float* X, const float* Y, const float* W, const float*
     // problem lies inside its regime is known on the device only, so the FP32 kernels below are enqueued as well and
     // return at once when it does.
     const unsigned* skip = nullptr;
-    if ((mode == 0 && kgrad_tc_eligible(N, M, d, m, pm)) || (mode == 1 && kgrad_tc_gbar_eligible(N, M, d, pm, G, ldg))) {
+    if ((mode == 0 && kgrad_tc_eligible(N, M, d, m, pm)) || (mode == 1 && kgrad_tc_gbar_eligible(N, M, d, pm, G, ldg, gtrans))) {
         void* tcs = scr.take<char>(kgrad_tc_workspace_bytes(N, M));
         if (int rc = kgrad_tc(X, Y, mode == 0 ? W : nullptr, G, gX, gs_rows, N, M, d, m, ldx, ldy, ldw, ldg, ldgx, ep.c, fac,
-                              fac_s, tcs, &skip, st))
+                              fac_s, gtrans, tcs, &skip, st))
             return rc;
     }
     const int64_t nblk = (N + KG_ROWS - 1) / KG_ROWS;
@@ -293,7 +297,8 @@ int kgrad(int mode, const float* X, const float* Y, const float* W, const float*
     rc = kg_launch<D_, MT_, MODE_, PM_>(grid, st, X, ldx, Y, ldy, d, W, ldw, G, ldg, m, N, M, p.cols_per_split, ep, part, stride, skip)
 #define KG_MT(D_, PM_)                                   \
     do {                                                 \
-        if (mode == 1) KG_GO(D_, 4, 1, PM_);             \
+        if (mode == 1 && gtrans) KG_GO(D_, 4, 2, PM_);   \
+        else if (mode == 1) KG_GO(D_, 4, 1, PM_);        \
         else if (MT == 4) KG_GO(D_, 4, 0, PM_);          \
         else if (MT == 16) KG_GO(D_, 16, 0, PM_);        \
         else KG_GO(D_, 32, 0, PM_);                      \

@@ -80,6 +80,8 @@ struct GtParams {
     float x_scale, inv_c;             // 2^-r of GEMM1;  1 / c (|x_i|^2 = xn_i / c)
     float fac, fac_s;
     int g256;                         // GBAR: rows of Gbar are 32-byte aligned (one 256-bit load per chunk)
+    int gtrans;                       // GBAR: the cotangent is given transposed (M x N): G[j * ldg + i] -- consecutive lanes
+                                      // (rows i) then read consecutive floats: one cache line per warp instruction
 };
 
 __device__ __forceinline__ void lds_2x64(uint32_t addr, f32x2& a, f32x2& b) {
@@ -268,6 +270,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
             }
             auto load_gbar = [&](int t, int ch, uint32_t (&gv)[GT_R][8]) {
                 const int64_t j0 = (int64_t)t * GT_NT + 8 * ch;
+                if (P.gtrans) {
+#pragma unroll
+                    for (int h = 0; h < GT_R; ++h) {
+                        const float* col = P.G + j0 * P.ldg + ((int64_t)u * GT_ROWS + h * GT_BM + quad * 32 + lane);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            gv[h][c] = (gok[h] && j0 + c < P.M) ? __float_as_uint(__ldg(col + (int64_t)c * P.ldg)) : 0u;
+                    }
+                    return;
+                }
 #pragma unroll
                 for (int h = 0; h < GT_R; ++h) {
                     if (gok[h] && j0 + 8 <= P.M && P.g256) {
@@ -291,7 +303,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                     }
                 }
             };
-            uint32_t gnext[GT_R][8];
+            uint32_t gnext[GT_R][8];        // (two chunks in flight spill registers and measured 20 % slower)
             if (GBAR && k < T) load_gbar(k, 0, gnext);
             for (int t = k; t < T; t += GT_EPQ) {
                 const uint32_t g = gt + (uint32_t)t, a = g % GT_NS, s = g % GT_SOP;
@@ -503,8 +515,8 @@ bool kgrad_tc_eligible(int64_t N, int64_t M, int d, int m, int pm) {
            jrk_option(JRK_OPT_TC_FAST) != 0;
 }
 // Gram cotangent (mode 1): Gbar rows must allow 16-byte loads
-bool kgrad_tc_gbar_eligible(int64_t N, int64_t M, int d, int pm, const float* Gbar, int64_t ldgb) {
-    return kgrad_tc_eligible(N, M, d, 1, pm) && (ldgb % 4 == 0) && ((uintptr_t)Gbar % 16 == 0);
+bool kgrad_tc_gbar_eligible(int64_t N, int64_t M, int d, int pm, const float* Gbar, int64_t ldgb, int transposed) {
+    return kgrad_tc_eligible(N, M, d, 1, pm) && (transposed || ((ldgb % 4 == 0) && ((uintptr_t)Gbar % 16 == 0)));
 }
 
 size_t kgrad_tc_workspace_bytes(int64_t N, int64_t M) {
@@ -514,10 +526,10 @@ size_t kgrad_tc_workspace_bytes(int64_t N, int64_t M) {
 
 // Enqueues the pre-pass and the tensor-core kernel; *nmax_out receives the device pointer of the two norm maxima, from
 // which the caller's FP32 kernels decide (on the device) whether the result is theirs to write.
-// W == nullptr: Gram cotangent, G = Gbar (N x M).
+// W == nullptr: Gram cotangent, G = Gbar (N x M, or M x N when gtrans).
 int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, float* gX, float* gs_rows, int64_t N, int64_t M,
              int d, int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldg, int64_t ldgx, float c, float fac, float fac_s,
-             void* scratch, const unsigned** nmax_out, cudaStream_t st) {
+             int gtrans, void* scratch, const unsigned** nmax_out, cudaStream_t st) {
     const bool gbar = W == nullptr;
     char* p = (char*)scratch;
     float* xn = (float*)p; p += align256((size_t)N * 4);
@@ -539,6 +551,7 @@ int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, flo
     P.gs_rows = gs_rows; P.N = N; P.M = M; P.n_tiles = n_tiles; P.n_units = (int)((N + GT_ROWS - 1) / GT_ROWS); P.nmax = nmax;
     P.x_scale = sc.x_scale; P.inv_c = 1.f / c; P.fac = fac; P.fac_s = fac_s;
     P.g256 = (gbar && ldg % 8 == 0 && (uintptr_t)G % 32 == 0) ? 1 : 0;
+    P.gtrans = (gbar && gtrans) ? 1 : 0;
     const int grid = P.n_units < tf_sm_count() ? P.n_units : tf_sm_count();
     if (gbar) {
         JRK_CUDA_OK(cudaFuncSetAttribute(kgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));

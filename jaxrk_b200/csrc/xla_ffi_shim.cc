@@ -156,10 +156,11 @@ static ffi::Error KmatwGradImpl(cudaStream_t stream, ffi::ScratchAllocator scrat
 
 // (gX, gs_rows) = VJP of K = K(X, Y) with cotangent Gbar (N x M)
 static ffi::Error GramGradImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, F32Buf x, F32Buf y, F32Buf gbar, float scale,
-                               float power, float nconst, F32Res gx, F32Res gs_rows, F32Res gp_rows) {
-    if (!is_mat(x) || !is_mat(y) || !is_mat(gbar) || x.dimensions()[1] != y.dimensions()[1] || gbar.dimensions()[0] != x.dimensions()[0] ||
-        gbar.dimensions()[1] != y.dimensions()[0])
-        return ffi::Error::InvalidArgument("X: N x d, Y: M x d, Gbar: N x M expected");
+                               float power, float nconst, int32_t gbar_transposed, F32Res gx, F32Res gs_rows, F32Res gp_rows) {
+    const int r0 = gbar_transposed ? 1 : 0;      // which dimension of gbar runs along X
+    if (!is_mat(x) || !is_mat(y) || !is_mat(gbar) || x.dimensions()[1] != y.dimensions()[1] ||
+        gbar.dimensions()[r0] != x.dimensions()[0] || gbar.dimensions()[1 - r0] != y.dimensions()[0])
+        return ffi::Error::InvalidArgument("X: N x d, Y: M x d, Gbar: N x M (or M x N when gbar_transposed) expected");
     const int64_t N = x.dimensions()[0], M = y.dimensions()[0];
     const int d = (int)x.dimensions()[1];
     void* ws;
@@ -167,7 +168,8 @@ static ffi::Error GramGradImpl(cudaStream_t stream, ffi::ScratchAllocator scratc
     if (!scratch_for(scratch, wsb, &ws)) return ffi::Error::Internal("jrk_gram_grad_f32: scratch allocation failed");
     return to_error(jrk_gram_grad_f32(x.typed_data(), y.typed_data(), gbar.typed_data(), gx->typed_data(),
                                       gs_rows->element_count() == 0 ? nullptr : gs_rows->typed_data(),
-                                      gp_rows->element_count() == 0 ? nullptr : gp_rows->typed_data(), N, M, d, d, d, M, d, scale,
+                                      gp_rows->element_count() == 0 ? nullptr : gp_rows->typed_data(), N, M, d, d, d,
+                                      gbar_transposed ? N : M, d, gbar_transposed, scale,
                                       power, nconst, ws, wsb, stream));
 }
 
@@ -234,7 +236,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(jrk_kmatw_grad_f32_ffi, KmatwGradImpl,
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(jrk_gram_grad_f32_ffi, GramGradImpl,
                               JRK_STREAM_SCRATCH.Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>()
-                                  .Attr<float>("scale").Attr<float>("power").Attr<float>("nconst")
+                                  .Attr<float>("scale").Attr<float>("power").Attr<float>("nconst").Attr<int32_t>("gbar_transposed")
                                   .Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>(),
                               {ffi::Traits::kCmdBufferCompatible});
 #endif  // __has_include("xla/ffi/api/ffi.h")

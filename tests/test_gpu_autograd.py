@@ -52,6 +52,17 @@ def test_gram_grad_against_oracle(kname, N, M, d):
     _check(gy_d.cpu().numpy(), gY, my, f"gram dL/dY {kname}")
 
 
+def test_gram_grad_transposed_cotangent_fp32_kernel():
+    """gbar_transposed on the FP32-pipe kernel (small / ineligible problems): identical sums, another read order."""
+    N, M, d = 257, 1025, 9
+    X, Y, A = gauss(0, N, d), gauss(1, M, d), gauss(4, N, M)
+    for kname in ("sqexp", "laplace"):
+        s, scale, p, nconst = kparams(kname, 3.0)
+        g0, s0 = nat.gram_grad(cu(X), cu(Y), cu(A), scale, p, nconst)
+        g1, s1 = nat.gram_grad(cu(X), cu(Y), cu(A.T.copy()), scale, p, nconst, transposed=True)
+        assert torch.allclose(g0, g1, rtol=1e-6, atol=1e-7) and torch.allclose(s0, s1, rtol=1e-6, atol=1e-7)
+
+
 def test_self_gram_with_coincident_points_has_finite_gradients():
     X = gauss(5, 200, 6)
     A = gauss(6, 200, 200)
@@ -376,7 +387,10 @@ def test_gram_grad_tensor_core_path(N, M, d, ls, positive):
     _, _, _, (mx, _, ms) = orc.gengauss_vjp_truth64(X[rows], Y, np.abs(Gb[rows]).astype(np.float64), s, 2.0, nconst=nconst)
     _check(gx.cpu().numpy()[rows], gX, mx, "tensor-core gram dL/dX")
     _check(float(gs.double()[torch.from_numpy(rows).to(gs.device)].sum()), gsum, ms, "tensor-core gram dL/dscale")
-    gy, _ = nat.gram_grad(cu(Y), cu(X), cu(np.ascontiguousarray(Gb.T)), scale, 2.0, nconst, want_scale=False)
+    gy, _ = nat.gram_grad(cu(Y), cu(X), cu(Gb), scale, 2.0, nconst, want_scale=False, transposed=True)   # dL/dK as it is
+    gxt, gst = nat.gram_grad(cu(X), cu(Y), cu(np.ascontiguousarray(Gb.T)), scale, 2.0, nconst, transposed=True)
+    _check(gxt.cpu().numpy()[rows], gX, mx, "tensor-core gram dL/dX from the transposed cotangent")
+    _check(float(gst.double()[torch.from_numpy(rows).to(gs.device)].sum()), gsum, ms, "tensor-core gram dL/dscale (transposed)")
     cols = np.r_[0:32, M - 32:M]
     _, gY, _, _ = orc.gengauss_vjp_truth64(X, Y[cols], Gb[:, cols].astype(np.float64), s, 2.0, nconst=nconst)
     _, _, _, (_, my, _) = orc.gengauss_vjp_truth64(X, Y[cols], np.abs(Gb[:, cols]).astype(np.float64), s, 2.0, nconst=nconst)

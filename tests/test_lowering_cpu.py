@@ -357,8 +357,10 @@ def fake_kmatw_grad(X, Y, W, G, scale, power, nconst, want_scale=True, want_powe
     return torch.from_numpy(gX.astype(f32)), gs_rows
 
 
-def fake_gram_grad(X, Y, Gbar, scale, power, nconst, want_scale=True, want_power=False):
+def fake_gram_grad(X, Y, Gbar, scale, power, nconst, want_scale=True, want_power=False, transposed=False):
     CALLS.append("gram_grad")
+    if transposed:
+        Gbar = Gbar.t()
     ones = torch.eye(Gbar.shape[1], dtype=torch.float32)
     return fake_kmatw_grad(X, Y, ones, Gbar, scale, power, nconst, want_scale, want_power)
 

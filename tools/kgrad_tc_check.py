@@ -71,15 +71,15 @@ def check_gram(N, M, d, ls, seed=0, positive=False):
     gX, _, gsum, (mx, _, ms) = orc.gengauss_vjp_truth64(X[rows], Y, Gb[rows].astype(np.float64), s, p, nconst=nconst)
     _, _, _, (mxa, _, msa) = orc.gengauss_vjp_truth64(X[rows], Y, np.abs(Gb[rows]).astype(np.float64), s, p, nconst=nconst)
     out = {"gram_grad": True, "N": N, "M": M, "d": d, "ls": ls, "positive": positive}
-    for tc in (1, 0):
+    for tc, tr in ((1, False), (1, True), (0, False), (0, True)):
         with nat.option(nat.OPT_KMATW_TC, tc):
             n0 = nat.launch_count()
-            gx, gs = nat.gram_grad(cu(X), cu(Y), cu(Gb), scale, p, nconst)
+            gx, gs = nat.gram_grad(cu(X), cu(Y), cu(np.ascontiguousarray(Gb.T)) if tr else cu(Gb), scale, p, nconst, transposed=tr)
             torch.cuda.synchronize()
             nl = nat.launch_count() - n0
         ex = np.abs(gx.cpu().numpy()[rows] - gX) / (AT + RT * mxa)
         es = abs(float(gs.cpu().numpy()[rows].astype(np.float64).sum()) - gsum) / (AT + RT * msa)
-        out["tc" if tc else "fp32"] = {"dX": float(ex.max()), "ds": float(es), "launches": nl}
+        out[("tc" if tc else "fp32") + ("_T" if tr else "")] = {"dX": float(ex.max()), "ds": float(es), "launches": nl}
     print(out, flush=True)
 
 
@@ -89,21 +89,23 @@ def timeit_gram(N, M, d):
     Gb = torch.randn(N, M, generator=g, device=dev)
     scale = float(0.70710695 / np.sqrt(d))
     out = {"gram_grad": True, "N": N, "M": M, "d": d}
-    for tc in (1, 0):
+    GbT = Gb.t().contiguous()
+    for tc, tr in ((1, False), (1, True), (0, False), (0, True)):
         with nat.option(nat.OPT_KMATW_TC, tc):
+            cot = GbT if tr else Gb
             for _ in range(2):
-                nat.gram_grad(X, Y, Gb, scale, 2.0, 0.25)
+                nat.gram_grad(X, Y, cot, scale, 2.0, 0.25, transposed=tr)
             torch.cuda.synchronize()
             ts = []
             for _ in range(3):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                nat.gram_grad(X, Y, Gb, scale, 2.0, 0.25)
+                nat.gram_grad(X, Y, cot, scale, 2.0, 0.25, transposed=tr)
                 e1.record()
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             t = min(ts)
-            out["tc" if tc else "fp32"] = {"ms": t, "pairs_per_s": N * M / t * 1e3, "hbm_read_GBps": 4 * N * M / t * 1e-6}
+            out[("tc" if tc else "fp32") + ("_T" if tr else "")] = {"ms": round(t, 3), "pairs_per_s": N * M / t * 1e3, "hbm_read_GBps": round(4 * N * M / t * 1e-6)}
     print(out, flush=True)
 
 
