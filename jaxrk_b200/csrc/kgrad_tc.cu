@@ -65,7 +65,7 @@ constexpr int GT_SMEM = GT_OFF_BAR + GT_NBAR * 8 + 16 + 1024;
 constexpr int GT_THREADS = (GT_EW + 2) * 32;
 static_assert(GT_COL_S + GT_NS * 64 * GT_R <= 512 && GT_R * GT_COL_BLK <= GT_COL_S, "TMEM budget");
 static_assert(GT_SMEM <= 227 * 1024, "shared memory budget");
-static_assert(GT_EPQ >= 3, "warps 0 / 1 / 2 of a lane quarter park x~ / G hi / G lo");
+static_assert(GT_EPQ >= 3 && GT_EPQ == GT_NS, "warps 0 / 1 / 2 of a lane quarter park x~ / G hi / G lo; one stage per warp");
 
 struct GtParams {
     const float* X; int64_t ldx; int d;
@@ -303,9 +303,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                     }
                 }
             };
+            // Tile t of the unit belongs to warp t mod EPQ (unit-local, so that a block of rows computed on its own -- another
+            // rank's shard -- sums in the same order and gives the same bits).  The stage of a tile goes by the global index
+            // gt + t, so the owner / stage pairing shifts from unit to unit when T is not a multiple of EPQ; that is safe
+            // for the parity waits because every warp has waited for x_free -- all MMAs of the previous unit complete --
+            // before its first tile of this one.
+            const int first = k;
             uint32_t gnext[GT_R][8];        // (two chunks in flight spill registers and measured 20 % slower)
-            if (GBAR && k < T) load_gbar(k, 0, gnext);
-            for (int t = k; t < T; t += GT_EPQ) {
+            if (GBAR && first < T) load_gbar(first, 0, gnext);
+            for (int t = first; t < T; t += GT_EPQ) {
                 const uint32_t g = gt + (uint32_t)t, a = g % GT_NS, s = g % GT_SOP;
                 bar_wait(b_sfull + a * 8, (g / GT_NS) & 1);
                 bar_wait(b_opfull + s * 8, (g / GT_SOP) & 1);     // (complete long ago: makes the TMA writes visible to this thread)
@@ -341,11 +347,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                             if (!GBAR) ld8_async(sc + h * 64 + 32 + 8 * (ch + 1), gv[h]);
                         }
                     } else {
-                        // every S / g value of the tile is in registers: the stage goes back to the MMA warp now, a quarter
-                        // of the tile's FMA work before this warp needs it again (NS = EPQ: it is the warp's next stage)
                         tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) bar_arrive(b_sempty + a * 8);
                     }
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
@@ -372,16 +374,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                         }
                     }
                 }
+                // (Handing the TMEM stage back earlier -- right after the last tcgen05.wait::ld, a quarter of the tile's FMA work
+                // before this point -- measured no faster, and gave wrong rows in the slowest lane quarter whenever a CTA
+                // processed more than one unit; not understood, not kept.)
                 __syncwarp();
-                if (lane == 0) bar_arrive(b_opempty + s * 8);
+                if (lane == 0) {
+                    bar_arrive(b_sempty + a * 8);
+                    bar_arrive(b_opempty + s * 8);
+                }
                 if (++since == GT_FLUSH) { flush(); since = 0; }
-            }
-            // once every MMA of this unit has completed the next block of x~ / G can be parked
-            const int un = u + gridDim.x;
-            if (un < P.n_units) {
-                bar_wait(b_xfree, uc & 1);
-                tc_fence_after();
-                park(un);
             }
             // the EPQ partial results of a lane quarter meet in shared memory
             flush();
@@ -417,6 +418,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                         if (P.gs_rows) P.gs_rows[i] = P.fac_s * rowf * (xn * P.inv_c * s0v - 2.f * xs1 + s2v);
                     }
                 }
+            }
+            // once every MMA of this unit has completed the next block of x~ / G can be parked
+            const int un = u + gridDim.x;
+            if (un < P.n_units) {
+                bar_wait(b_xfree, uc & 1);
+                tc_fence_after();
+                park(un);
             }
             gt += (uint32_t)T;
         }

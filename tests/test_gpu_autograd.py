@@ -395,3 +395,37 @@ def test_gram_grad_tensor_core_path(N, M, d, ls, positive):
     _, gY, _, _ = orc.gengauss_vjp_truth64(X, Y[cols], Gb[:, cols].astype(np.float64), s, 2.0, nconst=nconst)
     _, _, _, (_, my, _) = orc.gengauss_vjp_truth64(X, Y[cols], np.abs(Gb[:, cols]).astype(np.float64), s, 2.0, nconst=nconst)
     _check(gy.cpu().numpy()[cols], gY, my, "tensor-core gram dL/dY")
+
+
+@pytest.mark.parametrize("N,M", [(75776, 8192), (151552 + 100, 4096 + 32 * 5 + 7)])
+def test_tensor_core_backward_every_row_with_several_units_per_cta(N, M):
+    """More 256-row units than CTAs (a persistent CTA runs several units back to back) and a tile count that is not a
+    multiple of the warps per lane quarter: EVERY row of the tensor-core kernel against the FP32-pipe kernel, the same
+    call twice bit for bit, a row block on its own bit for bit -- for the K@W cotangent and for the Gram cotangent in
+    both layouts.  (A version that handed its TMEM stage back early was right with one unit per CTA and wrong, differently
+    from run to run, with two: sampled first / last rows never saw it.)"""
+    d, m = 16, 16
+    g = torch.Generator(device="cuda").manual_seed(N)
+    X, Y = torch.randn(N, d, generator=g, device="cuda"), torch.randn(M, d, generator=g, device="cuda")
+    W, G = torch.randn(M, m, generator=g, device="cuda"), torch.randn(N, m, generator=g, device="cuda")
+    scale, nconst = 0.70710695 / 4, 0.1
+    a, sa = nat.kmatw_grad(X, Y, W, G, scale, 2.0, nconst)
+    b, sb = nat.kmatw_grad(X, Y, W, G, scale, 2.0, nconst)
+    assert torch.equal(a, b) and torch.equal(sa, sb)
+    with nat.option(nat.OPT_KMATW_TC, 0):
+        r, sr = nat.kmatw_grad(X, Y, W, G, scale, 2.0, nconst)
+    assert float((a - r).abs().max()) <= 1e-3 * float(r.abs().max())
+    assert float((sa - sr).abs().max()) <= 1e-3 * float(sr.abs().max())
+    blk, _ = nat.kmatw_grad(X[256 * 150: 256 * 150 + 8192], Y, W, G[256 * 150: 256 * 150 + 8192], scale, 2.0, nconst)
+    assert torch.equal(blk, a[256 * 150: 256 * 150 + 8192])
+    if M % 4 == 0:
+        Gb = torch.randn(N, M, generator=g, device="cuda")
+        for tr in (False, True):
+            cot = Gb.t().contiguous() if tr else Gb
+            a, sa = nat.gram_grad(X, Y, cot, scale, 2.0, nconst, transposed=tr)
+            b, sb = nat.gram_grad(X, Y, cot, scale, 2.0, nconst, transposed=tr)
+            assert torch.equal(a, b) and torch.equal(sa, sb)
+            with nat.option(nat.OPT_KMATW_TC, 0):
+                r, sr = nat.gram_grad(X, Y, cot, scale, 2.0, nconst, transposed=tr)
+            assert float((a - r).abs().max()) <= 1e-3 * float(r.abs().max())
+            del cot

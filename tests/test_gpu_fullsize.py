@@ -200,3 +200,53 @@ def test_cfg5_cdo_through_the_operator_objects_full_size():
     # the estimated conditional density is evaluated on the reference grid without materialising anything else
     dens = res(Rf)
     assert tuple(dens.shape) == (T, R) and bool(torch.isfinite(dens).all())
+
+
+def test_cfg3_backward_2pow20_sampled_rows_linearity_and_row_blocks():
+    """The K@W vector-Jacobian product at the full cfg3 size (2^40 pairs, csrc/kgrad_tc.cu): sampled rows of dX and of the
+    dscale rows -- both row blocks of the 256-row units, every CTA of the schedule, the last unit -- against float64
+    (evaluated on the device in double precision, chunked over Y), linearity in the cotangent, row-block independence."""
+    N = M = 1 << 20
+    d, m = 16, 16
+    X, Y, W, G1, G2 = randn(100, N, d), randn(1, M, d), randn(2, M, m), randn(3, N, m), randn(4, N, m)
+    k, scale, power, nconst, s = kernel_for(d)
+    gx1, gs1 = nat.kmatw_grad(X, Y, W, G1, scale, power, nconst)
+    gx2, gs2 = nat.kmatw_grad(X, Y, W, G2, scale, power, nconst)
+    gx12, gs12 = nat.kmatw_grad(X, Y, W, 0.5 * G1 - 2.0 * G2, scale, power, nconst)
+    blk, blk_s = nat.kmatw_grad(X[N // 2: N // 2 + 65536], Y, W, G1[N // 2: N // 2 + 65536], scale, power, nconst)
+    assert torch.equal(blk, gx1[N // 2: N // 2 + 65536]) and torch.equal(blk_s, gs1[N // 2: N // 2 + 65536])
+    # sampled rows in float64 on the device
+    rng = np.random.RandomState(7)
+    n_units = N // 256
+    rows = [0, 127, 128, 255, 256, N - 256, N - 129, N - 128, N - 1]
+    for r in range(0, 148, 3):
+        u = r + 148 * rng.randint(0, (n_units - 1 - r) // 148 + 1)
+        rows.append(u * 256 + rng.randint(0, 256))
+    rows = torch.from_numpy(np.unique(np.array(rows))).to(dev)
+    Xr, Gr = X[rows].double(), G1[rows].double()
+    Gmix = 0.5 * G1[rows].double().abs() + 2.0 * G2[rows].double().abs()
+    mMix = torch.zeros((len(rows), d), dtype=torch.float64, device=dev)
+    sc = float(scale)
+    gX = torch.zeros((len(rows), d), dtype=torch.float64, device=dev)
+    gS = torch.zeros((len(rows),), dtype=torch.float64, device=dev)
+    mX = torch.zeros_like(gX)
+    mS = torch.zeros_like(gS)
+    for j0 in range(0, M, 1 << 16):
+        Yc, Wc = Y[j0:j0 + (1 << 16)].double(), W[j0:j0 + (1 << 16)].double()
+        diff = Xr[:, None, :] - Yc[None, :, :]                      # rows x chunk x d
+        sq = (diff ** 2).sum(-1)
+        Kc = float(nconst) * torch.exp(-(sc * sc) * sq)
+        A, Aabs = Gr @ Wc.T, Gr.abs() @ Wc.abs().T
+        T = A * Kc * (2.0 * sc * sc)                                # dK/dx_i = -K 2 s^2 (x_i - y_j)
+        gX -= (T[:, :, None] * diff).sum(1)
+        mX += ((Aabs * Kc * (2.0 * sc * sc))[:, :, None] * diff.abs()).sum(1)
+        mMix += (((Gmix @ Wc.abs().T) * Kc * (2.0 * sc * sc))[:, :, None] * diff.abs()).sum(1)
+        gS -= (A * Kc * 2.0 * sc * sq).sum(1)                       # dK/ds = -K 2 s r^2
+        mS += (Aabs * Kc * 2.0 * sc * sq).sum(1)
+    ex = ((gx1[rows].double() - gX).abs() / (2e-6 + 2e-5 * mX)).max()
+    es = ((gs1[rows].double() - gS).abs() / (2e-6 + 2e-5 * mS)).max()
+    assert float(ex) <= 1.0 and float(es) <= 1.0, (float(ex), float(es))
+    # linearity in the cotangent, judged like everything else against the accumulated magnitude (the sums cancel: |gX| is
+    # ~ 1e-3 of it at this size)
+    lin = ((gx12[rows] - (0.5 * gx1[rows] - 2.0 * gx2[rows])).double().abs() / (2e-6 + 2e-5 * 3 * mMix)).max()
+    assert float(lin) <= 1.0, float(lin)

@@ -11,4 +11,5 @@ ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,gpu__t
 ncu --set full --clock-control none --import-source on -k regex:gram_tf32_kernel -c 1 -s 1 -o gpurun_out/gram_cfg2_$TAG python bench.py --workload gram --steps 1 --warmup 1 --no-also > gpurun_out/ncu_gram_$TAG.log 2>&1
 python tools/configs_full.py all > gpurun_out/configs_full_$TAG.jsonl 2>&1
 python tools/quickbench.py all > gpurun_out/quickbench_$TAG.jsonl 2>&1
+python tools/profile_target.py kgrad_tc > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:kgrad_tc_kernel -c 1 -s 1 -o gpurun_out/kgrad_tc_$TAG python tools/profile_target.py kgrad_tc > gpurun_out/ncu_kgrad_tc_$TAG.log 2>&1
 tail -c 300 gpurun_out/bench_$TAG.json; tail -3 gpurun_out/configs_full_$TAG.jsonl
