@@ -153,3 +153,22 @@ def test_tc_path_with_sum_and_mean_over_rows(kname, rr, force):
         truth, bound = truth / N, bound / N
     assert_kmatw_close(T.cpu().numpy(), truth, bound, f"tc {kname} reduce {rr}")
     assert_kmatw_close(F.cpu().numpy(), truth, bound, f"fp32 {kname} reduce {rr}")
+
+
+@pytest.mark.parametrize("M", [4288, 4109, 6000, 8192 + 64 * 3])
+def test_tc2_every_row_with_several_units_per_cta(M):
+    """More 128-row units than CTAs and tile counts with every residue modulo the warps per lane quarter: EVERY row of the
+    tensor-core forward against the FP32-pipe kernel (tolerance from the accumulated magnitude K @ |W|), and the same call
+    twice bit for bit."""
+    N, d, m = 50000, 16, 16
+    g = torch.Generator(device="cuda").manual_seed(M)
+    X, Y, W = (torch.randn(n_, c_, generator=g, device="cuda") for n_, c_ in ((N, d), (M, d), (M, m)))
+    scale, nconst = 0.70710695 / 4, 0.1
+    assert nat.lib().jrk_kmatw_uses_tensor_cores(N, M, d, m, 0, 0) == 1
+    t1 = nat.kmatw(X, Y, W, scale, 2.0, nconst)
+    t2 = nat.kmatw(X, Y, W, scale, 2.0, nconst)
+    assert torch.equal(t1, t2)
+    with nat.option(nat.OPT_KMATW_TC, 0):
+        t0 = nat.kmatw(X, Y, W, scale, 2.0, nconst)
+        bound = nat.kmatw(X, Y, W.abs(), scale, 2.0, nconst)
+    assert bool(((t1 - t0).abs() <= 2e-6 + 3e-5 * bound).all())
