@@ -453,14 +453,14 @@ def run_kmatw_mean(args, torch, nat, dist_ctx):
 
 
 def run_kmatw_backward(args, torch, nat, dist_ctx):
-    """The K@W vector-Jacobian product (dX and dscale rows) at cfg3's M, d, m on a 151552-row block per run (strong: split
-    over the ranks): jrk_kmatw_grad_f32 -> csrc/kgrad_tc.cu (both inner products on tcgen05, d + 2 FP32 accumulations per
-    pair).  Kernel-only; the roofline is the FP32 pipe at d + 2 lane-operations per pair."""
+    """The K@W vector-Jacobian product (dX and dscale rows) at cfg3's M, d, m on a 151552-row block of X PER GPU (weak: four
+    256-row units per SM on every rank): jrk_kmatw_grad_f32 -> csrc/kgrad_tc.cu (both inner products on tcgen05, d + 2 FP32
+    accumulations per pair).  Kernel-only; the roofline is the FP32 pipe at d + 2 lane-operations per pair."""
     rank, world, dev = dist_ctx
     w = WORKLOADS["kmatw"]
     M, d, m = w["M"], w["d"], w["m"]
-    n_total = 148 * 256 * 4
-    n_local = n_total // world
+    n_local = 148 * 256 * 4
+    n_total = n_local * world
     scale, power, nconst = kernel_params(d)
 
     def randn(seed, *shape):
@@ -482,11 +482,11 @@ def run_kmatw_backward(args, torch, nat, dist_ctx):
     pk = fp32_pipe_peak()
     achieved = float(n_local) * M / (t_local / steps) * (d + 2)
     assert bool(torch.isfinite(keep["g"][0]).all())
-    return {"value": float(n_total) * M / t_step, "unit": "pairs/s", "ms_per_step": t_step * 1e3, "steps": steps, "scaling": "strong",
+    return {"value": float(n_total) * M / t_step, "unit": "pairs/s", "ms_per_step": t_step * 1e3, "steps": steps, "scaling": "weak",
             "roofline": {"bound": "fp32", "achieved": achieved / 1e12, "peak": pk[0] / 1e12, "unit": "T lane-ops/s",
                          "frac": achieved / pk[0], "traffic": None, "peak_source": pk[1], "lane_ops_per_pair": d + 2},
             "clocks": clocks, "gpu_launches": int(launches),
-            "config": {"workload": "backward of configs[2]: dX and dscale of K(X,Y)@W for a 151552-row block of X",
+            "config": {"workload": "backward of configs[2]: dX and dscale of K(X,Y)@W for a 151552-row block of X per GPU",
                        "rows_per_gpu": n_local, "global_rows": n_total, "M": M, "d": d, "m": m,
                        "kernel": "kgrad_tc.cu (tcgen05 inner products, FP32 accumulation)"}}
 
