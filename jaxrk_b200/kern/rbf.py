@@ -95,7 +95,8 @@ class GenGaussKernel(DensityKernel):
         X = as2d(X)
         Y = None if Y is None else as2d(Y, X.device)
         args = self.kernel_args()
-        if not diag and self.dim_scale_tensor is not None and self.wants_grad(X, Y):
+        if not diag and self.dim_scale_tensor is not None:
+            # a kernel made from a TENSOR of per-dimension length scales: one definition with and without autograd
             return self._call_dim_scale_grad(X, Y)
         if diag or args is None:
             if self.wants_grad(X, Y):
@@ -120,9 +121,9 @@ class GenGaussKernel(DensityKernel):
     def grad_inputs(self, X, Y):
         """(X', Y', scale argument, power argument, nconst argument) for the differentiable entry points of
         jaxrk_b200/autograd.py: per-dimension scales become a pre-scaling of the points (torch differentiates the
-        multiplication), and the reference's (1, d) normalising constant (quirk Q2: rbf.py:34 over a per-dimension scale)
-        is not reproduced under autograd -- the differentiable per-dimension kernel is exp(-||s * (x - y)||^p) times the
-        constant of a unit global scale."""
+        multiplication).  The reference's normalising constant for a per-dimension scale is a (1, d) array (quirk Q2:
+        rbf.py:34) that only broadcasts against an N x d Gram; a kernel made from a tensor of length scales is defined here
+        as  exp(-||(x - y) / length_scale||^p)  times the constant of a unit global scale -- with and without autograd."""
         pw = self.power_tensor if self.power_tensor is not None else float(self.dist.power)
         if self.dim_scale_tensor is not None:
             ds = self.dim_scale_tensor.to(X.device)

@@ -365,6 +365,8 @@ def test_api_gradients_to_shape_and_per_dimension_length_scales():
     (Kv64 * torch.tensor(Cn, dtype=torch.float64)).sum().backward()
     np.testing.assert_allclose(Kv.detach().cpu().numpy(), Kv64.detach().numpy(), rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(lsv.grad.cpu().numpy(), lsv64.grad.numpy(), rtol=3e-4, atol=3e-5)
+    with torch.no_grad():                                  # the same kernel object gives the same numbers without autograd
+        assert torch.equal(kv(cu(Xn), cu(Yn)), Kv.detach())
 
 
 @pytest.mark.parametrize("N,M,d,ls,positive", [(8192, 8192, 16, 4.0, False), (4096 + 300, 4096 + 12, 7, 2.5, True),
