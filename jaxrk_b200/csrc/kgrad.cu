@@ -21,6 +21,7 @@
 // the j range is split over blockIdx.y when there are few rows, partial sums are combined in a fixed order by
 // kgrad_finalize_kernel (deterministic, no float atomics).  FP32-pipe bound: 3d + m + ~8 lane-ops per pair (MODE 0).
 #include "common.cuh"
+#include "kmatw_tc2.cuh"
 
 namespace jrk {
 namespace tf32 { int tf_sm_count(); }
@@ -35,10 +36,8 @@ int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, flo
 
 namespace {
 
-// the regime test of kmatw_tc2.cuh (TC_FAST_BOUND = 12) on the two norm maxima of the pre-pass
-__device__ __forceinline__ bool kg_fast_regime(const unsigned* nmax) {
-    return (__uint_as_float(__ldg(nmax)) + __uint_as_float(__ldg(nmax + 1))) <= 12.0f;
-}
+// the regime test of kmatw_tc2.cuh on the two norm maxima of the pre-pass
+__device__ __forceinline__ bool kg_fast_regime(const unsigned* nmax) { return tc2_fast_regime(nmax); }
 
 constexpr int KG_ROWS = 128, KG_TJ = 32;
 

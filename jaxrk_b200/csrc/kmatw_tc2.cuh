@@ -9,7 +9,11 @@ namespace jrk {
 
 // p = 2 "factored" regime: |c| (max|x|^2 + max|y|^2) <= TC_FAST_BOUND, decided on the device from the pre-pass maxima
 // (no host synchronisation).  There K_ij = 2^(c|x_i|^2) . 2^(-2c x_i.y_j) . 2^(c|y_j|^2) with every factor inside
-// [2^-12, 2^12].
+// [2^-12, 2^12].  (What limits the bound: e = 2^S is handed to GEMM2 as fp16 hi / lo' with lo' = (e - hi) 2^11 < 2 ulp11(e)
+// 2^10, which reaches fp16's maximum for e >= 2^15 -- so S must stay below 15 -- and the exponent error of the 3-term
+// fp16 GEMM1 grows with the bound.  Measured up to 15.4 with adversarial aligned / opposed large-norm pairs
+// (tools/regime_edge_check.py): 0.18 - 0.24 of the tolerance, the generic epilogue 0.24 - 0.34; 12 keeps a factor of 8 below
+// the overflow.)
 constexpr float TC_FAST_BOUND = 12.0f;
 
 __device__ __forceinline__ bool tc2_fast_regime(const unsigned* nmax) {
