@@ -188,7 +188,8 @@ int jrk_gram_affine_f32(const float *K, float *out, int64_t N, int64_t M, int64_
 
 /* 1 when jrk_kmatw_f32 would run both contractions of this problem on the tensor cores (kmatw_tc.cu / kmatw_tc2.cu:
  * d <= 32, any m (column blocks of 16), no per-dimension scale, row_reduce NONE / SUM / MEAN, N >= 8192, M >= 4096,
- * JRK_OPT_KMATW_TC != 0), else 0 (FP32-pipe kernel).
+ * JRK_OPT_KMATW_TC != 0), else 0 (FP32-pipe kernel).  (32 < d <= 64 with power = 2 and row_reduce NONE also runs on the
+ * tensor cores when the data lie inside the factored regime -- known on the device only, so this function answers 0.)
  * Introspection only (bench.py picks the roofline by it); results agree within the documented tolerance. */
 int jrk_kmatw_uses_tensor_cores(int64_t N, int64_t M, int d, int m, int has_dim_scale, int row_reduce);
 

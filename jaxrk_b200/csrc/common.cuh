@@ -114,6 +114,9 @@ struct EpiParams {
     float a0;      // PERIODIC: 1 / length_scale;  THRESHSPIKE: (threshold^(1/p) / s)^2, the threshold on r^2
     float a1;      // THRESHSPIKE: spike
     float a2;      // THRESHSPIKE: non_spike
+    // kmatw.cu only: when set, the FP32-pipe K@W kernel returns at once inside the factored regime of kmatw_tc2.cuh (the
+    // tensor-core kernel enqueued next to it has written the result); two norm maxima, as bit patterns
+    const unsigned* skip_if_fast = nullptr;
 };
 
 // The sibling-kernel entry points (capi.cu) reuse the GenGauss launchers: the selector travels as an explicit argument

@@ -34,6 +34,10 @@ namespace jrk {
 // tensor-core variant (kmatw_tc.cu)
 bool kmatw_tc_eligible(int64_t N, int64_t M, int d, int m, const float* dim_scale, int row_reduce, float nconst);
 size_t kmatw_tc_workspace_bytes(int64_t N, int64_t M);
+size_t kmatw_tc64_workspace_bytes(int64_t N, int64_t M);
+int kmatw_tc64(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
+               int64_t ldy, int64_t ldw, int64_t ldo, float c, float nconst, const float* row_pref, const float* col_pref,
+               void* scratch, const unsigned** nmax_out, cudaStream_t st);
 int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
              int64_t ldy, int64_t ldw, int64_t ldo, float scale, float power, float nconst, const float* row_pref,
              const float* col_pref, int row_reduce, void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -42,7 +46,8 @@ int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t
 // (fixed summation order: deterministic).  part is [nsplit][rows][MT].
 __global__ void kw_finalize_kernel(const float* __restrict__ part, int nsplit, int64_t rows, int MT,
                                    int64_t group, float scale, float* __restrict__ out, int64_t ldo, int m,
-                                   int64_t ngroups) {
+                                   int64_t ngroups, const unsigned* __restrict__ skip_if_fast) {
+    if (skip_if_fast && tc2_fast_regime(skip_if_fast)) return;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= ngroups * m) return;
     const int64_t g = idx / m;
@@ -123,6 +128,7 @@ size_t kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce,
         const size_t t = kmatw_tc_workspace_bytes(N, M);
         if (t > total) total = t;
     }
+    if (d > 32 && d <= 64 && N >= 8192 && M >= 4096) total += kmatw_tc64_workspace_bytes(N, M) + 256;
     return total + 1024;
 }
 
@@ -131,9 +137,10 @@ static int kmatw_block(const float* X, const float* Y, const float* W, float* ou
                        int m, int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale,
                        const float* dim_scale, float power, float nconst, const float* row_pref,
                        const float* col_pref, int row_reduce, int64_t group, const ExtraKind& ex, Scratch& scr,
-                       cudaStream_t st) {
+                       cudaStream_t st, const unsigned* skip_if_fast = nullptr) {
     const KwPlan p = kw_plan(N, M, d, m);
-    const EpiParams ep = make_epi(scale, power, nconst, ex);
+    EpiParams ep = make_epi(scale, power, nconst, ex);
+    ep.skip_if_fast = skip_if_fast;
     const int pm = pick_pmode(power, ex);
 
     // ---- operands: dense, padded, pre-scaled copies where the caller's layout differs -----
@@ -198,7 +205,7 @@ static int kmatw_block(const float* X, const float* Y, const float* W, float* ou
         }
         const int64_t tot = ngroups * m;
         kw_finalize_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(kout, p.nsplit, part_rows, p.MT, fgroup,
-                                                                          fscale, out, ldo, m, ngroups);
+                                                                          fscale, out, ldo, m, ngroups, skip_if_fast);
         JRK_LAUNCHED();
     }
     return JRK_OK;
@@ -213,11 +220,38 @@ bool kmatw_uses_tc(int64_t N, int64_t M, int d, int m, bool has_dim_scale, int r
     return kmatw_tc_eligible(N, M, d, m, has_dim_scale ? &dummy : nullptr, row_reduce, 1.f);
 }
 
+// 32 < d <= 64, p = 2, plain problem: the second-generation tensor-core kernel with four GEMM1 k-steps serves the factored
+// regime (decided on the device); the FP32-pipe kernel is enqueued behind it and returns at once there.
+bool kmatw_tc64_eligible(int64_t N, int64_t M, int d, int m, bool has_dim_scale, float power, int row_reduce, const ExtraKind& ex) {
+    return jrk_option(JRK_OPT_KMATW_TC) != 0 && jrk_option(JRK_OPT_TC_FAST) != 0 && jrk_option(JRK_OPT_TC_V2) != 0 &&
+           ex.kind == 0 && !has_dim_scale && pick_pmode(power) == PM_SQEXP && d > 32 && d <= 64 && m >= 1 &&
+           row_reduce == JRK_REDUCE_NONE && N >= 8192 && M >= 4096 && M <= ((int64_t)1 << 30);
+}
+
 int kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,
           int64_t ldx, int64_t ldy, int64_t ldw, int64_t ldo, float scale, const float* dim_scale, float power,
           float nconst, const float* row_pref, const float* col_pref, int row_reduce, int64_t group,
           const ExtraKind& ex, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (d > 128) return fail(JRK_ERR_UNSUPPORTED, "kmatw: d = %d > 128 not supported by the fused kernel", d);
+    if (kmatw_tc64_eligible(N, M, d, m, dim_scale != nullptr, power, row_reduce, ex)) {
+        Scratch scr(workspace, workspace_bytes, st);
+        JRK_CUDA_OK(scr.reserve(kmatw_workspace_bytes(N, M, d, m, row_reduce, group)));
+        void* tcs = scr.take<char>(kmatw_tc64_workspace_bytes(N, M));
+        const size_t base = scr.used;
+        const EpiParams ep = make_epi(scale, power, nconst);
+        for (int c0 = 0; c0 < m; c0 += 16) {        // the tensor-core kernel: column blocks of 16
+            const int mb = (m - c0 < 16) ? m - c0 : 16;
+            const unsigned* skip = nullptr;
+            if (int rc = kmatw_tc64(X, Y, W + c0, out + c0, N, M, d, mb, ldx, ldy, ldw, ldo, ep.c, nconst, row_pref, col_pref, tcs,
+                                    &skip, st))
+                return rc;
+            scr.used = base;
+            if (int rc = kmatw_block(X, Y, W + c0, out + c0, N, M, d, mb, ldx, ldy, ldw, ldo, scale, dim_scale, power, nconst,
+                                     row_pref, col_pref, row_reduce, group, ex, scr, st, skip))
+                return rc;
+        }
+        return JRK_OK;
+    }
     // both contractions on the tensor cores when the problem is large, narrow and plain (kmatw_tc.cu)
     if (kmatw_uses_tc(N, M, d, m, dim_scale != nullptr, row_reduce, ex))
         return kmatw_tc(X, Y, W, out, N, M, d, m, ldx, ldy, ldw, ldo, scale, power, nconst, row_pref, col_pref,

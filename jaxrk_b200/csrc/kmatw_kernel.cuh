@@ -2,6 +2,7 @@
 // in kmatw_pm{0,1,2,3}.cu so that the 72 instantiations compile in parallel.
 #pragma once
 #include "common.cuh"
+#include "kmatw_tc2.cuh"
 
 namespace jrk {
 
@@ -26,6 +27,7 @@ kmatw_kernel(const float* __restrict__ X, int64_t ldx, int d, const float* __res
              float* __restrict__ out, int64_t ldo, int64_t out_split_stride,
              int64_t N, int64_t M, int m, int tiles_per_split,
              const float* __restrict__ row_pref, EpiParams ep, int epi_mode, int x_vec) {
+    if (ep.skip_if_fast && tc2_fast_regime(ep.skip_if_fast)) return;     // kmatw_tc2_kernel<4, 4> serves the problem
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_base = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + KwSmem<D, MT, RI>::kBarOff);

@@ -57,6 +57,21 @@ constexpr int T2_SOP = 12;                    // operand (tile image) stages in 
 constexpr int T2_STAGE = 12288;               // stage stride: the 12 KB image of 16 < d <= 32
 constexpr int T2_EPQ_MAX = 4;
 constexpr int T2_COL_X = 0, T2_COL_XLO = 16, T2_COL_O = 32, T2_COL_S = 128;
+// What depends on the number of GEMM1 k-steps KS (16 features each): KS = 1 (d <= 16, 8 KB packed image), 2 (d <= 32,
+// 12 KB), 4 (d <= 64, 20 KB: [Y hi 64 x 128 B][Y lo 64 x 128 B][W' 32 x 128 B]).  KS = 4 parks 32 + 32 columns of x~, so the
+// O windows and the S / e stages move up and one stage goes: x~ [0, 64) | O [64, 160) | five stages [160, 480).
+template <int KS>
+struct T2V {
+    static constexpr int COL_XLO = KS == 4 ? 32 : T2_COL_XLO;
+    static constexpr int COL_O = KS == 4 ? 64 : T2_COL_O;
+    static constexpr int COL_S = KS == 4 ? 160 : T2_COL_S;
+    static constexpr int NS = KS == 4 ? 5 : T2_NS;
+    static constexpr int SOP = KS == 4 ? 7 : T2_SOP;
+    static constexpr int STAGE = KS == 4 ? 20480 : T2_STAGE;
+    static constexpr int YLO = KS == 1 ? 2 : (KS == 2 ? 4 : 512);            // Y lo against Y hi, in 16-byte units
+    static constexpr int WOFF = KS == 4 ? 1024 : 512;                         // W' region (KS >= 2), in 16-byte units
+    static_assert(COL_S + NS * 64 <= 512 && COL_O + T2_NOB * 32 <= COL_S && SOP * STAGE <= T2_SOP * T2_STAGE, "budget");
+};
 constexpr int T2_OFF_RED = T2_SOP * T2_STAGE;                            // per-warp partial results of a unit (2 buffers)
 constexpr int T2_RED_WARP = T2_MT * 32 * 4;                              // [16 columns][32 lanes] floats
 constexpr int T2_OFF_BAR = T2_OFF_RED + 2 * 4 * T2_EPQ_MAX * T2_RED_WARP;
@@ -103,13 +118,14 @@ struct Tc2Params {
 };
 constexpr int T2_TRACE_TILES = 512;  // stamps per warp: [warp][tile][4]
 
-// EPQ: epilogue warps per TMEM lane quarter (= per SM sub-partition);  WIDE: 16 < d <= 32 (two k-steps in GEMM1, 12 KB
+// EPQ: epilogue warps per TMEM lane quarter (= per SM sub-partition);  KS: GEMM1 k-steps, 2 for 16 < d <= 32 (12 KB
 // images) -- compile-time, because the two MMA-issuing warps are serial latency chains (one elected thread each): every
 // instruction on their per-tile path counts (the first version spent ~430 clk per tile issuing 3 MMAs, and was what
 // bounded the kernel: tools/tc2_trace.py)
-template <int EPQ, bool WIDE, bool TRACE = false>
+template <int EPQ, int KS, bool TRACE = false>
 __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Params P) {
     if (!tc2_fast_regime(P.nmax)) return;     // the generic kernel (kmatw_tc.cu) serves the problem
+    using V = T2V<KS>;
     constexpr int EW = 4 * EPQ;
     extern __shared__ unsigned char t2_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(t2_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -161,11 +177,11 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
         const uint32_t bytes = (uint32_t)P.img_bytes;
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
             for (int t = 0; t < T; ++t, ++tc) {
-                const int s = tc % T2_SOP;
-                mbar_wait_hint(&op_empty[s], ((tc / T2_SOP) & 1) ^ 1);
+                const int s = tc % V::SOP;
+                mbar_wait_hint(&op_empty[s], ((tc / V::SOP) & 1) ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&op_full[s], bytes);
-                    bulk_g2s(smem + s * T2_STAGE, P.img + (int64_t)t * bytes, bytes, &op_full[s]);
+                    bulk_g2s(smem + s * V::STAGE, P.img + (int64_t)t * bytes, bytes, &op_full[s]);
                 }
                 __syncwarp();
             }
@@ -176,7 +192,7 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
         constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(T2_NT >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);       // N = 64
         constexpr uint32_t id16 = (1u << 4) | ((uint32_t)(T2_MT >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);         // N = 16
         constexpr uint32_t id32 = (1u << 4) | ((uint32_t)((2 * T2_MT) >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);   // N = 32
-        constexpr uint64_t YLO = WIDE ? 4 : 2;                       // Y lo: 64 or 32 bytes further inside the rows
+        constexpr uint64_t YLO = V::YLO;                             // Y lo: 32 / 64 bytes further inside the rows, or its own region
         const uint64_t dbase = make_b_desc(smem_u32(smem));
         const uint32_t b_opfull = smem_u32(op_full), b_opempty = smem_u32(op_empty), b_sfull = smem_u32(s_full),
                        b_eready = smem_u32(e_ready), b_sempty = smem_u32(s_empty), b_ofull = smem_u32(o_full),
@@ -199,26 +215,27 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
                 const int t0 = n * T2_WIN, t1 = (t0 + T2_WIN < T) ? t0 + T2_WIN : T;
                 // ---- GEMM1:  S[stage] = x~ . y''  (fp16 hi / lo, one accumulator) ----
                 for (int t = t0; t < t1; ++t) {
-                    const uint32_t g = gt + (uint32_t)t, s = g % T2_SOP, a = g % T2_NS;
+                    const uint32_t g = gt + (uint32_t)t, s = g % V::SOP, a = g % V::NS;
                     const long long tr0 = TRACE ? clock64() : 0;
-                    bar_wait(b_opfull + s * 8, (g / T2_SOP) & 1);
+                    bar_wait(b_opfull + s * 8, (g / V::SOP) & 1);
                     const long long tr1 = TRACE ? clock64() : 0;
-                    bar_wait(b_sempty + a * 8, ((g / T2_NS) & 1) ^ 1);
+                    bar_wait(b_sempty + a * 8, ((g / V::NS) & 1) ^ 1);
                     tc_fence_after();
                     const long long tr2 = TRACE ? clock64() : 0;
-                    const uint64_t dy = dbase + (uint64_t)((s * T2_STAGE) >> 4);
-                    const uint32_t cs = T2_COL_S + a * 64;
+                    const uint64_t dy = dbase + (uint64_t)((s * V::STAGE) >> 4);
+                    const uint32_t cs = V::COL_S + a * 64;
                     if (elect_one()) {
                         // the small cross terms first, the hi.hi terms last: the accumulator truncates, so only the last
                         // additions carry a rounding error that matters
                         mma_f16_ts(cs, T2_COL_X, dy + YLO, idesc1, 0u);                        // hi_x . lo_y
-                        mma_f16_ts(cs, T2_COL_XLO, dy, idesc1, 1u);                            // lo_x . hi_y
-                        if (WIDE) {
-                            mma_f16_ts(cs, T2_COL_X + 8, dy + YLO + 2, idesc1, 1u);
-                            mma_f16_ts(cs, T2_COL_XLO + 8, dy + 2, idesc1, 1u);
+                        mma_f16_ts(cs, V::COL_XLO, dy, idesc1, 1u);                            // lo_x . hi_y
+#pragma unroll
+                        for (int q = 1; q < KS; ++q) {
+                            mma_f16_ts(cs, T2_COL_X + 8 * q, dy + YLO + 2 * q, idesc1, 1u);
+                            mma_f16_ts(cs, V::COL_XLO + 8 * q, dy + 2 * q, idesc1, 1u);
                         }
-                        mma_f16_ts(cs, T2_COL_X, dy, idesc1, 1u);                              // hi_x . hi_y
-                        if (WIDE) mma_f16_ts(cs, T2_COL_X + 8, dy + 2, idesc1, 1u);
+#pragma unroll
+                        for (int q = 0; q < KS; ++q) mma_f16_ts(cs, T2_COL_X + 8 * q, dy + 2 * q, idesc1, 1u);   // hi_x . hi_y
                         commit_addr(b_sfull + a * 8);
                     }
                     __syncwarp();
@@ -232,24 +249,24 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
                 __syncwarp();
                 // ---- GEMM2:  O[window] += e . W'  (fp16 hi / lo' operands) ----
                 const uint32_t w = wg, ob = w % T2_NOB;
-                const uint32_t oc = T2_COL_O + ob * 32, ox = oc + T2_MT;
+                const uint32_t oc = V::COL_O + ob * 32, ox = oc + T2_MT;
                 const long long tq0 = TRACE ? clock64() : 0;
                 bar_wait(b_oempty + ob * 8, ((w / T2_NOB) & 1) ^ 1);
                 for (int t = t0; t < t1; ++t) {
-                    const uint32_t g = gt + (uint32_t)t, s = g % T2_SOP, a = g % T2_NS;
+                    const uint32_t g = gt + (uint32_t)t, s = g % V::SOP, a = g % V::NS;
                     const long long tr1 = TRACE ? clock64() : 0;
-                    bar_wait(b_eready + a * 8, (g / T2_NS) & 1);      // (this thread has already seen op_full of the tile)
+                    bar_wait(b_eready + a * 8, (g / V::NS) & 1);      // (this thread has already seen op_full of the tile)
                     tc_fence_after();
                     const long long tr2 = TRACE ? clock64() : 0;
-                    const uint64_t dw = dbase + (uint64_t)((s * T2_STAGE) >> 4);
-                    const uint32_t eh = T2_COL_S + a * 64;
+                    const uint64_t dw = dbase + (uint64_t)((s * V::STAGE) >> 4);
+                    const uint32_t eh = V::COL_S + a * 64;
                     if (elect_one()) {
                         // an MMA of N <= 32 costs the same whatever N is: e_hi meets [W'_hi ; W'_lo'] (stacked rows) in ONE
                         // MMA whose 32 result columns are {main | cross}
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             // offset (16-byte units) of the W' operand of k-step q in the image; W'_lo' sits 16 rows = 2048 B further
-                            const uint64_t dq = dw + (uint64_t)(WIDE ? (512 + 2 * q) : ((q >> 1) * 256 + 4 + 2 * (q & 1)));
+                            const uint64_t dq = dw + (uint64_t)(KS > 1 ? (V::WOFF + 2 * q) : ((q >> 1) * 256 + 4 + 2 * (q & 1)));
                             if (q == 0) mma_f16_ts(oc, eh, dq, id32, t == t0 ? 0u : 1u);    // e_hi . [W'_hi ; W'_lo'] -> {main | cross}
                             else mma_f16_ts(oc, eh + 16 * q, dq, id32, 1u);
                             mma_f16_ts(ox, eh + 16 * q + 8, dq, id16, 1u);                  // e_lo' . W'_hi -> cross
@@ -295,7 +312,7 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
         auto park_x = [&](int u) {
             // x~ = x 2^-r as fp16 hi / lo (unscaled lo): 16 values -> 8 packed columns; warps 0 and 1 of the quarter
             const int64_t i = (int64_t)u * T2_BM + quad * 32 + lane;
-            if (k * 16 < P.d) {
+            if (k < KS) {       // every k-step GEMM1 issues must hold data or zeros: TMEM is not cleared between kernels
                 const bool iok = i < P.N;
                 const float* xrow = P.X + (iok ? i : 0) * P.ldx;
                 uint32_t hi[8], lo[8];
@@ -307,7 +324,7 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
                     split_h16u_pair(v0 * P.x_scale, v1 * P.x_scale, hi[q], lo[q]);
                 }
                 tmem_st8(lane_base + T2_COL_X + k * 8, hi);
-                tmem_st8(lane_base + T2_COL_XLO + k * 8, lo);
+                tmem_st8(lane_base + V::COL_XLO + k * 8, lo);
                 tmem_st_wait();
             }
             tc_fence_before();
@@ -328,8 +345,8 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
                 bar_wait(b_ofull + ob * 8, (w / T2_NOB) & 1);
                 tc_fence_after();
                 uint32_t o[16], ox[16];
-                ld16_async(lane_base + T2_COL_O + ob * 32, o);
-                ld16_async(lane_base + T2_COL_O + ob * 32 + T2_MT, ox);
+                ld16_async(lane_base + V::COL_O + ob * 32, o);
+                ld16_async(lane_base + V::COL_O + ob * 32 + T2_MT, ox);
                 ld16_wait(o);
                 ld16_wait(ox);
                 tc_fence_before();
@@ -340,7 +357,7 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
                 next_w += EPQ;
             };
             for (int t = k; t < T; t += EPQ) {
-                const uint32_t g = gt + (uint32_t)t, a = g % T2_NS;
+                const uint32_t g = gt + (uint32_t)t, a = g % V::NS;
                 const long long tr0 = TRACE ? clock64() : 0;
                 if (token_rel && (t > 0 || uc > 0)) {
                     // EVERY tile but the very first waits for its predecessor, across unit boundaries too: a parity wait
@@ -353,10 +370,10 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
                     const uint32_t idx = (t > 0 ? uc : uc - 1) * tpu_q + (uint32_t)(tp / EPQ);   // ... and which of its arrivals
                     bar_wait(b_half + kq * 8, idx & 1);
                 }
-                bar_wait(b_sfull + a * 8, (g / T2_NS) & 1);
+                bar_wait(b_sfull + a * 8, (g / V::NS) & 1);
                 tc_fence_after();
                 const long long tr1 = TRACE ? clock64() : 0;
-                const uint32_t sc = lane_base + T2_COL_S + a * 64;
+                const uint32_t sc = lane_base + V::COL_S + a * 64;
                 // four chunks of 16 S columns -> 8 + 8 columns of e pairs, in place; the next chunk's load is in flight
                 // while the current one goes through the MUFU
                 uint32_t s0[16], s1[16], eo[16];
@@ -449,17 +466,24 @@ __global__ void tc2_pack_kernel(const float* __restrict__ Y, int64_t M, int d, i
     const int64_t t = idx / cpt;
     const int p = (int)(idx % cpt);
     const int rr = (p >> 3), cph = p & 7;
-    const int r = rr & 63;                       // row inside its region (Y region: 64 rows; wide W region: 32 rows)
+    const int r = rr & 63;                       // row inside its region (Y regions: 64 rows; W' region: 32 rows)
     const int cl = cph ^ (r & 7);                // logical 16-byte chunk of the row
-    const bool wregion = p >= 512;               // wide layout only
+    const bool ks4 = img_bytes == 20480;         // d <= 64: [Y hi 512 chunks][Y lo 512 chunks][W' 256 chunks]
+    const bool wregion = ks4 ? p >= 1024 : p >= 512;
     float v[8];
     bool is_w, is_lo;
     if (!wregion && (packed ? cl < 4 : true)) {
         // ---- Y: 8 consecutive features of row j ----
         is_w = false;
-        const int half = packed ? 2 : 4;
-        is_lo = cl >= half;
-        const int k0 = 8 * (cl - (is_lo ? half : 0));
+        int k0;
+        if (ks4) {
+            is_lo = p >= 512;
+            k0 = 8 * cl;
+        } else {
+            const int half = packed ? 2 : 4;
+            is_lo = cl >= half;
+            k0 = 8 * (cl - (is_lo ? half : 0));
+        }
         const int64_t j = t * T2_NT + r;
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = (j < M && k0 + q < d) ? __ldg(Y + j * ldy + k0 + q) * y_scale : 0.f;
@@ -516,6 +540,24 @@ __global__ void tc2_wmax_kernel(const float* __restrict__ W, int64_t M, int m, i
     if ((threadIdx.x & 31) == 0 && mx == mx && mx < 3.0e38f) atomicMax(gmax, __float_as_uint(mx));
 }
 
+// out[r] = c |row r|^2;  *gmax = max |c| |row|^2 (atomicMax on the bit pattern)
+__global__ void tc2_rownorm_kernel(const float* __restrict__ A, int64_t rows, int d, int64_t lda, float c,
+                                   float* __restrict__ out, unsigned* __restrict__ gmax) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float q = 0.f;
+    if (r < rows) {
+        for (int k = 0; k < d; ++k) {
+            const float v = __ldg(A + r * lda + k);
+            q = fmaf(v, v, q);
+        }
+        out[r] = c * q;
+    }
+    float mx = fabsf(c) * q;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx == mx) atomicMax(gmax, __float_as_uint(mx));
+}
+
 }  // namespace
 
 // debugging aid of tools/tc2_trace.py (not part of the C ABI in include/jrk.h): a device buffer of
@@ -523,7 +565,7 @@ __global__ void tc2_wmax_kernel(const float* __restrict__ W, int64_t M, int m, i
 static long long* g_tc2_trace = nullptr;
 extern "C" void jrk_debug_tc2_trace(void* device_buffer) { g_tc2_trace = (long long*)device_buffer; }
 
-int tc2_image_bytes(int d) { return d <= 16 ? 8192 : 12288; }
+int tc2_image_bytes(int d) { return d <= 16 ? 8192 : (d <= 32 ? 12288 : 20480); }
 
 // W maximum (nmax[2]) + tile images of the factored regime.  nmax[0..1] (norm maxima) and yn_all must already be
 // enqueued on `st`.  Both kernels return at once outside the factored regime.
@@ -564,25 +606,54 @@ int kmatw_tc2_apply(const float* X, int64_t N, int d, int64_t ldx, const float* 
     const int grid = P.n_units < tf_sm_count() ? P.n_units : tf_sm_count();
     // epilogue warps per SM sub-partition: 4; JRK_TC2_EPQ = 3 for A/B runs
     const int epq = jrk_option(JRK_OPT_TC2_EPQ);
-#define T2_LAUNCH(EPQ_, WIDE_, TRACE_)                                                                               \
+#define T2_LAUNCH(EPQ_, KS_, TRACE_)                                                                                 \
     do {                                                                                                             \
-        JRK_CUDA_OK(cudaFuncSetAttribute(kmatw_tc2_kernel<EPQ_, WIDE_, TRACE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        JRK_CUDA_OK(cudaFuncSetAttribute(kmatw_tc2_kernel<EPQ_, KS_, TRACE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          T2_SMEM));                                                                  \
-        kmatw_tc2_kernel<EPQ_, WIDE_, TRACE_><<<grid, (5 + 4 * EPQ_) * 32, T2_SMEM, st>>>(P);                         \
+        kmatw_tc2_kernel<EPQ_, KS_, TRACE_><<<grid, (5 + 4 * EPQ_) * 32, T2_SMEM, st>>>(P);                           \
     } while (0)
-    const bool wide = d > 16;
+    const int ks = d <= 16 ? 1 : (d <= 32 ? 2 : 4);
     if (g_tc2_trace) {
-        if (epq == 4) T2_LAUNCH(4, false, true);
-        else T2_LAUNCH(3, false, true);
+        if (epq == 4) T2_LAUNCH(4, 1, true);
+        else T2_LAUNCH(3, 1, true);
+    } else if (ks == 4) {
+        T2_LAUNCH(4, 4, false);                 // the x~ block of d <= 64 needs four parking warps per lane quarter
     } else if (epq == 3) {
-        if (wide) T2_LAUNCH(3, true, false);
-        else T2_LAUNCH(3, false, false);
+        if (ks == 2) T2_LAUNCH(3, 2, false);
+        else T2_LAUNCH(3, 1, false);
     } else {
-        if (wide) T2_LAUNCH(4, true, false);
-        else T2_LAUNCH(4, false, false);
+        if (ks == 2) T2_LAUNCH(4, 2, false);
+        else T2_LAUNCH(4, 1, false);
     }
 #undef T2_LAUNCH
     JRK_LAUNCHED();
+    return JRK_OK;
+}
+
+// ---- 32 < d <= 64: a self-contained path (norm pre-pass, images, kernel) for one block of <= 16 columns of W.  Outside the
+// factored regime every kernel of it returns at once; *nmax_out is what the caller's FP32-pipe kernel tests to know
+// whether the result is its to write (kmatw.cu). ----
+size_t kmatw_tc64_workspace_bytes(int64_t N, int64_t M) {
+    const int64_t n_tiles = (M + T2_NT - 1) / T2_NT;
+    return align256((size_t)N * 4) + align256((size_t)M * 4) + 256 + align256((size_t)n_tiles * 20480) + 1024;
+}
+
+int kmatw_tc64(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
+               int64_t ldy, int64_t ldw, int64_t ldo, float c, float nconst, const float* row_pref, const float* col_pref,
+               void* scratch, const unsigned** nmax_out, cudaStream_t st) {
+    char* p = (char*)scratch;
+    float* xn = (float*)p; p += align256((size_t)N * 4);
+    float* yn = (float*)p; p += align256((size_t)M * 4);
+    unsigned* nmax = (unsigned*)p; p += 256;
+    unsigned char* img = (unsigned char*)p;
+    JRK_CUDA_OK(cudaMemsetAsync(nmax, 0, 16, st));
+    tc2_rownorm_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(X, N, d, ldx, c, xn, nmax);
+    JRK_LAUNCHED();
+    tc2_rownorm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, c, yn, nmax + 1);
+    JRK_LAUNCHED();
+    if (int rc = kmatw_tc2_pack(Y, W, M, d, m, ldy, ldw, col_pref, c, yn, nmax, img, st)) return rc;
+    if (int rc = kmatw_tc2_apply(X, N, d, ldx, xn, img, M, nmax, c, nconst, row_pref, out, ldo, m, st)) return rc;
+    *nmax_out = nmax;
     return JRK_OK;
 }
 

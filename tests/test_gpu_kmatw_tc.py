@@ -172,3 +172,38 @@ def test_tc2_every_row_with_several_units_per_cta(M):
         t0 = nat.kmatw(X, Y, W, scale, 2.0, nconst)
         bound = nat.kmatw(X, Y, W.abs(), scale, 2.0, nconst)
     assert bool(((t1 - t0).abs() <= 2e-6 + 3e-5 * bound).all())
+
+
+@pytest.mark.parametrize("N,M,d,m,ls,positive", [(16384, 8192, 64, 16, 8.0, False), (50000, 4109, 48, 16, 7.0, True),
+                                                 (16384 + 77, 6000, 33, 5, 6.0, False), (20000, 8192, 64, 24, 8.0, True)])
+def test_tc2_d_up_to_64(N, M, d, m, ls, positive):
+    """32 < d <= 64 (kmatw_tc2_kernel<4, 4>: four GEMM1 k-steps, 20 KB tile images, five S / e stages): sampled rows against
+    float64, EVERY row against the FP32-pipe kernel (several units per CTA for N = 50000), bit-identical repeats."""
+    g = torch.Generator(device="cuda").manual_seed(N + d)
+    X, Y, W = (torch.randn(n_, c_, generator=g, device="cuda") for n_, c_ in ((N, d), (M, d), (M, m)))
+    if positive:
+        W = W.abs()
+    s, nc = float(0.70710695 / ls), 0.25
+    n0 = nat.launch_count()
+    A = nat.kmatw(X, Y, W, s, 2.0, nc)
+    blocks = -(-m // 16)
+    assert nat.launch_count() - n0 >= 6 * blocks          # per column block: 2 norm kernels, W maximum, images, tensor-core
+    assert torch.equal(A, nat.kmatw(X, Y, W, s, 2.0, nc))                               # kernel, FP32-pipe kernel (skipped)
+    with nat.option(nat.OPT_KMATW_TC, 0):
+        R = nat.kmatw(X, Y, W, s, 2.0, nc)
+        bound_all = nat.kmatw(X, Y, W.abs(), s, 2.0, nc)
+    assert bool(((A - R).abs() <= 2e-6 + 3e-5 * bound_all).all())
+    rows = torch.cat([torch.arange(0, 40, device="cuda"), torch.arange(40, N, (N - 40) // 88, device="cuda")[:88]])
+    Kt = nc * torch.exp(-(s * torch.cdist(X[rows].double(), Y.double())) ** 2)
+    T, bound = Kt @ W.double(), Kt @ W.double().abs()
+    assert bool(((A[rows].double() - T).abs() <= 1e-6 + 1e-5 * bound).all())
+
+
+def test_tc2_d64_outside_the_factored_regime_is_the_fp32_kernel():
+    g = torch.Generator(device="cuda").manual_seed(9)
+    X, Y, W = (torch.randn(n_, c_, generator=g, device="cuda") for n_, c_ in ((16384, 64), (8192, 64), (8192, 16)))
+    s = float(0.70710695 / 3.0)                     # |c| (max|x|^2 + max|y|^2) ~ 19 > 12
+    A = nat.kmatw(X, Y, W, s, 2.0, 0.25)
+    with nat.option(nat.OPT_KMATW_TC, 0):
+        R = nat.kmatw(X, Y, W, s, 2.0, 0.25)
+    assert torch.equal(A, R)

@@ -57,6 +57,8 @@ def bench_gram(only_tf32=False):
 def bench_kmatw():
     for (N, M, d, m) in [(131072, 1 << 20, 16, 16), (131072, 1 << 20, 16, 1), (131072, 1 << 20, 8, 16),
                          (131072, 1 << 20, 32, 16), (65536, 1 << 20, 64, 16), (131072, 1 << 20, 16, 32)]:
+        # (s = 1 / sqrt(d): d = 8 falls outside the factored regime -- the generic epilogue; d = 64 inside it runs
+        # kmatw_tc2_kernel<4, 4> for power = 2)
         X, Y, W = randn(0, N, d), randn(1, M, d), randn(2, M, m)
         for power in (2.0, 1.0, 1.5):
             s, p, nc = kp(power, d)
