@@ -336,13 +336,18 @@ def run_workload(name, args, torch, nat, dist_ctx, with_cpu):
     del out
     torch.cuda.empty_cache()
 
-    def time_host(fn):
+    each = {}
+
+    def time_host(fn, key="host"):
         fn()  # warm-up (page tables, allocator)
         if world > 1:
             torch.distributed.barrier()
         t0 = time.perf_counter()
+        marks = []
         for _ in range(e2e_steps):
             fn()
+            marks.append(time.perf_counter())
+        each[key] = [round((b - a) * 1e3, 2) for a, b in zip([t0] + marks[:-1], marks)]      # this rank's steps, ms
         return _max_over_ranks(torch, dev, world, time.perf_counter() - t0) / e2e_steps
 
     te = time_host(host_step)
@@ -353,17 +358,18 @@ def run_workload(name, args, torch, nat, dist_ctx, with_cpu):
         # the operator's fixed side (Y, W) kept on the device by a plan: a step moves X in and the result out
         plan = nat.KmatwPlan(Yh, Wh, scale, power, nconst, device=dev.index)
         ref4 = outh[:4].clone()
-        tp = time_host(lambda: plan.apply_host(Xh, outh))
+        tp = time_host(lambda: plan.apply_host(Xh, outh), "plan")
         assert bool(torch.equal(ref4, outh[:4])), "plan and one-shot results must agree bit for bit"
         plan.close()
         plan_e2e = {"value": float(n_total) * M / tp, "unit": "evals/s", "ms_per_step": tp * 1e3,
                     "h2d_bytes_per_step": int(4 * d * n_local), "d2h_bytes_per_step": int(d2h),
+                    "ms_each_step_rank0": each.get("plan"),
                     "what": "jrk_kmatw_plan_apply_host: Y / W and their tile images stay on the device"}
 
     res = {"value": value, "ms_per_step": t_step * 1e3, "steps": steps, "warmup": warm, "scaling": scaling,
            "roofline": roof, "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "steps": e2e_steps, "ms_per_step": te * 1e3,
+                   "steps": e2e_steps, "ms_per_step": te * 1e3, "ms_each_step_rank0": each.get("host"),
                    "what": "jrk_%s_f32_host: every input copied from pinned host memory, result copied back" % name},
            "config": workload_config(name, world)}
     if plan_e2e:
