@@ -34,10 +34,13 @@ namespace jrk {
 // tensor-core variant (kmatw_tc.cu)
 bool kmatw_tc_eligible(int64_t N, int64_t M, int d, int m, const float* dim_scale, int row_reduce, float nconst);
 size_t kmatw_tc_workspace_bytes(int64_t N, int64_t M);
+size_t kmatw_tc_rowsum_bytes(int64_t N);
+int kmatw_tc_rowsum(const float* T, int64_t N, int m, float scale, float* out, float* rpart, const unsigned* only_if_fast,
+                    cudaStream_t st);
 size_t kmatw_tc64_workspace_bytes(int64_t N, int64_t M);
 int kmatw_tc64(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
                int64_t ldy, int64_t ldw, int64_t ldo, float c, float nconst, const float* row_pref, const float* col_pref,
-               void* scratch, const unsigned** nmax_out, cudaStream_t st);
+               void* scratch, const unsigned** nmax_out, cudaStream_t st, int m_w = -1);
 int kmatw_tc(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
              int64_t ldy, int64_t ldw, int64_t ldo, float scale, float power, float nconst, const float* row_pref,
              const float* col_pref, int row_reduce, void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -128,7 +131,8 @@ size_t kmatw_workspace_bytes(int64_t N, int64_t M, int d, int m, int row_reduce,
         const size_t t = kmatw_tc_workspace_bytes(N, M);
         if (t > total) total = t;
     }
-    if (d > 32 && d <= 64 && N >= 8192 && M >= 4096) total += kmatw_tc64_workspace_bytes(N, M) + 256;
+    if (d > 32 && d <= 64 && N >= 8192 && M >= 4096)
+        total += kmatw_tc64_workspace_bytes(N, M) + align256((size_t)N * 64) + kmatw_tc_rowsum_bytes(N) + 1024;
     return total + 1024;
 }
 
@@ -225,7 +229,8 @@ bool kmatw_uses_tc(int64_t N, int64_t M, int d, int m, bool has_dim_scale, int r
 bool kmatw_tc64_eligible(int64_t N, int64_t M, int d, int m, bool has_dim_scale, float power, int row_reduce, const ExtraKind& ex) {
     return jrk_option(JRK_OPT_KMATW_TC) != 0 && jrk_option(JRK_OPT_TC_FAST) != 0 && jrk_option(JRK_OPT_TC_V2) != 0 &&
            ex.kind == 0 && !has_dim_scale && pick_pmode(power) == PM_SQEXP && d > 32 && d <= 64 && m >= 1 &&
-           row_reduce == JRK_REDUCE_NONE && N >= 8192 && M >= 4096 && M <= ((int64_t)1 << 30);
+           (row_reduce == JRK_REDUCE_NONE || row_reduce == JRK_REDUCE_SUM || row_reduce == JRK_REDUCE_MEAN) && N >= 8192 &&
+           M >= 4096 && M <= ((int64_t)1 << 30);
 }
 
 int kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m,
@@ -237,14 +242,23 @@ int kmatw(const float* X, const float* Y, const float* W, float* out, int64_t N,
         Scratch scr(workspace, workspace_bytes, st);
         JRK_CUDA_OK(scr.reserve(kmatw_workspace_bytes(N, M, d, m, row_reduce, group)));
         void* tcs = scr.take<char>(kmatw_tc64_workspace_bytes(N, M));
+        // Sum / Mean over rows: the tensor-core kernel writes the N x 16 block to scratch, reduced in a fixed order -- and
+        // only inside the factored regime; outside it the FP32-pipe kernel below writes the reduced result itself
+        const bool reduce_rows = row_reduce != JRK_REDUCE_NONE;
+        float* Tbuf = reduce_rows ? scr.take<float>((size_t)N * 16) : nullptr;
+        float* rpart = reduce_rows ? (float*)scr.take<char>(kmatw_tc_rowsum_bytes(N)) : nullptr;
         const size_t base = scr.used;
         const EpiParams ep = make_epi(scale, power, nconst);
         for (int c0 = 0; c0 < m; c0 += 16) {        // the tensor-core kernel: column blocks of 16
             const int mb = (m - c0 < 16) ? m - c0 : 16;
             const unsigned* skip = nullptr;
-            if (int rc = kmatw_tc64(X, Y, W + c0, out + c0, N, M, d, mb, ldx, ldy, ldw, ldo, ep.c, nconst, row_pref, col_pref, tcs,
-                                    &skip, st))
+            if (int rc = kmatw_tc64(X, Y, W + c0, reduce_rows ? Tbuf : out + c0, N, M, d, reduce_rows ? 16 : mb, ldx, ldy, ldw,
+                                    reduce_rows ? 16 : ldo, ep.c, nconst, row_pref, col_pref, tcs, &skip, st, mb))
                 return rc;
+            if (reduce_rows)
+                if (int rc = kmatw_tc_rowsum(Tbuf, N, mb, row_reduce == JRK_REDUCE_MEAN ? 1.f / (float)N : 1.f, out + c0, rpart,
+                                             skip, st))
+                    return rc;
             scr.used = base;
             if (int rc = kmatw_block(X, Y, W + c0, out + c0, N, M, d, mb, ldx, ldy, ldw, ldo, scale, dim_scale, power, nconst,
                                      row_pref, col_pref, row_reduce, group, ex, scr, st, skip))

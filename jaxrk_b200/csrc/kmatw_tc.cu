@@ -716,7 +716,11 @@ __global__ void tc_rowsum_kernel(const float* __restrict__ T, int64_t N, int64_t
         part[(int64_t)blockIdx.x * TC_MT + c] = s;
     }
 }
-__global__ void tc_rowsum_final_kernel(const float* __restrict__ part, int64_t nchunks, float scale, float* __restrict__ out, int m) {
+// only_if_fast (nullable): write only inside the factored regime (the d <= 64 path of kmatw.cu, whose FP32-pipe fallback
+// writes the reduced result itself outside it)
+__global__ void tc_rowsum_final_kernel(const float* __restrict__ part, int64_t nchunks, float scale, float* __restrict__ out, int m,
+                                       const unsigned* __restrict__ only_if_fast = nullptr) {
+    if (only_if_fast && !tc2_fast_regime(only_if_fast)) return;
     const int c = threadIdx.x;
     if (c >= m) return;
     float s = 0.f;
@@ -747,6 +751,18 @@ bool kmatw_tc_eligible(int64_t N, int64_t M, int d, int m, const float* dim_scal
 }
 
 constexpr int64_t TC_RS_CHUNK = 1024;    // rows per partial sum of the Sum / Mean reduction
+
+// Sum (scale = 1) / Mean (scale = 1 / N) over the rows of T (N x 16, dense) into out[0 .. m); rpart: ceil(N / 1024) x 16 floats
+size_t kmatw_tc_rowsum_bytes(int64_t N) { return align256((size_t)((N + TC_RS_CHUNK - 1) / TC_RS_CHUNK) * TC_MT * 4); }
+int kmatw_tc_rowsum(const float* T, int64_t N, int m, float scale, float* out, float* rpart, const unsigned* only_if_fast,
+                    cudaStream_t st) {
+    const int64_t nchunks = (N + TC_RS_CHUNK - 1) / TC_RS_CHUNK;
+    tc_rowsum_kernel<<<(unsigned)nchunks, 256, 0, st>>>(T, N, TC_RS_CHUNK, rpart);
+    JRK_LAUNCHED();
+    tc_rowsum_final_kernel<<<1, 32, 0, st>>>(rpart, nchunks, scale, out, m, only_if_fast);
+    JRK_LAUNCHED();
+    return JRK_OK;
+}
 
 // ---- the Y / W side (what a plan keeps: jrk_kmatw_plan_*) and the X side (what an apply needs) ----
 size_t kmatw_tc_prep_bytes(int64_t M, int d) {

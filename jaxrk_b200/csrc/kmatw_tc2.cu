@@ -638,9 +638,11 @@ size_t kmatw_tc64_workspace_bytes(int64_t N, int64_t M) {
     return align256((size_t)N * 4) + align256((size_t)M * 4) + 256 + align256((size_t)n_tiles * 20480) + 1024;
 }
 
+// m: columns written to `out` (16 when the caller reduces the full block afterwards); m_w: columns of W (default m).
 int kmatw_tc64(const float* X, const float* Y, const float* W, float* out, int64_t N, int64_t M, int d, int m, int64_t ldx,
                int64_t ldy, int64_t ldw, int64_t ldo, float c, float nconst, const float* row_pref, const float* col_pref,
-               void* scratch, const unsigned** nmax_out, cudaStream_t st) {
+               void* scratch, const unsigned** nmax_out, cudaStream_t st, int m_w) {
+    if (m_w < 0) m_w = m;
     char* p = (char*)scratch;
     float* xn = (float*)p; p += align256((size_t)N * 4);
     float* yn = (float*)p; p += align256((size_t)M * 4);
@@ -651,7 +653,7 @@ int kmatw_tc64(const float* X, const float* Y, const float* W, float* out, int64
     JRK_LAUNCHED();
     tc2_rownorm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(Y, M, d, ldy, c, yn, nmax + 1);
     JRK_LAUNCHED();
-    if (int rc = kmatw_tc2_pack(Y, W, M, d, m, ldy, ldw, col_pref, c, yn, nmax, img, st)) return rc;
+    if (int rc = kmatw_tc2_pack(Y, W, M, d, m_w, ldy, ldw, col_pref, c, yn, nmax, img, st)) return rc;
     if (int rc = kmatw_tc2_apply(X, N, d, ldx, xn, img, M, nmax, c, nconst, row_pref, out, ldo, m, st)) return rc;
     *nmax_out = nmax;
     return JRK_OK;

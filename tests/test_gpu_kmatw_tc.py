@@ -207,3 +207,27 @@ def test_tc2_d64_outside_the_factored_regime_is_the_fp32_kernel():
     with nat.option(nat.OPT_KMATW_TC, 0):
         R = nat.kmatw(X, Y, W, s, 2.0, 0.25)
     assert torch.equal(A, R)
+
+
+@pytest.mark.parametrize("rr", ["sum", "mean"])
+@pytest.mark.parametrize("ls", [8.0, 3.0])
+def test_tc2_d64_row_reduce(rr, ls):
+    """Sum / Mean over rows folded into the call at d = 64 (a mean embedding against an RKHS element): inside the factored
+    regime the tensor-core kernel + fixed-order row sums, outside it (ls = 3) the FP32-pipe kernel -- against float64."""
+    N, M, d, m = 20000, 8192, 64, 20
+    g = torch.Generator(device="cuda").manual_seed(17)
+    X, Y, W = (torch.randn(n_, c_, generator=g, device="cuda") for n_, c_ in ((N, d), (M, d), (M, m)))
+    s, nc = float(0.70710695 / ls), 0.25
+    code = nat.REDUCE_SUM if rr == "sum" else nat.REDUCE_MEAN
+    got = nat.kmatw(X, Y, W, s, 2.0, nc, row_reduce=code)
+    assert tuple(got.shape) == (1, m)
+    assert torch.equal(got, nat.kmatw(X, Y, W, s, 2.0, nc, row_reduce=code))
+    T = torch.zeros((1, m), dtype=torch.float64, device="cuda")
+    B = torch.zeros((1, m), dtype=torch.float64, device="cuda")
+    for r0 in range(0, N, 4000):
+        Kt = nc * torch.exp(-(s * torch.cdist(X[r0:r0 + 4000].double(), Y.double())) ** 2)
+        T += (Kt @ W.double()).sum(0, keepdim=True)
+        B += (Kt @ W.double().abs()).sum(0, keepdim=True)
+    if rr == "mean":
+        T, B = T / N, B / N
+    assert bool(((got.double() - T).abs() <= 1e-6 + 1e-5 * B).all())
