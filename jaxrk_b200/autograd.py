@@ -98,8 +98,11 @@ class _UnnormKmatw(torch.autograd.Function):
         G = G.contiguous().float()
         m = W.shape[1]
         gX = gY = gW = gs = gp = None
-        for c0 in range(0, m, 32):       # the fused backward kernel takes m <= 32; the gradient adds up over column blocks
-            Wb, Gb = W[:, c0:c0 + 32], G[:, c0:c0 + 32]
+        # the gradient adds up over column blocks: 32 columns for the FP32-pipe kernel, 16 where the tensor-core kernel
+        # (csrc/kgrad_tc.cu: p = 2, d <= 16, large problems) serves them -- two of its passes beat one FP32-pipe pass
+        blk = 16 if (p == 2.0 and X.shape[1] <= 16 and min(X.shape[0], Y.shape[0]) >= 4096) else 32
+        for c0 in range(0, m, blk):
+            Wb, Gb = W[:, c0:c0 + blk], G[:, c0:c0 + blk]
             if need_x or need_s or need_p:
                 res = nat.kmatw_grad(X, Y, Wb, Gb, s, p, 1.0, want_scale=need_s, want_power=need_p)
                 gx_b, gs_rows = res[0], res[1]
