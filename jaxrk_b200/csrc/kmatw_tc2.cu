@@ -58,18 +58,18 @@ constexpr int T2_STAGE = 12288;               // stage stride: the 12 KB image o
 constexpr int T2_EPQ_MAX = 4;
 constexpr int T2_COL_X = 0, T2_COL_XLO = 16, T2_COL_O = 32, T2_COL_S = 128;
 // What depends on the number of GEMM1 k-steps KS (16 features each): KS = 1 (d <= 16, 8 KB packed image), 2 (d <= 32,
-// 12 KB), 4 (d <= 64, 20 KB: [Y hi 64 x 128 B][Y lo 64 x 128 B][W' 32 x 128 B]).  KS = 4 parks 32 + 32 columns of x~, so the
+// 12 KB), 3 / 4 (d <= 48 / 64, 20 KB: [Y hi 64 x 128 B][Y lo 64 x 128 B][W' 32 x 128 B]).  These park 32 + 32 columns of x~, so the
 // O windows and the S / e stages move up and one stage goes: x~ [0, 64) | O [64, 160) | five stages [160, 480).
 template <int KS>
 struct T2V {
-    static constexpr int COL_XLO = KS == 4 ? 32 : T2_COL_XLO;
-    static constexpr int COL_O = KS == 4 ? 64 : T2_COL_O;
-    static constexpr int COL_S = KS == 4 ? 160 : T2_COL_S;
-    static constexpr int NS = KS == 4 ? 5 : T2_NS;
-    static constexpr int SOP = KS == 4 ? 7 : T2_SOP;
-    static constexpr int STAGE = KS == 4 ? 20480 : T2_STAGE;
+    static constexpr int COL_XLO = KS >= 3 ? 32 : T2_COL_XLO;
+    static constexpr int COL_O = KS >= 3 ? 64 : T2_COL_O;
+    static constexpr int COL_S = KS >= 3 ? 160 : T2_COL_S;
+    static constexpr int NS = KS >= 3 ? 5 : T2_NS;
+    static constexpr int SOP = KS >= 3 ? 7 : T2_SOP;
+    static constexpr int STAGE = KS >= 3 ? 20480 : T2_STAGE;
     static constexpr int YLO = KS == 1 ? 2 : (KS == 2 ? 4 : 512);            // Y lo against Y hi, in 16-byte units
-    static constexpr int WOFF = KS == 4 ? 1024 : 512;                         // W' region (KS >= 2), in 16-byte units
+    static constexpr int WOFF = KS >= 3 ? 1024 : 512;                         // W' region (KS >= 2), in 16-byte units
     static_assert(COL_S + NS * 64 <= 512 && COL_O + T2_NOB * 32 <= COL_S && SOP * STAGE <= T2_SOP * T2_STAGE, "budget");
 };
 constexpr int T2_OFF_RED = T2_SOP * T2_STAGE;                            // per-warp partial results of a unit (2 buffers)
@@ -612,12 +612,14 @@ int kmatw_tc2_apply(const float* X, int64_t N, int d, int64_t ldx, const float* 
                                          T2_SMEM));                                                                  \
         kmatw_tc2_kernel<EPQ_, KS_, TRACE_><<<grid, (5 + 4 * EPQ_) * 32, T2_SMEM, st>>>(P);                           \
     } while (0)
-    const int ks = d <= 16 ? 1 : (d <= 32 ? 2 : 4);
+    const int ks = d <= 16 ? 1 : (d <= 32 ? 2 : (d <= 48 ? 3 : 4));
     if (g_tc2_trace) {
         if (epq == 4) T2_LAUNCH(4, 1, true);
         else T2_LAUNCH(3, 1, true);
     } else if (ks == 4) {
         T2_LAUNCH(4, 4, false);                 // the x~ block of d <= 64 needs four parking warps per lane quarter
+    } else if (ks == 3) {
+        T2_LAUNCH(4, 3, false);
     } else if (epq == 3) {
         if (ks == 2) T2_LAUNCH(3, 2, false);
         else T2_LAUNCH(3, 1, false);

@@ -337,11 +337,13 @@ def reduced_gram_diag(k, X, chain) -> Optional[torch.Tensor]:
         return None
     dev = X.device
     f = fold_chain(chain, X.shape[0], dev)
+    n = X.shape[0]
     if f.post:
         return None
-    n = X.shape[0]
     if f.kind == NONE:
-        d0 = k(X, X, diag=True).reshape(-1)
+        if spec.kind != nat.KIND_GENGAUSS:                     # (ThreshSpikeKernel has no diag form: the full route)
+            return None
+        d0 = torch.full((n,), float(spec.kparams[2]), dtype=torch.float32, device=dev)     # k(x, x) = nconst
         return d0 if f.pref is None else d0 * f.pref * f.pref
     if f.kind in (SUM, MEAN):
         return None                                            # a 1 x 1 result: the full route is the same work
