@@ -479,3 +479,34 @@ def test_center_and_block_reduce_lowering():
     G6 = torch.from_numpy(rng.randn(6, 4).astype(f32))
     assert torch.allclose(b2(G6, 0), torch.stack([G6[0:2].sum(0), G6[2:5].sum(0), G6[5:6].sum(0)]), atol=1e-6)
     assert torch.allclose(b2(G6.T.contiguous(), 1), b2(G6, 0).T, atol=1e-6)
+
+
+def test_rkhs_cdist_uses_one_reduced_gram_and_diagonals_without_their_grams():
+    """dist(a, b) between vectors of mean embeddings (jaxrk/utilities/distances.py:28-42): one cross reduced Gram, the
+    diagonals from inner(full=False) -- block sums per BalancedRed group / one fused K(X, X) A^T for a LinearReduce -- and
+    one combining pass; against the reference's three-Gram form on the float64 Gram."""
+    from jaxrk_b200.utilities import dist, rkhs_gram_cdist
+    rng = np.random.RandomState(9)
+    X, Y = rng.randn(24, 3).astype(f32), (rng.randn(20, 3) + 0.2).astype(f32)
+    pp = (np.abs(rng.randn(24)) + 0.2).astype(f32)
+    A = rng.randn(4, 20).astype(f32)
+    k = GenGaussKernel.make_gauss(1.1)
+    a = FiniteVec(k, X, [Prefactors(pp), BalancedRed(6, True)])
+    b = FiniteVec(k, Y, [LinearReduce(A)])
+    CALLS.clear()
+    D = dist(a, b)
+    # nothing materialised: one cross K@W, one Sum-reduced K@W per group of `a`, one K(Y, Y) A^T for `b` (the combining
+    # pass is jrk_gram_affine_f32 on CUDA tensors, plain torch arithmetic on the 4 x 4 stand-in here)
+    assert CALLS == ["kmatw"] * 6, CALLS
+    args = k.kernel_args()
+    Kxy = _truth_gram(X, Y, args[0], args[2], args[3], None) * pp.astype(np.float64)[:, None]
+    Kxx = _truth_gram(X, None, args[0], args[2], args[3], None) * pp.astype(np.float64)[:, None] * pp.astype(np.float64)[None, :]
+    Kyy = _truth_gram(Y, None, args[0], args[2], args[3], None)
+    Gab = Kxy.reshape(4, 6, 20).mean(1) @ A.astype(np.float64).T
+    Gaa = Kxx.reshape(4, 6, 4, 6).mean((1, 3))
+    Gbb = A.astype(np.float64) @ Kyy @ A.astype(np.float64).T
+    want = np.diag(Gaa)[:, None] + np.diag(Gbb)[None, :] - 2 * Gab
+    np.testing.assert_allclose(D.numpy(), want, rtol=3e-5, atol=3e-6)
+    three = rkhs_gram_cdist(a.inner(b), a.inner(), b.inner())
+    np.testing.assert_allclose(D.numpy(), three.numpy(), rtol=3e-5, atol=3e-6)
+    np.testing.assert_allclose(a.inner(full=False).numpy(), np.diag(Gaa), rtol=3e-5, atol=3e-6)
