@@ -1,0 +1,51 @@
+"""Stress check of the tensor-core kernels: for a spread of shapes (several units per CTA, ragged tails, every tile-count
+residue, d from 3 to 64) the same call five times must give the same bits, and EVERY row must agree with the FP32-pipe
+kernel.  Usage: python tools/stress_determinism.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jaxrk_b200 import _native as nat  # noqa: E402
+
+dev = torch.device("cuda:0")
+
+
+def randn(seed, *shape):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    return torch.randn(*shape, generator=g, device=dev, dtype=torch.float32)
+
+
+bad = 0
+for i, (N, M, d, m) in enumerate([(75776, 8192, 16, 16), (50000, 4109, 8, 16), (151552 + 77, 4288, 5, 3), (40000, 6000, 16, 1),
+                                  (100000, 4330, 3, 16), (60000, 8384, 12, 7), (75776, 16384, 8, 1), (38000, 32768, 16, 16)]):
+    X, Y, W, G = randn(i, N, d), randn(i + 50, M, d), randn(i + 100, M, m), randn(i + 150, N, m)
+    scale = float(0.70710695 / (1.5 * np.sqrt(d)))
+    with nat.option(nat.OPT_KMATW_TC, 0):
+        r, sr = nat.kmatw_grad(X, Y, W, G, scale, 2.0, 0.1)
+        t0 = nat.kmatw(X, Y, W, scale, 2.0, 0.1)
+        tb = nat.kmatw(X, Y, W.abs(), scale, 2.0, 0.1)
+    outs = [nat.kmatw_grad(X, Y, W, G, scale, 2.0, 0.1) for _ in range(5)]
+    same = all(torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) for o in outs[1:])
+    off = int(((outs[0][0] - r).abs().max(1).values > 1e-3 * r.abs().max()).sum())
+    fw = [nat.kmatw(X, Y, W, scale, 2.0, 0.1) for _ in range(5)]
+    fsame = all(torch.equal(fw[0], o) for o in fw[1:])
+    foff = int((((fw[0] - t0).abs() > 2e-6 + 3e-5 * tb).any(1)).sum())
+    ok = same and off == 0 and fsame and foff == 0
+    bad += 0 if ok else 1
+    print(f"N={N} M={M} d={d} m={m}: backward repeat-identical {same}, rows off {off}; forward repeat-identical {fsame}, rows off {foff}", flush=True)
+for i, (N, M, d, m) in enumerate([(50000, 4109, 48, 16), (75776, 8192, 64, 5), (40000, 4288, 33, 16), (60000, 6000, 40, 20)]):
+    X, Y, W = randn(i + 7, N, d), randn(i + 57, M, d), randn(i + 107, M, m)
+    scale = float(0.70710695 / (1.2 * np.sqrt(d)))
+    with nat.option(nat.OPT_KMATW_TC, 0):
+        t0 = nat.kmatw(X, Y, W, scale, 2.0, 0.1)
+        tb = nat.kmatw(X, Y, W.abs(), scale, 2.0, 0.1)
+    fw = [nat.kmatw(X, Y, W, scale, 2.0, 0.1) for _ in range(5)]
+    fsame = all(torch.equal(fw[0], o) for o in fw[1:])
+    foff = int((((fw[0] - t0).abs() > 2e-6 + 3e-5 * tb).any(1)).sum())
+    bad += 0 if (fsame and foff == 0) else 1
+    print(f"N={N} M={M} d={d} m={m}: forward repeat-identical {fsame}, rows off {foff}", flush=True)
+print("FAILURES:", bad)
+sys.exit(1 if bad else 0)
