@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                             gv[h][c] = (gok[h] && j0 + c < P.M) ? __float_as_uint(__ldg(grow[h] + j0 + c)) : 0u;
                     }
                 }
+                __syncwarp();       // the branches above are per lane (rows past N): reconverge before the next .aligned tcgen05 op
             };
             // Tile t of the unit belongs to warp t mod EPQ (unit-local, so that a block of rows computed on its own -- another
             // rank's shard -- sums in the same order and gives the same bits).  The stage of a tile goes by the global index
