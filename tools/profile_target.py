@@ -42,6 +42,14 @@ def kmatw_tc():
     torch.cuda.synchronize()
 
 
+def kmatw_tc_d64():
+    N, M, d, m = 148 * 256, 131072, 64, 16
+    X, Y, W = randn(0, N, d), randn(1, M, d), randn(2, M, m)
+    for _ in range(2):
+        nat.kmatw(X, Y, W, 0.0883883, 2.0, 0.25)
+    torch.cuda.synchronize()
+
+
 def kgrad_tc():
     N, M, d, m = 148 * 256, 131072, 16, 16
     X, Y, W, G = randn(0, N, d), randn(1, M, d), randn(2, M, m), randn(3, N, m)
@@ -70,6 +78,8 @@ if __name__ == "__main__":
         kmatw()
     if what == "kmatw_tc":
         kmatw_tc()
+    if what == "kmatw_tc_d64":
+        kmatw_tc_d64()
     if what == "kgrad_tc":
         kgrad_tc()
     if what == "gram_grad_tc":
