@@ -116,13 +116,19 @@ class BlockReduce(Reduce):
         assert len(inp.shape) == 2
         assert self.block_boundaries[-1] <= len(inp), self.__class__.__name__ + " expects a longer gram to operate on"
         b = torch.as_tensor(self.block_boundaries, device=inp.device)
-        # block sums as differences of an exclusive prefix sum (float64 accumulation: the differences cancel)
-        cs = torch.zeros((inp.shape[0] + 1, inp.shape[1]), dtype=torch.float64, device=inp.device)
-        torch.cumsum(inp.double(), 0, out=cs[1:])
-        out = cs[b[1:]] - cs[b[:-1]]
-        if self.average:
-            out = out / (b[1:] - b[:-1]).double()[:, None]
-        return out.to(inp.dtype)
+        out = torch.empty((self.num_rows(), inp.shape[1]), dtype=inp.dtype, device=inp.device)
+        # block sums as differences of an exclusive prefix sum (float64 accumulation: the differences cancel), a slab of
+        # columns at a time so that the float64 scratch stays at ~1 GiB whatever the Gram's size
+        step = max(1, (1 << 27) // (inp.shape[0] + 1))
+        for c0 in range(0, inp.shape[1], step):
+            blk = inp[:, c0:c0 + step]
+            cs = torch.zeros((blk.shape[0] + 1, blk.shape[1]), dtype=torch.float64, device=inp.device)
+            torch.cumsum(blk.double(), 0, out=cs[1:])
+            o = cs[b[1:]] - cs[b[:-1]]
+            if self.average:
+                o = o / (b[1:] - b[:-1]).double()[:, None]
+            out[:, c0:c0 + step] = o.to(inp.dtype)
+        return out
 
     def new_len(self, original_len: int):
         assert self.block_boundaries[-1] <= original_len
