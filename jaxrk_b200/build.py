@@ -20,6 +20,12 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("JRK_EXTRA_NVCC_FLAGS", "").split()
 
 
+# Per-file additions.  kgrad_tc.cu: ptxas -O2.  At ptxas's default -O3 ONE instantiation of kgrad_tc_kernel (Gram
+# cotangent, 8 features, row-major cotangent) computed wrong, run-to-run different rows; at -O2 and -O1 it is right and
+# repeatable, and every instantiation runs at the same speed (1.262e12 pairs/s either way) -- profiles/README.md.
+PER_FILE_FLAGS = {"kgrad_tc.cu": ["-Xptxas", "-O2"]}
+
+
 def _deps_mtime():
     names = [f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     paths = [os.path.join(CSRC, f) for f in names] + [os.path.join(HERE, "..", "include", "jrk.h")]
@@ -31,7 +37,7 @@ def _compile(src, force, hdr_mtime, verbose):
     o = os.path.join(OBJ, src.replace(".cu", ".o"))
     if not force and os.path.exists(o) and os.path.getmtime(o) > max(os.path.getmtime(s), hdr_mtime):
         return o, ""
-    r = subprocess.run([NVCC] + FLAGS + ["-c", s, "-o", o], capture_output=True, text=True)
+    r = subprocess.run([NVCC] + FLAGS + PER_FILE_FLAGS.get(src, []) + ["-c", s, "-o", o], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
     return o, r.stderr

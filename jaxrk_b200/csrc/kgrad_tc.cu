@@ -562,10 +562,10 @@ int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, flo
         kgrad_tc_kernel<GBAR_, DK_><<<grid, GT_THREADS, GT_SMEM, st>>>(P);                                                  \
     } while (0)
     if (gbar) {
-        // (the 8-feature instantiation of the Gram-cotangent form gave wrong, run-to-run different rows with the row-major
-        // cotangent -- and only there; not understood, so that form always runs the 16-feature code, which every-row tests
-        // cover for d = 5, 8 and 16 in both cotangent layouts)
-        GT_LAUNCH(true, 16);
+        // (this file is compiled with ptxas -O2, jaxrk_b200/build.py: at -O3 the 8-feature instantiation of this form gave
+        // wrong, run-to-run different rows with the row-major cotangent; every-row tests cover d = 5, 8, 16 in both layouts)
+        if (d <= 8) GT_LAUNCH(true, 8);
+        else GT_LAUNCH(true, 16);
     } else {
         if (d <= 8) GT_LAUNCH(false, 8);
         else GT_LAUNCH(false, 16);
