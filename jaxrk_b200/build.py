@@ -20,10 +20,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("JRK_EXTRA_NVCC_FLAGS", "").split()
 
 
-# Per-file additions.  kgrad_tc.cu: ptxas -O2.  At ptxas's default -O3 ONE instantiation of kgrad_tc_kernel (Gram
-# cotangent, 8 features, row-major cotangent) computed wrong, run-to-run different rows; at -O2 and -O1 it is right and
-# repeatable, and every instantiation runs at the same speed (1.262e12 pairs/s either way) -- profiles/README.md.
-PER_FILE_FLAGS = {"kgrad_tc.cu": ["-Xptxas", "-O2"]}
+PER_FILE_FLAGS = {}      # {source: [extra nvcc flags]}
 
 
 def _deps_mtime():

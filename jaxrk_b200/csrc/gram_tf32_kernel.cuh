@@ -403,6 +403,7 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready);
+            __syncwarp();
             const float ys = jok ? __ldg(yn + j) : 0.f;   // (scaled) |y_j|^2 + half of the folded constant
             const f32x2 ys2 = pack2(ys, ys);
             // H16: x.y = 2^(ex+ey) (c1 + 2^-11 cross): the power of two rides in `a`
@@ -453,6 +454,7 @@ gram_tf32_kernel(const float* __restrict__ Ximg, const float* __restrict__ Xp, c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);   // TMEM stage free: the next tile's MMAs overlap the math below
+                __syncwarp();
 
                 // u = a * dot + (xs_i + ys_j)  and the near-zero test  w = u - tau * (xs_i + ys_j):
                 //   PM_SQEXP : a = -2c, xs/ys = c|.|^2 + log2(nconst)/2 (c < 0): u = log2 K;  refine if w > w0

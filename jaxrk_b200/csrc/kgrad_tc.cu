@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) bar_arrive(b_xready);
+            __syncwarp();       // reconverge: the next tcgen05 instruction of this warp is .sync.aligned
         };
 
         uint32_t gt = 0, uc = 0;
@@ -304,7 +305,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                             gv[h][c] = (gok[h] && j0 + c < P.M) ? __float_as_uint(__ldg(grow[h] + j0 + c)) : 0u;
                     }
                 }
-                __syncwarp();       // the branches above are per lane (rows past N): reconverge before the next .aligned tcgen05 op
+                // The branches above are per lane.  Every tcgen05.ld / st / wait is .sync.aligned: all 32 lanes must execute it
+                // together, and after divergent code that needs an explicit reconvergence point.  Without this line the
+                // 8-feature build of this form computed wrong, run-to-run different rows (the compiler happened to keep the
+                // other instantiations converged).
+                __syncwarp();
             };
             // Tile t of the unit belongs to warp t mod EPQ (unit-local, so that a block of rows computed on its own -- another
             // rank's shard -- sums in the same order and gives the same bits).  The stage of a tile goes by the global index
@@ -369,14 +374,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                         }
                     }
                 }
-                // (Handing the TMEM stage back earlier -- right after the last tcgen05.wait::ld, a quarter of the tile's FMA work
-                // before this point -- measured no faster, and gave wrong rows in the slowest lane quarter whenever a CTA
-                // processed more than one unit; not understood, not kept.)
+                // (Handing the TMEM stage back earlier -- an `if (lane == 0) arrive` in the middle of the chunk loop -- measured
+                // no faster and gave wrong rows; in hindsight the same fault as in load_gbar: lane-divergent code in front of
+                // .sync.aligned tcgen05 instructions without a reconvergence point.)
                 __syncwarp();
                 if (lane == 0) {
                     bar_arrive(b_sempty + a * 8);
                     bar_arrive(b_opempty + s * 8);
                 }
+                __syncwarp();   // reconverge before the next tile's .sync.aligned tcgen05.ld
                 if (++since == GT_FLUSH) { flush(); since = 0; }
             }
             // the EPQ partial results of a lane quarter meet in shared memory
@@ -562,8 +568,8 @@ int kgrad_tc(const float* X, const float* Y, const float* W, const float* G, flo
         kgrad_tc_kernel<GBAR_, DK_><<<grid, GT_THREADS, GT_SMEM, st>>>(P);                                                  \
     } while (0)
     if (gbar) {
-        // (this file is compiled with ptxas -O2, jaxrk_b200/build.py: at -O3 the 8-feature instantiation of this form gave
-        // wrong, run-to-run different rows with the row-major cotangent; every-row tests cover d = 5, 8, 16 in both layouts)
+        // (the 8-feature instantiation of this form is where the missing reconvergence in load_gbar showed: wrong,
+        // run-to-run different rows with the row-major cotangent; every-row tests cover d = 5, 8, 16 in both layouts)
         if (d <= 8) GT_LAUNCH(true, 8);
         else GT_LAUNCH(true, 16);
     } else {

@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(x_ready);
+            __syncwarp();
             float oacc[4] = {0.f, 0.f, 0.f, 0.f};
 
             auto fold_window = [&]() {   // O buffers of window wc, this warp's 4 columns -> registers
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(b_oempty + ob * 8);
+                __syncwarp();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) oacc[c] += o[c] + ox[c];
                 ++wc;
@@ -383,6 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(ber);
+                __syncwarp();
             };
             auto tile_dyn = [&](int t) {       // stage index in a register
                 convert_tile(b_sfull0 + sa * 8, b_sfull0 + TC_SS * 8 + sa * 8, s_col0 + sa * 128, sa_ph);
@@ -459,6 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(x_ready);
+            __syncwarp();
             const float xs = iok ? __ldg(P.xn + i) : 0.f;
             const f32x2 xs2 = pack2(xs, xs);
             float oacc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -474,6 +478,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(b_oempty + ob * 8);
+                __syncwarp();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) oacc[c] += o[c] + ox[c];
                 ++wc;
@@ -557,6 +562,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmatw_tc_kernel(TcParams P, Epi
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(b_eready + sa * 8);
+                __syncwarp();
             };
             auto tile_dyn = [&](int t) {       // stage indices in registers
                 if (check) tile(t, std::true_type{}, st, st_ph, sa, sa_ph);

@@ -204,6 +204,7 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
             bool xseen = false;
             const int n_first = (int)((j - gw) & 3u);
             if (n_first >= ngrp && lane == 0) bar_arrive(b_xfree);     // no group of this unit is ours
+            __syncwarp();
             for (int n = n_first; n < ngrp; n += 4) {
                 if (!xseen) { bar_wait(b_xready, uc & 1); xseen = true; }
                 // A parity wait is only meaningful when the waiter is at most ONE phase behind the barrier, and this warp
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
             tc_fence_before();
             __syncwarp();
             if (lane == 0) bar_arrive(b_xready);
+            __syncwarp();       // reconverge: what follows are .sync.aligned tcgen05 instructions
         };
 
         uint32_t gt = 0, gw = 0, uc = 0;           // tiles / windows / units this CTA has finished
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(b_oempty + ob * 8);
+                __syncwarp();
 #pragma unroll
                 for (int c = 0; c < T2_MT; ++c) oacc[c] += fmaf(__uint_as_float(ox[c]), 1.f / 2048.f, __uint_as_float(o[c]));
                 next_w += EPQ;
@@ -383,16 +386,19 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
                 exp_split16(s0, eo);
                 tmem_st16(sc, eo);
                 if (token_rel == 1 && lane == 0) bar_arrive(b_half + k * 8);
+                if (token_rel == 1) __syncwarp();
                 ld16_wait(s1);
                 ld16_async(sc + 32, s0);
                 exp_split16(s1, eo);
                 tmem_st16(sc + 16, eo);
                 if (token_rel == 2 && lane == 0) bar_arrive(b_half + k * 8);
+                if (token_rel == 2) __syncwarp();
                 ld16_wait(s0);
                 ld16_async(sc + 48, s1);
                 exp_split16(s0, eo);
                 tmem_st16(sc + 32, eo);
                 if (token_rel == 3 && lane == 0) bar_arrive(b_half + k * 8);
+                if (token_rel == 3) __syncwarp();
                 ld16_wait(s1);
                 exp_split16(s1, eo);
                 tmem_st16(sc + 48, eo);
@@ -401,6 +407,7 @@ __global__ void __launch_bounds__((5 + 4 * EPQ) * 32, 1) kmatw_tc2_kernel(Tc2Par
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(b_eready + a * 8);
+                __syncwarp();   // reconverge before the fold's / the next tile's .sync.aligned tcgen05.ld
                 if (TRACE && blockIdx.x == 0 && uc == 0 && t < T2_TRACE_TILES && lane == 0) {
                     long long* tr = P.trace + ((int64_t)warp * T2_TRACE_TILES + t) * 4;
                     tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = clock64();
