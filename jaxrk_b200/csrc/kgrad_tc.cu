@@ -374,9 +374,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) kgrad_tc_kernel(GtParams P) {
                         }
                     }
                 }
-                // (Handing the TMEM stage back earlier -- an `if (lane == 0) arrive` in the middle of the chunk loop -- measured
-                // no faster and gave wrong rows; in hindsight the same fault as in load_gbar: lane-divergent code in front of
-                // .sync.aligned tcgen05 instructions without a reconvergence point.)
+                // (Handing the TMEM stage back before the last chunk's FMAs -- all its values are in registers by then -- was
+                // tried twice.  Round-2 re-run with reconvergence points around the arrive: K@W cotangent 6 % SLOWER (16.7 vs
+                // 15.75 ms at 151552 x 131072), transposed Gram cotangent 5 % faster, and the row-major Gram cotangent came out
+                // wrong in whole warps, differently from run to run (profiles/README.md).  Not understood, not used.)
                 __syncwarp();
                 if (lane == 0) {
                     bar_arrive(b_sempty + a * 8);
