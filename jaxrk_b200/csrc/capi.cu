@@ -371,10 +371,18 @@ int jrk_gram_groupsum_f32(const float* X, const float* Y, float* out, int64_t N,
 }  // extern "C"
 
 namespace {
+// Device buffers of the host-buffer entry points: stream-ordered allocations from the device's default pool, whose memory
+// keep_pool_memory() retains across calls -- a call in steady state makes no cudaMalloc / cudaFree (those cost 0.2 .. 1.2 s
+// in four of ten calls on one box: profiles/README.md).  Freed in stream order by the destructor; the entry points
+// synchronise their streams before they return.
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    cudaStream_t s = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        s = stream;
+        return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+    }
     template <typename T> T* as() { return (T*)p; }
 };
 struct DeviceGuard {     // the host-buffer entry points run on `device` and leave the caller's current device alone
@@ -416,27 +424,27 @@ int jrk_gram_f32_host(const float* X, const float* Y, float* K, int64_t N, int64
     JRK_CUDA_OK(cudaStreamCreateWithFlags(&sc.s, cudaStreamNonBlocking));
     JRK_CUDA_OK(cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking));
     DevBuf dX, dY, dS, dK[2], dW;
-    JRK_CUDA_OK(dX.alloc((size_t)N * d * 4));
+    JRK_CUDA_OK(dX.alloc((size_t)N * d * 4, sc.s));
     JRK_CUDA_OK(cudaMemcpyAsync(dX.p, X, (size_t)N * d * 4, cudaMemcpyHostToDevice, sc.s));
     const float* dYp = dX.as<float>();
     if (!self) {
-        JRK_CUDA_OK(dY.alloc((size_t)M * d * 4));
+        JRK_CUDA_OK(dY.alloc((size_t)M * d * 4, sc.s));
         JRK_CUDA_OK(cudaMemcpyAsync(dY.p, Y, (size_t)M * d * 4, cudaMemcpyHostToDevice, sc.s));
         dYp = dY.as<float>();
     }
     const float* dSp = nullptr;
     if (dim_scale) {
-        JRK_CUDA_OK(dS.alloc((size_t)d * 4));
+        JRK_CUDA_OK(dS.alloc((size_t)d * 4, sc.s));
         JRK_CUDA_OK(cudaMemcpyAsync(dS.p, dim_scale, (size_t)d * 4, cudaMemcpyHostToDevice, sc.s));
         dSp = dS.as<float>();
     }
     // row blocks of ~256 MiB: block b+1 is computed while block b is copied out
     int64_t B = std::max<int64_t>(128, ((int64_t)256 << 20) / (M * 4) / 128 * 128);
     B = std::min(B, (N + 127) / 128 * 128);
-    JRK_CUDA_OK(dK[0].alloc((size_t)B * M * 4));
-    JRK_CUDA_OK(dK[1].alloc((size_t)B * M * 4));
+    JRK_CUDA_OK(dK[0].alloc((size_t)B * M * 4, sc.s));
+    JRK_CUDA_OK(dK[1].alloc((size_t)B * M * 4, sc.s));
     const size_t wsb = jrk_gram_workspace_bytes(B, M, d, path);
-    if (wsb) JRK_CUDA_OK(dW.alloc(wsb));
+    if (wsb) JRK_CUDA_OK(dW.alloc(wsb, sc.s));
     EventGuard done[2], freed[2];
     for (int i = 0; i < 2; ++i) {
         JRK_CUDA_OK(cudaEventCreateWithFlags(&done[i].e, cudaEventDisableTiming));
@@ -449,7 +457,10 @@ int jrk_gram_f32_host(const float* X, const float* Y, float* K, int64_t N, int64
         if (b >= 2) JRK_CUDA_OK(cudaStreamWaitEvent(sc.s, freed[s].e, 0));
         int rc = jrk_gram_f32(dX.as<float>() + r * d, dYp, dK[s].as<float>(), n, M, d, d, d, M, scale, dSp, power,
                               nconst, path, dW.p, wsb, sc.s);
-        if (rc) return rc;
+        if (rc) {
+            cudaStreamSynchronize(sd.s);    // the buffers go back to the pool in sc's order: no copy may still read them
+            return rc;
+        }
         JRK_CUDA_OK(cudaEventRecord(done[s].e, sc.s));
         JRK_CUDA_OK(cudaStreamWaitEvent(sd.s, done[s].e, 0));
         JRK_CUDA_OK(cudaMemcpyAsync(K + r * M, dK[s].p, (size_t)n * M * 4, cudaMemcpyDeviceToHost, sd.s));
@@ -475,7 +486,7 @@ int jrk_kmatw_f32_host(const float* X, const float* Y, const float* W, float* ou
     else if (row_reduce != JRK_REDUCE_NONE) out_rows = N / group;
     DevBuf dX, dY, dWt, dO, dS, dRP, dCP;
     auto up = [&](DevBuf& b, const float* h, size_t count) -> cudaError_t {
-        cudaError_t e = b.alloc(count * 4);
+        cudaError_t e = b.alloc(count * 4, sc.s);
         if (e != cudaSuccess) return e;
         return cudaMemcpyAsync(b.p, h, count * 4, cudaMemcpyHostToDevice, sc.s);
     };
@@ -485,7 +496,7 @@ int jrk_kmatw_f32_host(const float* X, const float* Y, const float* W, float* ou
     if (dim_scale) JRK_CUDA_OK(up(dS, dim_scale, (size_t)d));
     if (row_pref) JRK_CUDA_OK(up(dRP, row_pref, (size_t)N));
     if (col_pref) JRK_CUDA_OK(up(dCP, col_pref, (size_t)M));
-    JRK_CUDA_OK(dO.alloc((size_t)out_rows * m * 4));
+    JRK_CUDA_OK(dO.alloc((size_t)out_rows * m * 4, sc.s));
     int rc = jrk_kmatw_f32(dX.as<float>(), dY.as<float>(), dWt.as<float>(), dO.as<float>(), N, M, d, m, d, d, m, m,
                            scale, dim_scale ? dS.as<float>() : nullptr, power, nconst,
                            row_pref ? dRP.as<float>() : nullptr, col_pref ? dCP.as<float>() : nullptr, row_reduce,
