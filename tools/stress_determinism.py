@@ -47,5 +47,30 @@ for i, (N, M, d, m) in enumerate([(50000, 4109, 48, 16), (75776, 8192, 64, 5), (
     foff = int((((fw[0] - t0).abs() > 2e-6 + 3e-5 * tb).any(1)).sum())
     bad += 0 if (fsame and foff == 0) else 1
     print(f"N={N} M={M} d={d} m={m}: forward repeat-identical {fsame}, rows off {foff}", flush=True)
+# Gram cotangent on the tensor-core kernel, both layouts, quiet and with a copy loop hammering HBM / L2 on a second stream
+# (shifts the relative timing of the epilogue, MMA and TMA warps): the same bits five times, every row against the
+# FP32-pipe kernel.
+side = torch.cuda.Stream()
+junk_a = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+junk_b = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+for i, (N, M, d) in enumerate([(8192, 8192, 16), (4396, 4108, 7), (4224, 6000, 3), (40000, 4108, 7), (33000, 8200, 16), (20000, 16384, 12)]):
+    X, Y, Gb = randn(i + 11, N, d), randn(i + 61, M, d), randn(i + 111, N, M)
+    GbT = Gb.t().contiguous()
+    scale = float(0.70710695 / (1.5 * np.sqrt(d)))
+    with nat.option(nat.OPT_KMATW_TC, 0):
+        r, _ = nat.gram_grad(X, Y, Gb, scale, 2.0, 0.1)
+    for noisy in (False, True):
+        if noisy:
+            torch.cuda.synchronize()
+            with torch.cuda.stream(side):
+                for _ in range(40):
+                    junk_b.copy_(junk_a)
+        a = [nat.gram_grad(X, Y, Gb, scale, 2.0, 0.1)[0] for _ in range(5)]
+        b = [nat.gram_grad(X, Y, GbT, scale, 2.0, 0.1, transposed=True)[0] for _ in range(5)]
+        torch.cuda.synchronize()
+        same = all(torch.equal(a[0], o) for o in a[1:]) and all(torch.equal(b[0], o) for o in b[1:]) and torch.equal(a[0], b[0])
+        off = int(((a[0] - r).abs().max(1).values > 1e-3 * r.abs().max()).sum())
+        bad += 0 if (same and off == 0) else 1
+        print(f"gram cotangent N={N} M={M} d={d} noisy={noisy}: both layouts repeat-identical and equal {same}, rows off {off}", flush=True)
 print("FAILURES:", bad)
 sys.exit(1 if bad else 0)
