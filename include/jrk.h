@@ -16,6 +16,10 @@
  *     allocator (cudaMallocAsync / cudaFreeAsync on `stream`) otherwise.
  *   - *_host entry points take HOST pointers, run on CUDA device `device`, include
  *     the host<->device copies, and return after the result is in host memory.
+ *     Their device buffers come from the device's default stream-ordered pool, whose
+ *     release threshold they raise so that the memory stays with the process between
+ *     calls (no cudaMalloc / cudaFree in steady state); the caller's current device is
+ *     restored before they return.
  *   - Return value: 0 = ok; non-zero = JRK_ERR_*.  jrk_last_error() gives the text.
  *     Nothing throws.  There is no CPU fallback: without a CUDA device every compute
  *     entry point returns JRK_ERR_CUDA.
