@@ -25,7 +25,6 @@ done by libjaxrk_b200.so.
 """
 from __future__ import annotations
 
-import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -144,6 +143,7 @@ def _row_reduce_of(f: Folded):
 
 WIDE_M = 64                       # columns of W from which "Gram slab + library GEMM" beats the FP32-pipe kernel's column blocks
 WIDE_SLAB_BYTES = 2 << 30         # FP32 bytes of one materialised row slab of K
+GROUPSUM_TENSOR = True            # BalancedRed x BalancedRed inside the tensor-core window: group sums by the fused K@W kernel
 
 
 def _kmatw_wide(X, Y, W, spec, row_pref, col_pref) -> torch.Tensor:
@@ -389,7 +389,7 @@ def reduced_gram(k, X, chain_x, Y, chain_y, self_gram: bool = False) -> torch.Te
     elif fx.kind in skinny:
         out = _kmatw_side(Y, X, fy, fx, spec).t()
     elif (gg and fx.kind == BALANCED and fy.kind == BALANCED and dim_scale is None and 12 <= X.shape[1] <= 32
-          and X.shape[0] * fy.group * 16 >= (1 << 30) and os.environ.get("JRK_GROUPSUM_TC", "1") != "0"
+          and X.shape[0] * fy.group * 16 >= (1 << 30) and GROUPSUM_TENSOR
           and nat.lib().jrk_kmatw_uses_tensor_cores(X.shape[0] // 2, 16 * fy.group, X.shape[1], 16, 0, 0)):
         out = _groupsum_tensor(X, Y, fx, fy, scale, power, nconst, self_gram)
         if fx.average or fy.average:

@@ -11,7 +11,7 @@ from scipy.spatial.distance import cdist
 from jaxrk_b200 import _native as nat
 from jaxrk_b200.kern import GenGaussKernel
 from jaxrk_b200.reduce import BalancedRed, LinearReduce, Mean, Prefactors, Sum
-from jaxrk_b200.rkhs import Cdo, Cmo, Cov_inv, CovOp, FiniteOp, FiniteVec, inner
+from jaxrk_b200.rkhs import Cdo, Cmo, Cov_inv, CovOp, FiniteOp, FiniteVec, _lowering, inner
 from jaxrk_b200.utilities import dist, eucldist
 from oracle import jaxrk_oracle as orc
 from test_lowering_cpu import chains_x, chains_y
@@ -186,7 +186,7 @@ def test_balanced_inner_through_the_tensor_core_route(monkeypatch):
     vy = FiniteVec(k, Y, [BalancedRed(gy, False)])
     A = inner(vx, vy)
     S = FiniteVec(k, X, [BalancedRed(gy, True)]).inner()
-    monkeypatch.setenv("JRK_GROUPSUM_TC", "0")
+    monkeypatch.setattr(_lowering, "GROUPSUM_TENSOR", False)
     A0 = inner(vx, vy)
     S0 = FiniteVec(k, X, [BalancedRed(gy, True)]).inner()
     assert tuple(A.shape) == (N // gx, M // gy) and tuple(S.shape) == (N // gy, N // gy)
