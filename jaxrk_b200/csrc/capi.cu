@@ -399,6 +399,15 @@ struct StreamGuard {
     cudaStream_t s = nullptr;
     ~StreamGuard() { if (s) cudaStreamDestroy(s); }
 };
+// Declared AFTER the DevBufs of an entry point, so destroyed before them: whatever path leaves the function, no stream
+// still touches a buffer when it goes back to the pool.
+struct SyncOnExit {
+    cudaStream_t a = nullptr, b = nullptr;
+    ~SyncOnExit() {
+        if (a) cudaStreamSynchronize(a);
+        if (b) cudaStreamSynchronize(b);
+    }
+};
 struct EventGuard {
     cudaEvent_t e = nullptr;
     ~EventGuard() { if (e) cudaEventDestroy(e); }
@@ -424,6 +433,7 @@ int jrk_gram_f32_host(const float* X, const float* Y, float* K, int64_t N, int64
     JRK_CUDA_OK(cudaStreamCreateWithFlags(&sc.s, cudaStreamNonBlocking));
     JRK_CUDA_OK(cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking));
     DevBuf dX, dY, dS, dK[2], dW;
+    SyncOnExit sync_on_exit{sc.s, sd.s};
     JRK_CUDA_OK(dX.alloc((size_t)N * d * 4, sc.s));
     JRK_CUDA_OK(cudaMemcpyAsync(dX.p, X, (size_t)N * d * 4, cudaMemcpyHostToDevice, sc.s));
     const float* dYp = dX.as<float>();
@@ -457,10 +467,7 @@ int jrk_gram_f32_host(const float* X, const float* Y, float* K, int64_t N, int64
         if (b >= 2) JRK_CUDA_OK(cudaStreamWaitEvent(sc.s, freed[s].e, 0));
         int rc = jrk_gram_f32(dX.as<float>() + r * d, dYp, dK[s].as<float>(), n, M, d, d, d, M, scale, dSp, power,
                               nconst, path, dW.p, wsb, sc.s);
-        if (rc) {
-            cudaStreamSynchronize(sd.s);    // the buffers go back to the pool in sc's order: no copy may still read them
-            return rc;
-        }
+        if (rc) return rc;
         JRK_CUDA_OK(cudaEventRecord(done[s].e, sc.s));
         JRK_CUDA_OK(cudaStreamWaitEvent(sd.s, done[s].e, 0));
         JRK_CUDA_OK(cudaMemcpyAsync(K + r * M, dK[s].p, (size_t)n * M * 4, cudaMemcpyDeviceToHost, sd.s));
@@ -485,6 +492,7 @@ int jrk_kmatw_f32_host(const float* X, const float* Y, const float* W, float* ou
     if (row_reduce == JRK_REDUCE_SUM || row_reduce == JRK_REDUCE_MEAN) out_rows = 1;
     else if (row_reduce != JRK_REDUCE_NONE) out_rows = N / group;
     DevBuf dX, dY, dWt, dO, dS, dRP, dCP;
+    SyncOnExit sync_on_exit{sc.s, nullptr};
     auto up = [&](DevBuf& b, const float* h, size_t count) -> cudaError_t {
         cudaError_t e = b.alloc(count * 4, sc.s);
         if (e != cudaSuccess) return e;
